@@ -1,0 +1,80 @@
+"""Build recipe for the native pieces (run here on CPU: nvcc cross-compiles sm_100a).
+
+  libaby3cu.so  -- CUDA kernels + C ABI (include/aby3cu.h), one translation unit
+  libsh3.so     -- the C++ sh3 facade (aby3_b200/sh3) + its C harness, links libaby3cu
+  oracle/liboracle.so -- CPU oracle (test infrastructure only)
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "aby3_b200")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+    return r.stdout
+
+
+def _sources(d, exts):
+    out = []
+    for base, _, files in os.walk(d):
+        for f in files:
+            if f.endswith(exts):
+                out.append(os.path.join(base, f))
+    return out
+
+
+def build_cuda(force=False):
+    so = os.path.join(PKG, "libaby3cu.so")
+    srcs = _sources(os.path.join(PKG, "csrc"), (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "aby3cu.h")]
+    if force or _newer(so, srcs):
+        _run([NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+              "-o", so, os.path.join(PKG, "csrc", "aby3cu_all.cu")])
+    return so
+
+
+def build_sh3(force=False):
+    so = os.path.join(PKG, "libsh3.so")
+    d = os.path.join(PKG, "sh3")
+    if not os.path.isdir(d):
+        return None
+    srcs = _sources(d, (".cpp", ".h")) + [os.path.join(ROOT, "include", "aby3cu.h")]
+    cpps = [s for s in srcs if s.endswith(".cpp")]
+    if not cpps:
+        return None
+    if force or _newer(so, srcs + [os.path.join(PKG, "libaby3cu.so")]):
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall",
+              "-I", ROOT, "-I", os.path.join(ROOT, "include"), "-o", so, *cpps,
+              "-L", PKG, "-laby3cu", "-Wl,-rpath,$ORIGIN"])
+    return so
+
+
+def build_oracle(force=False):
+    d = os.path.join(ROOT, "oracle")
+    so = os.path.join(d, "liboracle.so")
+    if force or _newer(so, [os.path.join(d, "oracle.cpp"), os.path.join(d, "oracle.h")]):
+        _run(["make", "-C", d, "-B", "liboracle.so"])
+    return so
+
+
+def build_all(force=False):
+    return [build_cuda(force), build_sh3(force), build_oracle(force)]
+
+
+if __name__ == "__main__":
+    for p in build_all(force="--force" in sys.argv):
+        print("built", p)

@@ -1,0 +1,230 @@
+// binary.cu -- kernels behind Sh3BinaryEvaluator: bit-matrix transposes between
+// the row-major sbMatrix layout and the bit-sliced wire memory, the per-level
+// gate interpreter with in-register AES-CTR zero shares, and the send-buffer
+// pack / receive scatter.  All HBM-bound bitwise work on 128-bit words.
+#include "aes.cuh"
+
+namespace aby3cu {
+namespace {
+
+// ---------------------------------------------------------------------------------
+// Bit-matrix transpose (oc::transpose semantics, LSB first).  A CTA stages a
+// TR x (32*TCW)-bit tile in shared memory, warps transpose 32x32-bit blocks
+// with 32 ballots, and the transposed tile is written back in full words so
+// both the global reads and the global writes are coalesced.
+// ---------------------------------------------------------------------------------
+template <int TR, int TCW>
+__global__ void __launch_bounds__(256) k_bit_transpose(const u8* __restrict__ in, const u32* __restrict__ row_index,
+                                                       u64 rows, u64 cols, u64 in_stride,
+                                                       u8* __restrict__ out, u64 out_stride,
+                                                       const u8* __restrict__ invert) {
+    constexpr int TRW = TR / 32;
+    __shared__ u32 sIn[TR][TCW + 1];
+    __shared__ u32 sOut[TCW * 32][TRW + 1];
+    const u64 tiles_r = (rows + TR - 1) / TR, tiles_c = (cols + 32 * TCW - 1) / (32 * TCW);
+    const u64 in_row_words = (cols + 31) / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (u64 t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
+        const u64 r0 = (t / tiles_c) * TR, cw0 = (t % tiles_c) * TCW;
+        for (int idx = threadIdx.x; idx < TR * TCW; idx += blockDim.x) {
+            const int r = idx / TCW, cw = idx % TCW;
+            const u64 gr = r0 + r, gw = cw0 + cw;
+            u32 w = 0;
+            if (gr < rows && gw < in_row_words) {
+                const u64 src_row = row_index ? (u64)row_index[gr] : gr;
+                w = *reinterpret_cast<const u32*>(in + src_row * in_stride + gw * 4);
+                if (invert && invert[gr]) w = ~w;
+            }
+            sIn[r][cw] = w;
+        }
+        __syncthreads();
+        for (int b = warp; b < TRW * TCW; b += nwarps) {
+            const int rb = b / TCW, cw = b % TCW;
+            const u32 w = sIn[rb * 32 + lane][cw];
+            u32 mine = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const u32 bal = __ballot_sync(0xffffffffu, (w >> j) & 1u);
+                if (lane == j) mine = bal;
+            }
+            sOut[cw * 32 + lane][rb] = mine;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < TCW * 32 * TRW; idx += blockDim.x) {
+            const int orow = idx / TRW, ow = idx % TRW;
+            const u64 gc = cw0 * 32 + orow;          // output row = input column
+            const u64 gr = r0 + (u64)ow * 32;        // first input row covered by this word
+            if (gc < cols && gr < rows)
+                *reinterpret_cast<u32*>(out + gc * out_stride + (gr / 32) * 4) = sOut[orow][ow];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// One AND-depth level.  A thread owns one 16-byte column chunk of every wire row
+// and walks the level's gate list in order, so chains of linear gates inside a
+// level see their own earlier writes (same thread, same addresses).
+// ---------------------------------------------------------------------------------
+struct alignas(16) W2 { u64 a, b; };
+
+__device__ __forceinline__ W2 ldw(const u64* mem, u64 row, u64 rw, u64 c) { return *reinterpret_cast<const W2*>(mem + row * rw + 2 * c); }
+__device__ __forceinline__ void stw(u64* mem, u64 row, u64 rw, u64 c, W2 v) { *reinterpret_cast<W2*>(mem + row * rw + 2 * c) = v; }
+
+template <bool AES>
+__global__ void __launch_bounds__(256) k_bin_level(const uint4* __restrict__ gates, u32 n_gates, u64* mem0, u64* mem1, u64 rw,
+                                                   const __grid_constant__ AesKey kp, const __grid_constant__ AesKey kn, u64 and0) {
+    if (AES) { aes_table_init(); __syncthreads(); }
+    const u32 Tl = (threadIdx.x & 31) * 4;
+    const u64 chunks = rw / 2;
+    for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (u64)gridDim.x * blockDim.x) {
+        u64 and_idx = and0;
+        for (u32 g = 0; g < n_gates; ++g) {
+            const uint4 G = gates[g];
+            const u32 type = G.w;
+            const W2 a0 = ldw(mem0, G.x, rw, c), a1 = ldw(mem1, G.x, rw, c);
+            W2 b0 = {0, 0}, b1 = {0, 0};
+            if (type != 10) { b0 = ldw(mem0, G.y, rw, c); b1 = ldw(mem1, G.y, rw, c); }
+            W2 o0, o1;
+            bool linear = true;
+            switch (type) {
+            case 6:  o0 = {a0.a ^ b0.a, a0.b ^ b0.b}; o1 = {a1.a ^ b1.a, a1.b ^ b1.b}; break;          // Xor
+            case 9:  o0 = {~(a0.a ^ b0.a), ~(a0.b ^ b0.b)}; o1 = {~(a1.a ^ b1.a), ~(a1.b ^ b1.b)}; break; // Nxor
+            case 10: o0 = a0; o1 = a1; break;                                                          // copy
+            default: {
+                linear = false;
+                W2 x0 = a0, x1 = a1, y0 = b0, y1 = b1;
+                if (type == 1) { x0 = {~a0.a, ~a0.b}; x1 = {~a1.a, ~a1.b}; y0 = {~b0.a, ~b0.b}; y1 = {~b1.a, ~b1.b}; }  // Nor
+                else if (type == 4) { x0 = {~a0.a, ~a0.b}; x1 = {~a1.a, ~a1.b}; }                                        // na_And
+                o0.a = (x0.a & y0.a) ^ (x0.a & y1.a) ^ (x1.a & y0.a);
+                o0.b = (x0.b & y0.b) ^ (x0.b & y1.b) ^ (x1.b & y0.b);
+                if (type == 14) { o0.a ^= a0.a ^ b0.a; o0.b ^= a0.b ^ b0.b; }                                            // Or
+                if (AES) {
+                    u32 p[4], q[4];
+                    const u64 ctr = and_idx * chunks + c;
+                    aes_encrypt_ctr(Tl, kp, ctr, p);
+                    aes_encrypt_ctr(Tl, kn, ctr, q);
+                    o0.a ^= (((u64)(p[1] ^ q[1])) << 32) | (u64)(p[0] ^ q[0]);
+                    o0.b ^= (((u64)(p[3] ^ q[3])) << 32) | (u64)(p[2] ^ q[2]);
+                }
+                ++and_idx;
+                o1 = {0, 0};
+            }
+            }
+            stw(mem0, G.z, rw, c, o0);
+            if (linear) stw(mem1, G.z, rw, c, o1);
+        }
+    }
+}
+
+// rows <-> contiguous message; VEC = bytes moved per thread step (16 or 1)
+template <int VEC, bool PACK>
+__global__ void __launch_bounds__(256) k_bin_rows(u8* mem, u64 row_bytes, const u32* __restrict__ locs, u32 n_locs, u64 nbytes, u8* buf) {
+    const u64 per = nbytes / VEC, total = per * n_locs;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+        const u64 j = i / per, o = (i % per) * VEC;
+        u8* m = mem + (u64)locs[j] * row_bytes + o;
+        u8* b = buf + j * nbytes + o;
+        if (VEC == 16) {
+            if (PACK) *reinterpret_cast<uint4*>(b) = *reinterpret_cast<const uint4*>(m);
+            else *reinterpret_cast<uint4*>(m) = *reinterpret_cast<const uint4*>(b);
+        } else {
+            if (PACK) *b = *m; else *m = *b;
+        }
+    }
+}
+
+int launch_transpose(aby3cu_ctx* ctx, const void* in, const u32* row_index, u64 rows, u64 cols, u64 in_stride,
+                     void* out, u64 out_stride, const u8* invert) {
+    ABY3CU_REQUIRE(ctx && ((in && out) || !(rows * cols)), "bit_transpose: null argument");
+    if (!(rows * cols)) return 0;
+    ABY3CU_REQUIRE(in_stride % 4 == 0 && out_stride % 4 == 0, "bit_transpose: strides must be multiples of 4");
+    ABY3CU_REQUIRE(((cols + 31) / 32) * 4 <= in_stride, "bit_transpose: in_stride too small for cols");
+    ABY3CU_REQUIRE(((rows + 31) / 32) * 4 <= out_stride, "bit_transpose: out_stride too small for rows");
+    ABY3CU_REQUIRE((reinterpret_cast<uintptr_t>(in) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+                   "bit_transpose: pointers must be 4-byte aligned");
+    DeviceGuard g(ctx->device);
+    const u64 cap = (u64)ctx->sm_count * 4;
+#define ABY3CU_BT(TR, TCW)                                                                                        \
+    do {                                                                                                          \
+        const u64 tiles = ((rows + TR - 1) / TR) * ((cols + 32 * TCW - 1) / (32 * TCW));                          \
+        const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);                                              \
+        k_bit_transpose<TR, TCW><<<grid, 256, 0, ctx->stream>>>((const u8*)in, row_index, rows, cols, in_stride,  \
+                                                                (u8*)out, out_stride, invert);                    \
+    } while (0)
+    if (cols <= 64) ABY3CU_BT(1024, 2);
+    else if (rows <= 64) ABY3CU_BT(64, 32);
+    else ABY3CU_BT(256, 8);
+#undef ABY3CU_BT
+    return post_launch(ctx, "k_bit_transpose");
+}
+
+}  // namespace
+}  // namespace aby3cu
+
+using namespace aby3cu;
+
+extern "C" {
+
+uint64_t aby3cu_bin_row_bytes(uint64_t width) { return 256 * ((width + 2047) / 2048); }
+
+int aby3cu_bit_transpose(aby3cu_ctx* ctx, const void* d_in, u64 rows, u64 cols, u64 in_stride, void* d_out,
+                         u64 out_stride, const u8* d_invert_rows) {
+    return launch_transpose(ctx, d_in, nullptr, rows, cols, in_stride, d_out, out_stride, d_invert_rows);
+}
+
+int aby3cu_bit_transpose_gather(aby3cu_ctx* ctx, const void* d_in, const u32* d_row_index, u64 rows, u64 cols,
+                                u64 in_stride, void* d_out, u64 out_stride, const u8* d_invert_rows) {
+    ABY3CU_REQUIRE(d_row_index || !rows, "bit_transpose_gather: null row index");
+    return launch_transpose(ctx, d_in, d_row_index, rows, cols, in_stride, d_out, out_stride, d_invert_rows);
+}
+
+int aby3cu_bin_level(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void* d_mem0, void* d_mem1, u64 row_bytes,
+                     const u8 key_prev[16], const u8 key_next[16], u64 and_index0) {
+    ABY3CU_REQUIRE(ctx && ((d_gates && d_mem0 && d_mem1) || !n_gates), "bin_level: null argument");
+    ABY3CU_REQUIRE(row_bytes % 16 == 0, "bin_level: row_bytes must be a multiple of 16");
+    ABY3CU_REQUIRE((key_prev == nullptr) == (key_next == nullptr), "bin_level: give both keys or neither");
+    if (!n_gates || !row_bytes) return 0;
+    DeviceGuard g(ctx->device);
+    const u64 rw = row_bytes / 8, chunks = rw / 2;
+    if (key_prev) {
+        AesKey kp, kn; host_expand_key(key_prev, &kp); host_expand_key(key_next, &kn);
+        ABY3CU_CHECK(cudaFuncSetAttribute(k_bin_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
+        const unsigned grid = ew_grid(ctx, chunks, 256, 3);
+        k_bin_level<true><<<grid, 256, kAesTableBytes, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0, (u64*)d_mem1, rw, kp, kn, and_index0);
+    } else {
+        static const AesKey zero = {};
+        const unsigned grid = ew_grid(ctx, chunks, 256, 8);
+        k_bin_level<false><<<grid, 256, 0, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0, (u64*)d_mem1, rw, zero, zero, and_index0);
+    }
+    return post_launch(ctx, "k_bin_level");
+}
+
+static int rows_copy(aby3cu_ctx* ctx, bool pack, void* mem, u64 row_bytes, const u32* locs, u32 n_locs, u64 nbytes, void* buf) {
+    ABY3CU_REQUIRE(ctx && ((mem && locs && buf) || !(n_locs * nbytes)), "bin rows: null argument");
+    ABY3CU_REQUIRE(nbytes <= row_bytes, "bin rows: nbytes exceeds the row");
+    if (!(n_locs * nbytes)) return 0;
+    DeviceGuard g(ctx->device);
+    const bool v16 = nbytes % 16 == 0 && row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(mem) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(buf) & 15) == 0;
+    const u64 items = v16 ? (nbytes / 16) * n_locs : nbytes * n_locs;
+    const unsigned grid = ew_grid(ctx, items, 256, 8);
+    if (v16) {
+        if (pack) k_bin_rows<16, true><<<grid, 256, 0, ctx->stream>>>((u8*)mem, row_bytes, locs, n_locs, nbytes, (u8*)buf);
+        else k_bin_rows<16, false><<<grid, 256, 0, ctx->stream>>>((u8*)mem, row_bytes, locs, n_locs, nbytes, (u8*)buf);
+    } else {
+        if (pack) k_bin_rows<1, true><<<grid, 256, 0, ctx->stream>>>((u8*)mem, row_bytes, locs, n_locs, nbytes, (u8*)buf);
+        else k_bin_rows<1, false><<<grid, 256, 0, ctx->stream>>>((u8*)mem, row_bytes, locs, n_locs, nbytes, (u8*)buf);
+    }
+    return post_launch(ctx, "k_bin_rows");
+}
+
+int aby3cu_bin_pack_rows(aby3cu_ctx* ctx, const void* d_mem, u64 row_bytes, const u32* d_locs, u32 n_locs, u64 nbytes, void* d_out) {
+    return rows_copy(ctx, true, const_cast<void*>(d_mem), row_bytes, d_locs, n_locs, nbytes, d_out);
+}
+
+int aby3cu_bin_scatter_rows(aby3cu_ctx* ctx, void* d_mem, u64 row_bytes, const u32* d_locs, u32 n_locs, u64 nbytes, const void* d_in) {
+    return rows_copy(ctx, false, d_mem, row_bytes, d_locs, n_locs, nbytes, const_cast<void*>(d_in));
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// common.cuh -- context object, error plumbing and launch helpers shared by the
+// kernels behind include/aby3cu.h.  sm_100a only; no CPU fallback anywhere.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/aby3cu.h"
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+
+namespace aby3cu {
+
+// B200: 148 SMs.  Grids of the HBM-bound kernels are sized as a multiple of the
+// SM count the device reports (queried once per context).
+struct GemmWorkspace {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace aby3cu
+
+struct aby3cu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 148;
+    u64 launches = 0;
+    int last_gemm_algo = 0;
+    aby3cu::GemmWorkspace gemm_ws;   // limb planes for the tcgen05 GEMM
+};
+
+namespace aby3cu {
+
+void set_error(const char* fmt, ...);
+
+#define ABY3CU_CHECK(expr)                                                              \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            aby3cu::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                              __FILE__, __LINE__);                                      \
+            return 1;                                                                   \
+        }                                                                               \
+    } while (0)
+
+#define ABY3CU_REQUIRE(cond, msg)                                                       \
+    do {                                                                                \
+        if (!(cond)) {                                                                  \
+            aby3cu::set_error("%s (%s:%d)", msg, __FILE__, __LINE__);                   \
+            return 2;                                                                   \
+        }                                                                               \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        want = dev;
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
+    int want = -1;
+};
+
+inline int post_launch(aby3cu_ctx* ctx, const char* name) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("launch of %s failed: %s", name, cudaGetErrorString(e));
+        return 1;
+    }
+    ctx->launches++;
+    return 0;
+}
+
+// grid for a grid-stride elementwise kernel: enough CTAs to fill the machine a
+// few times over, never more than the work needs.
+inline unsigned ew_grid(const aby3cu_ctx* ctx, u64 work_items, unsigned threads, unsigned ctas_per_sm) {
+    u64 need = (work_items + threads - 1) / threads;
+    u64 cap = (u64)ctx->sm_count * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (unsigned)(need < cap ? need : cap);
+}
+
+}  // namespace aby3cu

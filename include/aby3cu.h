@@ -1,0 +1,174 @@
+/*
+ * aby3cu.h -- C ABI of the B200 (sm_100a) implementation of ABY3's
+ * replicated-share multiplication hot path.
+ *
+ * The reference (Fannxy/aby3) has no FFI seam: its hot loops sit inside the C++
+ * classes of aby3/sh3/.  Each entry point below replaces one of those CPU loops
+ * (cited as path:line relative to the reference root) and is what the sh3
+ * facade in aby3_b200/sh3/ binds.  INTEGRATION.md shows the binding a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure;
+ *    aby3cu_last_error() gives the message (thread local).  Nothing throws
+ *    across the ABI.
+ *  - pointers named d_* are device pointers owned by the caller; all work is
+ *    enqueued on the context's stream and is asynchronous unless stated.
+ *  - "key" is a 16-byte AES-128 key in memory order (oc::block / oc::AES::setKey).
+ *  - keystream KS_key = AES_key(toBlock(0)) || AES_key(toBlock(1)) || ...  where
+ *    toBlock(c) is c as 8 little-endian bytes followed by 8 zero bytes
+ *    (oc::AES::ecbEncCounterMode).  "stream element e" is the little-endian u64
+ *    at keystream bytes [8e, 8e+8).
+ *  - all arithmetic is wrapping 64-bit; right shifts are arithmetic.
+ *  - there is no CPU fallback: with no usable sm_100 device aby3cu_ctx_create fails.
+ */
+#ifndef ABY3CU_H
+#define ABY3CU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABY3CU_VERSION 1
+
+typedef struct aby3cu_ctx aby3cu_ctx;
+
+/* ---- library / context ---------------------------------------------------- */
+int aby3cu_version(void);
+const char* aby3cu_last_error(void);
+int aby3cu_device_count(int* count);
+/* One context per party: a device, a stream, scratch space. */
+int aby3cu_ctx_create(int device, aby3cu_ctx** out);
+/* Same, but work is enqueued on a caller-owned cudaStream_t (e.g. a torch stream). */
+int aby3cu_ctx_create_on_stream(int device, void* cuda_stream, aby3cu_ctx** out);
+int aby3cu_ctx_destroy(aby3cu_ctx* ctx);
+int aby3cu_ctx_device(const aby3cu_ctx* ctx);
+void* aby3cu_ctx_stream(const aby3cu_ctx* ctx);
+int aby3cu_sync(aby3cu_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t aby3cu_launch_count(const aby3cu_ctx* ctx);
+
+/* ---- memory, copies, events ------------------------------------------------ */
+int aby3cu_malloc(aby3cu_ctx* ctx, void** d_ptr, size_t bytes);
+int aby3cu_free(aby3cu_ctx* ctx, void* d_ptr);
+int aby3cu_memset(aby3cu_ctx* ctx, void* d_ptr, int byte, size_t bytes);
+int aby3cu_host_alloc(void** h_ptr, size_t bytes);          /* pinned host memory */
+int aby3cu_host_free(void* h_ptr);
+int aby3cu_h2d(aby3cu_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int aby3cu_d2h(aby3cu_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+/* device-to-device; dst_device/src_device may differ (NVLink peer copy) */
+int aby3cu_d2d(aby3cu_ctx* ctx, void* d_dst, int dst_device, const void* d_src, int src_device, size_t bytes);
+int aby3cu_event_create(aby3cu_ctx* ctx, void** event);
+int aby3cu_event_destroy(void* event);
+int aby3cu_event_record(aby3cu_ctx* ctx, void* event);       /* on ctx's stream */
+int aby3cu_event_wait(aby3cu_ctx* ctx, void* event);         /* ctx's stream waits */
+int aby3cu_event_sync(void* event);
+int aby3cu_event_elapsed_ms(void* start, void* stop, float* ms);
+
+/* ---- AES-CTR keystream ------------------------------------------------------ */
+/* Host-side keystream bytes for the small draws the facade makes itself
+ * (oc::PRNG::get<block>() at Sh3ShareGen.h:19-20, Sh3Evaluator.cpp:13-14,
+ * Sh3BinaryEvaluator.h:99-100).  Pure host code, bounded to 4096 bytes. */
+int aby3cu_host_keystream(const uint8_t key[16], uint64_t byte_off, size_t nbytes, uint8_t* out);
+/* Bulk oc::PRNG::get(ptr, n) (Sh3Evaluator.cpp:526-527): device fill with
+ * keystream bytes [byte_off, byte_off + nbytes); both must be multiples of 8. */
+int aby3cu_aes_ctr_fill(aby3cu_ctx* ctx, const uint8_t key[16], uint64_t byte_off,
+                        void* d_out, size_t nbytes);
+
+/* ---- zero sharing: Sh3ShareGen::getShare / getBinaryShare loops -------------- */
+/* out[i] = addend[i] (+ or ^) (KS_prev[e0+i] (- or ^) KS_next[e0+i]),  i < n.
+ * d_addend may be NULL (remoteIntMatrix).  Replaces the per-element loops at
+ * Sh3Encryptor.cpp:222-223, 258-259, 303-304 and Sh3ShareGen.h:60-92. */
+int aby3cu_zero_share(aby3cu_ctx* ctx, const uint8_t key_prev[16], const uint8_t key_next[16],
+                      uint64_t elem0, const int64_t* d_addend, int64_t* d_out, size_t n, int binary);
+
+/* ---- arithmetic multiplication: Sh3Evaluator::asyncMul ------------------------ */
+/* Hadamard form of this fork (Sh3Evaluator.cpp:101-105):
+ * C0[i] = A0[i]*B0[i] + A0[i]*B1[i] + A1[i]*B0[i] + z(e0+i). */
+int aby3cu_mul_hadamard(aby3cu_ctx* ctx, const int64_t* d_A0, const int64_t* d_A1,
+                        const int64_t* d_B0, const int64_t* d_B1,
+                        const uint8_t key_prev[16], const uint8_t key_next[16], uint64_t elem0,
+                        int64_t* d_C0, size_t n);
+/* Hadamard form with truncation pair (Sh3Evaluator.cpp:667-673 + 526-537):
+ * t0 = KS_nextCommon[e_next+i], t1 = KS_prevCommon[e_prev+i],
+ * V[i] = cross(i) - (t0 >> 2), RT0[i] = t0 >> (d+2), RT1[i] = t1 >> (d+2).
+ * keys NULL => DEBUG_disable_randomization (r = 0, RT = 0). */
+int aby3cu_mul_hadamard_trunc(aby3cu_ctx* ctx, const int64_t* d_A0, const int64_t* d_A1,
+                              const int64_t* d_B0, const int64_t* d_B1,
+                              const uint8_t key_next_common[16], uint64_t elem_next,
+                              const uint8_t key_prev_common[16], uint64_t elem_prev,
+                              uint64_t d, int64_t* d_V, int64_t* d_RT0, int64_t* d_RT1, size_t n);
+/* Sh3Evaluator::getTruncationTuple (Sh3Evaluator.cpp:503-566).  Writes RT0/RT1 and,
+ * when non-NULL, R[i] = t0>>2 and NEGR[i] = -(t0>>2) (NEGR pre-loads the GEMM
+ * accumulator so that abMinusR needs no extra pass).  keys NULL => all zero. */
+int aby3cu_trunc_tuple(aby3cu_ctx* ctx, const uint8_t key_next_common[16], uint64_t elem_next,
+                       const uint8_t key_prev_common[16], uint64_t elem_prev, uint64_t d,
+                       int64_t* d_R, int64_t* d_NEGR, int64_t* d_RT0, int64_t* d_RT1, size_t n);
+/* Open-and-truncate continuation (Sh3Evaluator.cpp:712-718):
+ * C[i] += (s0[i] + s1[i] + s2[i]) >> shift  (arithmetic). */
+int aby3cu_trunc_finish(aby3cu_ctx* ctx, const int64_t* d_s0, const int64_t* d_s1, const int64_t* d_s2,
+                        int64_t* d_C, size_t n, uint64_t shift);
+
+/* The matrix cross term  C (+)= A0*B0 + A0*B1 + A1*B0  over Z_2^64
+ * (Sh3Evaluator.cpp:662-665, upstream form of :96-99), A* row-major MxK,
+ * B* row-major KxN, C row-major MxN.  accumulate != 0 adds into C (C was
+ * pre-loaded with the zero share z or with -r). */
+enum { ABY3CU_GEMM_AUTO = 0, ABY3CU_GEMM_IMAD = 1, ABY3CU_GEMM_TCGEN05 = 2 };
+int aby3cu_gemm_cross(aby3cu_ctx* ctx, int algo,
+                      const int64_t* d_A0, const int64_t* d_A1,
+                      const int64_t* d_B0, const int64_t* d_B1,
+                      uint64_t M, uint64_t K, uint64_t N, int64_t* d_C, int accumulate);
+/* algo actually used by the last aby3cu_gemm_cross on this context */
+int aby3cu_gemm_last_algo(const aby3cu_ctx* ctx);
+
+/* ---- local share arithmetic / reveal ------------------------------------------- */
+enum { ABY3CU_OP_ADD = 0, ABY3CU_OP_SUB = 1, ABY3CU_OP_XOR = 2 };
+/* out = x op y  (sMatrix +,-: Sh3Types.h:805-820) */
+int aby3cu_share_op(aby3cu_ctx* ctx, int op, const int64_t* d_x, const int64_t* d_y, int64_t* d_out, size_t n);
+/* out = x0 op x1 op x2 (reveal: Sh3Encryptor.cpp:497-536), op ADD or XOR */
+int aby3cu_combine3(aby3cu_ctx* ctx, int op, const int64_t* d_x0, const int64_t* d_x1, const int64_t* d_x2,
+                    int64_t* d_out, size_t n);
+/* row-major transpose of an int64 matrix (sMatrix::transpose, Sh3Types.h:822-838) */
+int aby3cu_transpose_i64(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t rows, uint64_t cols, int64_t* d_out);
+/* gather rows: out[r,:] = in[idx[r],:]  (extractBatch, aby3-ML/Regression.h:43-58) */
+int aby3cu_gather_rows(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t cols, const uint64_t* d_idx,
+                       uint64_t nrows, int64_t* d_out);
+
+/* ---- binary engine: Sh3BinaryEvaluator ----------------------------------------- */
+/* row stride (bytes) of the bit-sliced wire memory for `width` instances
+ * (mMem.reset(width, wires, 8) with 256-bit blocks, Sh3BinaryEvaluator.cpp:84). */
+uint64_t aby3cu_bin_row_bytes(uint64_t width);
+/* oc::transpose (Sh3BinaryEvaluator.cpp:252,1365): out bit (r,c) = in bit (c,r),
+ * LSB first.  in: rows x cols bits, in_stride bytes per row; out: cols x rows
+ * bits, out_stride bytes per row; strides multiples of 4.  Bits of each written
+ * out row beyond `rows` (up to the next 32-bit word) are zeroed; if invert_rows
+ * (device, one byte per OUT... see below) is non-NULL it flags IN rows to complement
+ * (getOutput's isInvert, :1329-1335) -- indexed by in row. */
+int aby3cu_bit_transpose(aby3cu_ctx* ctx, const void* d_in, uint64_t rows, uint64_t cols, uint64_t in_stride,
+                         void* d_out, uint64_t out_stride, const uint8_t* d_invert_rows);
+/* transpose where IN rows are gathered through row_index (wire ids): in row r is
+ * at d_in + row_index[r]*in_stride (getOutput gathers output wires, :1300-1327) */
+int aby3cu_bit_transpose_gather(aby3cu_ctx* ctx, const void* d_in, const uint32_t* d_row_index, uint64_t rows,
+                                uint64_t cols, uint64_t in_stride, void* d_out, uint64_t out_stride,
+                                const uint8_t* d_invert_rows);
+/* One AND-depth level of roundCallback (Sh3BinaryEvaluator.cpp:671-1080).
+ * d_gates: [n][4] u32 = in0, in1, out, type (cryptoTools GateType encoding:
+ * Nor=1, na_And=4, Xor=6, And=8, Nxor=9, a(copy)=10, Or=14), executed in order.
+ * mem0/mem1: the two share planes, wires x row_bytes.  Nonlinear gates use
+ * z = KS_prev ^ KS_next starting at AES block  and_index0*(row_bytes/16)
+ * (getShares, :1406-1442), and_index0 = number of nonlinear gates before this level. */
+int aby3cu_bin_level(aby3cu_ctx* ctx, const uint32_t* d_gates, uint32_t n_gates,
+                     void* d_mem0, void* d_mem1, uint64_t row_bytes,
+                     const uint8_t key_prev[16], const uint8_t key_next[16], uint64_t and_index0);
+/* sendBuff packing (:795-796): out[j*nbytes .. ) = first nbytes of row locs[j] of mem */
+int aby3cu_bin_pack_rows(aby3cu_ctx* ctx, const void* d_mem, uint64_t row_bytes, const uint32_t* d_locs,
+                         uint32_t n_locs, uint64_t nbytes, void* d_out);
+/* receive scatter (:555-573): first nbytes of row locs[j] of mem = in[j*nbytes ..) */
+int aby3cu_bin_scatter_rows(aby3cu_ctx* ctx, void* d_mem, uint64_t row_bytes, const uint32_t* d_locs,
+                            uint32_t n_locs, uint64_t nbytes, const void* d_in);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABY3CU_H */
