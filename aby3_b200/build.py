@@ -2,7 +2,8 @@
 
   libaby3cu.so  -- CUDA kernels + C ABI (include/aby3cu.h), one translation unit
   libsh3.so     -- the C++ sh3 facade (aby3_b200/sh3) + its C harness, links libaby3cu
-  oracle/liboracle.so -- CPU oracle (test infrastructure only)
+(The CPU checker under the repo's top-level checker directory has its own Makefile
+and is built by __graft_entry__.build() / tests/conftest.py, not from here.)
 """
 import os
 import subprocess
@@ -63,16 +64,8 @@ def build_sh3(force=False):
     return so
 
 
-def build_oracle(force=False):
-    d = os.path.join(ROOT, "oracle")
-    so = os.path.join(d, "liboracle.so")
-    if force or _newer(so, [os.path.join(d, "oracle.cpp"), os.path.join(d, "oracle.h")]):
-        _run(["make", "-C", d, "-B", "liboracle.so"])
-    return so
-
-
 def build_all(force=False):
-    return [build_cuda(force), build_sh3(force), build_oracle(force)]
+    return [build_cuda(force), build_sh3(force)]
 
 
 if __name__ == "__main__":

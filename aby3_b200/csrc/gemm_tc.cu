@@ -1,9 +1,378 @@
-// gemm_tc.cu -- tcgen05 / TMEM u8-limb GEMM (placeholder until the kernel lands).
+// gemm_tc.cu -- the int64 (mod 2^64) cross-term GEMM on the 5th-generation tensor
+// cores:  C (+)= A0*(B0+B1) + A1*B0   (reference: three Eigen i64 products at
+// aby3/sh3/Sh3Evaluator.cpp:662-665).
+//
+// Arithmetic.  Write every 64-bit operand in base 256: a = sum_i a_i 2^(8i),
+// b = sum_j b_j 2^(8j).  Modulo 2^64 only the 36 limb pairs with i+j < 8 matter:
+//     C = sum_{s<8} 2^(8s) S_s ,   S_s = sum_{i+j=s} sum_k a_i[m,k] b_j[k,n].
+// S_s is a u8 x u8 -> s32 contraction: tcgen05.mma kind::i8 with unsigned
+// operands.  Accumulators wrap mod 2^32 (saturate bit off).  For s >= 4 only
+// S_s mod 2^(64-8s) <= 2^32 is needed, so wrapping is harmless for any K; for
+// s <= 3 the exact value is needed, and S_s <= (s+1) * Ke * 255^2 < 2^32 holds
+// while Ke <= 16512, i.e. K <= 8256 per launch (Ke = 2K, both products of the
+// factored cross term run as ONE contraction [A0|A1] x [B0+B1 ; B0]).  Larger K
+// is split on the host and accumulated through C.
+//
+// Mapping.  One CTA per SM, persistent over 128 x 64 output tiles.  The eight
+// accumulators D_0..D_7 of a tile live side by side in TMEM (8 x 64 = 512
+// columns, all of it).  Because D_(i+j) sits 64 columns after D_(i+j-1) and the
+// B limb planes of a tile are stacked along the MMA's N dimension, ONE
+// instruction  D[64i ...] += A_i x [B_0|B_1|...|B_(7-i)]^T  (N = 64(8-i), cut
+// into pieces of <= 256) updates every accumulator that limb i of A feeds:
+// 12 MMA instructions per 32-deep K step instead of 36.
+//
+// Data movement.  A pre-pass splits the int64 operands into limb planes stored
+// directly in the no-swizzle K-major core-matrix layout the MMA descriptors
+// want, one contiguous 32 KiB (A) / 16 KiB (B) chunk per (tile, k-block), so a
+// pipeline stage is filled by two bulk TMA copies (cp.async.bulk, UBLKCP) that
+// complete on an mbarrier.  Warp 0 = TMA producer, warp 1 = MMA issuer (one
+// elected thread), warps 2..5 = epilogue (tcgen05.ld -> recombine limbs mod 2^64
+// -> C (+)=).
 #include "common.cuh"
+
 namespace aby3cu {
-bool gemm_tc_profitable(u64, u64, u64) { return false; }
-int gemm_cross_tc(aby3cu_ctx*, const i64*, const i64*, const i64*, const i64*, u64, u64, u64, i64*, int) {
-    set_error("tcgen05 GEMM not built yet");
-    return 4;
+namespace tc {
+
+constexpr int TM = 128;            // tile rows  (= MMA M, TMEM lanes)
+constexpr int TN = 64;             // tile cols  (per limb accumulator)
+constexpr int TK = 32;             // k per stage (= MMA K for 8-bit operands)
+constexpr int STAGES = 4;
+constexpr u32 A_CHUNK = 8 * TM * TK;      // 32768 B
+constexpr u32 B_CHUNK = 8 * TN * TK;      // 16384 B
+constexpr u32 STAGE_BYTES = A_CHUNK + B_CHUNK;
+constexpr u32 SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // + barriers, tmem slot, alignment slack
+constexpr int THREADS = 192;
+constexpr u64 K_MAX = 8192;        // per launch, see the exactness bound above
+
+// ------------------------------------------------------------------ PTX wrappers --
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u32 bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    u32 done = 0;
+    for (u32 spin = 0; spin < (1u << 28); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(u32 bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_i8(u32 d_tmem, u64 a_desc, u64 b_desc, u32 idesc, u32 accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(u32 taddr, u32 v[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no swizzle (canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units):
+// LBO = byte distance between the two 16-byte K halves, SBO = between 8-row groups.
+__device__ __forceinline__ u64 smem_desc(u32 addr, u32 lbo, u32 sbo) {
+    return (u64)((addr & 0x3FFFF) >> 4) | ((u64)(lbo >> 4) << 16) | ((u64)(sbo >> 4) << 32) | (1ull << 46);
+}
+// kind::i8, D = s32, A and B unsigned 8-bit, both K-major, M = 128
+__device__ __forceinline__ constexpr u32 make_idesc(u32 n) {
+    return (2u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ limb packing --
+// A chunk (mt, kb): [limb 8][kc 2][row-group 16][row 8][16 B]; one thread = one
+// row x 16 k: reads 128 contiguous bytes, writes 8 x 16 bytes.
+__global__ void __launch_bounds__(256) k_pack_a(const u64* __restrict__ A0, const u64* __restrict__ A1,
+                                                u64 row0, u64 rows, u64 M, u64 K, u64 k0, u64 kblocks_half, u8* __restrict__ out) {
+    const u64 kb = blockIdx.x, mt = blockIdx.y;          // kb over both halves
+    const int r = threadIdx.x & 127, kc = threadIdx.x >> 7;
+    const u64* A = (kb < kblocks_half) ? A0 : A1;
+    const u64 kbase = k0 + (kb % kblocks_half) * TK + kc * 16;
+    const u64 m = row0 + mt * TM + r;
+    u64 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const u64 k = kbase + j;
+        v[j] = (m < row0 + rows && m < M && k < K) ? A[m * K + k] : 0;
+    }
+    u8* chunk = out + (mt * (2 * kblocks_half) + kb) * A_CHUNK + kc * 2048 + (r >> 3) * 128 + (r & 7) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        u32 w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            u32 b0 = (u32)(v[4 * q + 0] >> (8 * i)) & 0xFF, b1 = (u32)(v[4 * q + 1] >> (8 * i)) & 0xFF;
+            u32 b2 = (u32)(v[4 * q + 2] >> (8 * i)) & 0xFF, b3 = (u32)(v[4 * q + 3] >> (8 * i)) & 0xFF;
+            w[q] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        }
+        *reinterpret_cast<uint4*>(chunk + i * 4096) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// B chunk (nt, kb): [kc 2][limb 8][row-group 8][row 8][16 B], rows = output columns n.
+// First half of K carries B0+B1, second half B0.  One thread = one n x 16 k.
+__global__ void __launch_bounds__(128) k_pack_b(const u64* __restrict__ B0, const u64* __restrict__ B1,
+                                                u64 K, u64 N, u64 k0, u64 kblocks_half, u8* __restrict__ out) {
+    const u64 kb = blockIdx.x, nt = blockIdx.y;
+    const int nl = threadIdx.x & 63, kc = threadIdx.x >> 6;
+    const bool first = kb < kblocks_half;
+    const u64 kbase = k0 + (kb % kblocks_half) * TK + kc * 16;
+    const u64 n = nt * TN + nl;
+    u64 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const u64 k = kbase + j;
+        u64 x = 0;
+        if (n < N && k < K) {
+            x = B0[k * N + n];
+            if (first) x += B1[k * N + n];
+        }
+        v[j] = x;
+    }
+    u8* chunk = out + (nt * (2 * kblocks_half) + kb) * B_CHUNK + kc * 8192 + (nl >> 3) * 128 + (nl & 7) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        u32 w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            u32 b0 = (u32)(v[4 * q + 0] >> (8 * i)) & 0xFF, b1 = (u32)(v[4 * q + 1] >> (8 * i)) & 0xFF;
+            u32 b2 = (u32)(v[4 * q + 2] >> (8 * i)) & 0xFF, b3 = (u32)(v[4 * q + 3] >> (8 * i)) & 0xFF;
+            w[q] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        }
+        *reinterpret_cast<uint4*>(chunk + i * 1024) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// ------------------------------------------------------------------ the GEMM -----
+struct Params {
+    const u8* pa;       // packed A: [mtiles][kblocks][A_CHUNK]
+    const u8* pb;       // packed B: [ntiles][kblocks][B_CHUNK]
+    u64* C;             // row-major, leading dimension N
+    u64 row0;           // first row of C covered by tile row 0
+    u64 rows_end;       // one past the last valid row (global)
+    u64 N;
+    u32 mtiles, ntiles, kblocks;
+    int accumulate;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) u8 smem[];
+    const u32 sbase = (smem_u32(smem) + 1023u) & ~1023u;          // stage buffers, 1 KiB aligned
+    u8* sgen = smem + (sbase - smem_u32(smem));
+    const u32 bar_base = sbase + STAGES * STAGE_BYTES;             // full[S], empty[S], tmem_full, tmem_empty
+    u32* tmem_slot = reinterpret_cast<u32*>(sgen + STAGES * STAGE_BYTES + 128);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const u32 tmem_full = bar_base + 8u * (2 * STAGES), tmem_empty = bar_base + 8u * (2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tmem = *tmem_slot;
+
+    const u32 ntiles_total = p.mtiles * p.ntiles;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            u32 stage = 0, phase = 0;
+            for (u32 t = blockIdx.x; t < ntiles_total; t += gridDim.x) {
+                const u32 mt = t / p.ntiles, nt = t % p.ntiles;
+                const u8* a = p.pa + (u64)mt * p.kblocks * A_CHUNK;
+                const u8* b = p.pb + (u64)nt * p.kblocks * B_CHUNK;
+                for (u32 kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    const u32 dst = sbase + stage * STAGE_BYTES;
+                    bulk_g2s(dst, a + (u64)kb * A_CHUNK, A_CHUNK, full_bar(stage));
+                    bulk_g2s(dst + A_CHUNK, b + (u64)kb * B_CHUNK, B_CHUNK, full_bar(stage));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            u32 stage = 0, phase = 0, tile_iter = 0;
+            for (u32 t = blockIdx.x; t < ntiles_total; t += gridDim.x, ++tile_iter) {
+                // the epilogue must have drained the previous tile's accumulators
+                mbar_wait(tmem_empty, (tile_iter & 1) ^ 1);
+                tc_fence_after();
+                for (u32 kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const u32 sa = sbase + stage * STAGE_BYTES, sb = sa + A_CHUNK;
+                    const u64 bd0 = smem_desc(sb, 8192, 128);            // B rows 0..
+                    const u64 bd1 = smem_desc(sb + 4096, 8192, 128);     // B rows 256..
+                    const u32 first = kb != 0;                            // kb 0 overwrites all 512 columns via limb 0
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const u64 ad = smem_desc(sa + i * 4096, 2048, 128);
+                        const int n = TN * (8 - i);
+                        const u32 acc = (i == 0) ? first : 1u;
+                        if (n > 256) {
+                            mma_i8(tmem + 64 * i, ad, bd0, make_idesc(256), acc);
+                            mma_i8(tmem + 64 * i + 256, ad, bd1, make_idesc(n - 256), acc);
+                        } else {
+                            mma_i8(tmem + 64 * i, ad, bd0, make_idesc(n), acc);
+                        }
+                    }
+                    tc_commit(empty_bar(stage));                           // frees the stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tmem_full);                                      // accumulators complete
+            }
+        }
+    } else {
+        // ================================ epilogue ====================================
+        const u32 quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
+        const u32 row_in_tile = quarter * 32 + lane;
+        u32 tile_iter = 0;
+        for (u32 t = blockIdx.x; t < ntiles_total; t += gridDim.x, ++tile_iter) {
+            const u32 mt = t / p.ntiles, nt = t % p.ntiles;
+            mbar_wait(tmem_full, tile_iter & 1);
+            tc_fence_after();
+            const u64 grow = p.row0 + (u64)mt * TM + row_in_tile;
+            const u64 gcol0 = (u64)nt * TN;
+            const u32 tlane = tmem + ((quarter * 32u) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < TN; c0 += 8) {
+                u32 d[8][8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) tmem_ld8(tlane + 64 * s + c0, d[s]);
+                tmem_ld_wait();
+                u64 out[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    u64 acc = 0;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) acc += (u64)d[s][j] << (8 * s);
+                    out[j] = acc;
+                }
+                if (grow < p.rows_end) {
+                    u64* dst = p.C + grow * p.N + gcol0 + c0;
+                    if (gcol0 + c0 + 8 <= p.N && ((p.N & 1) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2) {
+                            ulonglong2 v = make_ulonglong2(out[j], out[j + 1]);
+                            if (p.accumulate) {
+                                const ulonglong2 o = *reinterpret_cast<const ulonglong2*>(dst + j);
+                                v.x += o.x; v.y += o.y;
+                            }
+                            *reinterpret_cast<ulonglong2*>(dst + j) = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (gcol0 + c0 + j < p.N) dst[j] = p.accumulate ? dst[j] + out[j] : out[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tmem_empty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+}  // namespace tc
+
+bool gemm_tc_profitable(u64 M, u64 K, u64 N) {
+    // a 128x64 tile must be reasonably full and the contraction long enough to
+    // amortise the limb-split pre-pass; skinny shapes go to the CUDA-core kernels
+    return N >= 32 && M >= 64 && K >= 64 && M * N * K >= (1ull << 21);
+}
+
+static int ensure_ws(aby3cu_ctx* ctx, size_t bytes) {
+    if (ctx->gemm_ws.bytes >= bytes) return 0;
+    if (ctx->gemm_ws.ptr) {
+        ABY3CU_CHECK(cudaStreamSynchronize(ctx->stream));
+        ABY3CU_CHECK(cudaFree(ctx->gemm_ws.ptr));
+        ctx->gemm_ws.ptr = nullptr; ctx->gemm_ws.bytes = 0;
+    }
+    ABY3CU_CHECK(cudaMalloc(&ctx->gemm_ws.ptr, bytes));
+    ctx->gemm_ws.bytes = bytes;
+    return 0;
+}
+
+int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, const i64* B1,
+                  u64 M, u64 K, u64 N, i64* C, int accumulate) {
+    using namespace tc;
+    ABY3CU_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm_cross(tcgen05): C must be 16-byte aligned");
+    ABY3CU_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const u64 ntiles = (N + TN - 1) / TN;
+    // bound the limb-plane workspace: B panel for one K chunk + A panel for one row block
+    const size_t WS_A_LIMIT = 1ull << 30;
+    for (u64 k0 = 0; k0 < K; k0 += K_MAX) {
+        const u64 kc = (K - k0 < K_MAX) ? (K - k0) : K_MAX;
+        const u64 kbh = (kc + TK - 1) / TK, kblocks = 2 * kbh;
+        const size_t b_bytes = (size_t)ntiles * kblocks * B_CHUNK;
+        u64 rows_per_block = (WS_A_LIMIT / ((size_t)kblocks * A_CHUNK)) * TM;
+        if (rows_per_block < TM) rows_per_block = TM;
+        if (rows_per_block > M) rows_per_block = ((M + TM - 1) / TM) * TM;
+        const size_t a_bytes = (size_t)(rows_per_block / TM) * kblocks * A_CHUNK;
+        if (ensure_ws(ctx, a_bytes + b_bytes)) return 1;
+        u8* pa = (u8*)ctx->gemm_ws.ptr;
+        u8* pb = pa + a_bytes;
+        k_pack_b<<<dim3((unsigned)kblocks, (unsigned)ntiles), 128, 0, ctx->stream>>>((const u64*)B0, (const u64*)B1, K, N, k0, kbh, pb);
+        if (post_launch(ctx, "k_pack_b")) return 1;
+        const int acc_this = accumulate || k0 > 0;
+        for (u64 r0 = 0; r0 < M; r0 += rows_per_block) {
+            const u64 rows = (M - r0 < rows_per_block) ? (M - r0) : rows_per_block;
+            const u64 mtiles = (rows + TM - 1) / TM;
+            k_pack_a<<<dim3((unsigned)kblocks, (unsigned)mtiles), 256, 0, ctx->stream>>>((const u64*)A0, (const u64*)A1, r0, rows, M, K, k0, kbh, pa);
+            if (post_launch(ctx, "k_pack_a")) return 1;
+            Params p;
+            p.pa = pa; p.pb = pb; p.C = (u64*)C; p.row0 = r0; p.rows_end = r0 + rows; p.N = N;
+            p.mtiles = (u32)mtiles; p.ntiles = (u32)ntiles; p.kblocks = (u32)kblocks; p.accumulate = acc_this;
+            const u64 tiles = mtiles * ntiles;
+            const unsigned grid = (unsigned)(tiles < (u64)ctx->sm_count ? tiles : (u64)ctx->sm_count);
+            k_gemm_tc<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(p);
+            if (post_launch(ctx, "k_gemm_tc")) return 1;
+        }
+    }
+    return 0;
+}
+
 }  // namespace aby3cu

@@ -1,0 +1,205 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (include/aby3cu.h),
+against the CPU oracle on the same keys and offsets.  Bit-exact: all integer."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as o
+from aby3_b200 import abi
+
+pytestmark = pytest.mark.gpu
+U64 = np.uint64
+P = C.c_void_p
+lib = abi.lib
+
+KEY_A = bytes(range(16))
+KEY_B = bytes(range(100, 116))
+SIZES = [1, 2, 3, 16, 511, 512, 513, 4097, (1 << 20) + 5]
+
+
+def rnd(seed, n):
+    return np.random.default_rng(seed).integers(-2**63, 2**63, n, dtype=np.int64)
+
+
+def test_aes_ctr_fill_matches_oracle(ctx):
+    for n in SIZES:
+        for e0 in (0, 4, 7, 2**33 + 1):
+            buf = ctx.alloc(8 * n + 16)
+            abi.check(lib.aby3cu_aes_ctr_fill(ctx.h, KEY_A, 8 * e0, buf.p, 8 * n))
+            got = ctx.download(buf, n, U64)
+            assert np.array_equal(got, o.stream_u64(KEY_A, e0, n)), (n, e0)
+            buf.free()
+
+
+def test_aes_ctr_fill_unaligned_destination(ctx):
+    n = 1001
+    buf = ctx.alloc(8 * n + 64)
+    abi.check(lib.aby3cu_aes_ctr_fill(ctx.h, KEY_B, 8 * 3, buf.at(8), 8 * n))
+    got = ctx.download(buf, n, U64, byte_off=8)
+    assert np.array_equal(got, o.stream_u64(KEY_B, 3, n))
+
+
+def test_aes_fips197_on_device(ctx):
+    """AES_key(toBlock(c)) for the FIPS-197 C.1 key equals the software AES of the
+    same counter block -- pins the device T-tables to the standard."""
+    key = bytes.fromhex("000102030405060708090a0b0c0d0e0f")
+    buf = ctx.alloc(16 * 4)
+    abi.check(lib.aby3cu_aes_ctr_fill(ctx.h, key, 16 * 0x0766554433221100, buf.p, 64))
+    got = ctx.download(buf, 64, np.uint8)
+    for i in range(4):
+        ref = np.zeros(16, np.uint8)
+        pt = (0x0766554433221100 + i).to_bytes(8, "little") + bytes(8)
+        o.lib.orc_aes128_encrypt(key, pt, o.ptr(ref), 1)
+        assert got[16 * i:16 * i + 16].tobytes() == ref.tobytes()
+
+
+@pytest.mark.parametrize("binary", [0, 1])
+def test_zero_share(ctx, binary):
+    for n in SIZES:
+        for e0 in (0, 1, 511):
+            add = rnd(n, n)
+            d_add, d_out = ctx.upload(add), ctx.alloc(8 * n + 16)
+            abi.check(lib.aby3cu_zero_share(ctx.h, KEY_A, KEY_B, e0, d_add.p, d_out.p, n, binary))
+            got = ctx.download(d_out, n, U64)
+            a, b = o.stream_u64(KEY_A, e0, n), o.stream_u64(KEY_B, e0, n)
+            exp = (add.view(U64) ^ a ^ b) if binary else (add.view(U64) + (a - b))
+            assert np.array_equal(got, exp), (n, e0)
+            abi.check(lib.aby3cu_zero_share(ctx.h, KEY_A, KEY_B, e0, None, d_out.p, n, binary))
+            got = ctx.download(d_out, n, U64)
+            assert np.array_equal(got, (a ^ b) if binary else (a - b))
+            d_add.free(); d_out.free()
+
+
+def test_mul_hadamard(ctx):
+    for n in SIZES:
+        a0, a1, b0, b1 = (rnd(s + n, n) for s in range(4))
+        d = [ctx.upload(x) for x in (a0, a1, b0, b1)]
+        out = ctx.alloc(8 * n + 16)
+        e0 = 77
+        abi.check(lib.aby3cu_mul_hadamard(ctx.h, d[0].p, d[1].p, d[2].p, d[3].p, KEY_A, KEY_B, e0, out.p, n))
+        got = ctx.download(out, n, U64)
+        cross = o.cross_term(a0.reshape(1, n), a1.reshape(1, n), b0.reshape(1, n), b1.reshape(1, n), mode=1).reshape(n).view(U64)
+        z = o.stream_u64(KEY_A, e0, n) - o.stream_u64(KEY_B, e0, n)
+        assert np.array_equal(got, cross + z)
+        abi.check(lib.aby3cu_mul_hadamard(ctx.h, d[0].p, d[1].p, d[2].p, d[3].p, None, None, 0, out.p, n))
+        assert np.array_equal(ctx.download(out, n, U64), cross)
+        for x in d + [out]:
+            x.free()
+
+
+@pytest.mark.parametrize("rand", [True, False])
+def test_trunc_tuple_and_hadamard_trunc(ctx, rand):
+    for n in [1, 2, 513, 100003]:
+        for d, en, ep in [(8, 4, 4), (16, 5, 4), (33, 4, 9)]:
+            kn, kp = (KEY_A, KEY_B) if rand else (None, None)
+            R, NEG, T0, T1 = (ctx.alloc(8 * n + 16) for _ in range(4))
+            abi.check(lib.aby3cu_trunc_tuple(ctx.h, kn, en, kp, ep, d, R.p, NEG.p, T0.p, T1.p, n))
+            r, neg, t0, t1 = (ctx.download(x, n, np.int64) for x in (R, NEG, T0, T1))
+            s0 = o.stream_u64(KEY_A, en, n).view(np.int64) if rand else np.zeros(n, np.int64)
+            s1 = o.stream_u64(KEY_B, ep, n).view(np.int64) if rand else np.zeros(n, np.int64)
+            assert np.array_equal(r, s0 >> 2)
+            assert np.array_equal(neg.view(U64), U64(0) - (s0 >> 2).view(U64))
+            assert np.array_equal(t0, s0 >> (d + 2))
+            assert np.array_equal(t1, s1 >> (d + 2))
+            a0, a1, b0, b1 = (rnd(s + 11 * n, n) for s in range(4))
+            dd = [ctx.upload(x) for x in (a0, a1, b0, b1)]
+            V = ctx.alloc(8 * n + 16)
+            abi.check(lib.aby3cu_mul_hadamard_trunc(ctx.h, dd[0].p, dd[1].p, dd[2].p, dd[3].p, kn, en, kp, ep, d,
+                                                    V.p, T0.p, T1.p, n))
+            v = ctx.download(V, n, U64)
+            cross = o.cross_term(a0.reshape(1, n), a1.reshape(1, n), b0.reshape(1, n), b1.reshape(1, n), mode=1).reshape(n).view(U64)
+            assert np.array_equal(v, cross - (s0 >> 2).view(U64))
+            assert np.array_equal(ctx.download(T0, n, np.int64), s0 >> (d + 2))
+            assert np.array_equal(ctx.download(T1, n, np.int64), s1 >> (d + 2))
+            for x in dd + [R, NEG, T0, T1, V]:
+                x.free()
+
+
+def test_trunc_finish(ctx):
+    for n in [1, 2, 513, 100003]:
+        for shift in (8, 16, 33):
+            s0, s1, s2, c = (rnd(s + n, n) for s in range(4))
+            d = [ctx.upload(x) for x in (s0, s1, s2, c)]
+            abi.check(lib.aby3cu_trunc_finish(ctx.h, d[0].p, d[1].p, d[2].p, d[3].p, n, shift))
+            got = ctx.download(d[3], n, U64)
+            tot = (s0.view(U64) + s1.view(U64) + s2.view(U64)).view(np.int64)
+            assert np.array_equal(got, c.view(U64) + (tot >> shift).view(U64))
+            for x in d:
+                x.free()
+
+
+def test_share_ops_and_combine(ctx):
+    n = 70001
+    x, y, z = rnd(1, n), rnd(2, n), rnd(3, n)
+    dx, dy, dz, out = ctx.upload(x), ctx.upload(y), ctx.upload(z), ctx.alloc(8 * n)
+    for op, f in [(abi.OP_ADD, lambda a, b: a + b), (abi.OP_SUB, lambda a, b: a - b), (abi.OP_XOR, lambda a, b: a ^ b)]:
+        abi.check(lib.aby3cu_share_op(ctx.h, op, dx.p, dy.p, out.p, n))
+        assert np.array_equal(ctx.download(out, n, U64), f(x.view(U64), y.view(U64)))
+    abi.check(lib.aby3cu_combine3(ctx.h, abi.OP_ADD, dx.p, dy.p, dz.p, out.p, n))
+    assert np.array_equal(ctx.download(out, n, U64), x.view(U64) + y.view(U64) + z.view(U64))
+    abi.check(lib.aby3cu_combine3(ctx.h, abi.OP_XOR, dx.p, dy.p, dz.p, out.p, n))
+    assert np.array_equal(ctx.download(out, n, U64), x.view(U64) ^ y.view(U64) ^ z.view(U64))
+
+
+def test_transpose_and_gather(ctx):
+    for r, c in [(1, 1), (128, 1024), (33, 65), (1000, 3)]:
+        m = rnd(r * c, r * c).reshape(r, c)
+        dm, out = ctx.upload(m), ctx.alloc(8 * r * c)
+        abi.check(lib.aby3cu_transpose_i64(ctx.h, dm.p, r, c, out.p))
+        assert np.array_equal(ctx.download(out, (c, r)), m.T)
+    m = rnd(5, 500 * 37).reshape(500, 37)
+    idx = np.random.default_rng(0).integers(0, 500, 128).astype(np.uint64)
+    dm, di, out = ctx.upload(m), ctx.upload(idx), ctx.alloc(8 * 128 * 37)
+    abi.check(lib.aby3cu_gather_rows(ctx.h, dm.p, 37, di.p, 128, out.p))
+    assert np.array_equal(ctx.download(out, (128, 37)), m[idx.astype(np.int64)])
+
+
+GEMM_SHAPES = [(1, 1, 1), (10, 10, 10), (128, 64, 16), (129, 65, 17), (200, 300, 70), (128, 1024, 1),
+               (1024, 128, 1), (77, 513, 3), (64, 64, 8), (5, 2000, 9), (256, 256, 256)]
+
+
+@pytest.mark.parametrize("algo", [abi.GEMM_IMAD, abi.GEMM_AUTO])
+def test_gemm_cross(ctx, algo):
+    for (M, K, N) in GEMM_SHAPES:
+        a0, a1 = rnd(1, M * K).reshape(M, K), rnd(2, M * K).reshape(M, K)
+        b0, b1 = rnd(3, K * N).reshape(K, N), rnd(4, K * N).reshape(K, N)
+        c0 = rnd(5, M * N).reshape(M, N)
+        d = [ctx.upload(x) for x in (a0, a1, b0, b1)]
+        exp = o.cross_term(a0, a1, b0, b1).view(U64)
+        dc = ctx.upload(c0)
+        abi.check(lib.aby3cu_gemm_cross(ctx.h, algo, d[0].p, d[1].p, d[2].p, d[3].p, M, K, N, dc.p, 1))
+        assert np.array_equal(ctx.download(dc, (M, N), U64), exp + c0.view(U64)), (M, K, N, "acc")
+        abi.check(lib.aby3cu_gemm_cross(ctx.h, algo, d[0].p, d[1].p, d[2].p, d[3].p, M, K, N, dc.p, 0))
+        assert np.array_equal(ctx.download(dc, (M, N), U64), exp), (M, K, N)
+        for x in d + [dc]:
+            x.free()
+
+
+def test_bit_transpose_matches_oracle(ctx):
+    rng = np.random.default_rng(8)
+    for rows, cols in [(1, 1), (7, 64), (100, 13), (256, 256), (65, 130), (5000, 64), (64, 5000), (3000, 128), (1025, 33)]:
+        ins = ((cols + 31) // 32) * 4 + 8
+        outs = ((rows + 31) // 32) * 4 + 4
+        m = rng.integers(0, 256, rows * ins, dtype=np.uint8)
+        d_in, d_out = ctx.upload(m), ctx.alloc(cols * outs)
+        abi.check(lib.aby3cu_memset(ctx.h, d_out.p, 0, cols * outs))
+        abi.check(lib.aby3cu_bit_transpose(ctx.h, d_in.p, rows, cols, ins, d_out.p, outs, None))
+        got = ctx.download(d_out, cols * outs, np.uint8).reshape(cols, outs)
+        exp = o.bit_transpose(m, rows, cols, ins, outs).reshape(cols, outs)
+        nb = (rows + 7) // 8
+        gb = np.unpackbits(got[:, :nb], axis=1, bitorder="little")[:, :rows]
+        eb = np.unpackbits(exp[:, :nb], axis=1, bitorder="little")[:, :rows]
+        assert np.array_equal(gb, eb), (rows, cols)
+        d_in.free(); d_out.free()
+
+
+def test_bit_transpose_round_trip_full_size(ctx):
+    """size-independent property at a BASELINE-scale width: T(T(x)) == x."""
+    width, bits = 1 << 22, 64
+    x = rnd(3, width)
+    rb = lib.aby3cu_bin_row_bytes(width)
+    d_x, d_m, d_y = ctx.upload(x), ctx.alloc(bits * rb), ctx.alloc(8 * width)
+    abi.check(lib.aby3cu_bit_transpose(ctx.h, d_x.p, width, bits, 8, d_m.p, rb, None))
+    abi.check(lib.aby3cu_bit_transpose(ctx.h, d_m.p, bits, width, rb, d_y.p, 8, None))
+    assert np.array_equal(ctx.download(d_y, width), x)
