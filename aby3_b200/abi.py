@@ -69,6 +69,7 @@ PROTOTYPES = {
     "aby3cu_trunc_finish": (_int, [_p, _p, _p, _p, _p, _sz, _u64]),
     "aby3cu_gemm_cross": (_int, [_p, _int, _p, _p, _p, _p, _u64, _u64, _u64, _p, _int]),
     "aby3cu_gemm_last_algo": (_int, [_p]),
+    "aby3cu_gemm_last_main_kernel_ms": (_int, [_p, C.POINTER(C.c_float)]),
     "aby3cu_share_op": (_int, [_p, _int, _p, _p, _p, _sz]),
     "aby3cu_combine3": (_int, [_p, _int, _p, _p, _p, _p, _sz]),
     "aby3cu_transpose_i64": (_int, [_p, _p, _u64, _u64, _p]),

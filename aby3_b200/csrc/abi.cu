@@ -123,6 +123,8 @@ static int init_ctx(int device, cudaStream_t stream, bool owns, aby3cu_ctx** out
     }
     c->owns_stream = owns;
     if (upload_aes_constants()) { delete c; return 1; }
+    ABY3CU_CHECK(cudaEventCreate(&c->ev_gemm0));
+    ABY3CU_CHECK(cudaEventCreate(&c->ev_gemm1));
     *out = c;
     return 0;
 }
@@ -157,6 +159,8 @@ int aby3cu_ctx_destroy(aby3cu_ctx* ctx) {
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->gemm_ws.ptr) cudaFree(ctx->gemm_ws.ptr);
+    if (ctx->ev_gemm0) cudaEventDestroy(ctx->ev_gemm0);
+    if (ctx->ev_gemm1) cudaEventDestroy(ctx->ev_gemm1);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -301,5 +305,13 @@ int aby3cu_gemm_cross(aby3cu_ctx* ctx, int algo, const i64* A0, const i64* A1, c
 }
 
 int aby3cu_gemm_last_algo(const aby3cu_ctx* ctx) { return ctx ? ctx->last_gemm_algo : 0; }
+
+int aby3cu_gemm_last_main_kernel_ms(aby3cu_ctx* ctx, float* ms) {
+    ABY3CU_REQUIRE(ctx && ms, "gemm_last_main_kernel_ms: null argument");
+    DeviceGuard g(ctx->device);
+    ABY3CU_CHECK(cudaEventSynchronize(ctx->ev_gemm1));
+    ABY3CU_CHECK(cudaEventElapsedTime(ms, ctx->ev_gemm0, ctx->ev_gemm1));
+    return 0;
+}
 
 }  // extern "C"

@@ -33,6 +33,7 @@ struct aby3cu_ctx {
     u64 launches = 0;
     int last_gemm_algo = 0;
     aby3cu::GemmWorkspace gemm_ws;   // limb planes for the tcgen05 GEMM
+    cudaEvent_t ev_gemm0 = nullptr, ev_gemm1 = nullptr;   // bracket the main GEMM kernel
 };
 
 namespace aby3cu {

@@ -144,8 +144,11 @@ int gemm_cross_imad(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0
     const u64 tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const u64 cap = (u64)ctx->sm_count * 2;
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+    ABY3CU_CHECK(cudaEventRecord(ctx->ev_gemm0, ctx->stream));
     k_gemm_imad<<<grid, 256, 0, ctx->stream>>>((const u64*)A0, (const u64*)A1, (const u64*)B0, (const u64*)B1, M, K, N, (u64*)C, accumulate);
-    return post_launch(ctx, "k_gemm_imad");
+    if (post_launch(ctx, "k_gemm_imad")) return 1;
+    ABY3CU_CHECK(cudaEventRecord(ctx->ev_gemm1, ctx->stream));
+    return 0;
 }
 
 }  // namespace aby3cu

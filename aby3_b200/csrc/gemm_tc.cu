@@ -368,8 +368,10 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
             p.mtiles = (u32)mtiles; p.ntiles = (u32)ntiles; p.kblocks = (u32)kblocks; p.accumulate = acc_this;
             const u64 tiles = mtiles * ntiles;
             const unsigned grid = (unsigned)(tiles < (u64)ctx->sm_count ? tiles : (u64)ctx->sm_count);
+            if (k0 == 0 && r0 == 0) ABY3CU_CHECK(cudaEventRecord(ctx->ev_gemm0, ctx->stream));
             k_gemm_tc<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(p);
             if (post_launch(ctx, "k_gemm_tc")) return 1;
+            ABY3CU_CHECK(cudaEventRecord(ctx->ev_gemm1, ctx->stream));
         }
     }
     return 0;

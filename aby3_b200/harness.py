@@ -1,0 +1,237 @@
+"""ctypes binding of the sh3 facade's C harness (aby3_b200/sh3/harness.cpp, libsh3.so):
+three in-process parties, each a worker thread with its own Sh3Runtime /
+Sh3Encryptor / Sh3Evaluator and device stream.  Used by tests and bench.py."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsh3.so")
+
+
+class Sh3Error(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise Sh3Error("libsh3.so is missing (%s); build it with `python -m aby3_b200.build` -- there is no CPU fallback" % LIB_PATH)
+    C.CDLL(os.path.join(_HERE, "libaby3cu.so"), mode=C.RTLD_GLOBAL)
+    l = C.CDLL(LIB_PATH)
+    p, u64, i64, i32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_int
+    l.sh3h_last_error.restype = C.c_char_p
+    l.sh3h_create.restype = p
+    l.sh3h_create.argtypes = [i32, i32, i32, C.c_char_p, C.c_char_p]
+    l.sh3h_destroy.argtypes = [p]
+    l.sh3h_set_disable_randomization.argtypes = [p, i32]
+    l.sh3h_set_gemm_algo.argtypes = [p, i32]
+    l.sh3h_cursors.argtypes = [p, i32, p]
+    l.sh3h_plain_create.argtypes = [p, i32, u64, u64, C.POINTER(p)]
+    l.sh3h_plain_touch.argtypes = [p, i32, i32]
+    l.sh3h_share.argtypes = [p, i32, i32, u64, u64, i32, u64]
+    l.sh3h_set_shares.argtypes = [p, p, u64, u64, i32, u64]
+    l.sh3h_get_shares.argtypes = [p, i32, i32, p]
+    l.sh3h_shape.argtypes = [p, i32, i32, C.POINTER(u64), C.POINTER(u64)]
+    l.sh3h_free.argtypes = [p, i32]
+    l.sh3h_mul.argtypes = [p, i32, i32, i64, i32]
+    l.sh3h_addsub.argtypes = [p, i32, i32, i32]
+    l.sh3h_reveal.argtypes = [p, i32, i32, i32, p]
+    l.sh3h_trunc_tuple.argtypes = [p, i32, u64, u64, u64, p, p, p]
+    l.sh3h_bin_eval.argtypes = [p, p, C.c_uint32, C.c_uint32, p, C.c_uint32, p, p, C.c_uint32, p, p, p, p, C.c_uint32, p, p]
+    l.sh3h_timer_begin.argtypes = [p]
+    l.sh3h_timer_end.argtypes = [p, C.POINTER(C.c_float)]
+    l.sh3h_sync.argtypes = [p]
+    l.sh3h_launch_count.restype = u64
+    l.sh3h_launch_count.argtypes = [p]
+    l.sh3h_bytes_sent.restype = u64
+    l.sh3h_bytes_sent.argtypes = [p]
+    return l
+
+
+lib = _load()
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def to_block(hi, lo):
+    return int(lo & (2**64 - 1)).to_bytes(8, "little") + int(hi & (2**64 - 1)).to_bytes(8, "little")
+
+
+def default_seeds():
+    """aby3_tests/Sh3EvaluatorTests.cpp:41-47"""
+    enc = b"".join(to_block(0, i) + to_block(0, (i + 1) % 3) for i in range(3))
+    ev = b"".join(to_block(1, i) + to_block(1, (i + 1) % 3) for i in range(3))
+    return enc, ev
+
+
+class Session:
+    """Three parties on devices (d0, d1, d2) -- all 0 by default (co-located)."""
+
+    def __init__(self, devices=(0, 0, 0), enc_seeds=None, eval_seeds=None):
+        e, v = default_seeds()
+        self.h = lib.sh3h_create(devices[0], devices[1], devices[2], enc_seeds or e, eval_seeds or v)
+        if not self.h:
+            raise Sh3Error(lib.sh3h_last_error().decode())
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise Sh3Error(lib.sh3h_last_error().decode())
+
+    def _id(self, rc):
+        if rc < 0:
+            raise Sh3Error(lib.sh3h_last_error().decode())
+        return rc
+
+    def close(self):
+        if self.h:
+            lib.sh3h_destroy(self.h)
+            self.h = None
+
+    def disable_randomization(self, on=True):
+        lib.sh3h_set_disable_randomization(self.h, int(on))
+
+    def set_gemm_algo(self, algo):
+        lib.sh3h_set_gemm_algo(self.h, int(algo))
+
+    def cursors(self, party):
+        c = np.zeros(6, dtype=np.uint64)
+        lib.sh3h_cursors(self.h, party, _ptr(c))
+        return c
+
+    def plain(self, owner, rows, cols):
+        """Plaintext matrix held by `owner` in page-locked host memory.
+        Returns (handle, numpy view to fill)."""
+        hp = C.c_void_p()
+        hid = self._id(lib.sh3h_plain_create(self.h, owner, rows, cols, C.byref(hp)))
+        buf = (C.c_int64 * (rows * cols)).from_address(hp.value)
+        return hid, np.frombuffer(buf, dtype=np.int64).reshape(rows, cols)
+
+    def plain_touch(self, owner, hid):
+        self._chk(lib.sh3h_plain_touch(self.h, owner, hid))
+
+    def share_int(self, owner, values):
+        values = np.ascontiguousarray(values, dtype=np.int64)
+        if values.ndim == 1:
+            values = values.reshape(-1, 1)
+        pid, view = self.plain(owner, values.shape[0], values.shape[1])
+        view[...] = values
+        hid = self._id(lib.sh3h_share(self.h, owner, pid, values.shape[0], values.shape[1], 0, 0))
+        self.free(pid)
+        return hid
+
+    def share_plain(self, owner, pid, rows, cols):
+        return self._id(lib.sh3h_share(self.h, owner, pid, rows, cols, 0, 0))
+
+    def share_bin(self, owner, values, bit_count):
+        values = np.ascontiguousarray(values, dtype=np.int64)
+        if values.ndim == 1:
+            values = values.reshape(-1, 1)
+        assert values.shape[1] == (bit_count + 63) // 64
+        pid, view = self.plain(owner, values.shape[0], values.shape[1])
+        view[...] = values
+        hid = self._id(lib.sh3h_share(self.h, owner, pid, values.shape[0], values.shape[1], 1, bit_count))
+        self.free(pid)
+        return hid
+
+    def set_shares(self, shares, binary=False, bit_count=0):
+        shares = np.ascontiguousarray(shares, dtype=np.int64)
+        rows, cols = shares.shape[2], shares.shape[3]
+        return self._id(lib.sh3h_set_shares(self.h, _ptr(shares), rows, cols if not binary else 0, int(binary), bit_count))
+
+    def shape(self, hid, binary=False):
+        r, c = C.c_uint64(), C.c_uint64()
+        self._chk(lib.sh3h_shape(self.h, hid, int(binary), C.byref(r), C.byref(c)))
+        return r.value, c.value
+
+    def get_shares(self, hid, binary=False):
+        r, c = self.shape(hid, binary)
+        out = np.empty((3, 2, r, c), dtype=np.int64)
+        self._chk(lib.sh3h_get_shares(self.h, hid, int(binary), _ptr(out)))
+        return out
+
+    def free(self, hid):
+        self._chk(lib.sh3h_free(self.h, hid))
+
+    def mul(self, a, b, shift=None, out=0):
+        return self._id(lib.sh3h_mul(self.h, a, b, -1 if shift is None else int(shift), out))
+
+    def add(self, a, b):
+        return self._id(lib.sh3h_addsub(self.h, a, b, 0))
+
+    def sub(self, a, b):
+        return self._id(lib.sh3h_addsub(self.h, a, b, 1))
+
+    def reveal(self, hid, party=0, binary=False, out=None):
+        r, c = self.shape(hid, binary)
+        if out is None:
+            out = np.empty((r, c), dtype=np.int64)
+        self._chk(lib.sh3h_reveal(self.h, hid, int(binary), party, _ptr(out)))
+        return out
+
+    def trunc_tuple(self, party, rows, cols, d):
+        n = rows * cols
+        R, T0, T1 = (np.empty(n, dtype=np.int64) for _ in range(3))
+        self._chk(lib.sh3h_trunc_tuple(self.h, party, rows, cols, d, _ptr(R), _ptr(T0), _ptr(T1)))
+        return R, T0, T1
+
+    def bin_eval(self, cir, input_ids):
+        """cir: a dict of flat uint32 arrays (tests/circuits.py). Returns output handles."""
+        ins = np.asarray(input_ids, dtype=np.int32)
+        outs = np.zeros(len(cir["output_bits"]), dtype=np.int32)
+        inv = cir.get("output_invert")
+        self._chk(lib.sh3h_bin_eval(
+            self.h, _ptr(cir["gates"]), len(cir["gates"]) // 4, cir["wire_count"], _ptr(cir["level_gates"]),
+            len(cir["level_gates"]), _ptr(cir["input_first"]), _ptr(cir["input_bits"]), len(cir["input_bits"]),
+            _ptr(cir["output_off"]), _ptr(cir["output_bits"]), _ptr(cir["output_wires"]),
+            _ptr(inv) if inv is not None else None, len(cir["output_bits"]), _ptr(ins), _ptr(outs)))
+        return [int(x) for x in outs]
+
+    def timer_begin(self):
+        self._chk(lib.sh3h_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_float(0)
+        self._chk(lib.sh3h_timer_end(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def sync(self):
+        self._chk(lib.sh3h_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(lib.sh3h_launch_count(self.h))
+
+    @property
+    def bytes_sent(self):
+        return int(lib.sh3h_bytes_sent(self.h))
+
+
+lib.sh3h_circuit_build.restype = C.c_void_p
+lib.sh3h_circuit_build.argtypes = [C.c_char_p, C.c_uint32]
+lib.sh3h_circuit_free.argtypes = [C.c_void_p]
+lib.sh3h_circuit_sizes.argtypes = [C.c_void_p, C.c_void_p]
+lib.sh3h_circuit_copy.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+
+
+def library_circuit(name, bits):
+    """Flat description of a circuit from the facade's BetaLibrary (host only)."""
+    h = lib.sh3h_circuit_build(name.encode(), bits)
+    if not h:
+        raise Sh3Error(lib.sh3h_last_error().decode())
+    s = np.zeros(7, dtype=np.uint32)
+    lib.sh3h_circuit_sizes(h, _ptr(s))
+    ng, nw, nl, ni, no, now, nand = (int(x) for x in s)
+    cir = {
+        "wire_count": nw, "nonlinear": nand,
+        "gates": np.zeros(4 * ng, dtype=np.uint32), "level_gates": np.zeros(nl, dtype=np.uint32),
+        "input_first": np.zeros(ni, dtype=np.uint32), "input_bits": np.zeros(ni, dtype=np.uint32),
+        "output_off": np.zeros(no, dtype=np.uint32), "output_bits": np.zeros(no, dtype=np.uint32),
+        "output_wires": np.zeros(now, dtype=np.uint32), "output_invert": np.zeros(now, dtype=np.uint8),
+    }
+    lib.sh3h_circuit_copy(h, _ptr(cir["gates"]), _ptr(cir["level_gates"]), _ptr(cir["input_first"]), _ptr(cir["input_bits"]),
+                          _ptr(cir["output_off"]), _ptr(cir["output_bits"]), _ptr(cir["output_wires"]), _ptr(cir["output_invert"]))
+    lib.sh3h_circuit_free(h)
+    return cir

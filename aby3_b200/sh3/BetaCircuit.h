@@ -1,0 +1,334 @@
+// BetaCircuit.h -- the Boolean-circuit container the binary engine consumes, and a
+// small library of the circuits the aby3 apps ask for.  In the reference these
+// are cryptoTools' oc::BetaCircuit / oc::BetaLibrary (libOTe @ cf537295, not in
+// the reference tree; field list per SURVEY 9.2).  The circuit is DATA for the
+// engine: gate order and levelisation here are this implementation's own (the
+// cryptoTools ones cannot be inspected), reconstructed outputs do not depend on
+// them.  Host-only code.
+#pragma once
+#include <algorithm>
+#include <map>
+
+#include "Defines.h"
+
+namespace oc {
+
+// 4-bit truth tables, cryptoTools Gate.h numbering
+enum class GateType : u8 {
+    Zero = 0, Nor = 1, nb_And = 2, nb = 3, na_And = 4, na = 5, Xor = 6, Nand = 7,
+    And = 8, Nxor = 9, a = 10, nb_Or = 11, b = 12, na_Or = 13, Or = 14, One = 15
+};
+
+inline bool isLinear(GateType t) { return t == GateType::Xor || t == GateType::Nxor || t == GateType::a; }
+
+typedef u32 BetaWire;
+
+struct BetaGate {
+    std::array<BetaWire, 2> mInput;
+    BetaWire mOutput;
+    GateType mType;
+    BetaGate() = default;
+    BetaGate(BetaWire in0, BetaWire in1, GateType t, BetaWire out) : mInput{{in0, in1}}, mOutput(out), mType(t) {}
+};
+
+struct BetaBundle {
+    std::vector<BetaWire> mWires;
+    BetaBundle() = default;
+    explicit BetaBundle(u64 n) : mWires(n, (BetaWire)-1) {}
+    u64 size() const { return mWires.size(); }
+    BetaWire& operator[](u64 i) { return mWires[i]; }
+    const BetaWire& operator[](u64 i) const { return mWires[i]; }
+    BetaWire front() const { return mWires.front(); }
+    BetaWire back() const { return mWires.back(); }
+};
+
+enum class BetaWireFlag : u8 { Zero, One, Wire, InvWire, Uninitialized };
+
+class BetaCircuit {
+public:
+    u64 mNonlinearGateCount = 0;
+    BetaWire mWireCount = 0;
+    std::vector<BetaGate> mGates;
+    std::vector<BetaBundle> mInputs, mOutputs;
+    std::vector<u64> mLevelCounts, mLevelAndCounts;
+    std::vector<BetaWireFlag> mWireFlags;
+
+    void addInputBundle(BetaBundle& in) {
+        for (u64 i = 0; i < in.size(); ++i) in[i] = newWire(BetaWireFlag::Wire);
+        mInputs.push_back(in);
+    }
+    void addTempWireBundle(BetaBundle& b) {
+        for (u64 i = 0; i < b.size(); ++i) b[i] = newWire(BetaWireFlag::Uninitialized);
+    }
+    void addOutputBundle(BetaBundle& out) {
+        for (u64 i = 0; i < out.size(); ++i) out[i] = newWire(BetaWireFlag::Uninitialized);
+        mOutputs.push_back(out);
+    }
+    // register already-existing wires as an output bundle
+    void addOutputWires(const BetaBundle& out) { mOutputs.push_back(out); }
+    BetaWire addTempWire() { return newWire(BetaWireFlag::Uninitialized); }
+
+    void addGate(BetaWire in0, BetaWire in1, GateType t, BetaWire out) {
+        if (t == GateType::a) { addCopy(in0, out); return; }
+        if (in0 >= mWireCount || in1 >= mWireCount || out >= mWireCount) throw RTE_LOC;
+        // inverted inputs are folded into the gate type (Xor/Nxor) or materialised
+        const bool inv0 = mWireFlags[in0] == BetaWireFlag::InvWire, inv1 = mWireFlags[in1] == BetaWireFlag::InvWire;
+        if (inv0 || inv1) throw std::runtime_error("BetaCircuit: gates on inverted wires are not supported; use addInvert on outputs only " LOCATION);
+        mGates.emplace_back(in0, in1, t, out);
+        mWireFlags[out] = BetaWireFlag::Wire;
+        if (!isLinear(t)) ++mNonlinearGateCount;
+        mLevelCounts.clear(); mLevelAndCounts.clear();
+    }
+    void addCopy(BetaWire src, BetaWire dst) {
+        mGates.emplace_back(src, src, GateType::a, dst);
+        mWireFlags[dst] = BetaWireFlag::Wire;
+        mLevelCounts.clear(); mLevelAndCounts.clear();
+    }
+    // mark a wire as logically inverted; applied when the wire is read as an output
+    void addInvert(BetaWire w) {
+        if (mWireFlags[w] == BetaWireFlag::Wire) mWireFlags[w] = BetaWireFlag::InvWire;
+        else if (mWireFlags[w] == BetaWireFlag::InvWire) mWireFlags[w] = BetaWireFlag::Wire;
+        else throw RTE_LOC;
+    }
+    bool isInvert(BetaWire w) const { return mWireFlags[w] == BetaWireFlag::InvWire; }
+
+    // Order gates by AND depth.  level(g) = max over inputs of (level of the gate
+    // that produced it + 1 if that gate is nonlinear); a nonlinear gate's output
+    // is only usable one communication round later (Sh3BinaryEvaluator.cpp:555-573).
+    // Gate order inside a level keeps the construction order (stable).
+    void levelByAndDepth() {
+        std::vector<u32> ready(mWireCount, 0);     // first level at which the wire's value is usable
+        std::vector<u32> lvl(mGates.size());
+        u32 maxLevel = 0;
+        for (u64 g = 0; g < mGates.size(); ++g) {
+            const auto& G = mGates[g];
+            u32 l = std::max(ready[G.mInput[0]], ready[G.mInput[1]]);
+            lvl[g] = l;
+            ready[G.mOutput] = isLinear(G.mType) ? l : l + 1;
+            maxLevel = std::max(maxLevel, l);
+        }
+        std::vector<u64> order(mGates.size());
+        for (u64 g = 0; g < order.size(); ++g) order[g] = g;
+        std::stable_sort(order.begin(), order.end(), [&](u64 x, u64 y) { return lvl[x] < lvl[y]; });
+        std::vector<BetaGate> sorted(mGates.size());
+        mLevelCounts.assign(mGates.empty() ? 0 : maxLevel + 1, 0);
+        mLevelAndCounts.assign(mLevelCounts.size(), 0);
+        for (u64 k = 0; k < order.size(); ++k) {
+            sorted[k] = mGates[order[k]];
+            ++mLevelCounts[lvl[order[k]]];
+            if (!isLinear(sorted[k].mType)) ++mLevelAndCounts[lvl[order[k]]];
+        }
+        mGates.swap(sorted);
+    }
+
+    // rebuild from the flat description used by the test harness / oracle
+    void loadFlat(const u32* gates, u32 gateCount, u32 wireCount, const u32* levelGates, u32 levelCount,
+                  const u32* inputFirst, const u32* inputBits, u32 numInputs, const u32* outputOff,
+                  const u32* outputBits, const u32* outputWires, const u8* outputInvert, u32 numOutputs) {
+        *this = BetaCircuit();
+        mWireCount = wireCount;
+        mWireFlags.assign(wireCount, BetaWireFlag::Wire);
+        for (u32 g = 0; g < gateCount; ++g) {
+            mGates.emplace_back(gates[4 * g], gates[4 * g + 1], (GateType)gates[4 * g + 3], gates[4 * g + 2]);
+            if (!isLinear(mGates.back().mType)) ++mNonlinearGateCount;
+        }
+        u64 pos = 0;
+        for (u32 l = 0; l < levelCount; ++l) {
+            mLevelCounts.push_back(levelGates[l]);
+            u64 ands = 0;
+            for (u64 g = pos; g < pos + levelGates[l]; ++g) ands += !isLinear(mGates[g].mType);
+            mLevelAndCounts.push_back(ands);
+            pos += levelGates[l];
+        }
+        for (u32 k = 0; k < numInputs; ++k) {
+            BetaBundle b(inputBits[k]);
+            for (u32 i = 0; i < inputBits[k]; ++i) b[i] = inputFirst[k] + i;
+            mInputs.push_back(b);
+        }
+        for (u32 k = 0; k < numOutputs; ++k) {
+            BetaBundle b(outputBits[k]);
+            for (u32 i = 0; i < outputBits[k]; ++i) {
+                b[i] = outputWires[outputOff[k] + i];
+                if (outputInvert && outputInvert[outputOff[k] + i]) mWireFlags[b[i]] = BetaWireFlag::InvWire;
+            }
+            mOutputs.push_back(b);
+        }
+    }
+
+private:
+    BetaWire newWire(BetaWireFlag f) {
+        mWireFlags.push_back(f);
+        return mWireCount++;
+    }
+};
+
+// A few of the circuits aby3-Basic / aby3-ML request from oc::BetaLibrary
+// (BoolBasic.cpp:29,51,111,152; CircuitLibrary.cpp:379-394).  Built once, cached.
+class BetaLibrary {
+public:
+    enum class Optimized { Size, Depth };
+    ~BetaLibrary() { for (auto& kv : mCache) delete kv.second; }
+
+    BetaCircuit* int_int_bitwiseAnd(u64 a, u64 b, u64 c) { return bitwise("and", GateType::And, a, b, c); }
+    BetaCircuit* int_int_bitwiseOr(u64 a, u64 b, u64 c) { return bitwise("or", GateType::Or, a, b, c); }
+    BetaCircuit* int_int_bitwiseXor(u64 a, u64 b, u64 c) { return bitwise("xor", GateType::Xor, a, b, c); }
+
+    // c = a + b (two's complement, cBits low bits)
+    BetaCircuit* int_int_add(u64 aBits, u64 bBits, u64 cBits, Optimized op = Optimized::Size) {
+        const std::string key = "add" + std::to_string(aBits) + "_" + std::to_string(bBits) + "_" + std::to_string(cBits) +
+                                (op == Optimized::Depth ? "d" : "s");
+        return cached(key, [&](BetaCircuit& cd) {
+            BetaBundle a(aBits), b(bBits), c(cBits);
+            cd.addInputBundle(a); cd.addInputBundle(b); cd.addOutputBundle(c);
+            if (op == Optimized::Depth) prefixAdd(cd, a, b, c, false);
+            else rippleAdd(cd, a, b, c);
+        });
+    }
+    // the most significant bit of a + b (int_comp_helper / fetch_msb)
+    BetaCircuit* int_int_add_msb(u64 bits) {
+        return cached("addmsb" + std::to_string(bits), [&](BetaCircuit& cd) {
+            BetaBundle a(bits), b(bits), c(1), t(bits);
+            cd.addInputBundle(a); cd.addInputBundle(b); cd.addOutputBundle(c);
+            cd.addTempWireBundle(t);
+            prefixAdd(cd, a, b, t, false);
+            cd.addCopy(t[bits - 1], c[0]);
+        });
+    }
+    // c = (a < b) for signed two's-complement inputs of equal width
+    BetaCircuit* int_int_lt(u64 aBits, u64 bBits) {
+        if (aBits != bBits) throw RTE_LOC;
+        return cached("lt" + std::to_string(aBits), [&](BetaCircuit& cd) {
+            const u64 n = aBits;
+            BetaBundle a(n), b(n), c(1);
+            cd.addInputBundle(a); cd.addInputBundle(b); cd.addOutputBundle(c);
+            // a < b  <=>  sign of (a - b) computed on n+1 bits (sign-extended operands):
+            // a - b = a + ~b + 1.  Borrow-chain formulation: lt = MSB(diff_ext).
+            // diff_ext bit n = a_s ^ ~b_s ^ carry_n, with carry from a + ~b + 1.
+            BetaBundle nb(n);
+            cd.addTempWireBundle(nb);
+            // carry chain with generate/propagate on (a, ~b), carry-in = 1:
+            // g_i = a_i & ~b_i = na_And(b_i, a_i), p_i = a_i ^ ~b_i = Nxor(a_i, b_i)
+            std::vector<BetaWire> g(n), p(n);
+            for (u64 i = 0; i < n; ++i) {
+                g[i] = cd.addTempWire(); p[i] = cd.addTempWire();
+                cd.addGate(b[i], a[i], GateType::na_And, g[i]);
+                cd.addGate(a[i], b[i], GateType::Nxor, p[i]);
+            }
+            // carry_n (out of bit n-1) with carry-in 1: fold cin into bit 0: g0' = g0 | p0 = Or(g0,p0)... use
+            // g0' = g0 ^ p0 (g0 & p0 == 0 because g = a&~b implies p = a^~b = 0)
+            BetaWire g0 = cd.addTempWire();
+            cd.addGate(g[0], p[0], GateType::Xor, g0);
+            g[0] = g0;
+            BetaWire carry = prefixCarry(cd, g, p);
+            // sign bit of the (n+1)-bit difference: a_s ^ ~b_s ^ carry = p[n-1] ^ carry
+            cd.addGate(p[n - 1], carry, GateType::Xor, c[0]);
+        });
+    }
+    // c = (a == b)
+    BetaCircuit* int_eq(u64 bits) {
+        return cached("eq" + std::to_string(bits), [&](BetaCircuit& cd) {
+            BetaBundle a(bits), b(bits), c(1);
+            cd.addInputBundle(a); cd.addInputBundle(b); cd.addOutputBundle(c);
+            std::vector<BetaWire> e(bits);
+            for (u64 i = 0; i < bits; ++i) { e[i] = cd.addTempWire(); cd.addGate(a[i], b[i], GateType::Nxor, e[i]); }
+            while (e.size() > 1) {            // AND tree, depth log2(bits)
+                std::vector<BetaWire> nx;
+                for (u64 i = 0; i + 1 < e.size(); i += 2) {
+                    BetaWire w = cd.addTempWire();
+                    cd.addGate(e[i], e[i + 1], GateType::And, w);
+                    nx.push_back(w);
+                }
+                if (e.size() & 1) nx.push_back(e.back());
+                e.swap(nx);
+            }
+            cd.addCopy(e[0], c[0]);
+        });
+    }
+
+private:
+    std::map<std::string, BetaCircuit*> mCache;
+
+    template <typename F>
+    BetaCircuit* cached(const std::string& key, F build) {
+        auto it = mCache.find(key);
+        if (it != mCache.end()) return it->second;
+        auto* cd = new BetaCircuit;
+        build(*cd);
+        cd->levelByAndDepth();
+        mCache[key] = cd;
+        return cd;
+    }
+    BetaCircuit* bitwise(const char* name, GateType t, u64 aBits, u64 bBits, u64 cBits) {
+        if (aBits != bBits || aBits != cBits) throw RTE_LOC;
+        return cached(std::string(name) + std::to_string(aBits), [&](BetaCircuit& cd) {
+            BetaBundle a(aBits), b(bBits), c(cBits);
+            cd.addInputBundle(a); cd.addInputBundle(b); cd.addOutputBundle(c);
+            for (u64 i = 0; i < aBits; ++i) cd.addGate(a[i], b[i], t, c[i]);
+        });
+    }
+    static BetaWire at(const BetaBundle& x, u64 i) { return x[std::min<u64>(i, x.size() - 1)]; }   // sign extension
+    // ripple-carry: 1 AND per bit, depth = bits
+    static void rippleAdd(BetaCircuit& cd, const BetaBundle& a, const BetaBundle& b, const BetaBundle& c) {
+        const u64 n = c.size();
+        BetaWire carry = (BetaWire)-1;
+        for (u64 i = 0; i < n; ++i) {
+            BetaWire x = at(a, i), y = at(b, i);
+            BetaWire axb = cd.addTempWire();
+            cd.addGate(x, y, GateType::Xor, axb);
+            if (i == 0) {
+                cd.addCopy(axb, c[0]);
+                if (n > 1) { carry = cd.addTempWire(); cd.addGate(x, y, GateType::And, carry); }
+            } else {
+                cd.addGate(axb, carry, GateType::Xor, c[i]);
+                if (i + 1 < n) {
+                    // carry' = carry ^ ((x ^ carry) & (y ^ carry))
+                    BetaWire xc = cd.addTempWire(), yc = cd.addTempWire(), t = cd.addTempWire(), nc = cd.addTempWire();
+                    cd.addGate(x, carry, GateType::Xor, xc);
+                    cd.addGate(y, carry, GateType::Xor, yc);
+                    cd.addGate(xc, yc, GateType::And, t);
+                    cd.addGate(t, carry, GateType::Xor, nc);
+                    carry = nc;
+                }
+            }
+        }
+    }
+    // Kogge-Stone prefix network on (g, p); returns every prefix generate G[i] = carry out of bit i.
+    static std::vector<BetaWire> prefixAll(BetaCircuit& cd, std::vector<BetaWire> g, std::vector<BetaWire> p) {
+        const u64 n = g.size();
+        for (u64 d = 1; d < n; d <<= 1) {
+            std::vector<BetaWire> ng = g, np = p;
+            for (u64 i = d; i < n; ++i) {
+                // G = g_i ^ (p_i & g_{i-d})   (g_i and p_i & x are never both 1), P = p_i & p_{i-d}
+                BetaWire t = cd.addTempWire(), G = cd.addTempWire();
+                cd.addGate(p[i], g[i - d], GateType::And, t);
+                cd.addGate(g[i], t, GateType::Xor, G);
+                ng[i] = G;
+                if (i >= 2 * d || true) {
+                    BetaWire P = cd.addTempWire();
+                    cd.addGate(p[i], p[i - d], GateType::And, P);
+                    np[i] = P;
+                }
+            }
+            g.swap(ng); p.swap(np);
+        }
+        return g;
+    }
+    static BetaWire prefixCarry(BetaCircuit& cd, const std::vector<BetaWire>& g, const std::vector<BetaWire>& p) {
+        return prefixAll(cd, g, p).back();
+    }
+    // depth-optimised adder: log2(bits)+1 AND levels
+    static void prefixAdd(BetaCircuit& cd, const BetaBundle& a, const BetaBundle& b, const BetaBundle& c, bool) {
+        const u64 n = c.size();
+        std::vector<BetaWire> g(n), p(n);
+        for (u64 i = 0; i < n; ++i) {
+            g[i] = cd.addTempWire(); p[i] = cd.addTempWire();
+            cd.addGate(at(a, i), at(b, i), GateType::And, g[i]);
+            cd.addGate(at(a, i), at(b, i), GateType::Xor, p[i]);
+        }
+        std::vector<BetaWire> G = prefixAll(cd, g, p);
+        cd.addCopy(p[0], c[0]);
+        for (u64 i = 1; i < n; ++i) cd.addGate(p[i], G[i - 1], GateType::Xor, c[i]);
+    }
+};
+
+}  // namespace oc

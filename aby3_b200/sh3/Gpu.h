@@ -1,0 +1,167 @@
+// Gpu.h -- the facade's only door to the device: a per-party context over the
+// C ABI (include/aby3cu.h) with a small stream-ordered buffer pool.  There is no
+// host implementation behind it; without libaby3cu.so + a B200 every call throws.
+#pragma once
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "Defines.h"
+#include "aby3cu.h"
+
+namespace aby3 {
+namespace gpu {
+
+inline void check(int rc) {
+    if (rc != 0) throw std::runtime_error(std::string("aby3cu: ") + aby3cu_last_error());
+}
+
+// One party's device, stream and buffer pool.  Buffers released to the pool are
+// reused in stream order; a buffer another party's stream may still be reading
+// is parked together with the event that marks the end of that read.
+class Context {
+public:
+    explicit Context(int device = 0) {
+        check(aby3cu_ctx_create(device, &mCtx));
+        mDevice = device;
+    }
+    Context(int device, void* stream) {
+        check(aby3cu_ctx_create_on_stream(device, stream, &mCtx));
+        mDevice = device;
+    }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    ~Context() {
+        if (!mCtx) return;
+        aby3cu_sync(mCtx);
+        for (auto& kv : mFree)
+            for (auto& e : kv.second) {
+                if (e.event) aby3cu_event_destroy(e.event);
+                aby3cu_free(mCtx, e.ptr);
+            }
+        aby3cu_ctx_destroy(mCtx);
+    }
+
+    aby3cu_ctx* h() const { return mCtx; }
+    int device() const { return mDevice; }
+    void sync() { check(aby3cu_sync(mCtx)); }
+
+    void* alloc(size_t bytes) {
+        if (bytes == 0) return nullptr;
+        bytes = roundSize(bytes);
+        Entry e{nullptr, nullptr};
+        {
+            std::lock_guard<std::mutex> g(mMtx);
+            auto it = mFree.find(bytes);
+            if (it != mFree.end() && !it->second.empty()) {
+                e = it->second.back();
+                it->second.pop_back();
+            }
+        }
+        if (e.ptr) {
+            if (e.event) {
+                check(aby3cu_event_wait(mCtx, e.event));
+                aby3cu_event_destroy(e.event);
+            }
+            return e.ptr;
+        }
+        void* p = nullptr;
+        check(aby3cu_malloc(mCtx, &p, bytes));
+        return p;
+    }
+    // `after` (may be null): an event recorded on ANOTHER stream that still reads the buffer
+    void release(void* p, size_t bytes, void* after = nullptr) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mMtx);
+        mFree[roundSize(bytes)].push_back(Entry{p, after});
+    }
+
+    static size_t roundSize(size_t b) { return (b + 511) & ~size_t(511); }
+
+private:
+    struct Entry { void* ptr; void* event; };
+    aby3cu_ctx* mCtx = nullptr;
+    int mDevice = 0;
+    std::mutex mMtx;
+    std::map<size_t, std::vector<Entry>> mFree;
+};
+
+// The context of the calling thread (one thread per party, as in the reference:
+// frontend/aby3Tutorial.cpp:393-394).  Sh3Runtime::init adopts the context of
+// its CommPkg; tests may set it directly.
+Context*& currentSlot();
+inline Context* current() {
+    Context* c = currentSlot();
+    if (!c) throw std::runtime_error("aby3::gpu: no device context bound to this thread (call gpu::setCurrent)");
+    return c;
+}
+inline void setCurrent(Context* c) { currentSlot() = c; }
+
+// RAII device allocation drawn from a context's pool
+class Buffer {
+public:
+    Buffer() = default;
+    Buffer(Context* c, size_t bytes) { reset(c, bytes); }
+    Buffer(const Buffer&) = delete;
+    Buffer& operator=(const Buffer&) = delete;
+    Buffer(Buffer&& o) noexcept { *this = std::move(o); }
+    Buffer& operator=(Buffer&& o) noexcept {
+        if (this != &o) {
+            free();
+            mCtx = o.mCtx; mPtr = o.mPtr; mBytes = o.mBytes;
+            o.mCtx = nullptr; o.mPtr = nullptr; o.mBytes = 0;
+        }
+        return *this;
+    }
+    ~Buffer() { free(); }
+    void reset(Context* c, size_t bytes) {
+        if (mCtx == c && mBytes >= bytes && mBytes <= 2 * Context::roundSize(bytes)) return;
+        free();
+        mCtx = c; mBytes = bytes; mPtr = c->alloc(bytes);
+    }
+    void free(void* after = nullptr) {
+        if (mPtr && mCtx) mCtx->release(mPtr, mBytes, after);
+        else if (after) aby3cu_event_destroy(after);
+        mPtr = nullptr; mBytes = 0; mCtx = nullptr;
+    }
+    void* ptr() const { return mPtr; }
+    size_t bytes() const { return mBytes; }
+    Context* ctx() const { return mCtx; }
+    explicit operator bool() const { return mPtr != nullptr; }
+private:
+    Context* mCtx = nullptr;
+    void* mPtr = nullptr;
+    size_t mBytes = 0;
+};
+
+// Host storage of matrices: page-locked once it is big enough to matter, so the
+// h2d / d2h copies behind eMatrix run at full PCIe rate and truly asynchronously.
+template <typename T>
+struct HostAllocator {
+    using value_type = T;
+    static constexpr size_t kPinThreshold = 1u << 16;
+    HostAllocator() = default;
+    template <typename U>
+    HostAllocator(const HostAllocator<U>&) {}
+    T* allocate(size_t n) {
+        const size_t bytes = n * sizeof(T);
+        if (bytes >= kPinThreshold) {
+            void* p = nullptr;
+            if (aby3cu_host_alloc(&p, bytes) == 0) return static_cast<T*>(p);
+            throw std::bad_alloc();
+        }
+        void* p = ::operator new(bytes);
+        return static_cast<T*>(p);
+    }
+    void deallocate(T* p, size_t n) {
+        if (n * sizeof(T) >= kPinThreshold) aby3cu_host_free(p);
+        else ::operator delete(p);
+    }
+    template <typename U>
+    bool operator==(const HostAllocator<U>&) const { return true; }
+    template <typename U>
+    bool operator!=(const HostAllocator<U>&) const { return false; }
+};
+
+}  // namespace gpu
+}  // namespace aby3

@@ -1,0 +1,167 @@
+// Sh3BinaryEvaluator.cpp -- see Sh3BinaryEvaluator.h.
+#include "Sh3BinaryEvaluator.h"
+
+namespace aby3 {
+
+using oc::GateType;
+
+void Sh3BinaryEvaluator::setCir(oc::BetaCircuit* cir, u64 width, block prevSeed, block nextSeed) {
+    if (cir->mLevelCounts.size() == 0) cir->levelByAndDepth();        // .cpp:69-78
+    mCir = cir;
+    mCtx = gpu::current();
+    mWidth = width;
+    mRowBytes = aby3cu_bin_row_bytes(width);                           // mMem.reset(width, wires, 8)  :84
+    mShareIdx = 0;
+    mLevel = 0;
+    mShareAES[0].setKey(prevSeed);                                     // :87-88
+    mShareAES[1].setKey(nextSeed);
+
+    const u64 planeBytes = std::max<u64>((u64)cir->mWireCount * mRowBytes, 16);
+    for (int s = 0; s < 2; ++s) {
+        mMem[s].reset(mCtx, planeBytes);
+        gpu::check(aby3cu_memset(mCtx->h(), mMem[s].ptr(), 0, planeBytes));
+    }
+    // gate list and the per-level AND output wires, uploaded once
+    std::vector<u32> flat(4 * cir->mGates.size()), locs;
+    for (u64 g = 0; g < cir->mGates.size(); ++g) {
+        const auto& G = cir->mGates[g];
+        switch (G.mType) {
+        case GateType::Xor: case GateType::And: case GateType::Nor: case GateType::Or:
+        case GateType::Nxor: case GateType::a: case GateType::na_And: break;
+        default: throw std::runtime_error("BinaryEngine unsupported GateType " LOCATION);   // :1066-1079
+        }
+        if (G.mOutput == G.mInput[0] || G.mOutput == G.mInput[1]) throw RTE_LOC;             // :684-689
+        if (G.mInput[0] == G.mInput[1] && G.mType != GateType::a) throw RTE_LOC;
+        flat[4 * g] = G.mInput[0]; flat[4 * g + 1] = G.mInput[1]; flat[4 * g + 2] = G.mOutput; flat[4 * g + 3] = (u32)G.mType;
+        if (!oc::isLinear(G.mType)) locs.push_back(G.mOutput);
+    }
+    mLevelGateOff.assign(1, 0);
+    mLevelAndOff.assign(1, 0);
+    for (u64 l = 0; l < cir->mLevelCounts.size(); ++l) {
+        mLevelGateOff.push_back(mLevelGateOff.back() + cir->mLevelCounts[l]);
+        mLevelAndOff.push_back(mLevelAndOff.back() + cir->mLevelAndCounts[l]);
+    }
+    mGatesDev.reset(mCtx, std::max<size_t>(flat.size() * 4, 16));
+    mAndLocsDev.reset(mCtx, std::max<size_t>(locs.size() * 4, 16));
+    if (!flat.empty()) gpu::check(aby3cu_h2d(mCtx->h(), mGatesDev.ptr(), flat.data(), flat.size() * 4));
+    if (!locs.empty()) gpu::check(aby3cu_h2d(mCtx->h(), mAndLocsDev.ptr(), locs.data(), locs.size() * 4));
+    mCtx->sync();          // `flat` / `locs` are pageable temporaries
+}
+
+void Sh3BinaryEvaluator::setInput(u64 i, const sbMatrix& in) {
+    if (!mCir || i >= mCir->mInputs.size()) throw std::runtime_error(LOCATION);
+    setInput(mCir->mInputs[i], in);
+}
+
+// transpose both share planes of `in` into the wire rows of the bundle (.cpp:200-253)
+void Sh3BinaryEvaluator::setInput(const oc::BetaBundle& inWires, const sbMatrix& in) {
+    mLevel = 0;
+    if (!mCir) throw std::runtime_error(LOCATION);
+    if (in.bitCount() != inWires.size()) throw std::invalid_argument("input data wrong size");
+    if (in.rows() != mWidth) throw std::invalid_argument("incorrect number of rows");
+    for (u64 k = 0; k + 1 < inWires.size(); ++k)
+        if (inWires[k] + 1 != inWires[k + 1]) throw std::runtime_error("expecting contiguous input wires. " LOCATION);
+    for (int s = 0; s < 2; ++s) {
+        u8* dst = (u8*)mMem[s].ptr() + (u64)inWires.front() * mRowBytes;
+        gpu::check(aby3cu_bit_transpose(mCtx->h(), in.mShares[s].dev(), mWidth, in.bitCount(), in.i64Cols() * 8,
+                                        dst, mRowBytes, nullptr));
+    }
+}
+
+Sh3Task Sh3BinaryEvaluator::asyncEvaluate(Sh3Task dependency) {
+    return dependency.then([this](CommPkg& comm, Sh3Task& self) { roundCallback(comm, self); }, "bin-eval-closure")
+        .getClosure();
+}
+
+Sh3Task Sh3BinaryEvaluator::asyncEvaluate(Sh3Task dependency, oc::BetaCircuit* cir, Sh3ShareGen& gen,
+                                          std::vector<const sbMatrix*> inputs, std::vector<sbMatrix*> outputs) {
+    if (cir->mInputs.size() != inputs.size()) throw std::runtime_error(LOCATION);
+    if (cir->mOutputs.size() != outputs.size()) throw std::runtime_error(LOCATION);
+    return dependency.then([this, cir, &gen, inputs = std::move(inputs)](CommPkg&, Sh3Task& self) {
+        const u64 width = inputs[0]->rows();
+        setCir(cir, width, gen);
+        for (u64 i = 0; i < inputs.size(); ++i) {
+            if (inputs[i]->rows() != width) throw std::runtime_error(LOCATION);
+            setInput(i, *inputs[i]);
+        }
+        self.then([this](CommPkg& comm, Sh3Task& self) { roundCallback(comm, self); });
+    }).getClosure().then([this, outputs = std::move(outputs)](Sh3Task&) {
+        for (u64 i = 0; i < outputs.size(); ++i) getOutput(i, *outputs[i]);
+    });
+}
+
+// One AND-depth level per call (.cpp:539-1196): finish the previous level's
+// receive, run this level's gates, reshare its AND outputs, re-schedule.
+void Sh3BinaryEvaluator::roundCallback(CommPkg& comm, Sh3Task task) {
+    const u64 levels = mCir->mLevelCounts.size();
+    if (mLevel > levels) throw std::runtime_error("evaluateRound() was called but no rounds remain... " LOCATION);
+    const u64 sendBytes = (mWidth + 7) / 8;
+
+    if (mLevel) {                                                     // :555-573
+        const u64 prev = mLevel - 1;
+        const u64 nAnd = mLevelAndOff[prev + 1] - mLevelAndOff[prev];
+        if (nAnd) {
+            for (auto& fu : mRecvFutr) fu.get();
+            mRecvFutr.clear();
+            gpu::check(aby3cu_bin_scatter_rows(mCtx->h(), mMem[1].ptr(), mRowBytes,
+                                               (const u32*)mAndLocsDev.ptr() + mLevelAndOff[prev], (u32)nAnd, sendBytes,
+                                               mRecvBuf.ptr()));
+        }
+    }
+
+    if (mLevel < levels) {
+        const u64 g0 = mLevelGateOff[mLevel], ng = mLevelGateOff[mLevel + 1] - g0;
+        const u64 a0 = mLevelAndOff[mLevel], nAnd = mLevelAndOff[mLevel + 1] - a0;
+        if (a0 != mShareIdx) throw RTE_LOC;
+        gpu::check(aby3cu_bin_level(mCtx->h(), (const u32*)mGatesDev.ptr() + 4 * g0, (u32)ng, mMem[0].ptr(),
+                                    mMem[1].ptr(), mRowBytes, nAnd ? mShareAES[0].key().data() : nullptr,
+                                    nAnd ? mShareAES[1].key().data() : nullptr, mShareIdx));
+        mShareIdx += nAnd;
+        if (nAnd) {                                                   // :795-796, :1161-1171
+            const size_t bytes = nAnd * sendBytes;
+            gpu::Buffer send(mCtx, std::max<size_t>(bytes, 16));
+            gpu::check(aby3cu_bin_pack_rows(mCtx->h(), mMem[0].ptr(), mRowBytes, (const u32*)mAndLocsDev.ptr() + a0,
+                                            (u32)nAnd, sendBytes, send.ptr()));
+            comm.mNext.asyncSendDevice(send.ptr(), bytes);
+            mRecvBuf.reset(mCtx, std::max<size_t>(bytes, 16));
+            mRecvFutr.emplace_back(comm.mPrev.asyncRecvDevice(mRecvBuf.ptr(), bytes));
+        }
+    }
+
+    mLevel++;
+    if (hasMoreRounds()) {
+        auto t = task.then([this](CommPkg& comm, Sh3Task& task) { roundCallback(comm, task); });
+        t.name() = "callback";
+    }
+}
+
+void Sh3BinaryEvaluator::getOutput(u64 i, sbMatrix& out, bool allowUninitialized) {
+    if (mCir->mOutputs.size() <= i) throw std::runtime_error(LOCATION);
+    getOutput(mCir->mOutputs[i].mWires, out, allowUninitialized);
+}
+
+// gather the output wires (complementing inverted ones) and transpose back (.cpp:1285-1404)
+void Sh3BinaryEvaluator::getOutput(const std::vector<oc::BetaWire>& outWires, sbMatrix& out, bool) {
+    if (outWires.size() != out.bitCount()) throw std::runtime_error(LOCATION);
+    if (out.rows() != mWidth) out.resize(mWidth, out.bitCount());
+    const u64 bits = outWires.size();
+    std::vector<u32> idx(outWires.begin(), outWires.end());
+    std::vector<u8> inv(bits, 0);
+    bool anyInv = false;
+    for (u64 b = 0; b < bits; ++b) {
+        inv[b] = mCir->isInvert(outWires[b]) ? 1 : 0;
+        anyInv |= inv[b] != 0;
+    }
+    gpu::Buffer dIdx(mCtx, std::max<size_t>(bits * 4, 16)), dInv(mCtx, std::max<size_t>(bits, 16));
+    gpu::check(aby3cu_h2d(mCtx->h(), dIdx.ptr(), idx.data(), bits * 4));
+    if (anyInv) gpu::check(aby3cu_h2d(mCtx->h(), dInv.ptr(), inv.data(), bits));
+    for (int s = 0; s < 2; ++s) {
+        i64* dst = out.mShares[s].devOut();
+        gpu::check(aby3cu_memset(mCtx->h(), dst, 0, out.i64Size() * 8));
+        gpu::check(aby3cu_bit_transpose_gather(mCtx->h(), mMem[s].ptr(), (const u32*)dIdx.ptr(), bits, mWidth, mRowBytes,
+                                               dst, out.i64Cols() * 8, anyInv ? (const u8*)dInv.ptr() : nullptr));
+    }
+    mCtx->sync();          // idx / inv are pageable temporaries
+}
+
+}  // namespace aby3

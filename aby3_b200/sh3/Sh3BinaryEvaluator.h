@@ -1,0 +1,63 @@
+// Sh3BinaryEvaluator.h -- bit-sliced evaluation of a Boolean circuit over
+// replicated binary shares (aby3/sh3/Sh3BinaryEvaluator.h:16-146,
+// Sh3BinaryEvaluator.cpp:66-103, 200-253, 477-491, 539-1196, 1285-1442).
+// Same call sequence as the reference: setCir -> setInput* -> asyncEvaluate ->
+// getOutput.  The wire memory (one row per wire, one bit per instance, two share
+// planes) lives in HBM; each AND-depth level is one gate-interpreter kernel with
+// in-register AES-CTR zero shares, followed by the reshare of the level's AND
+// outputs to the next party.  The BINARY_ENGINE_DEBUG shadow evaluator of the
+// reference is not part of this round.
+#pragma once
+#include "BetaCircuit.h"
+#include "Sh3Runtime.h"
+#include "Sh3ShareGen.h"
+
+namespace aby3 {
+
+class Sh3BinaryEvaluator {
+public:
+    oc::BetaCircuit* mCir = nullptr;
+    u64 mLevel = 0;
+
+    void setCir(oc::BetaCircuit* cir, u64 width, Sh3ShareGen& gen) {
+        block p = gen.mPrevCommon.get<block>();          // Sh3BinaryEvaluator.h:98-101
+        block n = gen.mNextCommon.get<block>();
+        setCir(cir, width, p, n);
+    }
+    void setCir(oc::BetaCircuit* cir, u64 width, block prevSeed, block nextSeed);
+
+    void setInput(u64 i, const sbMatrix& in);
+    void setInput(const oc::BetaBundle& wires, const sbMatrix& in);
+    void setReplicatedInput(u64 i, const sbMatrix& in) { setInput(i, in); }
+
+    Sh3Task asyncEvaluate(Sh3Task dependency);
+    Sh3Task asyncEvaluate(Sh3Task dependency, oc::BetaCircuit* cir, Sh3ShareGen& gen,
+                          std::vector<const sbMatrix*> inputs, std::vector<sbMatrix*> outputs);
+    void roundCallback(CommPkg& comm, Sh3Task task);
+
+    void getOutput(u64 i, sbMatrix& out, bool allowUninitialized = false);
+    void getOutput(const std::vector<oc::BetaWire>& wires, sbMatrix& out, bool allowUninitialized = false);
+
+    bool hasMoreRounds() const { return mLevel <= mCir->mLevelCounts.size(); }
+
+    u64 shareCount() const { return mWidth; }
+    u64 rowBytes() const { return mRowBytes; }
+    // raw wire memory of one share plane (tests): wires x rowBytes
+    const void* planeDevice(int s) const { return mMem[s].ptr(); }
+
+    std::array<oc::AES, 2> mShareAES;   // [0] prev key, [1] next key
+    u64 mShareIdx = 0;                  // nonlinear gates evaluated so far (z counter = mShareIdx * rowBytes/16)
+
+private:
+    gpu::Context* mCtx = nullptr;
+    u64 mWidth = 0, mRowBytes = 0;
+    std::array<gpu::Buffer, 2> mMem;
+    gpu::Buffer mGatesDev;              // [gates][4] u32
+    gpu::Buffer mAndLocsDev;            // output wires of the nonlinear gates, in gate order
+    std::vector<u64> mLevelGateOff, mLevelAndOff;
+    gpu::Buffer mRecvBuf;
+    std::vector<std::future<void>> mRecvFutr;
+    u64 mRecvLevel = 0;
+};
+
+}  // namespace aby3

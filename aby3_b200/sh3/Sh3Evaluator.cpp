@@ -1,0 +1,190 @@
+// Sh3Evaluator.cpp -- see Sh3Evaluator.h.
+#include "Sh3Evaluator.h"
+
+namespace aby3 {
+
+void Sh3Evaluator::init(u64 partyIdx, block prevSeed, block nextSeed, u64 buffSize) {
+    mShareGen.init(prevSeed, nextSeed, buffSize);
+    mPartyIdx = partyIdx;
+    mOtPrevRecver.setSeed(mShareGen.mNextCommon.get<block>());     // Sh3Evaluator.cpp:13
+    mOtNextRecver.setSeed(mShareGen.mPrevCommon.get<block>());     // :14
+}
+
+void Sh3Evaluator::init(u64 partyIdx, CommPkg& comm, block seed, u64 buffSize) {
+    mShareGen.init(comm, seed, buffSize);
+    mPartyIdx = partyIdx;
+    mOtPrevRecver.setSeed(mShareGen.mNextCommon.get<block>());
+    mOtNextRecver.setSeed(mShareGen.mPrevCommon.get<block>());
+}
+
+Sh3Evaluator::MulMode Sh3Evaluator::mulMode(const si64Matrix& A, const si64Matrix& B) {
+    if (A.cols() == B.rows()) return MulMode::Matmul;
+    if (A.rows() == B.rows() && A.cols() == B.cols()) return MulMode::Hadamard;
+    throw std::runtime_error("asyncMul: operand shapes allow neither a matrix nor an element-wise product " LOCATION);
+}
+
+u64 Sh3Evaluator::streamElem(const oc::PRNG& p) {
+    if (p.byteCursor() % 8) throw std::runtime_error("common PRNG cursor is not 8-byte aligned " LOCATION);
+    return p.byteCursor() / 8;
+}
+
+// ---- scalar, no truncation -- Sh3Evaluator.cpp:71-89 ----------------------------
+Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64& A, const si64& B, si64& C) {
+    return dependency.then([&](CommPkg& comm, Sh3Task self) {
+        C[0] = (i64)((u64)A[0] * (u64)B[0] + (u64)A[0] * (u64)B[1] + (u64)A[1] * (u64)B[0] + (u64)mShareGen.getShare());
+        comm.mNext.asyncSendCopy(C[0]);
+        auto fu = comm.mPrev.asyncRecv(C[1]);
+        self.then([fu = std::move(fu)](CommPkg&, Sh3Task&) mutable { fu.get(); });
+    }).getClosure();
+}
+
+// ---- matrix, no truncation -- Sh3Evaluator.cpp:92-116 ---------------------------
+Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64Matrix& A, const si64Matrix& B, si64Matrix& C) {
+    return dependency.then([&](CommPkg& comm, Sh3Task self) {
+        gpu::Context* ctx = gpu::current();
+        const MulMode mode = mulMode(A, B);
+        // the product is built in a fresh matrix so that C may alias A or B
+        eMatrix<i64> c0;
+        if (mode == MulMode::Matmul) {
+            const u64 M = A.rows(), K = A.cols(), N = B.cols();
+            c0.resize(M, N);
+            // z first, then the contraction accumulates on top of it
+            mShareGen.getShares(ctx, nullptr, c0.devOut(), M * N, false);
+            gpu::check(aby3cu_gemm_cross(ctx->h(), mGemmAlgo, A.mShares[0].dev(), A.mShares[1].dev(),
+                                         B.mShares[0].dev(), B.mShares[1].dev(), M, K, N, c0.devMut(), 1));
+        } else {
+            c0.resize(A.rows(), A.cols());
+            const u64 n = c0.size();
+            gpu::check(aby3cu_mul_hadamard(ctx->h(), A.mShares[0].dev(), A.mShares[1].dev(), B.mShares[0].dev(),
+                                           B.mShares[1].dev(), mShareGen.mShareGen[0].key().data(),
+                                           mShareGen.mShareGen[1].key().data(), mShareGen.mShareElemIdx, c0.devOut(), n));
+            mShareGen.mShareElemIdx += n;
+        }
+        auto& C0 = C.mShares[0];
+        C0 = std::move(c0);
+        C.mShares[1].resizeLike(C0);
+        const size_t bytes = C0.size() * sizeof(i64);
+        comm.mNext.asyncSendDevice(C0.dev(), bytes);                               // :109
+        auto fu = comm.mPrev.asyncRecvDevice(C.mShares[1].devOut(), bytes);        // :110
+        self.then([fu = std::move(fu)](CommPkg&, Sh3Task&) mutable { fu.get(); });
+    }).getClosure();
+}
+
+// ---- truncation pair -- Sh3Evaluator.cpp:503-566 ---------------------------------
+TruncationPair Sh3Evaluator::getTruncationTuple(u64 xSize, u64 ySize, u64 d) {
+    gpu::Context* ctx = gpu::current();
+    TruncationPair pair;
+    pair.mR.resize(xSize, ySize);
+    pair.mRTrunc.resize(xSize, ySize);
+    const u64 n = xSize * ySize;
+    if (DEBUG_disable_randomization) {
+        gpu::check(aby3cu_trunc_tuple(ctx->h(), nullptr, 0, nullptr, 0, d, pair.mR.devOut(), nullptr,
+                                      pair.mRTrunc.mShares[0].devOut(), pair.mRTrunc.mShares[1].devOut(), n));
+    } else {
+        auto& g = mShareGen;
+        gpu::check(aby3cu_trunc_tuple(ctx->h(), g.mNextCommon.getSeed().data(), streamElem(g.mNextCommon),
+                                      g.mPrevCommon.getSeed().data(), streamElem(g.mPrevCommon), d, pair.mR.devOut(),
+                                      nullptr, pair.mRTrunc.mShares[0].devOut(), pair.mRTrunc.mShares[1].devOut(), n));
+        g.mNextCommon.skip(8 * n);     // :526
+        g.mPrevCommon.skip(8 * n);     // :527
+    }
+    return pair;
+}
+
+// ---- scalar with truncation -- Sh3Evaluator.cpp:568-648 --------------------------
+Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64& A, const si64& B, si64& C, u64 shift) {
+    return dependency.then([&, shift](CommPkg& comm, Sh3Task& self) -> void {
+        i64 r = 0, t0 = 0, t1 = 0;
+        if (!DEBUG_disable_randomization) {
+            t0 = mShareGen.mNextCommon.get<i64>();
+            t1 = mShareGen.mPrevCommon.get<i64>();
+            r = t0 >> 2; t0 >>= (shift + 2); t1 >>= (shift + 2);
+        }
+        i64 abMinusR = (i64)((u64)A[0] * (u64)B[0] + (u64)A[0] * (u64)B[1] + (u64)A[1] * (u64)B[0] - (u64)r);
+        C[0] = t0; C[1] = t1;
+        auto& rt = self.getRuntime();
+        const u64 next = (rt.mPartyIdx + 1) % 3, prev = (rt.mPartyIdx + 2) % 3;
+        if (next < 2) comm.mNext.asyncSendCopy(abMinusR);
+        if (prev < 2) comm.mPrev.asyncSendCopy(abMinusR);
+        if (rt.mPartyIdx < 2) {
+            auto shares = std::make_shared<std::array<i64, 3>>();
+            auto fu0 = comm.mNext.asyncRecv((*shares)[0]).share();
+            auto fu1 = comm.mPrev.asyncRecv((*shares)[1]).share();
+            (*shares)[2] = abMinusR;
+            self.then([fu0, fu1, shares, &C, shift, this](CommPkg&, Sh3Task&) mutable {
+                fu0.get(); fu1.get();
+                const i64 sum = (i64)((u64)(*shares)[0] + (u64)(*shares)[1] + (u64)(*shares)[2]);
+                C.mData[mPartyIdx] = (i64)((u64)C.mData[mPartyIdx] + (u64)(sum >> shift));
+            });
+        }
+    }).getClosure();
+}
+
+// ---- matrix with truncation -- Sh3Evaluator.cpp:651-730 --------------------------
+Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64Matrix& A, const si64Matrix& B, si64Matrix& C, u64 shift) {
+    return dependency.then([&, shift](CommPkg& comm, Sh3Task& self) -> void {
+        gpu::Context* ctx = gpu::current();
+        const MulMode mode = mulMode(A, B);
+        const u64 M = A.rows(), N = (mode == MulMode::Matmul) ? B.cols() : A.cols(), n = M * N;
+        const bool rnd = !DEBUG_disable_randomization;
+        auto& g = mShareGen;
+        const u8* kn = rnd ? g.mNextCommon.getSeed().data() : nullptr;
+        const u8* kp = rnd ? g.mPrevCommon.getSeed().data() : nullptr;
+        const u64 en = rnd ? streamElem(g.mNextCommon) : 0, ep = rnd ? streamElem(g.mPrevCommon) : 0;
+
+        // abMinusR and the two receive buffers live until the continuation has run
+        struct Scratch { gpu::Buffer v, s0, s1; };
+        auto sc = std::make_shared<Scratch>();
+        const size_t bytes = std::max<size_t>(n * sizeof(i64), 16);
+        sc->v.reset(ctx, bytes);
+        i64* V = (i64*)sc->v.ptr();
+
+        // RTrunc is produced into fresh matrices and moved into C only after the
+        // cross term has been enqueued, so C may alias A or B (as in the reference,
+        // where C.mShares = move(RTrunc.mShares) follows the product, :673)
+        eMatrix<i64> rt0(M, N), rt1(M, N);
+        i64* RT0 = rt0.devOut();
+        i64* RT1 = rt1.devOut();
+        if (mode == MulMode::Matmul) {
+            // V = -r (pre-load), then V += A0*B0 + A0*B1 + A1*B0   (:662-665, :672)
+            gpu::check(aby3cu_trunc_tuple(ctx->h(), kn, en, kp, ep, shift, nullptr, V, RT0, RT1, n));
+            gpu::check(aby3cu_gemm_cross(ctx->h(), mGemmAlgo, A.mShares[0].dev(), A.mShares[1].dev(),
+                                         B.mShares[0].dev(), B.mShares[1].dev(), M, A.cols(), N, V, 1));
+        } else {
+            gpu::check(aby3cu_mul_hadamard_trunc(ctx->h(), A.mShares[0].dev(), A.mShares[1].dev(), B.mShares[0].dev(),
+                                                 B.mShares[1].dev(), kn, en, kp, ep, shift, V, RT0, RT1, n));
+        }
+        if (rnd) { g.mNextCommon.skip(8 * n); g.mPrevCommon.skip(8 * n); }
+        C.mShares[0] = std::move(rt0);
+        C.mShares[1] = std::move(rt1);
+
+        // open xy - r to parties 0 and 1 (:676-684)
+        auto& rt = self.getRuntime();
+        const u64 next = (rt.mPartyIdx + 1) % 3, prev = (rt.mPartyIdx + 2) % 3;
+        if (next < 2) comm.mNext.asyncSendDevice(V, n * sizeof(i64));
+        if (prev < 2) comm.mPrev.asyncSendDevice(V, n * sizeof(i64));
+        if (rt.mPartyIdx < 2) {
+            sc->s0.reset(ctx, bytes);
+            sc->s1.reset(ctx, bytes);
+            auto fu0 = comm.mNext.asyncRecvDevice(sc->s0.ptr(), n * sizeof(i64)).share();
+            auto fu1 = comm.mPrev.asyncRecvDevice(sc->s1.ptr(), n * sizeof(i64)).share();
+            self.then([fu0, fu1, sc, &C, shift, n, ctx, this](CommPkg&, Sh3Task&) mutable {
+                fu0.get(); fu1.get();
+                // C[mPartyIdx] += (s0 + s1 + v) >> shift   (:712-718)
+                gpu::check(aby3cu_trunc_finish(ctx->h(), (const i64*)sc->s0.ptr(), (const i64*)sc->s1.ptr(),
+                                               (const i64*)sc->v.ptr(), C.mShares[mPartyIdx].devMut(), n, shift));
+            });
+        }
+    }).getClosure();
+}
+
+Sh3Task Sh3Evaluator::asyncMul(Sh3Task, const si64Matrix&, const sbMatrix&, si64Matrix&) {
+    throw std::runtime_error("asyncMul(si64Matrix, sbMatrix): bit x arithmetic product (SharedOT) is scheduled after the "
+                             "hot path (SURVEY 8f-1) " LOCATION);
+}
+Sh3Task Sh3Evaluator::asyncMul(Sh3Task, const i64&, const sbMatrix&, si64Matrix&) {
+    throw std::runtime_error("asyncMul(i64, sbMatrix): bit x arithmetic product (SharedOT) is scheduled after the "
+                             "hot path (SURVEY 8f-1) " LOCATION);
+}
+
+}  // namespace aby3

@@ -1,0 +1,295 @@
+// eMatrix.h -- the dense row-major matrix the sh3 API is written against.
+// The reference aliases Eigen (aby3/sh3/Sh3Types.h:38-39,
+// `eMatrix<T> = Eigen::Matrix<T, Dynamic, Dynamic, RowMajor>`); Eigen is not in
+// the reference tree, and here the storage of record is HBM.  This class keeps
+// the subset of the Eigen surface that aby3's sh3 / ML / Basic code uses
+//  and adds lazy host<->device coherence:
+//   * protocol code reads/writes the device copy (dev(), devMut(), devOut());
+//   * application code that indexes m(i) / m.data() on the host gets a host
+//     copy that is downloaded on first touch and re-uploaded on next device use.
+// Bulk arithmetic on device-resident matrices runs as aby3cu kernels on the
+// calling party's stream; purely host-resident (plaintext) matrices use plain
+// loops, exactly like the reference's plaintext side.
+#pragma once
+#include <type_traits>
+
+#include "Gpu.h"
+
+namespace aby3 {
+
+template <typename T>
+class eMatrix {
+    static_assert(std::is_trivially_copyable<T>::value, "eMatrix needs POD elements");
+    static constexpr bool kDeviceOps = sizeof(T) == 8 && std::is_integral<T>::value;
+
+public:
+    using Scalar = T;
+    using value_type = T;
+
+    eMatrix() = default;
+    eMatrix(u64 r, u64 c) { resize(r, c); }
+    eMatrix(const eMatrix& o) { copyFrom(o); }
+    eMatrix(eMatrix&& o) noexcept { moveFrom(std::move(o)); }
+    eMatrix& operator=(const eMatrix& o) { if (this != &o) copyFrom(o); return *this; }
+    eMatrix& operator=(eMatrix&& o) noexcept { if (this != &o) moveFrom(std::move(o)); return *this; }
+
+    // -------------------------------------------------------------- shape ----
+    u64 rows() const { return mRows; }
+    u64 cols() const { return mCols; }
+    u64 size() const { return mRows * mCols; }
+    // Eigen semantics: contents are unspecified after a size change
+    void resize(u64 r, u64 c) {
+        if (r == mRows && c == mCols) return;
+        mRows = r; mCols = c;
+        // no storage is touched here: a matrix that only ever lives on the device
+        // never allocates (or zero-fills) a host copy
+        mHost.clear();
+        mHostValid = false; mDevValid = false;
+        mDev.free();
+    }
+    template <typename M>
+    void resizeLike(const M& m) { resize(m.rows(), m.cols()); }
+    void conservativeResize(u64 r, u64 c) {
+        eMatrix n(r, c);
+        const u64 rr = std::min(r, mRows), cc = std::min(c, mCols);
+        const T* src = hostData();
+        T* dst = n.data();
+        for (u64 i = 0; i < rr; ++i)
+            for (u64 j = 0; j < cc; ++j) dst[i * c + j] = src[i * mCols + j];
+        *this = std::move(n);
+    }
+
+    // ------------------------------------------------------ host access ------
+    T* data() { touchHost(true); return mHost.data(); }
+    const T* data() const { touchHost(false); return mHost.data(); }
+    T& operator()(u64 i) { touchHost(true); return mHost[i]; }
+    const T& operator()(u64 i) const { touchHost(false); return mHost[i]; }
+    T& operator()(u64 r, u64 c) { touchHost(true); return mHost[r * mCols + c]; }
+    const T& operator()(u64 r, u64 c) const { touchHost(false); return mHost[r * mCols + c]; }
+    const T* hostData() const { touchHost(false); return mHost.data(); }
+
+    // ---------------------------------------------------- device access ------
+    bool onDevice() const { return mDevValid; }
+    // read-only device pointer (uploads the host copy if that is the fresh one)
+    const T* dev() const { touchDev(); return static_cast<const T*>(mDev.ptr()); }
+    // read-write device pointer; the host copy becomes stale
+    T* devMut() { touchDev(); mHostValid = false; return static_cast<T*>(mDev.ptr()); }
+    // write-only device pointer: no upload, previous contents are dropped
+    T* devOut() {
+        ensureDevBuffer();
+        mDevValid = true; mHostValid = false;
+        return static_cast<T*>(mDev.ptr());
+    }
+    // adopt a device buffer produced elsewhere (e.g. a received message)
+    void adoptDevice(gpu::Buffer&& b) {
+        mDev = std::move(b);
+        mDevValid = true; mHostValid = false;
+    }
+    gpu::Context* ctx() const { return mDev.ctx() ? mDev.ctx() : gpu::current(); }
+
+    // -------------------------------------------------------- fills ----------
+    void setZero() {
+        if (mDevValid && !mHostValid) {
+            gpu::check(aby3cu_memset(ctx()->h(), mDev.ptr(), 0, size() * sizeof(T)));
+        } else {
+            mHost.assign(size(), T{});
+            mHostValid = true; mDevValid = false;
+        }
+    }
+    void setConstant(T v) {
+        touchHost(true);
+        std::fill(mHost.begin(), mHost.end(), v);
+    }
+
+    // ------------------------------------------------------ arithmetic -------
+    eMatrix operator+(const eMatrix& b) const { return binary(b, ABY3CU_OP_ADD); }
+    eMatrix operator-(const eMatrix& b) const { return binary(b, ABY3CU_OP_SUB); }
+    eMatrix& operator+=(const eMatrix& b) { return inplace(b, ABY3CU_OP_ADD); }
+    eMatrix& operator-=(const eMatrix& b) { return inplace(b, ABY3CU_OP_SUB); }
+    eMatrix operator-() const {
+        eMatrix z(mRows, mCols);
+        return z - *this;
+    }
+    // plaintext matrix product (wrapping), used by callers for expected values
+    eMatrix operator*(const eMatrix& b) const {
+        if (mCols != b.mRows) throw std::runtime_error("eMatrix product: shape mismatch " LOCATION);
+        eMatrix c(mRows, b.mCols);
+        const T* A = hostData();
+        const T* B = b.hostData();
+        T* C = c.data();
+        for (u64 i = 0; i < mRows; ++i)
+            for (u64 k = 0; k < mCols; ++k) {
+                const u64 a = (u64)A[i * mCols + k];
+                for (u64 j = 0; j < b.mCols; ++j)
+                    C[i * b.mCols + j] = (T)((u64)C[i * b.mCols + j] + a * (u64)B[k * b.mCols + j]);
+            }
+        return c;
+    }
+    eMatrix& operator*=(const eMatrix& b) { *this = *this * b; return *this; }
+    eMatrix operator*(T s) const {
+        eMatrix c(mRows, mCols);
+        const T* A = hostData();
+        T* C = c.data();
+        for (u64 i = 0; i < size(); ++i) C[i] = (T)((u64)A[i] * (u64)s);
+        return c;
+    }
+
+    eMatrix transpose() const {
+        eMatrix t;
+        t.mRows = mCols; t.mCols = mRows;
+        if constexpr (kDeviceOps) {
+            if (mDevValid) {
+                gpu::check(aby3cu_transpose_i64(ctx()->h(), (const int64_t*)dev(), mRows, mCols, (int64_t*)t.devOut()));
+                return t;
+            }
+        }
+        t.mHost.assign(size(), T{});
+        t.mHostValid = true;
+        const T* A = hostData();
+        for (u64 i = 0; i < mRows; ++i)
+            for (u64 j = 0; j < mCols; ++j) t.mHost[j * mRows + i] = A[i * mCols + j];
+        return t;
+    }
+    void transposeInPlace() { *this = transpose(); }
+
+    bool operator==(const eMatrix& b) const {
+        if (mRows != b.mRows || mCols != b.mCols) return false;
+        return size() == 0 || memcmp(hostData(), b.hostData(), size() * sizeof(T)) == 0;
+    }
+    bool operator!=(const eMatrix& b) const { return !(*this == b); }
+
+    // ------------------------------------------ row / col / block proxies ----
+    struct RowRef {
+        eMatrix& m; u64 i;
+        RowRef& operator=(const RowRef& o) { for (u64 j = 0; j < m.cols(); ++j) m(i, j) = o.m(o.i, j); return *this; }
+        T& operator()(u64 j) { return m(i, j); }
+    };
+    struct ColRef {
+        eMatrix& m; u64 j;
+        ColRef& operator=(const ColRef& o) { for (u64 i = 0; i < m.rows(); ++i) m(i, j) = o.m(i, o.j); return *this; }
+        T& operator()(u64 i) { return m(i, j); }
+    };
+    RowRef row(u64 i) { return RowRef{*this, i}; }
+    ColRef col(u64 j) { return ColRef{*this, j}; }
+    eMatrix block(u64 r, u64 c, u64 h, u64 w) const {
+        eMatrix b(h, w);
+        const T* A = hostData();
+        T* B = b.data();
+        for (u64 i = 0; i < h; ++i)
+            for (u64 j = 0; j < w; ++j) B[i * w + j] = A[(r + i) * mCols + c + j];
+        return b;
+    }
+
+private:
+    void ensureDevBuffer() {
+        const size_t bytes = std::max<size_t>(size() * sizeof(T), 16);
+        if (!mDev || mDev.bytes() < bytes) mDev.reset(gpu::current(), bytes);
+    }
+    void touchDev() const {
+        if (mDevValid) return;
+        auto* self = const_cast<eMatrix*>(this);
+        self->ensureDevBuffer();
+        // cudaMemcpyAsync from pageable memory is staged before it returns, so the
+        // host vector may be modified right after this call.
+        if (mHostValid && size()) {
+            gpu::check(aby3cu_h2d(mDev.ctx()->h(), mDev.ptr(), mHost.data(), size() * sizeof(T)));
+            // large host copies are page-locked (gpu::HostAllocator): the upload is truly
+            // asynchronous and the host copy must not be written before it has run
+            self->mUploadInFlight = size() * sizeof(T) >= gpu::HostAllocator<T>::kPinThreshold;
+        }
+        self->mDevValid = true;
+    }
+    void touchHost(bool willWrite) const {
+        auto* self = const_cast<eMatrix*>(this);
+        if (!mHostValid) {
+            self->mHost.assign(size(), T{});
+            if (mDevValid && size()) {
+                gpu::check(aby3cu_d2h(mDev.ctx()->h(), self->mHost.data(), mDev.ptr(), size() * sizeof(T)));
+                mDev.ctx()->sync();
+            }
+            self->mHostValid = true;
+        }
+        if (willWrite) {
+            if (mUploadInFlight && mDev.ctx()) mDev.ctx()->sync();
+            self->mUploadInFlight = false;
+            self->mDevValid = false;
+        }
+    }
+    void copyFrom(const eMatrix& o) {
+        mRows = o.mRows; mCols = o.mCols;
+        if (o.mDevValid && !o.mHostValid) {
+            mHost.clear(); mHostValid = false;
+            mDev.reset(o.mDev.ctx(), std::max<size_t>(size() * sizeof(T), 16));
+            if (size())
+                gpu::check(aby3cu_d2d(mDev.ctx()->h(), mDev.ptr(), mDev.ctx()->device(), o.mDev.ptr(),
+                                      o.mDev.ctx()->device(), size() * sizeof(T)));
+            mDevValid = true;
+        } else {
+            mHost = o.mHost; mHostValid = o.mHostValid; mDevValid = false;
+            mDev.free();
+        }
+    }
+    void moveFrom(eMatrix&& o) {
+        mRows = o.mRows; mCols = o.mCols;
+        mHost = std::move(o.mHost); mHostValid = o.mHostValid;
+        mDev = std::move(o.mDev); mDevValid = o.mDevValid;
+        mUploadInFlight = o.mUploadInFlight; o.mUploadInFlight = false;
+        o.mRows = o.mCols = 0; o.mHostValid = false; o.mDevValid = false; o.mHost.clear();
+    }
+    eMatrix binary(const eMatrix& b, int op) const {
+        if (mRows != b.mRows || mCols != b.mCols) throw std::runtime_error("eMatrix: shape mismatch " LOCATION);
+        eMatrix c;
+        c.mRows = mRows; c.mCols = mCols;
+        if constexpr (kDeviceOps) {
+            if (mDevValid || b.mDevValid) {
+                const int64_t* x = (const int64_t*)dev();
+                const int64_t* y = (const int64_t*)b.dev();
+                gpu::check(aby3cu_share_op(ctx()->h(), op, x, y, (int64_t*)c.devOut(), size()));
+                return c;
+            }
+        }
+        c.mHost.resize(size());
+        c.mHostValid = true;
+        const T* A = hostData();
+        const T* B = b.hostData();
+        for (u64 i = 0; i < size(); ++i)
+            c.mHost[i] = op == ABY3CU_OP_ADD ? (T)((u64)A[i] + (u64)B[i]) : (T)((u64)A[i] - (u64)B[i]);
+        return c;
+    }
+    eMatrix& inplace(const eMatrix& b, int op) {
+        if (mRows != b.mRows || mCols != b.mCols) throw std::runtime_error("eMatrix: shape mismatch " LOCATION);
+        if constexpr (kDeviceOps) {
+            if (mDevValid || b.mDevValid) {
+                const int64_t* y = (const int64_t*)b.dev();
+                int64_t* x = (int64_t*)devMut();
+                gpu::check(aby3cu_share_op(ctx()->h(), op, x, y, x, size()));
+                return *this;
+            }
+        }
+        T* A = data();
+        const T* B = b.hostData();
+        for (u64 i = 0; i < size(); ++i)
+            A[i] = op == ABY3CU_OP_ADD ? (T)((u64)A[i] + (u64)B[i]) : (T)((u64)A[i] - (u64)B[i]);
+        return *this;
+    }
+
+    u64 mRows = 0, mCols = 0;
+    mutable std::vector<T, gpu::HostAllocator<T>> mHost;
+    mutable bool mHostValid = false;
+    mutable gpu::Buffer mDev;
+    mutable bool mDevValid = false;
+    mutable bool mUploadInFlight = false;
+};
+
+template <typename T>
+std::ostream& operator<<(std::ostream& o, const eMatrix<T>& m) {
+    for (u64 i = 0; i < m.rows(); ++i) {
+        for (u64 j = 0; j < m.cols(); ++j) o << m(i, j) << (j + 1 < m.cols() ? " " : "");
+        o << "\n";
+    }
+    return o;
+}
+
+using i64Matrix = eMatrix<i64>;
+
+}  // namespace aby3

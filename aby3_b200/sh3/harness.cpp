@@ -1,0 +1,430 @@
+// harness.cpp -- a small C API over the sh3 facade so that tests/ and bench.py
+// (Python, ctypes) can drive three in-process parties exactly the way the
+// reference's unit tests do (three threads, one Sh3Runtime / Sh3Encryptor /
+// Sh3Evaluator each: aby3_tests/Sh3EvaluatorTests.cpp:20-135).  Every party is a
+// persistent worker thread with its own device context and stream; the parties
+// may sit on one GPU or on three.  Not part of the reference API.
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <map>
+#include <memory>
+#include <thread>
+
+#include "Sh3BinaryEvaluator.h"
+#include "Sh3Encryptor.h"
+#include "Sh3Evaluator.h"
+
+using namespace aby3;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Worker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has = false, stop = false, done = false;
+    std::string error;
+    void loop() {
+        for (;;) {
+            std::function<void()> j;
+            {
+                std::unique_lock<std::mutex> l(m);
+                cv.wait(l, [&] { return has || stop; });
+                if (stop) return;
+                j = std::move(job);
+                has = false;
+            }
+            std::string err;
+            try { j(); } catch (const std::exception& e) { err = e.what(); } catch (...) { err = "unknown exception"; }
+            {
+                std::lock_guard<std::mutex> l(m);
+                error = err;
+                done = true;
+            }
+            cv.notify_all();
+        }
+    }
+    void submit(std::function<void()> j) {
+        {
+            std::lock_guard<std::mutex> l(m);
+            job = std::move(j); has = true; done = false;
+        }
+        cv.notify_all();
+    }
+    std::string wait() {
+        std::unique_lock<std::mutex> l(m);
+        cv.wait(l, [&] { return done; });
+        return error;
+    }
+};
+
+struct Party {
+    std::unique_ptr<gpu::Context> ctx;
+    CommPkg comm;
+    Sh3Runtime rt;
+    Sh3Encryptor enc;
+    Sh3Evaluator eval;
+    std::map<int, std::unique_ptr<si64Matrix>> ints;
+    std::map<int, std::unique_ptr<sbMatrix>> bins;
+    std::map<int, std::unique_ptr<i64Matrix>> plains;
+    void* ev_start = nullptr;
+    void* ev_stop = nullptr;
+};
+
+}  // namespace
+
+struct sh3h {
+    Party p[3];
+    Worker w[3];
+    int next_handle = 1;
+    void* ev_end = nullptr;
+
+    // run f(party) on the three party threads, wait for all; returns 0 / sets g_err
+    int run(const std::function<void(int)>& f) {
+        for (int i = 0; i < 3; ++i) w[i].submit([=] { f(i); });
+        std::string err;
+        for (int i = 0; i < 3; ++i) {
+            std::string e = w[i].wait();
+            if (!e.empty() && err.empty()) err = "party " + std::to_string(i) + ": " + e;
+        }
+        if (!err.empty()) { g_err = err; return 1; }
+        return 0;
+    }
+};
+
+extern "C" {
+
+const char* sh3h_last_error(void) { return g_err.c_str(); }
+
+// seeds: [party][0 = prev, 1 = next][16] for the encryptor and the evaluator
+sh3h* sh3h_create(int dev0, int dev1, int dev2, const uint8_t* enc_seeds, const uint8_t* eval_seeds) {
+    try {
+        std::unique_ptr<sh3h> h(new sh3h);
+        const int dev[3] = {dev0, dev1, dev2};
+        for (int i = 0; i < 3; ++i) h->p[i].ctx.reset(new gpu::Context(dev[i]));
+        // chl01 / chl02 / chl12 exactly as Sh3EvaluatorTests.cpp:23-36; comm = {prev, next}
+        auto c01 = oc::Channel::makePair(h->p[0].ctx.get(), h->p[1].ctx.get());
+        auto c02 = oc::Channel::makePair(h->p[0].ctx.get(), h->p[2].ctx.get());
+        auto c12 = oc::Channel::makePair(h->p[1].ctx.get(), h->p[2].ctx.get());
+        h->p[0].comm = CommPkg{c02.first, c01.first};
+        h->p[1].comm = CommPkg{c01.second, c12.first};
+        h->p[2].comm = CommPkg{c12.second, c02.second};
+        for (int i = 0; i < 3; ++i) h->w[i].th = std::thread([hp = h.get(), i] { hp->w[i].loop(); });
+        auto blk = [](const uint8_t* p) { block b; memcpy(b.data(), p, 16); return b; };
+        int rc = h->run([&](int i) {
+            Party& P = h->p[i];
+            gpu::setCurrent(P.ctx.get());
+            P.rt.init(i, P.comm);
+            P.enc.init(i, blk(enc_seeds + (2 * i) * 16), blk(enc_seeds + (2 * i + 1) * 16));
+            P.eval.init(i, blk(eval_seeds + (2 * i) * 16), blk(eval_seeds + (2 * i + 1) * 16));
+            gpu::check(aby3cu_event_create(P.ctx->h(), &P.ev_start));
+            gpu::check(aby3cu_event_create(P.ctx->h(), &P.ev_stop));
+        });
+        if (rc) return nullptr;
+        gpu::check(aby3cu_event_create(h->p[0].ctx->h(), &h->ev_end));
+        return h.release();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+void sh3h_destroy(sh3h* h) {
+    if (!h) return;
+    h->run([&](int i) {
+        Party& P = h->p[i];
+        P.ints.clear(); P.bins.clear(); P.plains.clear();
+        P.ctx->sync();
+    });
+    for (int i = 0; i < 3; ++i) {
+        { std::lock_guard<std::mutex> l(h->w[i].m); h->w[i].stop = true; }
+        h->w[i].cv.notify_all();
+        h->w[i].th.join();
+    }
+    delete h;
+}
+
+int sh3h_set_disable_randomization(sh3h* h, int on) {
+    for (int i = 0; i < 3; ++i) h->p[i].eval.DEBUG_disable_randomization = on != 0;
+    return 0;
+}
+int sh3h_set_gemm_algo(sh3h* h, int algo) {
+    for (int i = 0; i < 3; ++i) h->p[i].eval.mGemmAlgo = algo;
+    return 0;
+}
+
+// cursors: same six numbers as orc_session_cursors
+int sh3h_cursors(sh3h* h, int party, uint64_t c[6]) {
+    Party& P = h->p[party];
+    c[0] = P.enc.mShareGen.mShareElemIdx; c[1] = P.eval.mShareGen.mShareElemIdx;
+    c[2] = P.eval.mShareGen.mPrevCommon.byteCursor(); c[3] = P.eval.mShareGen.mNextCommon.byteCursor();
+    c[4] = P.enc.mShareGen.mPrevCommon.byteCursor(); c[5] = P.enc.mShareGen.mNextCommon.byteCursor();
+    return 0;
+}
+
+// A plaintext matrix living at `owner` (page-locked host storage).  Returns a handle;
+// *host_ptr is where the caller writes the values (rows*cols int64, row-major).
+int sh3h_plain_create(sh3h* h, int owner, uint64_t rows, uint64_t cols, int64_t** host_ptr) {
+    const int id = h->next_handle++;
+    int rc = h->run([&](int i) {
+        if (i != owner) return;
+        auto m = std::make_unique<i64Matrix>(rows, cols);
+        *host_ptr = m->data();
+        h->p[i].plains[id] = std::move(m);
+    });
+    return rc ? -1 : id;
+}
+// after the caller has (re)written the host values
+int sh3h_plain_touch(sh3h* h, int owner, int id) {
+    return h->run([&](int i) { if (i == owner) (void)h->p[i].plains.at(id)->data(); });
+}
+
+// Sh3Encryptor::localIntMatrix at `owner`, remoteIntMatrix elsewhere (binary: *BinMatrix).
+int sh3h_share(sh3h* h, int owner, int plain_id, uint64_t rows, uint64_t cols, int binary, uint64_t bit_count) {
+    const int id = h->next_handle++;
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        if (!binary) {
+            auto m = std::make_unique<si64Matrix>(rows, cols);
+            if (i == owner) P.enc.localIntMatrix(P.comm, *P.plains.at(plain_id), *m);
+            else P.enc.remoteIntMatrix(P.comm, *m);
+            P.ints[id] = std::move(m);
+        } else {
+            auto m = std::make_unique<sbMatrix>(rows, bit_count);
+            if (i == owner) P.enc.localBinMatrix(P.comm, *P.plains.at(plain_id), *m);
+            else P.enc.remoteBinMatrix(P.comm, *m);
+            P.bins[id] = std::move(m);
+        }
+    });
+    return rc ? -1 : id;
+}
+
+// install raw share planes (tests: start from the oracle's shares). shares = [3][2][rows*cols]
+int sh3h_set_shares(sh3h* h, const int64_t* shares, uint64_t rows, uint64_t cols, int binary, uint64_t bit_count) {
+    const int id = h->next_handle++;
+    const uint64_t wcols = binary ? (bit_count + 63) / 64 : cols;
+    const uint64_t n = rows * wcols;
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        eMatrix<i64>* pl[2];
+        if (!binary) {
+            auto m = std::make_unique<si64Matrix>(rows, cols);
+            pl[0] = &m->mShares[0]; pl[1] = &m->mShares[1];
+            P.ints[id] = std::move(m);
+        } else {
+            auto m = std::make_unique<sbMatrix>(rows, bit_count);
+            pl[0] = &m->mShares[0]; pl[1] = &m->mShares[1];
+            P.bins[id] = std::move(m);
+        }
+        for (int s = 0; s < 2; ++s) {
+            memcpy(pl[s]->data(), shares + ((uint64_t)i * 2 + s) * n, n * 8);
+            (void)pl[s]->dev();
+        }
+        P.ctx->sync();
+    });
+    return rc ? -1 : id;
+}
+
+int sh3h_get_shares(sh3h* h, int id, int binary, int64_t* out) {
+    return h->run([&](int i) {
+        Party& P = h->p[i];
+        const eMatrix<i64>* pl[2];
+        if (!binary) { auto& m = *P.ints.at(id); pl[0] = &m.mShares[0]; pl[1] = &m.mShares[1]; }
+        else { auto& m = *P.bins.at(id); pl[0] = &m.mShares[0]; pl[1] = &m.mShares[1]; }
+        const uint64_t n = pl[0]->size();
+        for (int s = 0; s < 2; ++s) memcpy(out + ((uint64_t)i * 2 + s) * n, pl[s]->hostData(), n * 8);
+    });
+}
+
+int sh3h_shape(sh3h* h, int id, int binary, uint64_t* rows, uint64_t* cols) {
+    try {
+        Party& P = h->p[0];
+        if (!binary) { *rows = P.ints.at(id)->rows(); *cols = P.ints.at(id)->cols(); }
+        else { *rows = P.bins.at(id)->rows(); *cols = P.bins.at(id)->i64Cols(); }
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+int sh3h_free(sh3h* h, int id) {
+    return h->run([&](int i) { h->p[i].ints.erase(id); h->p[i].bins.erase(id); h->p[i].plains.erase(id); });
+}
+
+// eval.asyncMul(rt, A, B, C [, shift]).get() on every party.  shift < 0: no truncation.
+// out_id == 0: allocate a new result handle; otherwise reuse that matrix.
+int sh3h_mul(sh3h* h, int a, int b, int64_t shift, int out_id) {
+    const int id = out_id ? out_id : h->next_handle++;
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        auto& A = *P.ints.at(a);
+        auto& B = *P.ints.at(b);
+        auto& slot = P.ints[id];
+        if (!slot) slot = std::make_unique<si64Matrix>();
+        if (shift < 0) P.eval.asyncMul(P.rt, A, B, *slot).get();
+        else P.eval.asyncMul(P.rt, A, B, *slot, (u64)shift).get();
+    });
+    return rc ? -1 : id;
+}
+
+// C = A + B / A - B on shares (local)
+int sh3h_addsub(sh3h* h, int a, int b, int sub) {
+    const int id = h->next_handle++;
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        auto m = std::make_unique<si64Matrix>();
+        *m = sub ? (*P.ints.at(a) - *P.ints.at(b)) : (*P.ints.at(a) + *P.ints.at(b));
+        P.ints[id] = std::move(m);
+    });
+    return rc ? -1 : id;
+}
+
+// enc.revealAll on every party; party `who`'s result is copied to out
+int sh3h_reveal(sh3h* h, int id, int binary, int who, int64_t* out) {
+    return h->run([&](int i) {
+        Party& P = h->p[i];
+        i64Matrix dest;
+        if (!binary) P.enc.revealAll(P.comm, *P.ints.at(id), dest);
+        else P.enc.revealAll(P.comm, *P.bins.at(id), dest);
+        if (i == who) memcpy(out, dest.hostData(), dest.size() * 8);
+        else P.ctx->sync();
+    });
+}
+
+// getTruncationTuple on one party (advances its cursors): R, RT0, RT1 of n = rows*cols
+int sh3h_trunc_tuple(sh3h* h, int party, uint64_t rows, uint64_t cols, uint64_t d, int64_t* R, int64_t* RT0, int64_t* RT1) {
+    return h->run([&](int i) {
+        if (i != party) return;
+        Party& P = h->p[i];
+        TruncationPair t = P.eval.getTruncationTuple(rows, cols, d);
+        const uint64_t n = rows * cols;
+        memcpy(R, t.mR.hostData(), n * 8);
+        memcpy(RT0, t.mRTrunc.mShares[0].hostData(), n * 8);
+        memcpy(RT1, t.mRTrunc.mShares[1].hostData(), n * 8);
+    });
+}
+
+// ---- binary engine -------------------------------------------------------------
+// Evaluate a circuit given as flat arrays (same layout as the oracle's orc_circuit) on
+// sbMatrix inputs; returns output handles.  width = number of instances (rows).
+int sh3h_bin_eval(sh3h* h, const uint32_t* gates, uint32_t gate_count, uint32_t wire_count,
+                  const uint32_t* level_gates, uint32_t level_count,
+                  const uint32_t* input_first, const uint32_t* input_bits, uint32_t num_inputs,
+                  const uint32_t* output_off, const uint32_t* output_bits, const uint32_t* output_wires,
+                  const uint8_t* output_invert, uint32_t num_outputs,
+                  const int* input_ids, int* output_ids) {
+    for (uint32_t k = 0; k < num_outputs; ++k) output_ids[k] = h->next_handle++;
+    return h->run([&](int i) {
+        Party& P = h->p[i];
+        oc::BetaCircuit cir;
+        cir.loadFlat(gates, gate_count, wire_count, level_gates, level_count, input_first, input_bits, num_inputs,
+                     output_off, output_bits, output_wires, output_invert, num_outputs);
+        Sh3BinaryEvaluator ev;
+        const u64 width = P.bins.at(input_ids[0])->rows();
+        ev.setCir(&cir, width, P.eval.mShareGen);
+        for (uint32_t k = 0; k < num_inputs; ++k) ev.setInput(k, *P.bins.at(input_ids[k]));
+        ev.asyncEvaluate(P.rt).get();
+        for (uint32_t k = 0; k < num_outputs; ++k) {
+            auto m = std::make_unique<sbMatrix>(width, output_bits[k]);
+            ev.getOutput(k, *m);
+            P.bins[output_ids[k]] = std::move(m);
+        }
+        P.ctx->sync();
+    });
+}
+
+// ---- device timing over all three parties' streams -------------------------------
+// begin: every party stream waits for one common start event; end: returns the time
+// from that event until the last party stream has drained.  (Parties on one GPU.)
+int sh3h_timer_begin(sh3h* h) {
+    int rc = h->run([&](int i) { h->p[i].ctx->sync(); });
+    if (rc) return rc;
+    try {
+        gpu::check(aby3cu_event_record(h->p[0].ctx->h(), h->p[0].ev_start));
+        for (int i = 1; i < 3; ++i) gpu::check(aby3cu_event_wait(h->p[i].ctx->h(), h->p[0].ev_start));
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+    return 0;
+}
+int sh3h_timer_end(sh3h* h, float* ms) {
+    try {
+        for (int i = 0; i < 3; ++i) gpu::check(aby3cu_event_record(h->p[i].ctx->h(), h->p[i].ev_stop));
+        for (int i = 1; i < 3; ++i) gpu::check(aby3cu_event_wait(h->p[0].ctx->h(), h->p[i].ev_stop));
+        gpu::check(aby3cu_event_record(h->p[0].ctx->h(), h->ev_end));
+        gpu::check(aby3cu_event_sync(h->ev_end));
+        gpu::check(aby3cu_event_elapsed_ms(h->p[0].ev_start, h->ev_end, ms));
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+    return 0;
+}
+int sh3h_sync(sh3h* h) { return h->run([&](int i) { h->p[i].ctx->sync(); }); }
+uint64_t sh3h_launch_count(sh3h* h) {
+    uint64_t n = 0;
+    for (int i = 0; i < 3; ++i) n += aby3cu_launch_count(h->p[i].ctx->h());
+    return n;
+}
+uint64_t sh3h_bytes_sent(sh3h* h) {
+    uint64_t n = 0;
+    for (int i = 0; i < 3; ++i) n += h->p[i].comm.mNext.getTotalDataSent() + h->p[i].comm.mPrev.getTotalDataSent();
+    return n;
+}
+
+}  // extern "C"
+
+// ---- circuit library export (host only; no device needed) -------------------------
+// name: "and" | "or" | "xor" | "add" (ripple) | "add_depth" (prefix) | "add_msb" | "lt" | "eq"
+extern "C" {
+
+struct sh3h_circuit {
+    oc::BetaLibrary lib;
+    oc::BetaCircuit* cir = nullptr;
+};
+
+sh3h_circuit* sh3h_circuit_build(const char* name, uint32_t bits) {
+    try {
+        std::unique_ptr<sh3h_circuit> c(new sh3h_circuit);
+        const std::string n(name);
+        if (n == "and") c->cir = c->lib.int_int_bitwiseAnd(bits, bits, bits);
+        else if (n == "or") c->cir = c->lib.int_int_bitwiseOr(bits, bits, bits);
+        else if (n == "xor") c->cir = c->lib.int_int_bitwiseXor(bits, bits, bits);
+        else if (n == "add") c->cir = c->lib.int_int_add(bits, bits, bits, oc::BetaLibrary::Optimized::Size);
+        else if (n == "add_depth") c->cir = c->lib.int_int_add(bits, bits, bits, oc::BetaLibrary::Optimized::Depth);
+        else if (n == "add_msb") c->cir = c->lib.int_int_add_msb(bits);
+        else if (n == "lt") c->cir = c->lib.int_int_lt(bits, bits);
+        else if (n == "eq") c->cir = c->lib.int_eq(bits);
+        else { g_err = "unknown circuit " + n; return nullptr; }
+        return c.release();
+    } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void sh3h_circuit_free(sh3h_circuit* c) { delete c; }
+// sizes: gates, wires, levels, inputs, outputs, total output wires, nonlinear gates
+void sh3h_circuit_sizes(const sh3h_circuit* c, uint32_t s[7]) {
+    const auto& cir = *c->cir;
+    s[0] = (uint32_t)cir.mGates.size(); s[1] = cir.mWireCount; s[2] = (uint32_t)cir.mLevelCounts.size();
+    s[3] = (uint32_t)cir.mInputs.size(); s[4] = (uint32_t)cir.mOutputs.size();
+    uint32_t ow = 0;
+    for (auto& o : cir.mOutputs) ow += (uint32_t)o.size();
+    s[5] = ow; s[6] = (uint32_t)cir.mNonlinearGateCount;
+}
+void sh3h_circuit_copy(const sh3h_circuit* c, uint32_t* gates, uint32_t* level_gates, uint32_t* input_first,
+                       uint32_t* input_bits, uint32_t* output_off, uint32_t* output_bits, uint32_t* output_wires,
+                       uint8_t* output_invert) {
+    const auto& cir = *c->cir;
+    for (size_t g = 0; g < cir.mGates.size(); ++g) {
+        gates[4 * g] = cir.mGates[g].mInput[0]; gates[4 * g + 1] = cir.mGates[g].mInput[1];
+        gates[4 * g + 2] = cir.mGates[g].mOutput; gates[4 * g + 3] = (uint32_t)cir.mGates[g].mType;
+    }
+    for (size_t l = 0; l < cir.mLevelCounts.size(); ++l) level_gates[l] = (uint32_t)cir.mLevelCounts[l];
+    for (size_t k = 0; k < cir.mInputs.size(); ++k) { input_first[k] = cir.mInputs[k].front(); input_bits[k] = (uint32_t)cir.mInputs[k].size(); }
+    uint32_t off = 0;
+    for (size_t k = 0; k < cir.mOutputs.size(); ++k) {
+        output_off[k] = off; output_bits[k] = (uint32_t)cir.mOutputs[k].size();
+        for (size_t b = 0; b < cir.mOutputs[k].size(); ++b) {
+            output_wires[off + b] = cir.mOutputs[k][b];
+            output_invert[off + b] = cir.isInvert(cir.mOutputs[k][b]) ? 1 : 0;
+        }
+        off += (uint32_t)cir.mOutputs[k].size();
+    }
+}
+
+}  // extern "C"

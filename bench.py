@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json):
+
+  metric   3PC si64/sf64 matrix multiplication, ring-MAC/s, device-timed
+  workload sf64Matrix<D16> fixed-point matmul WITH truncation, 4096 x 4096 x 4096
+           (BASELINE.json configs[1]); one "step" = one complete three-party
+           product: every party's cross-term GEMM (tcgen05 limb GEMM), truncation
+           pair, the open of xy-r to parties 0/1, and the open-and-truncate pass,
+           driven through the sh3 facade (eval.asyncMul(rt, A, B, C, shift).get()
+           on three party threads, one stream each, all on this rank's GPU).
+  N > 1    weak scaling: every rank owns an independent 4096-row block of a
+           (4096*N) x 4096 x 4096 product (B replicated); no data-path collective.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`--impl reference` times the reference's CPU algorithm (the oracle port, all host
+threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZE = 4096
+SHIFT = 16          # sf64<D16>
+METRIC = "3pc_sf64_matmul_trunc_ring_mac_per_s"
+UNIT = "ring-MAC/s"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def synth_inputs(M, K, N, seed):
+    """test recipe of aby3_tests/Sh3EvaluatorTests.cpp:469-470: (u32 >> 8) / 100.0 as fixed point"""
+    rng = np.random.default_rng(seed)
+    a = ((rng.integers(0, 2**32, (M, K), dtype=np.uint64) >> np.uint64(8)).astype(np.float64) / 100.0 * (1 << SHIFT)).astype(np.int64)
+    b = ((rng.integers(0, 2**32, (K, N), dtype=np.uint64) >> np.uint64(8)).astype(np.float64) / 100.0 * (1 << SHIFT)).astype(np.int64)
+    return a, b
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [l.strip().split(", ") for l in open(self.path) if l.strip()]
+            os.unlink(self.path)
+        except Exception:
+            rows = []
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def cpu_baseline(nthreads, rows, steps=1, warmup=0):
+    """The reference's CPU algorithm (oracle port) on a bounded sample: the first `rows`
+    rows of A of the 4096^3 workload -> (rows x 4096) * (4096 x 4096), truncation included."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as o
+    a, b = synth_inputs(rows, SIZE, SIZE, 7)
+    s = o.Session()
+    A, B = s.share_int(0, a), s.share_int(0, b)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        s.mul_trunc(A, B, SHIFT, mode=0, nthreads=nthreads)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    return {"value": rows * SIZE * SIZE / t, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": "first %d rows of A: (%dx%d)*(%dx%d) with truncation, %d step(s), %.2f s/step" % (rows, rows, SIZE, SIZE, SIZE, steps, t)}, t
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    rows = 256
+    cb, t = cpu_baseline(max(3, cores), rows, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "sf64<D16> 3PC matmul+truncation 4096x4096x4096 (CPU: bounded sample, %s)" % cb["sample"],
+                       "note": "oracle port of the reference algorithm (the reference itself cannot be built here: Eigen/Boost/libOTe absent)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def gemm_roofline(device):
+    """Dominant kernel: k_gemm_tc (tcgen05 u8-limb GEMM).  Algorithmic work per launch =
+    144*M*N*K int8 ops (36 limb pairs x 2 products x 2 ops); timed with CUDA events on the
+    launching stream, inputs (4 x 128 MiB + 512 MiB limb planes) larger than L2."""
+    from aby3_b200 import abi
+    lib = abi.lib
+    ctx = abi.Ctx(device)
+    n = SIZE * SIZE
+    bufs = [ctx.alloc(8 * n) for _ in range(5)]
+    for i, b in enumerate(bufs):
+        abi.check(lib.aby3cu_aes_ctr_fill(ctx.h, bytes([i + 1] * 16), 0, b.p, 8 * n))
+    p = [b.p for b in bufs]
+    ms_all = []
+    for it in range(6):
+        abi.check(lib.aby3cu_gemm_cross(ctx.h, abi.GEMM_TCGEN05, p[0], p[1], p[2], p[3], SIZE, SIZE, SIZE, p[4], 1))
+        ctx.sync()
+        ms = abi.C.c_float(0)
+        abi.check(lib.aby3cu_gemm_last_main_kernel_ms(ctx.h, abi.C.byref(ms)))
+        if it >= 2:
+            ms_all.append(ms.value)
+    ctx.close()
+    ms = float(np.mean(ms_all))
+    ops = 144.0 * SIZE ** 3
+    achieved = ops / (ms * 1e-3) / 1e12
+    pk = peaks()
+    bf16 = pk.get("bf16_tflops")
+    peak = 2.0 * bf16 if bf16 else 2.0 * 1590.0
+    return {"bound": "tensor", "kernel": "k_gemm_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None, "ms_per_launch": ms,
+            "note": "int8 TOP/s; peak = 2 x %s dense bf16 (kind::i8 issues at twice the bf16 rate), %s"
+                    % ("measured" if bf16 else "fallback", "of measured" if bf16 else "of fallback")}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=SIZE, help=argparse.SUPPRESS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from aby3_b200 import harness
+    M = K = N = args.size
+    sess = harness.Session(devices=(local, local, local))
+    # inputs resident in HBM before the timed region: party 0 shares a and b
+    a, b = synth_inputs(M, K, N, 1000 + rank)
+    A, B = sess.share_int(0, a), sess.share_int(0, b)
+    Cid = sess.mul(A, B, shift=SHIFT)
+    for _ in range(max(args.warmup, 3) - 1):
+        sess.mul(A, B, shift=SHIFT, out=Cid)
+    sess.sync()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    sampler = ClockSampler(local)
+    barrier()
+    sess.sync()
+    launches0 = sess.launches
+    sampler.start()
+    sess.timer_begin()
+    for _ in range(args.steps):
+        sess.mul(A, B, shift=SHIFT, out=Cid)
+    ms = sess.timer_end()
+    sess.sync()
+    clocks = sampler.stop()
+    launches = sess.launches - launches0
+    barrier()
+
+    ms_max = ms
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    # ---- end to end through the public API with HOST buffers (every step: h2d of the
+    # plaintext inputs from page-locked memory, share, multiply, reveal, d2h of the result)
+    e2e_steps = max(1, min(args.steps, 3))
+    pa, va = sess.plain(0, M, K)
+    pb, vb = sess.plain(0, K, N)
+    out = np.empty((M, N), dtype=np.int64)
+    va[...] = a
+    vb[...] = b
+
+    def e2e_once():
+        sess.plain_touch(0, pa)
+        sess.plain_touch(0, pb)
+        ha = sess.share_plain(0, pa, M, K)
+        hb = sess.share_plain(0, pb, K, N)
+        hc = sess.mul(ha, hb, shift=SHIFT)
+        sess.reveal(hc, 0, out=out)
+        for h in (ha, hb, hc):
+            sess.free(h)
+
+    e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_once()
+    sess.sync()
+    e2e_t = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t.item())
+    # sanity: the revealed product equals the plaintext fixed-point product within the protocol's ulp bound
+    chk_rows = 4
+    ref = (a[:chk_rows].astype(object).dot(b.astype(object)))
+    ref = np.array([[int(v) >> SHIFT for v in row] for row in ref], dtype=object)
+    got = out[:chk_rows].astype(object)
+    max_err = int(np.max(np.abs(got - ref)))
+    sess.close()
+
+    if rank == 0:
+        step_macs = float(M) * K * N
+        value = world * step_macs * args.steps / (ms_max * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "sf64<D16> 3PC matmul+truncation %dx%dx%d per GPU (BASELINE configs[1]); three parties co-located on each GPU" % (M, K, N),
+                       "global_rows": M * world, "gemm": "tcgen05 u8-limb (kind::i8), 128x64 tiles, 12 MMA per 32-deep k-step",
+                       "l2": "inputs larger than L2 (per party 4 x %d MiB share planes + %d MiB limb planes)" % (8 * M * K >> 20, 2 * 16 * M * K >> 20),
+                       "timing": "CUDA events across the three party streams (fork/join on one start and one end event), max over ranks",
+                       "executed_u64_mac_per_s": 6.0 * value, "max_abs_err_ulp_vs_plain": max_err},
+            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+            "e2e": {"value": world * step_macs / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * (M * K + K * N), "d2h_bytes_per_step": 8 * M * N,
+                    "ms_per_step": e2e_t * 1e3, "steps": e2e_steps,
+                    "path": "enc.localIntMatrix(host a,b) -> eval.asyncMul(..., shift) -> enc.revealAll -> host c"},
+            "gpu_launches": launches,
+        }
+        try:
+            line["roofline"] = gemm_roofline(local)
+        except Exception as e:  # keep the headline even if the side measurement fails
+            line["roofline"] = {"error": str(e)}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cb, _ = cpu_baseline(3, 128, steps=1)
+                line["cpu_baseline"] = cb
+            except Exception as e:
+                line["cpu_baseline"] = {"error": str(e)}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

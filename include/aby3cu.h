@@ -121,6 +121,10 @@ int aby3cu_gemm_cross(aby3cu_ctx* ctx, int algo,
                       uint64_t M, uint64_t K, uint64_t N, int64_t* d_C, int accumulate);
 /* algo actually used by the last aby3cu_gemm_cross on this context */
 int aby3cu_gemm_last_algo(const aby3cu_ctx* ctx);
+/* device time (CUDA events on the context's stream) of the main GEMM kernel of the
+ * last aby3cu_gemm_cross call, pre-pass excluded; exact when that call needed a
+ * single main-kernel launch (it synchronises on the closing event). */
+int aby3cu_gemm_last_main_kernel_ms(aby3cu_ctx* ctx, float* ms);
 
 /* ---- local share arithmetic / reveal ------------------------------------------- */
 enum { ABY3CU_OP_ADD = 0, ABY3CU_OP_SUB = 1, ABY3CU_OP_XOR = 2 };

@@ -191,3 +191,28 @@ class Circuit(C.Structure):
                 ("num_inputs", C.c_uint32), ("input_first", _p), ("input_bits", _p),
                 ("num_outputs", C.c_uint32), ("output_off", _p), ("output_bits", _p),
                 ("output_wires", _p), ("output_invert", _p)]
+
+
+def bin_eval(session, cir, width, inputs):
+    """Run the oracle's Sh3BinaryEvaluator restatement.  cir: flat dict (harness.library_circuit
+    layout); inputs: list of share arrays [3][2][width][words].  Returns (outputs, wire memory)."""
+    c = Circuit()
+    keep = []
+
+    def arr(a):
+        keep.append(a)
+        return a.ctypes.data_as(_p)
+
+    c.wire_count, c.gate_count = cir["wire_count"], len(cir["gates"]) // 4
+    c.gates, c.level_count, c.level_gates = arr(cir["gates"]), len(cir["level_gates"]), arr(cir["level_gates"])
+    c.num_inputs, c.input_first, c.input_bits = len(cir["input_bits"]), arr(cir["input_first"]), arr(cir["input_bits"])
+    c.num_outputs, c.output_off, c.output_bits = len(cir["output_bits"]), arr(cir["output_off"]), arr(cir["output_bits"])
+    c.output_wires, c.output_invert = arr(cir["output_wires"]), arr(cir["output_invert"])
+    ins = [np.ascontiguousarray(x, dtype=np.int64) for x in inputs]
+    outs = [np.zeros((3, 2, width, (int(b) + 63) // 64), dtype=np.int64) for b in cir["output_bits"]]
+    in_ptrs = (_p * len(ins))(*[x.ctypes.data_as(_p) for x in ins])
+    out_ptrs = (_p * len(outs))(*[x.ctypes.data_as(_p) for x in outs])
+    rb = lib.orc_bin_row_bytes(width)
+    mem = np.zeros((3, 2, cir["wire_count"], rb), dtype=np.uint8)
+    lib.orc_bin_eval(session.h, C.byref(c), width, in_ptrs, out_ptrs, ptr(mem))
+    return outs, mem

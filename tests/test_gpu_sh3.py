@@ -1,0 +1,225 @@
+"""GPU parity tests of the sh3 facade (C++ Sh3Encryptor / Sh3Evaluator /
+Sh3BinaryEvaluator over the C ABI) against the CPU oracle: same seeds, same
+inputs, every party's two share planes compared bit for bit, plus the
+reference's own reconstruction-level assertions."""
+import numpy as np
+import pytest
+
+import oracle_lib as o
+from aby3_b200 import abi, harness
+
+pytestmark = pytest.mark.gpu
+U64 = np.uint64
+
+
+@pytest.fixture()
+def pair():
+    s, r = harness.Session(), o.Session()
+    yield s, r
+    s.close()
+    r.close()
+
+
+def rnd(seed, shape):
+    return np.random.default_rng(seed).integers(-2**63, 2**63, shape, dtype=np.int64)
+
+
+def assert_cursors(s, r):
+    for p in range(3):
+        assert list(s.cursors(p)) == list(r.cursors(p)), p
+
+
+def test_init_cursors(pair):
+    s, r = pair
+    assert_cursors(s, r)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (10, 10), (16, 1), (511, 3), (1, 513), (300, 700)])
+def test_share_and_reveal_int(pair, shape):
+    s, r = pair
+    for owner in range(3):
+        m = rnd(owner + shape[0], shape)
+        h = s.share_int(owner, m)
+        assert np.array_equal(s.get_shares(h), r.share_int(owner, m))
+        for p in range(3):
+            assert np.array_equal(s.reveal(h, p), m)
+    assert_cursors(s, r)
+
+
+def test_share_and_reveal_bin(pair):
+    s, r = pair
+    m = rnd(1, (77, 2))
+    h = s.share_bin(1, m, 128)
+    assert np.array_equal(s.get_shares(h, binary=True), r.share_bin(1, m))
+    assert np.array_equal(s.reveal(h, 2, binary=True), m)
+
+
+@pytest.mark.parametrize("algo", [abi.GEMM_IMAD, abi.GEMM_TCGEN05, abi.GEMM_AUTO])
+@pytest.mark.parametrize("dims", [(10, 10, 10), (128, 64, 64), (129, 200, 70), (128, 1024, 1), (1024, 128, 1), (256, 256, 256)])
+def test_mul_matmul_shares_bit_exact(pair, algo, dims):
+    s, r = pair
+    s.set_gemm_algo(algo)
+    M, K, N = dims
+    a, b = rnd(1, (M, K)), rnd(2, (K, N))
+    A, B = s.share_int(0, a), s.share_int(1, b)
+    Ao, Bo = r.share_int(0, a), r.share_int(1, b)
+    C = s.mul(A, B)
+    Co = r.mul(Ao, Bo, mode=0)
+    assert np.array_equal(s.get_shares(C), Co)
+    assert np.array_equal(s.reveal(C, 0), o.plain_mul(a, b))
+    assert_cursors(s, r)
+
+
+def test_Sh3_Evaluator_asyncMul_test_chain(pair):
+    """aby3_tests/Sh3EvaluatorTests.cpp:20-135: ten chained 10x10 products with A = C + A."""
+    s, r = pair
+    n = 10
+    a, b = rnd(3, (n, n)), rnd(4, (n, n))
+    A, B = s.share_int(0, a), s.share_int(0, b)
+    Ao, Bo = r.share_int(0, a), r.share_int(0, b)
+    for _ in range(n):
+        C = s.mul(A, B)
+        A = s.add(C, A)
+        Co = r.mul(Ao, Bo)
+        Ao = (Co.view(U64) + Ao.view(U64)).view(np.int64)
+        c = o.plain_mul(a, b)
+        a = (c.view(U64) + a.view(U64)).view(np.int64)
+    assert np.array_equal(s.get_shares(C), Co)
+    for p in range(3):
+        assert np.array_equal(s.reveal(C, p), c)
+
+
+@pytest.mark.parametrize("n", [1, 16, 513, 100001])
+def test_mul_hadamard_fork_semantics(pair, n):
+    """n x 1 operands multiply element-wise (aby3_tests/Test.cpp:116,153,184)."""
+    s, r = pair
+    a, b = rnd(5, (n, 1)), rnd(6, (n, 1))
+    if n == 16:
+        a = np.arange(n, dtype=np.int64).reshape(n, 1)
+        b = (n - np.arange(n, dtype=np.int64)).reshape(n, 1)
+    A, B = s.share_int(0, a), s.share_int(2, b)
+    Ao, Bo = r.share_int(0, a), r.share_int(2, b)
+    if n == 1:
+        return      # 1x1: cols == rows, the matmul rule applies and coincides
+    C = s.mul(A, B)
+    Co = r.mul(Ao, Bo, mode=1)
+    assert np.array_equal(s.get_shares(C), Co)
+    assert np.array_equal(s.reveal(C, 1), (a.view(U64) * b.view(U64)).view(np.int64))
+    assert_cursors(s, r)
+
+
+def test_truncation_tuple_matches_oracle_and_bound(pair):
+    """Sh3EvaluatorTests.cpp:350-410."""
+    s, r = pair
+    d = 8
+    for _ in range(5):
+        ts = [s.trunc_tuple(p, 4, 4, d) for p in range(3)]
+        to = [r.trunc_tuple(p, 16, d) for p in range(3)]
+        for p in range(3):
+            for k in range(3):
+                assert np.array_equal(ts[p][k], to[p][k])
+        tr = (ts[0][1].view(U64) + ts[1][1].view(U64) + ts[2][1].view(U64)).view(np.int64)
+        rr = (ts[0][0].view(U64) + ts[1][0].view(U64) + ts[2][0].view(U64)).view(np.int64)
+        assert np.all(np.abs(tr - (rr >> d)) < 4)
+    assert_cursors(s, r)
+
+
+def fixed(vals, d):
+    return (vals * (1 << d)).astype(np.int64)
+
+
+@pytest.mark.parametrize("algo", [abi.GEMM_IMAD, abi.GEMM_TCGEN05])
+def test_Sh3_Evaluator_asyncMul_matrixFixed_test(pair, algo):
+    """Sh3EvaluatorTests.cpp:413-589: D8, randomisation off, reveal within 1 ulp; shares bit-exact."""
+    s, r = pair
+    s.set_gemm_algo(algo)
+    s.disable_randomization(True)
+    r.disable_randomization(True)
+    d = 8
+    for size in (4, 130):
+        rng = np.random.default_rng(size)
+        a = fixed((rng.integers(0, 2**32, (size, size), dtype=np.uint64) >> U64(8)).astype(np.float64) / 100.0, d)
+        b = fixed((rng.integers(0, 2**32, (size, size), dtype=np.uint64) >> U64(8)).astype(np.float64) / 100.0, d)
+        A, B = s.share_int(0, a), s.share_int(0, b)
+        Ao, Bo = r.share_int(0, a), r.share_int(0, b)
+        C = s.mul(A, B, shift=d)
+        Co = r.mul_trunc(Ao, Bo, d)
+        assert np.array_equal(s.get_shares(C), Co)
+        c = o.plain_mul(a, b) >> d
+        for p in range(3):
+            assert np.all(np.abs(s.reveal(C, p) - c) <= 1)
+
+
+@pytest.mark.parametrize("dims,shift", [((9, 6, 5), 16), ((128, 1024, 1), 16), ((1024, 128, 1), 33), ((200, 300, 70), 16)])
+def test_mul_trunc_randomised_shares_bit_exact(pair, dims, shift):
+    s, r = pair
+    M, K, N = dims
+    rng = np.random.default_rng(M)
+    a, b = fixed(rng.normal(0, 20, (M, K)), 16), fixed(rng.normal(0, 20, (K, N)), 16)
+    A, B = s.share_int(0, a), s.share_int(1, b)
+    Ao, Bo = r.share_int(0, a), r.share_int(1, b)
+    C = s.mul(A, B, shift=shift)
+    Co = r.mul_trunc(Ao, Bo, shift)
+    assert np.array_equal(s.get_shares(C), Co)
+    c = o.plain_mul(a, b) >> shift
+    for p in range(3):
+        assert np.all(np.abs(s.reveal(C, p) - c) <= 4)
+    # a second product continues the PRNG streams where the first stopped
+    C2 = s.mul(A, B, shift=shift)
+    assert np.array_equal(s.get_shares(C2), r.mul_trunc(Ao, Bo, shift))
+    assert_cursors(s, r)
+
+
+def test_mul_trunc_hadamard(pair):
+    s, r = pair
+    n = 1000
+    a, b = fixed(np.random.default_rng(1).normal(0, 5, (n, 1)), 16), fixed(np.random.default_rng(2).normal(0, 5, (n, 1)), 16)
+    A, B = s.share_int(0, a), s.share_int(0, b)
+    Ao, Bo = r.share_int(0, a), r.share_int(0, b)
+    C = s.mul(A, B, shift=16)
+    assert np.array_equal(s.get_shares(C), r.mul_trunc(Ao, Bo, 16, mode=1))
+
+
+def test_result_may_alias_an_operand(pair):
+    s, r = pair
+    a, b = rnd(1, (40, 40)), rnd(2, (40, 40))
+    A, B = s.share_int(0, a), s.share_int(0, b)
+    Ao, Bo = r.share_int(0, a), r.share_int(0, b)
+    s.mul(A, B, out=A)
+    assert np.array_equal(s.get_shares(A), r.mul(Ao, Bo))
+
+
+def test_bad_shapes_throw(pair):
+    s, _ = pair
+    A, B = s.share_int(0, rnd(1, (4, 5))), s.share_int(0, rnd(2, (4, 6)))
+    with pytest.raises(harness.Sh3Error):
+        s.mul(A, B)
+
+
+BIN_CASES = [("and", 8, 256), ("and", 64, 5000), ("or", 64, 300), ("add", 8, 256), ("add_depth", 64, 3000),
+             ("add_msb", 64, 2049), ("lt", 64, 4097), ("eq", 64, 100)]
+
+
+@pytest.mark.parametrize("name,bits,width", BIN_CASES)
+def test_binary_engine_matches_oracle(pair, name, bits, width):
+    """Sh3BinaryEvaluatorTests.cpp:333-424 semantics + share-level parity with the oracle."""
+    s, r = pair
+    rng = np.random.default_rng(width)
+    m = U64((1 << bits) - 1) if bits < 64 else U64(2**64 - 1)
+    a = (rng.integers(0, 2**63, width, dtype=np.uint64) * U64(2) + rng.integers(0, 2, width, dtype=np.uint64)) & m
+    b = (rng.integers(0, 2**63, width, dtype=np.uint64) * U64(2) + rng.integers(0, 2, width, dtype=np.uint64)) & m
+    b[: width // 4] = a[: width // 4]
+    cir = harness.library_circuit(name, bits)
+    A = s.share_bin(0, a.view(np.int64).reshape(width, 1), bits)
+    B = s.share_bin(1, b.view(np.int64).reshape(width, 1), bits)
+    Ao = r.share_bin(0, a.view(np.int64).reshape(width, 1))
+    Bo = r.share_bin(1, b.view(np.int64).reshape(width, 1))
+    outs = s.bin_eval(cir, [A, B])
+    outs_o, _ = o.bin_eval(r, cir, width, [Ao, Bo])
+    obits = int(cir["output_bits"][0])
+    om = np.int64(-1) if obits == 64 else np.int64((1 << obits) - 1)
+    got = s.get_shares(outs[0], binary=True)
+    assert np.array_equal(got & om, outs_o[0] & om)
+    rev = s.reveal(outs[0], 0, binary=True) & om
+    assert np.array_equal(rev, o.reveal(outs_o[0], 0, binary=True) & om)
+    assert_cursors(s, r)
