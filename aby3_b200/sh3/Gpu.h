@@ -134,6 +134,46 @@ private:
     size_t mBytes = 0;
 };
 
+// Page-locked host blocks are expensive to create (cudaHostAlloc is a syscall-heavy
+// path), so freed blocks are kept for reuse, up to a cap.
+class PinnedPool {
+public:
+    static PinnedPool& get() { static PinnedPool p; return p; }
+    void* alloc(size_t bytes) {
+        bytes = (bytes + 4095) & ~size_t(4095);
+        {
+            std::lock_guard<std::mutex> g(mMtx);
+            auto it = mFree.find(bytes);
+            if (it != mFree.end() && !it->second.empty()) {
+                void* p = it->second.back();
+                it->second.pop_back();
+                mCached -= bytes;
+                return p;
+            }
+        }
+        void* p = nullptr;
+        if (aby3cu_host_alloc(&p, bytes) != 0) throw std::bad_alloc();
+        return p;
+    }
+    void release(void* p, size_t bytes) {
+        bytes = (bytes + 4095) & ~size_t(4095);
+        {
+            std::lock_guard<std::mutex> g(mMtx);
+            if (mCached + bytes <= kCap) {
+                mFree[bytes].push_back(p);
+                mCached += bytes;
+                return;
+            }
+        }
+        aby3cu_host_free(p);
+    }
+private:
+    static constexpr size_t kCap = size_t(4) << 30;
+    std::mutex mMtx;
+    std::map<size_t, std::vector<void*>> mFree;
+    size_t mCached = 0;
+};
+
 // Host storage of matrices: page-locked once it is big enough to matter, so the
 // h2d / d2h copies behind eMatrix run at full PCIe rate and truly asynchronously.
 template <typename T>
@@ -145,18 +185,20 @@ struct HostAllocator {
     HostAllocator(const HostAllocator<U>&) {}
     T* allocate(size_t n) {
         const size_t bytes = n * sizeof(T);
-        if (bytes >= kPinThreshold) {
-            void* p = nullptr;
-            if (aby3cu_host_alloc(&p, bytes) == 0) return static_cast<T*>(p);
-            throw std::bad_alloc();
-        }
+        if (bytes >= kPinThreshold) return static_cast<T*>(PinnedPool::get().alloc(bytes));
         void* p = ::operator new(bytes);
         return static_cast<T*>(p);
     }
     void deallocate(T* p, size_t n) {
-        if (n * sizeof(T) >= kPinThreshold) aby3cu_host_free(p);
+        if (n * sizeof(T) >= kPinThreshold) PinnedPool::get().release(p, n * sizeof(T));
         else ::operator delete(p);
     }
+    // value-initialisation is skipped for trivial types: resize() must not sweep
+    // hundreds of MiB that a d2h copy is about to overwrite
+    template <typename U>
+    void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void*>(p)) U; }
+    template <typename U, typename... Args>
+    void construct(U* p, Args&&... args) { ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...); }
     template <typename U>
     bool operator==(const HostAllocator<U>&) const { return true; }
     template <typename U>

@@ -128,8 +128,9 @@ Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64Matrix& A, const si
         const u64 M = A.rows(), N = (mode == MulMode::Matmul) ? B.cols() : A.cols(), n = M * N;
         const bool rnd = !DEBUG_disable_randomization;
         auto& g = mShareGen;
-        const u8* kn = rnd ? g.mNextCommon.getSeed().data() : nullptr;
-        const u8* kp = rnd ? g.mPrevCommon.getSeed().data() : nullptr;
+        const block seedNext = g.mNextCommon.getSeed(), seedPrev = g.mPrevCommon.getSeed();
+        const u8* kn = rnd ? seedNext.data() : nullptr;
+        const u8* kp = rnd ? seedPrev.data() : nullptr;
         const u64 en = rnd ? streamElem(g.mNextCommon) : 0, ep = rnd ? streamElem(g.mPrevCommon) : 0;
 
         // abMinusR and the two receive buffers live until the continuation has run

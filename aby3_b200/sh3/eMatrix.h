@@ -32,6 +32,7 @@ public:
     eMatrix(eMatrix&& o) noexcept { moveFrom(std::move(o)); }
     eMatrix& operator=(const eMatrix& o) { if (this != &o) copyFrom(o); return *this; }
     eMatrix& operator=(eMatrix&& o) noexcept { if (this != &o) moveFrom(std::move(o)); return *this; }
+    ~eMatrix() { settleUpload(); }
 
     // -------------------------------------------------------------- shape ----
     u64 rows() const { return mRows; }
@@ -40,6 +41,7 @@ public:
     // Eigen semantics: contents are unspecified after a size change
     void resize(u64 r, u64 c) {
         if (r == mRows && c == mCols) return;
+        settleUpload();
         mRows = r; mCols = c;
         // no storage is touched here: a matrix that only ever lives on the device
         // never allocates (or zero-fills) a host copy
@@ -92,6 +94,7 @@ public:
         if (mDevValid && !mHostValid) {
             gpu::check(aby3cu_memset(ctx()->h(), mDev.ptr(), 0, size() * sizeof(T)));
         } else {
+            settleUpload();
             mHost.assign(size(), T{});
             mHostValid = true; mDevValid = false;
         }
@@ -202,7 +205,8 @@ private:
     void touchHost(bool willWrite) const {
         auto* self = const_cast<eMatrix*>(this);
         if (!mHostValid) {
-            self->mHost.assign(size(), T{});
+            if (mDevValid) self->mHost.resize(size());        // no fill: the d2h below overwrites it
+            else self->mHost.assign(size(), T{});
             if (mDevValid && size()) {
                 gpu::check(aby3cu_d2h(mDev.ctx()->h(), self->mHost.data(), mDev.ptr(), size() * sizeof(T)));
                 mDev.ctx()->sync();
@@ -215,7 +219,16 @@ private:
             self->mDevValid = false;
         }
     }
+    // page-locked host blocks are recycled (gpu::PinnedPool): an asynchronous upload
+    // reading this matrix's host copy must have run before that copy is released
+    void settleUpload() {
+        if (mUploadInFlight && mDev.ctx()) {
+            try { mDev.ctx()->sync(); } catch (...) {}
+        }
+        mUploadInFlight = false;
+    }
     void copyFrom(const eMatrix& o) {
+        settleUpload();
         mRows = o.mRows; mCols = o.mCols;
         if (o.mDevValid && !o.mHostValid) {
             mHost.clear(); mHostValid = false;
@@ -230,6 +243,7 @@ private:
         }
     }
     void moveFrom(eMatrix&& o) {
+        settleUpload();
         mRows = o.mRows; mCols = o.mCols;
         mHost = std::move(o.mHost); mHostValid = o.mHostValid;
         mDev = std::move(o.mDev); mDevValid = o.mDevValid;
