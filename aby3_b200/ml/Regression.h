@@ -1,0 +1,60 @@
+// Regression.h -- mini-batch SGD for linear regression over secret shares
+// (aby3-ML/Regression.h:14-184).  Same loop as the reference: sample a batch,
+// error = XX*w - YY, update = (XX^T * error) >> log2(|B| / lr), w -= update.
+// The reference copies the batch row by row on the host (extractBatch, :43-58);
+// here the rows are gathered on the device (aby3cu_gather_rows), the transpose and
+// the subtractions are device kernels too, so an iteration never touches host data.
+#pragma once
+#include <cmath>
+
+#include "aby3ML.h"
+
+namespace aby3 {
+
+struct RegressionParam {
+    u64 mIterations;
+    u64 mBatchSize;
+    double mLearningRate;
+};
+
+// rows of X (both share planes) selected by `indices` -> XX, on the device
+template <Decimal D>
+void extractBatch(sf64Matrix<D>& XX, sf64Matrix<D>& YY, const sf64Matrix<D>& X, const sf64Matrix<D>& Y,
+                  const u64* d_indices, u64 count) {
+    gpu::Context* ctx = gpu::current();
+    if (XX.rows() != count || XX.cols() != X.cols()) XX.resize(count, X.cols());
+    if (YY.rows() != count || YY.cols() != Y.cols()) YY.resize(count, Y.cols());
+    for (int s = 0; s < 2; ++s) {
+        gpu::check(aby3cu_gather_rows(ctx->h(), X[s].dev(), X.cols(), d_indices, count, XX[s].devOut()));
+        gpu::check(aby3cu_gather_rows(ctx->h(), Y[s].dev(), Y.cols(), d_indices, count, YY[s].devOut()));
+    }
+}
+
+// batchIndices: mIterations * mBatchSize row indices (the public mini-batch order).  The
+// reference derives it from PRNG(toBlock(234543234)) + std::random_shuffle (:24-40,127),
+// which is libstdc++-specific; the order is public data, so the caller supplies it.
+template <typename Engine, Decimal D>
+void SGD_Linear(RegressionParam& params, Engine& engine, sf64Matrix<D>& X, sf64Matrix<D>& Y, sf64Matrix<D>& w,
+                const std::vector<u64>& batchIndices) {
+    if (X.rows() != Y.rows() || Y.cols() != 1) throw std::runtime_error(LOCATION);
+    if (batchIndices.size() != params.mIterations * params.mBatchSize) throw std::runtime_error(LOCATION);
+    gpu::Context* ctx = gpu::current();
+    gpu::Buffer dIdx(ctx, std::max<size_t>(batchIndices.size() * 8, 16));
+    gpu::check(aby3cu_h2d(ctx->h(), dIdx.ptr(), batchIndices.data(), batchIndices.size() * 8));
+    ctx->sync();
+
+    sf64Matrix<D> XX(params.mBatchSize, X.cols()), YY(params.mBatchSize, 1);
+    // the learning rate in log2 form: this many extra bits are truncated (:139)
+    const u64 aB = (u64)std::log2(1 / (params.mLearningRate / params.mBatchSize));
+
+    for (u64 i = 0; i < params.mIterations; ++i) {
+        extractBatch(XX, YY, X, Y, (const u64*)dIdx.ptr() + i * params.mBatchSize, params.mBatchSize);
+        sf64Matrix<D> error = engine.mul(XX, w);             // :157
+        error -= YY;
+        XX.transposeInPlace();                               // :163
+        sf64Matrix<D> update = engine.mulTruncate(XX, error, aB);   // :166
+        w = w - update;
+    }
+}
+
+}  // namespace aby3

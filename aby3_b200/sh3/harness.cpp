@@ -14,6 +14,7 @@
 #include "Sh3BinaryEvaluator.h"
 #include "Sh3Encryptor.h"
 #include "Sh3Evaluator.h"
+#include "../ml/Regression.h"
 
 using namespace aby3;
 
@@ -303,6 +304,44 @@ int sh3h_trunc_tuple(sh3h* h, int party, uint64_t rows, uint64_t cols, uint64_t 
         memcpy(R, t.mR.hostData(), n * 8);
         memcpy(RT0, t.mRTrunc.mShares[0].hostData(), n * 8);
         memcpy(RT1, t.mRTrunc.mShares[1].hostData(), n * 8);
+    });
+}
+
+}  // extern "C"
+
+// ---- aby3-ML linear regression (ml/Regression.h) on sf64<D16> ---------------------
+namespace {
+struct PartyEngine {
+    Party& P;
+    template <Decimal D>
+    sf64Matrix<D> mul(const sf64Matrix<D>& l, const sf64Matrix<D>& r) {
+        sf64Matrix<D> d;
+        P.eval.asyncMul(P.rt, l, r, d).get();
+        return d;
+    }
+    template <Decimal D>
+    sf64Matrix<D> mulTruncate(const sf64Matrix<D>& l, const sf64Matrix<D>& r, u64 shift) {
+        sf64Matrix<D> d;
+        P.eval.asyncMul(P.rt, l, r, d, shift).get();
+        return d;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+int sh3h_linreg(sh3h* h, int x_id, int y_id, int w_id, const uint64_t* batch_idx, uint64_t iters,
+                           uint64_t batch, double lr) {
+    return h->run([&](int i) {
+        Party& P = h->p[i];
+        // same layout cast the reference uses between si64Matrix and sf64Matrix<D> (Sh3Encryptor.h:214-219)
+        auto& X = reinterpret_cast<sf64Matrix<D16>&>(*P.ints.at(x_id));
+        auto& Y = reinterpret_cast<sf64Matrix<D16>&>(*P.ints.at(y_id));
+        auto& W = reinterpret_cast<sf64Matrix<D16>&>(*P.ints.at(w_id));
+        RegressionParam params{iters, batch, lr};
+        std::vector<u64> idx(batch_idx, batch_idx + iters * batch);
+        PartyEngine eng{P};
+        SGD_Linear(params, eng, X, Y, W, idx);
     });
 }
 

@@ -66,7 +66,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -95,7 +95,14 @@ class ClockSampler:
             except Exception:
                 pass
         if sm:
-            out["sm_mhz"] = float(np.median(sm))
+            # "under load": the upper half of the samples by power draw
+            try:
+                pw = [float(r[3]) for r in rows][:len(sm)]
+                order = np.argsort(pw)[len(pw) // 2:]
+                out["sm_mhz"] = float(np.median(np.array(sm)[order]))
+                out["power_w_max"] = float(np.max(pw))
+            except Exception:
+                out["sm_mhz"] = float(np.median(sm))
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
         return out
@@ -164,9 +171,43 @@ def gemm_roofline(device):
     bf16 = pk.get("bf16_tflops")
     peak = 2.0 * bf16 if bf16 else 2.0 * 1590.0
     return {"bound": "tensor", "kernel": "k_gemm_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "ms_per_launch": ms,
+            "traffic": 4.47e9, "traffic_source": "profiles/r1_summary.md: dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full", "ms_per_launch": ms,
             "note": "int8 TOP/s; peak = 2 x %s dense bf16 (kind::i8 issues at twice the bf16 rate), %s"
                     % ("measured" if bf16 else "fallback", "of measured" if bf16 else "of fallback")}
+
+
+def linreg_bench(sess, samples, features=1024, batch=128, iters=300, lr=2.0 ** -10):
+    """BASELINE configs[2]: aby3-ML linear regression training (main-linear), batch 128 x 1024
+    features, sf64<D16>, lr = 2^-10 (aby3-ML/main-linear.cpp:59, Regression.h:112-184).  One
+    iteration = two 3-party truncating products (B x F)*(F x 1) and (F x B)*(B x 1) plus the
+    local updates; inputs are shared once, before the timed region.  Wall clock around the
+    whole loop (the path is latency-bound: 2 communication rounds per iteration)."""
+    rng = np.random.default_rng(11)
+    pid, xv = sess.plain(0, samples, features)
+    step = 1 << 14
+    for r0 in range(0, samples, step):
+        xv[r0:r0 + step] = (rng.normal(1.0, 1.0, (min(step, samples - r0), features)) * (1 << SHIFT)).astype(np.int64)
+    model = np.zeros((features, 1))
+    model[:10, 0] = rng.integers(0, 10, 10)
+    yv = ((xv[:, :10].astype(np.float64) / (1 << SHIFT)) @ model[:10] * (1 << SHIFT)).astype(np.int64)
+    X = sess.share_plain(0, pid, samples, features)
+    sess.free(pid)
+    Y = sess.share_int(0, yv)
+    W = sess.share_int(0, np.zeros((features, 1), dtype=np.int64))
+    idx = rng.integers(0, samples, iters * batch).astype(np.uint64)
+    sess.linreg(X, Y, W, idx[:20 * batch], 20, batch, lr)          # warm-up
+    sess.sync()
+    l0 = sess.launches
+    t0 = time.perf_counter()
+    sess.linreg(X, Y, W, idx, iters, batch, lr)
+    sess.sync()
+    dt = time.perf_counter() - t0
+    out = {"iters_per_s": iters / dt, "iters": iters, "batch": batch, "features": features, "samples": samples,
+           "decimal": "D16", "lr": lr, "kernel_launches_per_iter": (sess.launches - l0) / iters,
+           "timing": "host wall clock around SGD_Linear on three party threads, device drained at the end"}
+    for h in (X, Y, W):
+        sess.free(h)
+    return out
 
 
 def main():
@@ -177,6 +218,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=SIZE, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--linreg-samples", type=int, default=1 << 20)
+    ap.add_argument("--no-linreg", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -200,6 +243,8 @@ def main():
     # inputs resident in HBM before the timed region: party 0 shares a and b
     a, b = synth_inputs(M, K, N, 1000 + rank)
     A, B = sess.share_int(0, a), sess.share_int(0, b)
+    sampler = ClockSampler(local)
+    sampler.start()                      # samples cover warm-up + timed region (same load)
     Cid = sess.mul(A, B, shift=SHIFT)
     for _ in range(max(args.warmup, 3) - 1):
         sess.mul(A, B, shift=SHIFT, out=Cid)
@@ -209,11 +254,9 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    sampler = ClockSampler(local)
     barrier()
     sess.sync()
     launches0 = sess.launches
-    sampler.start()
     sess.timer_begin()
     for _ in range(args.steps):
         sess.mul(A, B, shift=SHIFT, out=Cid)
@@ -270,6 +313,12 @@ def main():
     max_err = int(np.max(np.abs(out[:chk_rows] - ref)))
     if max_err > 4:
         raise SystemExit("bench: revealed product is off by %d ulp (> 4) from the plaintext product" % max_err)
+    linreg = None
+    if rank == 0 and not args.no_linreg:
+        try:
+            linreg = linreg_bench(sess, args.linreg_samples)
+        except Exception as e:
+            linreg = {"error": str(e)}
     sess.close()
 
     if rank == 0:
@@ -284,11 +333,12 @@ def main():
                        "l2": "inputs larger than L2 (per party 4 x %d MiB share planes + %d MiB limb planes)" % (8 * M * K >> 20, 2 * 16 * M * K >> 20),
                        "timing": "CUDA events across the three party streams (fork/join on one start and one end event), max over ranks",
                        "executed_u64_mac_per_s": 6.0 * value, "max_abs_err_ulp_vs_plain": max_err},
-            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+            "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "power_w_max", "samples")},
             "e2e": {"value": world * step_macs / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * (M * K + K * N), "d2h_bytes_per_step": 8 * M * N,
                     "ms_per_step": e2e_t * 1e3, "steps": e2e_steps,
                     "path": "enc.localIntMatrix(host a,b) -> eval.asyncMul(..., shift) -> enc.revealAll -> host c"},
             "gpu_launches": launches,
+            "linreg": linreg,
         }
         try:
             line["roofline"] = gemm_roofline(local)

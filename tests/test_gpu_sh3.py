@@ -223,3 +223,40 @@ def test_binary_engine_matches_oracle(pair, name, bits, width):
     rev = s.reveal(outs[0], 0, binary=True) & om
     assert np.array_equal(rev, o.reveal(outs_o[0], 0, binary=True) & om)
     assert_cursors(s, r)
+
+
+def oracle_linreg(r, X, Y, w, idx, iters, B, lr, D=16):
+    """aby3-ML/Regression.h:142-171 on the oracle's share arrays."""
+    import math
+    aB = int(math.log2(1 / (lr / B)))
+    for i in range(iters):
+        bi = idx[i * B:(i + 1) * B].astype(np.int64)
+        XX = np.ascontiguousarray(X[:, :, bi, :])
+        YY = np.ascontiguousarray(Y[:, :, bi, :])
+        err = r.mul_trunc(XX, w, D)
+        err = (err.view(U64) - YY.view(U64)).view(np.int64)
+        XXt = np.ascontiguousarray(np.swapaxes(XX, 2, 3))
+        upd = r.mul_trunc(XXt, np.ascontiguousarray(err), D + aB)
+        w = np.ascontiguousarray((w.view(U64) - upd.view(U64)).view(np.int64))
+    return w
+
+
+def test_linear_regression_sgd_matches_oracle(pair):
+    """config 3 in miniature: SGD_Linear (aby3-ML/Regression.h:112-184) on sf64<D16>,
+    w shares after k iterations bit-exact against the oracle, and the model is learnt."""
+    s, r = pair
+    N, F, B, iters, lr, D = 512, 24, 16, 120, 2.0 ** -6, 16
+    rng = np.random.default_rng(5)
+    model = np.zeros((F, 1)); model[:5, 0] = [3, -2, 1, 4, -1]
+    x = rng.normal(1, 1, (N, F))
+    y = x @ model + rng.normal(0, 0.01, (N, 1))
+    fx, fy, fw = fixed(x, D), fixed(y, D), np.zeros((F, 1), dtype=np.int64)
+    idx = np.concatenate([rng.permutation(N) for _ in range((iters * B + N - 1) // N)])[:iters * B].astype(np.uint64)
+    X, Y, W = s.share_int(0, fx), s.share_int(0, fy), s.share_int(0, fw)
+    Xo, Yo, Wo = r.share_int(0, fx), r.share_int(0, fy), r.share_int(0, fw)
+    s.linreg(X, Y, W, idx, iters, B, lr)
+    Wo = oracle_linreg(r, Xo, Yo, Wo, idx, iters, B, lr, D)
+    assert np.array_equal(s.get_shares(W), Wo)
+    learnt = s.reveal(W, 0).astype(np.float64) / (1 << D)
+    assert np.linalg.norm(learnt - model) < 0.5 * np.linalg.norm(model)
+    assert_cursors(s, r)
