@@ -23,6 +23,8 @@ def _load():
     l.sh3h_last_error.restype = C.c_char_p
     l.sh3h_create.restype = p
     l.sh3h_create.argtypes = [i32, i32, i32, C.c_char_p, C.c_char_p]
+    l.sh3h_create_nccl.restype = p
+    l.sh3h_create_nccl.argtypes = [i32, i32, i32, C.c_char_p, C.c_char_p]
     l.sh3h_destroy.argtypes = [p]
     l.sh3h_set_disable_randomization.argtypes = [p, i32]
     l.sh3h_set_gemm_algo.argtypes = [p, i32]
@@ -71,9 +73,12 @@ def default_seeds():
 class Session:
     """Three parties on devices (d0, d1, d2) -- all 0 by default (co-located)."""
 
-    def __init__(self, devices=(0, 0, 0), enc_seeds=None, eval_seeds=None):
+    def __init__(self, devices=(0, 0, 0), enc_seeds=None, eval_seeds=None, transport="local"):
+        """transport "local": in-process hand-off (same GPU: D2D, other GPU: NVLink peer copy);
+        "nccl": three different GPUs, ncclSend/ncclRecv over NVLink."""
         e, v = default_seeds()
-        self.h = lib.sh3h_create(devices[0], devices[1], devices[2], enc_seeds or e, eval_seeds or v)
+        create = lib.sh3h_create_nccl if transport == "nccl" else lib.sh3h_create
+        self.h = create(devices[0], devices[1], devices[2], enc_seeds or e, eval_seeds or v)
         if not self.h:
             raise Sh3Error(lib.sh3h_last_error().decode())
 

@@ -102,11 +102,11 @@ i64 Sh3Encryptor::reveal(CommPkg& comm, const si64& x) {
     return (i64)((u64)s + (u64)x[0] + (u64)x[1]);
 }
 i64 Sh3Encryptor::revealAll(CommPkg& comm, const si64& x) {
-    reveal(comm, (mPartyIdx + 2) % 3, x);
+    comm.mPrev.asyncSendCopy(x[0]);          // = reveal(comm, prev, x); goes out grouped with the receive below
     return reveal(comm, x);
 }
 void Sh3Encryptor::reveal(CommPkg& comm, u64 partyIdx, const si64& x) {
-    if ((mPartyIdx + 2) % 3 == partyIdx) comm.mPrev.asyncSendCopy(x[0]);
+    if ((mPartyIdx + 2) % 3 == partyIdx) { comm.mPrev.asyncSendCopy(x[0]); comm.mPrev.flush(); }
 }
 Sh3Task Sh3Encryptor::reveal(Sh3Task dep, const si64& x, i64& dest) {
     return dep.then([&x, &dest](CommPkg& comm, Sh3Task&) {
@@ -130,11 +130,11 @@ i64 Sh3Encryptor::reveal(CommPkg& comm, const sb64& x) {
     return s ^ x[0] ^ x[1];
 }
 i64 Sh3Encryptor::revealAll(CommPkg& comm, const sb64& x) {
-    reveal(comm, (mPartyIdx + 2) % 3, x);
+    comm.mPrev.asyncSendCopy(x[0]);
     return reveal(comm, x);
 }
 void Sh3Encryptor::reveal(CommPkg& comm, u64 partyIdx, const sb64& x) {
-    if ((mPartyIdx + 2) % 3 == partyIdx) comm.mPrev.asyncSendCopy(x[0]);
+    if ((mPartyIdx + 2) % 3 == partyIdx) { comm.mPrev.asyncSendCopy(x[0]); comm.mPrev.flush(); }
 }
 Sh3Task Sh3Encryptor::reveal(Sh3Task dep, const sb64& x, i64& dest) {
     return dep.then([&x, &dest](CommPkg& comm, Sh3Task&) {
@@ -167,21 +167,27 @@ void Sh3Encryptor::reveal(CommPkg& comm, const si64Matrix& x, i64Matrix& dest) {
     revealMatrix(comm, x.mShares[0], x.mShares[1], dest, false);
 }
 void Sh3Encryptor::revealAll(CommPkg& comm, const si64Matrix& x, i64Matrix& dest) {
-    reveal(comm, (mPartyIdx + 2) % 3, x);
+    comm.mPrev.asyncSendDevice(x.mShares[0].dev(), x.size() * sizeof(i64));
     reveal(comm, x, dest);
 }
 void Sh3Encryptor::reveal(CommPkg& comm, u64 partyIdx, const si64Matrix& x) {
-    if ((mPartyIdx + 2) % 3 == partyIdx) comm.mPrev.asyncSendDevice(x.mShares[0].dev(), x.size() * sizeof(i64));
+    if ((mPartyIdx + 2) % 3 == partyIdx) {
+        comm.mPrev.asyncSendDevice(x.mShares[0].dev(), x.size() * sizeof(i64));
+        comm.mPrev.flush();      // a pure send: nothing later in this call would carry it out (NCCL transport)
+    }
 }
 void Sh3Encryptor::reveal(CommPkg& comm, const sbMatrix& x, i64Matrix& dest) {
     revealMatrix(comm, x.mShares[0], x.mShares[1], dest, true);
 }
 void Sh3Encryptor::revealAll(CommPkg& comm, const sbMatrix& x, i64Matrix& dest) {
-    reveal(comm, (mPartyIdx + 2) % 3, x);
+    comm.mPrev.asyncSendDevice(x.mShares[0].dev(), x.i64Size() * sizeof(i64));
     reveal(comm, x, dest);
 }
 void Sh3Encryptor::reveal(CommPkg& comm, u64 partyIdx, const sbMatrix& x) {
-    if ((mPartyIdx + 2) % 3 == partyIdx) comm.mPrev.asyncSendDevice(x.mShares[0].dev(), x.i64Size() * sizeof(i64));
+    if ((mPartyIdx + 2) % 3 == partyIdx) {
+        comm.mPrev.asyncSendDevice(x.mShares[0].dev(), x.i64Size() * sizeof(i64));
+        comm.mPrev.flush();
+    }
 }
 Sh3Task Sh3Encryptor::reveal(Sh3Task dep, const si64Matrix& x, i64Matrix& dest) {
     return dep.then([this, &x, &dest](CommPkg& comm, Sh3Task&) { revealMatrix(comm, x.mShares[0], x.mShares[1], dest, false); });

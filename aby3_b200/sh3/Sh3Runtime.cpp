@@ -104,6 +104,9 @@ void Sh3Runtime::runNext() {
         throw;
     }
     mIsActive = false;
+    // NCCL transport: everything the task queued (sends, posted receives) goes out as one group
+    mComm.mNext.flush();
+    mComm.mPrev.flush();
     mTasks.erase((u64)tt.mTaskIdx);
     mSched.popTask();
 }

@@ -83,10 +83,16 @@ struct sh3h {
     Worker w[3];
     int next_handle = 1;
     void* ev_end = nullptr;
+    std::vector<oc::detail::NcclApi::comm_t> nccl_comms;
 
     // run f(party) on the three party threads, wait for all; returns 0 / sets g_err
     int run(const std::function<void(int)>& f) {
-        for (int i = 0; i < 3; ++i) w[i].submit([=] { f(i); });
+        for (int i = 0; i < 3; ++i)
+            w[i].submit([=] {
+                f(i);
+                // NCCL transport: nothing may stay queued when the party goes idle
+                if (p[i].comm.mNext.isConnected()) { p[i].comm.mNext.flush(); p[i].comm.mPrev.flush(); }
+            });
         std::string err;
         for (int i = 0; i < 3; ++i) {
             std::string e = w[i].wait();
@@ -102,11 +108,34 @@ extern "C" {
 const char* sh3h_last_error(void) { return g_err.c_str(); }
 
 // seeds: [party][0 = prev, 1 = next][16] for the encryptor and the evaluator
+static sh3h* create_impl(int dev0, int dev1, int dev2, const uint8_t* enc_seeds, const uint8_t* eval_seeds, int use_nccl);
+
 sh3h* sh3h_create(int dev0, int dev1, int dev2, const uint8_t* enc_seeds, const uint8_t* eval_seeds) {
+    return create_impl(dev0, dev1, dev2, enc_seeds, eval_seeds, 0);
+}
+// parties on three DIFFERENT GPUs, reshare by ncclSend/ncclRecv over NVLink
+sh3h* sh3h_create_nccl(int dev0, int dev1, int dev2, const uint8_t* enc_seeds, const uint8_t* eval_seeds) {
+    return create_impl(dev0, dev1, dev2, enc_seeds, eval_seeds, 1);
+}
+
+static sh3h* create_impl(int dev0, int dev1, int dev2, const uint8_t* enc_seeds, const uint8_t* eval_seeds, int use_nccl) {
     try {
         std::unique_ptr<sh3h> h(new sh3h);
         const int dev[3] = {dev0, dev1, dev2};
         for (int i = 0; i < 3; ++i) h->p[i].ctx.reset(new gpu::Context(dev[i]));
+        if (use_nccl) {
+            if (dev0 == dev1 || dev1 == dev2 || dev0 == dev2)
+                throw std::runtime_error("NCCL transport needs three different GPUs (kernels that wait on each other must not share a device)");
+            auto& api = oc::detail::NcclApi::get();
+            h->nccl_comms.resize(3);
+            api.check(api.CommInitAll(h->nccl_comms.data(), 3, dev), "CommInitAll");
+            for (int i = 0; i < 3; ++i) {
+                auto ep = std::make_shared<oc::detail::NcclEndpoint>();
+                ep->comm = h->nccl_comms[i];
+                ep->ctx = h->p[i].ctx.get();
+                h->p[i].comm = CommPkg{oc::Channel::makeNccl(ep, (i + 2) % 3), oc::Channel::makeNccl(ep, (i + 1) % 3)};
+            }
+        } else {
         // chl01 / chl02 / chl12 exactly as Sh3EvaluatorTests.cpp:23-36; comm = {prev, next}
         auto c01 = oc::Channel::makePair(h->p[0].ctx.get(), h->p[1].ctx.get());
         auto c02 = oc::Channel::makePair(h->p[0].ctx.get(), h->p[2].ctx.get());
@@ -114,6 +143,7 @@ sh3h* sh3h_create(int dev0, int dev1, int dev2, const uint8_t* enc_seeds, const 
         h->p[0].comm = CommPkg{c02.first, c01.first};
         h->p[1].comm = CommPkg{c01.second, c12.first};
         h->p[2].comm = CommPkg{c12.second, c02.second};
+        }
         for (int i = 0; i < 3; ++i) h->w[i].th = std::thread([hp = h.get(), i] { hp->w[i].loop(); });
         auto blk = [](const uint8_t* p) { block b; memcpy(b.data(), p, 16); return b; };
         int rc = h->run([&](int i) {
@@ -145,6 +175,10 @@ void sh3h_destroy(sh3h* h) {
         { std::lock_guard<std::mutex> l(h->w[i].m); h->w[i].stop = true; }
         h->w[i].cv.notify_all();
         h->w[i].th.join();
+    }
+    if (!h->nccl_comms.empty()) {
+        auto& api = oc::detail::NcclApi::get();
+        for (auto c : h->nccl_comms) api.CommDestroy(c);
     }
     delete h;
 }

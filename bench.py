@@ -266,15 +266,9 @@ def main():
     launches = sess.launches - launches0
     barrier()
 
-    ms_max = ms
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
-        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
-        dist.all_reduce(lt)
-        launches = int(lt.item())
+    from aby3_b200 import distutil
+    step_macs = float(M) * K * N
+    ms_max, launches, units_total = distutil.combine(dist, "cuda", ms, launches, step_macs * args.steps)
 
     # ---- end to end through the public API with HOST buffers (every step: h2d of the
     # plaintext inputs from page-locked memory, share, multiply, reveal, d2h of the result)
@@ -322,8 +316,7 @@ def main():
     sess.close()
 
     if rank == 0:
-        step_macs = float(M) * K * N
-        value = world * step_macs * args.steps / (ms_max * 1e-3)
+        value = distutil.throughput(units_total, ms_max)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
