@@ -62,6 +62,114 @@ __global__ void __launch_bounds__(256) k_bit_transpose(const u8* __restrict__ in
 }
 
 // ---------------------------------------------------------------------------------
+// Fast paths for the two shapes the binary engine actually uses: rows of 64-bit
+// words <-> bit-sliced rows.  A thread owns 8 instances: it holds an 8 x 64 bit
+// matrix in registers, transposes it as eight 8x8 bit blocks (three masked
+// exchange steps each), and the bytes are staged through shared memory so that
+// both global sides move whole 128-byte lines.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ u64 transpose8x8(u64 x) {
+    u64 t;
+    t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;  x ^= t ^ (t << 7);
+    t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull; x ^= t ^ (t << 14);
+    t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull; x ^= t ^ (t << 28);
+    return x;
+}
+// byte K of each of four 32-bit words -> one word
+template <int K>
+__device__ __forceinline__ u32 gather_byte(u32 a, u32 b, u32 c, u32 d) {
+    const u32 ab = __byte_perm(a, b, K | ((4 + K) << 4));
+    const u32 cd = __byte_perm(c, d, K | ((4 + K) << 4));
+    return __byte_perm(ab, cd, 0x5410);
+}
+template <int K>
+__device__ __forceinline__ u64 block_of(const u64 r[8]) {
+    // byte i of the result = byte K of row i
+    constexpr int W = K >> 2, B = K & 3;
+    const u32 lo = gather_byte<B>((u32)(r[0] >> (32 * W)), (u32)(r[1] >> (32 * W)), (u32)(r[2] >> (32 * W)), (u32)(r[3] >> (32 * W)));
+    const u32 hi = gather_byte<B>((u32)(r[4] >> (32 * W)), (u32)(r[5] >> (32 * W)), (u32)(r[6] >> (32 * W)), (u32)(r[7] >> (32 * W)));
+    return ((u64)hi << 32) | lo;
+}
+
+constexpr int kFastInst = 2048;      // instances per CTA tile (256 threads x 8)
+
+// in: `rows` instances x W words of 64 bits (in_stride = 8*W bytes); out row (64*w + b) holds
+// bit b of word w of every instance.  Only the first `cols` bit-rows are written.
+__global__ void __launch_bounds__(256) k_bits_to_sliced(const u64* __restrict__ in, u64 rows, u64 cols, u64 W,
+                                                        u8* __restrict__ out, u64 out_stride) {
+    __shared__ __align__(16) u8 sOut[64][kFastInst / 8 + 16];
+    const u64 tiles_r = (rows + kFastInst - 1) / kFastInst;
+    for (u64 t = blockIdx.x; t < tiles_r * W; t += gridDim.x) {
+        const u64 r0 = (t / W) * kFastInst, w = t % W;
+        const u64 i0 = r0 + (u64)threadIdx.x * 8;
+        u64 r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = (i0 + i < rows) ? in[(i0 + i) * W + w] : 0;
+#define ABY3CU_BLK(K)                                                                   \
+        {                                                                               \
+            const u64 x = transpose8x8(block_of<K>(r));                                 \
+            _Pragma("unroll") for (int j = 0; j < 8; ++j) sOut[8 * K + j][threadIdx.x] = (u8)(x >> (8 * j)); \
+        }
+        ABY3CU_BLK(0) ABY3CU_BLK(1) ABY3CU_BLK(2) ABY3CU_BLK(3) ABY3CU_BLK(4) ABY3CU_BLK(5) ABY3CU_BLK(6) ABY3CU_BLK(7)
+#undef ABY3CU_BLK
+        __syncthreads();
+        // 64 bit-rows x 256 bytes, written as 16-byte pieces
+        const u64 valid_bytes = (rows - r0 + 7) / 8 < (u64)(kFastInst / 8) ? (rows - r0 + 7) / 8 : (u64)(kFastInst / 8);
+        for (int idx = threadIdx.x; idx < 64 * (kFastInst / 8 / 16); idx += blockDim.x) {
+            const int b = idx / (kFastInst / 8 / 16), piece = idx % (kFastInst / 8 / 16);
+            const u64 bitrow = 64 * w + b;
+            if (bitrow >= cols || (u64)piece * 16 >= valid_bytes) continue;
+            u8* dst = out + bitrow * out_stride + r0 / 8 + piece * 16;
+            const uint4 v = *reinterpret_cast<const uint4*>(&sOut[b][piece * 16]);
+            // the caller guarantees out_stride covers the 16-byte piece (dispatch in launch_transpose)
+            *reinterpret_cast<uint4*>(dst) = v;
+        }
+        __syncthreads();
+    }
+}
+
+// inverse: `bits` bit-rows (gathered through row_index, optionally complemented) of `width`
+// instances -> width x W words; bits beyond `bits` in the last word are zero.
+__global__ void __launch_bounds__(256) k_sliced_to_bits(const u8* __restrict__ in, const u32* __restrict__ row_index, u64 bits,
+                                                        u64 width, u64 in_stride, u64* __restrict__ out, u64 W,
+                                                        const u8* __restrict__ invert) {
+    __shared__ __align__(16) u8 sIn[64][kFastInst / 8 + 16];
+    const u64 tiles_c = (width + kFastInst - 1) / kFastInst;
+    for (u64 t = blockIdx.x; t < tiles_c * W; t += gridDim.x) {
+        const u64 c0 = (t / W) * kFastInst, w = t % W;
+        for (int idx = threadIdx.x; idx < 64 * (kFastInst / 8 / 16); idx += blockDim.x) {
+            const int b = idx / (kFastInst / 8 / 16), piece = idx % (kFastInst / 8 / 16);
+            const u64 bitrow = 64 * w + b;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (bitrow < bits && c0 / 8 + (u64)piece * 16 < in_stride) {
+                const u64 src_row = row_index ? (u64)row_index[bitrow] : bitrow;
+                v = *reinterpret_cast<const uint4*>(in + src_row * in_stride + c0 / 8 + piece * 16);
+                if (invert && invert[bitrow]) { v.x = ~v.x; v.y = ~v.y; v.z = ~v.z; v.w = ~v.w; }
+            }
+            *reinterpret_cast<uint4*>(&sIn[b][piece * 16]) = v;
+        }
+        __syncthreads();
+        const u64 i0 = c0 + (u64)threadIdx.x * 8;
+        u64 blk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            u64 x = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x |= (u64)sIn[8 * k + j][threadIdx.x] << (8 * j);
+            blk[k] = transpose8x8(x);        // byte i = bits 8k..8k+7 of instance i
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            u64 v = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v |= ((blk[k] >> (8 * i)) & 0xFFull) << (8 * k);
+            if (i0 + i < width) out[(i0 + i) * W + w] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // One AND-depth level.  A thread owns one 16-byte column chunk of every wire row
 // and walks the level's gate list in order, so chains of linear gates inside a
 // level see their own earlier writes (same thread, same addresses).
@@ -145,6 +253,23 @@ int launch_transpose(aby3cu_ctx* ctx, const void* in, const u32* row_index, u64 
                    "bit_transpose: pointers must be 4-byte aligned");
     DeviceGuard g(ctx->device);
     const u64 cap = (u64)ctx->sm_count * 4;
+    const auto al = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+    // fast path 1: instances x 64-bit words -> bit-sliced rows (setInput)
+    if (!row_index && !invert && in_stride % 8 == 0 && in_stride <= 128 && rows > cols && cols <= in_stride * 8 &&
+        out_stride % 16 == 0 && out_stride >= ((((rows + 7) / 8) + 15) & ~15ull) && al(in, 8) && al(out, 16)) {
+        const u64 W = in_stride / 8, tiles = ((rows + kFastInst - 1) / kFastInst) * W;
+        const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+        k_bits_to_sliced<<<grid, 256, 0, ctx->stream>>>((const u64*)in, rows, cols, W, (u8*)out, out_stride);
+        return post_launch(ctx, "k_bits_to_sliced");
+    }
+    // fast path 2: bit-sliced rows -> instances x 64-bit words (getOutput)
+    if (out_stride % 8 == 0 && out_stride <= 128 && cols > rows && rows <= out_stride * 8 && in_stride % 16 == 0 &&
+        in_stride >= ((((cols + 7) / 8) + 15) & ~15ull) && al(in, 16) && al(out, 8)) {
+        const u64 W = out_stride / 8, tiles = ((cols + kFastInst - 1) / kFastInst) * W;
+        const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+        k_sliced_to_bits<<<grid, 256, 0, ctx->stream>>>((const u8*)in, row_index, rows, cols, in_stride, (u64*)out, W, invert);
+        return post_launch(ctx, "k_sliced_to_bits");
+    }
 #define ABY3CU_BT(TR, TCW)                                                                                        \
     do {                                                                                                          \
         const u64 tiles = ((rows + TR - 1) / TR) * ((cols + 32 * TCW - 1) / (32 * TCW));                          \
