@@ -225,19 +225,28 @@ __global__ void __launch_bounds__(256) k_bin_level(const uint4* __restrict__ gat
     }
 }
 
-// rows <-> contiguous message; VEC = bytes moved per thread step (16 or 1)
+// rows <-> contiguous message; VEC = bytes moved per thread step (16, 8 or 1).  PACK may
+// complement the rows flagged in `invert` (inverted output wires, getOutput :1252-1258).
 template <int VEC, bool PACK>
-__global__ void __launch_bounds__(256) k_bin_rows(u8* mem, u64 row_bytes, const u32* __restrict__ locs, u32 n_locs, u64 nbytes, u8* buf) {
+__global__ void __launch_bounds__(256) k_bin_rows(u8* mem, u64 row_bytes, const u32* __restrict__ locs, u32 n_locs, u64 nbytes, u8* buf,
+                                                  const u8* __restrict__ invert) {
     const u64 per = nbytes / VEC, total = per * n_locs;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
         const u64 j = i / per, o = (i % per) * VEC;
         u8* m = mem + (u64)locs[j] * row_bytes + o;
         u8* b = buf + j * nbytes + o;
+        const bool inv = PACK && invert && invert[j];
         if (VEC == 16) {
-            if (PACK) *reinterpret_cast<uint4*>(b) = *reinterpret_cast<const uint4*>(m);
-            else *reinterpret_cast<uint4*>(m) = *reinterpret_cast<const uint4*>(b);
+            if (PACK) {
+                uint4 v = *reinterpret_cast<const uint4*>(m);
+                if (inv) { v.x = ~v.x; v.y = ~v.y; v.z = ~v.z; v.w = ~v.w; }
+                *reinterpret_cast<uint4*>(b) = v;
+            } else *reinterpret_cast<uint4*>(m) = *reinterpret_cast<const uint4*>(b);
+        } else if (VEC == 8) {
+            if (PACK) { u64 v = *reinterpret_cast<const u64*>(m); *reinterpret_cast<u64*>(b) = inv ? ~v : v; }
+            else *reinterpret_cast<u64*>(m) = *reinterpret_cast<const u64*>(b);
         } else {
-            if (PACK) *b = *m; else *m = *b;
+            if (PACK) *b = inv ? (u8)~*m : *m; else *m = *b;
         }
     }
 }
@@ -325,31 +334,31 @@ int aby3cu_bin_level(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void* d_m
     return post_launch(ctx, "k_bin_level");
 }
 
-static int rows_copy(aby3cu_ctx* ctx, bool pack, void* mem, u64 row_bytes, const u32* locs, u32 n_locs, u64 nbytes, void* buf) {
+static int rows_copy(aby3cu_ctx* ctx, bool pack, void* mem, u64 row_bytes, const u32* locs, u32 n_locs, u64 nbytes, void* buf,
+                     const u8* invert) {
     ABY3CU_REQUIRE(ctx && ((mem && locs && buf) || !(n_locs * nbytes)), "bin rows: null argument");
     ABY3CU_REQUIRE(nbytes <= row_bytes, "bin rows: nbytes exceeds the row");
     if (!(n_locs * nbytes)) return 0;
     DeviceGuard g(ctx->device);
-    const bool v16 = nbytes % 16 == 0 && row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(mem) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(buf) & 15) == 0;
-    const u64 items = v16 ? (nbytes / 16) * n_locs : nbytes * n_locs;
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(mem) | reinterpret_cast<uintptr_t>(buf) | nbytes | row_bytes;
+    const int vec = (bits & 15) == 0 ? 16 : (bits & 7) == 0 ? 8 : 1;
+    const u64 items = (nbytes / vec) * n_locs;
     const unsigned grid = ew_grid(ctx, items, 256, 8);
-    if (v16) {
-        if (pack) k_bin_rows<16, true><<<grid, 256, 0, ctx->stream>>>((u8*)mem, row_bytes, locs, n_locs, nbytes, (u8*)buf);
-        else k_bin_rows<16, false><<<grid, 256, 0, ctx->stream>>>((u8*)mem, row_bytes, locs, n_locs, nbytes, (u8*)buf);
-    } else {
-        if (pack) k_bin_rows<1, true><<<grid, 256, 0, ctx->stream>>>((u8*)mem, row_bytes, locs, n_locs, nbytes, (u8*)buf);
-        else k_bin_rows<1, false><<<grid, 256, 0, ctx->stream>>>((u8*)mem, row_bytes, locs, n_locs, nbytes, (u8*)buf);
-    }
+#define ABY3CU_ROWS(V, P) k_bin_rows<V, P><<<grid, 256, 0, ctx->stream>>>((u8*)mem, row_bytes, locs, n_locs, nbytes, (u8*)buf, invert)
+    if (vec == 16) { if (pack) ABY3CU_ROWS(16, true); else ABY3CU_ROWS(16, false); }
+    else if (vec == 8) { if (pack) ABY3CU_ROWS(8, true); else ABY3CU_ROWS(8, false); }
+    else { if (pack) ABY3CU_ROWS(1, true); else ABY3CU_ROWS(1, false); }
+#undef ABY3CU_ROWS
     return post_launch(ctx, "k_bin_rows");
 }
 
-int aby3cu_bin_pack_rows(aby3cu_ctx* ctx, const void* d_mem, u64 row_bytes, const u32* d_locs, u32 n_locs, u64 nbytes, void* d_out) {
-    return rows_copy(ctx, true, const_cast<void*>(d_mem), row_bytes, d_locs, n_locs, nbytes, d_out);
+int aby3cu_bin_pack_rows(aby3cu_ctx* ctx, const void* d_mem, u64 row_bytes, const u32* d_locs, u32 n_locs, u64 nbytes, void* d_out,
+                         const u8* d_invert) {
+    return rows_copy(ctx, true, const_cast<void*>(d_mem), row_bytes, d_locs, n_locs, nbytes, d_out, d_invert);
 }
 
 int aby3cu_bin_scatter_rows(aby3cu_ctx* ctx, void* d_mem, u64 row_bytes, const u32* d_locs, u32 n_locs, u64 nbytes, const void* d_in) {
-    return rows_copy(ctx, false, d_mem, row_bytes, d_locs, n_locs, nbytes, const_cast<void*>(d_in));
+    return rows_copy(ctx, false, d_mem, row_bytes, d_locs, n_locs, nbytes, const_cast<void*>(d_in), nullptr);
 }
 
 }  // extern "C"

@@ -28,6 +28,8 @@
 // complete on an mbarrier.  Warp 0 = TMA producer, warp 1 = MMA issuer (one
 // elected thread), warps 2..5 = epilogue (tcgen05.ld -> recombine limbs mod 2^64
 // -> C (+)=).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace aby3cu {
@@ -343,7 +345,12 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
     ABY3CU_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const u64 ntiles = (N + TN - 1) / TN;
     // bound the limb-plane workspace: B panel for one K chunk + A panel for one row block
-    const size_t WS_A_LIMIT = 1ull << 30;
+    // (ABY3CU_WS_LIMIT_MB shrinks it so that tests can exercise the row-block loop)
+    size_t WS_A_LIMIT = 1ull << 30;
+    if (const char* e = getenv("ABY3CU_WS_LIMIT_MB")) {
+        const long mb = atol(e);
+        if (mb > 0) WS_A_LIMIT = (size_t)mb << 20;
+    }
     for (u64 k0 = 0; k0 < K; k0 += K_MAX) {
         const u64 kc = (K - k0 < K_MAX) ? (K - k0) : K_MAX;
         const u64 kbh = (kc + TK - 1) / TK, kblocks = 2 * kbh;

@@ -42,6 +42,7 @@ def _load():
     l.sh3h_trunc_tuple.argtypes = [p, i32, u64, u64, u64, p, p, p]
     l.sh3h_bin_eval.argtypes = [p, p, C.c_uint32, C.c_uint32, p, C.c_uint32, p, p, C.c_uint32, p, p, p, p, C.c_uint32, p, p]
     l.sh3h_linreg.argtypes = [p, i32, i32, i32, p, u64, u64, C.c_double]
+    l.sh3h_bin_eval_packed.argtypes = l.sh3h_bin_eval.argtypes
     l.sh3h_timer_begin.argtypes = [p]
     l.sh3h_timer_end.argtypes = [p, C.POINTER(C.c_float)]
     l.sh3h_sync.argtypes = [p]
@@ -183,12 +184,14 @@ class Session:
         self._chk(lib.sh3h_trunc_tuple(self.h, party, rows, cols, d, _ptr(R), _ptr(T0), _ptr(T1)))
         return R, T0, T1
 
-    def bin_eval(self, cir, input_ids):
-        """cir: a dict of flat uint32 arrays (tests/circuits.py). Returns output handles."""
+    def bin_eval(self, cir, input_ids, packed=False):
+        """cir: flat circuit dict (library_circuit). Returns output handles.  packed=True routes
+        inputs/outputs through sPackedBin (setInput/getOutput bit-sliced forms)."""
         ins = np.asarray(input_ids, dtype=np.int32)
         outs = np.zeros(len(cir["output_bits"]), dtype=np.int32)
         inv = cir.get("output_invert")
-        self._chk(lib.sh3h_bin_eval(
+        fn = lib.sh3h_bin_eval_packed if packed else lib.sh3h_bin_eval
+        self._chk(fn(
             self.h, _ptr(cir["gates"]), len(cir["gates"]) // 4, cir["wire_count"], _ptr(cir["level_gates"]),
             len(cir["level_gates"]), _ptr(cir["input_first"]), _ptr(cir["input_bits"]), len(cir["input_bits"]),
             _ptr(cir["output_off"]), _ptr(cir["output_bits"]), _ptr(cir["output_wires"]),

@@ -68,6 +68,23 @@ void Sh3BinaryEvaluator::setInput(const oc::BetaBundle& inWires, const sbMatrix&
     }
 }
 
+// already bit-sliced input: copy each row into its wire (.cpp:279-309)
+void Sh3BinaryEvaluator::setInput(u64 idx, const sPackedBin& in) {
+    if (!mCir) throw std::runtime_error(LOCATION);
+    if (idx >= mCir->mInputs.size()) throw std::invalid_argument("input index out of bounds");
+    if (in.shareCount() != mWidth) throw std::runtime_error(LOCATION);
+    const auto& wires = mCir->mInputs[idx].mWires;
+    if (in.bitCount() != wires.size()) throw std::runtime_error(LOCATION);
+    mLevel = 0;
+    std::vector<u32> idxs(wires.begin(), wires.end());
+    gpu::Buffer dIdx(mCtx, std::max<size_t>(idxs.size() * 4, 16));
+    gpu::check(aby3cu_h2d(mCtx->h(), dIdx.ptr(), idxs.data(), idxs.size() * 4));
+    for (int s = 0; s < 2; ++s)
+        gpu::check(aby3cu_bin_scatter_rows(mCtx->h(), mMem[s].ptr(), mRowBytes, (const u32*)dIdx.ptr(), (u32)idxs.size(),
+                                           in.simdWidth() * 8, in.mShares[s].dev()));
+    mCtx->sync();
+}
+
 Sh3Task Sh3BinaryEvaluator::asyncEvaluate(Sh3Task dependency) {
     return dependency.then([this](CommPkg& comm, Sh3Task& self) { roundCallback(comm, self); }, "bin-eval-closure")
         .getClosure();
@@ -121,7 +138,7 @@ void Sh3BinaryEvaluator::roundCallback(CommPkg& comm, Sh3Task task) {
             const size_t bytes = nAnd * sendBytes;
             gpu::Buffer send(mCtx, std::max<size_t>(bytes, 16));
             gpu::check(aby3cu_bin_pack_rows(mCtx->h(), mMem[0].ptr(), mRowBytes, (const u32*)mAndLocsDev.ptr() + a0,
-                                            (u32)nAnd, sendBytes, send.ptr()));
+                                            (u32)nAnd, sendBytes, send.ptr(), nullptr));
             comm.mNext.asyncSendDevice(send.ptr(), bytes);
             mRecvBuf.reset(mCtx, std::max<size_t>(bytes, 16));
             mRecvFutr.emplace_back(comm.mPrev.asyncRecvDevice(mRecvBuf.ptr(), bytes));
@@ -162,6 +179,32 @@ void Sh3BinaryEvaluator::getOutput(const std::vector<oc::BetaWire>& outWires, sb
                                                dst, out.i64Cols() * 8, anyInv ? (const u8*)dInv.ptr() : nullptr));
     }
     mCtx->sync();          // idx / inv are pageable temporaries
+}
+
+void Sh3BinaryEvaluator::getOutput(u64 i, sPackedBin& out, bool allowUninitialized) {
+    if (mCir->mOutputs.size() <= i) throw std::runtime_error(LOCATION);
+    getOutput(mCir->mOutputs[i].mWires, out, allowUninitialized);
+}
+
+// bit-sliced output: gather the wire rows, complementing inverted wires (.cpp:1213-1283)
+void Sh3BinaryEvaluator::getOutput(const std::vector<oc::BetaWire>& outWires, sPackedBin& out, bool) {
+    out.reset(mWidth, outWires.size());
+    const u64 n = outWires.size();
+    std::vector<u32> idx(outWires.begin(), outWires.end());
+    std::vector<u8> inv(n, 0);
+    bool anyInv = false;
+    for (u64 b = 0; b < n; ++b) {
+        if (outWires[b] >= mCir->mWireCount) throw RTE_LOC;
+        inv[b] = mCir->isInvert(outWires[b]) ? 1 : 0;
+        anyInv |= inv[b] != 0;
+    }
+    gpu::Buffer dIdx(mCtx, std::max<size_t>(n * 4, 16)), dInv(mCtx, std::max<size_t>(n, 16));
+    gpu::check(aby3cu_h2d(mCtx->h(), dIdx.ptr(), idx.data(), n * 4));
+    if (anyInv) gpu::check(aby3cu_h2d(mCtx->h(), dInv.ptr(), inv.data(), n));
+    for (int s = 0; s < 2; ++s)
+        gpu::check(aby3cu_bin_pack_rows(mCtx->h(), mMem[s].ptr(), mRowBytes, (const u32*)dIdx.ptr(), (u32)n, out.simdWidth() * 8,
+                                        out.mShares[s].devOut(), anyInv ? (const u8*)dInv.ptr() : nullptr));
+    mCtx->sync();
 }
 
 }  // namespace aby3

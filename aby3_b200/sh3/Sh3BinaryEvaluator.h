@@ -28,6 +28,7 @@ public:
 
     void setInput(u64 i, const sbMatrix& in);
     void setInput(const oc::BetaBundle& wires, const sbMatrix& in);
+    void setInput(u64 i, const sPackedBin& in);
     void setReplicatedInput(u64 i, const sbMatrix& in) { setInput(i, in); }
 
     Sh3Task asyncEvaluate(Sh3Task dependency);
@@ -37,6 +38,8 @@ public:
 
     void getOutput(u64 i, sbMatrix& out, bool allowUninitialized = false);
     void getOutput(const std::vector<oc::BetaWire>& wires, sbMatrix& out, bool allowUninitialized = false);
+    void getOutput(u64 i, sPackedBin& out, bool allowUninitialized = false);
+    void getOutput(const std::vector<oc::BetaWire>& wires, sPackedBin& out, bool allowUninitialized = false);
 
     bool hasMoreRounds() const { return mLevel <= mCir->mLevelCounts.size(); }
 

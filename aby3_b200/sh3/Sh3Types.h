@@ -177,4 +177,31 @@ struct sbMatrix {
     bool operator!=(const sbMatrix& b) const { return !(*this == b); }
 };
 
+// A packed (bit-sliced) set of binary secrets: row i holds bit i of every share, one bit per
+// instance, LSB first (Sh3Types.h:445-652).  Rows are `simdWidth()` 64-bit words long.
+template <typename T = i64>
+struct sPackedBinBase {
+    static_assert(sizeof(T) == 8, "the device layout uses 64-bit words");
+    u64 mShareCount = 0;
+    std::array<eMatrix<i64>, 2> mShares;
+    sPackedBinBase() = default;
+    sPackedBinBase(u64 shareCount, u64 bitCount, u64 rowAlignment = 1) { reset(shareCount, bitCount, rowAlignment); }
+    // shareCount independent secrets of bitCount bits each; rows start on multiples of rowAlignment words
+    void reset(u64 shareCount, u64 bitCount, u64 rowAlignment = 1) {
+        const u64 rowSizeT = oc::divCeil(shareCount, rowAlignment * 64) * rowAlignment;     // :545
+        mShareCount = shareCount;
+        mShares[0].resize(bitCount, rowSizeT);
+        mShares[1].resize(bitCount, rowSizeT);
+    }
+    void reshape(u64 shareCount) {
+        if (shareCount > mShares[0].cols() * 64) throw RTE_LOC;
+        mShareCount = shareCount;
+    }
+    u64 size() const { return mShares[0].size(); }
+    u64 shareCount() const { return mShareCount; }
+    u64 bitCount() const { return mShares[0].rows(); }
+    u64 simdWidth() const { return mShares[0].cols(); }
+};
+using sPackedBin = sPackedBinBase<i64>;
+
 }  // namespace aby3

@@ -408,6 +408,53 @@ int sh3h_bin_eval(sh3h* h, const uint32_t* gates, uint32_t gate_count, uint32_t 
     });
 }
 
+// Same evaluation, but inputs and outputs travel through the engine as sPackedBin (bit-sliced):
+// sbMatrix -> sPackedBin by a first engine pass, setInput(sPackedBin), getOutput(sPackedBin),
+// and the packed output is transposed back to an sbMatrix for comparison.
+int sh3h_bin_eval_packed(sh3h* h, const uint32_t* gates, uint32_t gate_count, uint32_t wire_count,
+                         const uint32_t* level_gates, uint32_t level_count,
+                         const uint32_t* input_first, const uint32_t* input_bits, uint32_t num_inputs,
+                         const uint32_t* output_off, const uint32_t* output_bits, const uint32_t* output_wires,
+                         const uint8_t* output_invert, uint32_t num_outputs,
+                         const int* input_ids, int* output_ids) {
+    for (uint32_t k = 0; k < num_outputs; ++k) output_ids[k] = h->next_handle++;
+    return h->run([&](int i) {
+        Party& P = h->p[i];
+        oc::BetaCircuit cir;
+        cir.loadFlat(gates, gate_count, wire_count, level_gates, level_count, input_first, input_bits, num_inputs,
+                     output_off, output_bits, output_wires, output_invert, num_outputs);
+        const u64 width = P.bins.at(input_ids[0])->rows();
+        std::vector<sPackedBin> packed(num_inputs);
+        {
+            // conversion pass (no PRNG draw: explicit keys), wires read back bit-sliced
+            Sh3BinaryEvaluator conv;
+            conv.setCir(&cir, width, oc::ZeroBlock, oc::ZeroBlock);
+            for (uint32_t k = 0; k < num_inputs; ++k) {
+                conv.setInput(k, *P.bins.at(input_ids[k]));
+                conv.getOutput(cir.mInputs[k].mWires, packed[k]);
+            }
+        }
+        Sh3BinaryEvaluator ev;
+        ev.setCir(&cir, width, P.eval.mShareGen);
+        for (uint32_t k = 0; k < num_inputs; ++k) ev.setInput(k, packed[k]);
+        ev.asyncEvaluate(P.rt).get();
+        for (uint32_t k = 0; k < num_outputs; ++k) {
+            sPackedBin po;
+            ev.getOutput(k, po);
+            if (po.shareCount() != width || po.bitCount() != output_bits[k]) throw RTE_LOC;
+            auto m = std::make_unique<sbMatrix>(width, output_bits[k]);
+            for (int s = 0; s < 2; ++s) {
+                i64* dst = m->mShares[s].devOut();
+                gpu::check(aby3cu_memset(P.ctx->h(), dst, 0, m->i64Size() * 8));
+                gpu::check(aby3cu_bit_transpose(P.ctx->h(), po.mShares[s].dev(), output_bits[k], width, po.simdWidth() * 8,
+                                                dst, m->i64Cols() * 8, nullptr));
+            }
+            P.bins[output_ids[k]] = std::move(m);
+        }
+        P.ctx->sync();
+    });
+}
+
 // ---- device timing over all three parties' streams -------------------------------
 // begin: every party stream waits for one common start event; end: returns the time
 // from that event until the last party stream has drained.  (Parties on one GPU.)

@@ -165,9 +165,11 @@ int aby3cu_bit_transpose_gather(aby3cu_ctx* ctx, const void* d_in, const uint32_
 int aby3cu_bin_level(aby3cu_ctx* ctx, const uint32_t* d_gates, uint32_t n_gates,
                      void* d_mem0, void* d_mem1, uint64_t row_bytes,
                      const uint8_t key_prev[16], const uint8_t key_next[16], uint64_t and_index0);
-/* sendBuff packing (:795-796): out[j*nbytes .. ) = first nbytes of row locs[j] of mem */
+/* sendBuff packing (:795-796) and getOutput(sPackedBin) (:1213-1283):
+ * out[j*nbytes .. ) = first nbytes of row locs[j] of mem, complemented where d_invert[j] != 0
+ * (d_invert may be NULL). */
 int aby3cu_bin_pack_rows(aby3cu_ctx* ctx, const void* d_mem, uint64_t row_bytes, const uint32_t* d_locs,
-                         uint32_t n_locs, uint64_t nbytes, void* d_out);
+                         uint32_t n_locs, uint64_t nbytes, void* d_out, const uint8_t* d_invert);
 /* receive scatter (:555-573): first nbytes of row locs[j] of mem = in[j*nbytes ..) */
 int aby3cu_bin_scatter_rows(aby3cu_ctx* ctx, void* d_mem, uint64_t row_bytes, const uint32_t* d_locs,
                             uint32_t n_locs, uint64_t nbytes, const void* d_in);

@@ -1,0 +1,156 @@
+"""BASELINE-size checks through size-independent properties (the oracle would need
+minutes at these sizes): Freivalds' check of the revealed product, share consistency
+between neighbours, agreement of all three reveals, sampled rows against numpy; plus
+the edge cases: empty inputs, K beyond the per-launch exactness bound, forced row-blocking."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as o
+from aby3_b200 import abi, harness
+
+pytestmark = pytest.mark.gpu
+U64 = np.uint64
+lib = abi.lib
+
+
+def rnd(seed, shape):
+    return np.random.default_rng(seed).integers(-2**63, 2**63, shape, dtype=np.int64)
+
+
+def test_si64_matmul_4096_cubed_freivalds():
+    """config 1/2 size: reveal(C) v == a (b v) mod 2^64 for random v; replicated-share consistency."""
+    n = 4096
+    s = harness.Session()
+    try:
+        a, b = rnd(1, (n, n)), rnd(2, (n, n))
+        A, B = s.share_int(0, a), s.share_int(1, b)
+        C = s.mul(A, B)
+        assert lib.aby3cu_version() == 1
+        sh = s.get_shares(C)
+        for p in range(3):
+            assert np.array_equal(sh[(p + 1) % 3, 1], sh[p, 0])
+        c = (sh[0, 0].view(U64) + sh[1, 0].view(U64) + sh[2, 0].view(U64)).view(np.int64)
+        for p in range(3):
+            assert np.array_equal(s.reveal(C, p), c)
+        for seed in range(3):
+            v = rnd(10 + seed, (n, 1))
+            assert np.array_equal(c @ v, a @ (b @ v))
+    finally:
+        s.close()
+
+
+def test_sf64_matmul_trunc_4096_cubed_properties():
+    """config 2: shares stay a consistent replicated sharing, all parties reveal the same matrix,
+    sampled rows are within the protocol's +-4 ulp of the plaintext fixed-point product."""
+    n, d = 4096, 16
+    s = harness.Session()
+    try:
+        rng = np.random.default_rng(3)
+        a = (rng.uniform(-4, 4, (n, n)) * (1 << d)).astype(np.int64)
+        b = (rng.uniform(-4, 4, (n, n)) * (1 << d)).astype(np.int64)
+        A, B = s.share_int(0, a), s.share_int(0, b)
+        C = s.mul(A, B, shift=d)
+        sh = s.get_shares(C)
+        for p in range(3):
+            assert np.array_equal(sh[(p + 1) % 3, 1], sh[p, 0])
+        c = s.reveal(C, 0)
+        assert np.array_equal(s.reveal(C, 1), c) and np.array_equal(s.reveal(C, 2), c)
+        rows = rng.integers(0, n, 16)
+        ref = (a[rows] @ b) >> d
+        assert np.max(np.abs(c[rows] - ref)) <= 4
+    finally:
+        s.close()
+
+
+def test_binary_and_layer_2_pow_22_instances():
+    """config 5 scale (bitwiseAnd(64) over millions of instances): reveal == a & b, consistency."""
+    width = 1 << 22
+    s = harness.Session()
+    try:
+        x, y = rnd(5, (width, 1)), rnd(6, (width, 1))
+        X, Y = s.share_bin(0, x, 64), s.share_bin(1, y, 64)
+        out = s.bin_eval(harness.library_circuit("and", 64), [X, Y])[0]
+        sh = s.get_shares(out, binary=True)
+        for p in range(3):
+            assert np.array_equal(sh[(p + 1) % 3, 1], sh[p, 0])
+        assert np.array_equal(s.reveal(out, 0, binary=True), x & y)
+    finally:
+        s.close()
+
+
+def test_empty_inputs_are_no_ops(ctx):
+    z = abi.C.c_void_p(None)
+    before = ctx.launches
+    key = bytes(16)
+    abi.check(lib.aby3cu_aes_ctr_fill(ctx.h, key, 0, z, 0))
+    abi.check(lib.aby3cu_zero_share(ctx.h, key, key, 0, z, z, 0, 0))
+    abi.check(lib.aby3cu_mul_hadamard(ctx.h, z, z, z, z, key, key, 0, z, 0))
+    abi.check(lib.aby3cu_trunc_finish(ctx.h, z, z, z, z, 0, 16))
+    abi.check(lib.aby3cu_share_op(ctx.h, 0, z, z, z, 0))
+    abi.check(lib.aby3cu_gemm_cross(ctx.h, abi.GEMM_AUTO, z, z, z, z, 0, 5, 7, z, 0))
+    abi.check(lib.aby3cu_gemm_cross(ctx.h, abi.GEMM_AUTO, z, z, z, z, 5, 5, 0, z, 0))
+    abi.check(lib.aby3cu_bit_transpose(ctx.h, z, 0, 0, 8, z, 8, z))
+    assert ctx.launches == before
+    # K == 0: the product is the zero matrix (or leaves C alone when accumulating)
+    c = ctx.upload(np.full(6, 9, dtype=np.int64))
+    abi.check(lib.aby3cu_gemm_cross(ctx.h, abi.GEMM_AUTO, z, z, z, z, 2, 0, 3, c.p, 1))
+    assert np.array_equal(ctx.download(c, 6), np.full(6, 9))
+    abi.check(lib.aby3cu_gemm_cross(ctx.h, abi.GEMM_AUTO, z, z, z, z, 2, 0, 3, c.p, 0))
+    assert np.array_equal(ctx.download(c, 6), np.zeros(6, dtype=np.int64))
+
+
+def test_bad_arguments_fail_loudly(ctx):
+    z = abi.C.c_void_p(None)
+    with pytest.raises(abi.Aby3CudaError):
+        abi.check(lib.aby3cu_aes_ctr_fill(ctx.h, bytes(16), 4, ctx.alloc(64).p, 16))      # offset not a multiple of 8
+    with pytest.raises(abi.Aby3CudaError):
+        abi.check(lib.aby3cu_gemm_cross(ctx.h, 7, z, z, z, z, 1, 1, 1, z, 0))              # unknown algo
+    with pytest.raises(abi.Aby3CudaError):
+        abi.check(lib.aby3cu_trunc_finish(ctx.h, z, z, z, z, 4, 64))                       # shift out of range
+    with pytest.raises(abi.Aby3CudaError):
+        abi.check(lib.aby3cu_gemm_cross(ctx.h, abi.GEMM_AUTO, z, z, z, z, 2, 2, 2, z, 0))  # null operands
+
+
+def test_k_beyond_the_per_launch_exactness_bound(ctx):
+    """K = 8300 > 8256: the host splits K and accumulates through C; worst-case limbs (all 0xFF)."""
+    M, K, N = 128, 8300, 64
+    a = np.full((M, K), -1, dtype=np.int64)
+    b = np.full((K, N), -1, dtype=np.int64)
+    zb = np.zeros((K, N), dtype=np.int64)
+    d = [ctx.upload(x) for x in (a, a, b, zb)]
+    c = ctx.alloc(8 * M * N)
+    abi.check(lib.aby3cu_gemm_cross(ctx.h, abi.GEMM_TCGEN05, d[0].p, d[1].p, d[2].p, d[3].p, M, K, N, c.p, 0))
+    assert np.array_equal(ctx.download(c, (M, N)), o.cross_term(a, a, b, zb))
+    ra, rb, rb1 = rnd(1, (M, K)), rnd(2, (K, N)), rnd(3, (K, N))
+    d = [ctx.upload(x) for x in (ra, a, rb, rb1)]
+    abi.check(lib.aby3cu_gemm_cross(ctx.h, abi.GEMM_TCGEN05, d[0].p, d[1].p, d[2].p, d[3].p, M, K, N, c.p, 0))
+    assert np.array_equal(ctx.download(c, (M, N)), o.cross_term(ra, a, rb, rb1))
+
+
+def test_forced_row_blocking_of_the_limb_workspace():
+    """ABY3CU_WS_LIMIT_MB=1 makes the tcgen05 path loop over several row blocks."""
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle_lib as o
+from aby3_b200 import abi
+ctx = abi.Ctx(0)
+rng = np.random.default_rng(0)
+M, K, N = 1200, 160, 200
+a0, a1 = (rng.integers(-2**63, 2**63, (M, K), dtype=np.int64) for _ in range(2))
+b0, b1 = (rng.integers(-2**63, 2**63, (K, N), dtype=np.int64) for _ in range(2))
+d = [ctx.upload(x) for x in (a0, a1, b0, b1)]
+c = ctx.alloc(8 * M * N)
+abi.check(abi.lib.aby3cu_gemm_cross(ctx.h, abi.GEMM_TCGEN05, d[0].p, d[1].p, d[2].p, d[3].p, M, K, N, c.p, 0))
+assert np.array_equal(ctx.download(c, (M, N)), o.cross_term(a0, a1, b0, b1))
+print("ROWBLOCK OK", ctx.launches)
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ABY3CU_WS_LIMIT_MB="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0 and "ROWBLOCK OK" in out.stdout, out.stdout
+    launches = int(out.stdout.strip().split()[-1])
+    assert launches >= 1 + 2 * 3          # pack_b + several (pack_a, gemm) pairs

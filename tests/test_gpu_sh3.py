@@ -260,3 +260,21 @@ def test_linear_regression_sgd_matches_oracle(pair):
     learnt = s.reveal(W, 0).astype(np.float64) / (1 << D)
     assert np.linalg.norm(learnt - model) < 0.5 * np.linalg.norm(model)
     assert_cursors(s, r)
+
+
+@pytest.mark.parametrize("name,bits,width", [("and", 64, 777), ("add_depth", 64, 4100), ("lt", 64, 64)])
+def test_binary_engine_packed_io_matches_oracle(pair, name, bits, width):
+    """setInput(i, sPackedBin) / getOutput(i, sPackedBin) (Sh3BinaryEvaluator.cpp:279-309, 1213-1283)
+    give the same shares as the sbMatrix forms."""
+    s, r = pair
+    rng = np.random.default_rng(width)
+    a, b = rng.integers(-2**63, 2**63, (width, 1), dtype=np.int64), rng.integers(-2**63, 2**63, (width, 1), dtype=np.int64)
+    cir = harness.library_circuit(name, bits)
+    A, B = s.share_bin(0, a, bits), s.share_bin(1, b, bits)
+    Ao, Bo = r.share_bin(0, a), r.share_bin(1, b)
+    outs = s.bin_eval(cir, [A, B], packed=True)
+    outs_o, _ = o.bin_eval(r, cir, width, [Ao, Bo])
+    obits = int(cir["output_bits"][0])
+    om = np.int64(-1) if obits == 64 else np.int64((1 << obits) - 1)
+    assert np.array_equal(s.get_shares(outs[0], binary=True) & om, outs_o[0] & om)
+    assert_cursors(s, r)
