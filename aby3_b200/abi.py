@@ -70,6 +70,12 @@ PROTOTYPES = {
     "aby3cu_gemm_cross": (_int, [_p, _int, _p, _p, _p, _p, _u64, _u64, _u64, _p, _int]),
     "aby3cu_gemm_last_algo": (_int, [_p]),
     "aby3cu_gemm_last_main_kernel_ms": (_int, [_p, C.POINTER(C.c_float)]),
+    "aby3cu_ot_send": (_int, [_p, _key, _u64, _p, _p, _sz]),
+    "aby3cu_ot_help": (_int, [_p, _key, _u64, _p, _p, _sz]),
+    "aby3cu_ot_recv": (_int, [_p, _p, _p, _p, _p, _sz, _int]),
+    "aby3cu_bitmul_msgs_p0": (_int, [_p, _p, _p, _p, _p, _key, _u64, _key, _u64, _p, _p, _p, _sz]),
+    "aby3cu_bitmul_msgs_p2": (_int, [_p, _p, _p, _p, _key, _u64, _p, _p, _sz]),
+    "aby3cu_bitmul_pub_msgs": (_int, [_p, C.c_int64, _p, _p, _key, _key, _u64, _p, _sz]),
     "aby3cu_share_op": (_int, [_p, _int, _p, _p, _p, _sz]),
     "aby3cu_combine3": (_int, [_p, _int, _p, _p, _p, _p, _sz]),
     "aby3cu_transpose_i64": (_int, [_p, _p, _u64, _u64, _p]),

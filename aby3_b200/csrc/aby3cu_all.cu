@@ -6,3 +6,4 @@
 #include "gemm_imad.cu"
 #include "gemm_tc.cu"
 #include "binary.cu"
+#include "sharedot.cu"

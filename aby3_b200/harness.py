@@ -38,6 +38,7 @@ def _load():
     l.sh3h_free.argtypes = [p, i32]
     l.sh3h_mul.argtypes = [p, i32, i32, i64, i32]
     l.sh3h_addsub.argtypes = [p, i32, i32, i32]
+    l.sh3h_mul_bit.argtypes = [p, i32, i32, i32, i64]
     l.sh3h_reveal.argtypes = [p, i32, i32, i32, p]
     l.sh3h_trunc_tuple.argtypes = [p, i32, u64, u64, u64, p, p, p]
     l.sh3h_bin_eval.argtypes = [p, p, C.c_uint32, C.c_uint32, p, C.c_uint32, p, p, C.c_uint32, p, p, p, p, C.c_uint32, p, p]
@@ -164,6 +165,14 @@ class Session:
 
     def mul(self, a, b, shift=None, out=0):
         return self._id(lib.sh3h_mul(self.h, a, b, -1 if shift is None else int(shift), out))
+
+    def mul_bit(self, a, b):
+        """c = b * a for a one-bit binary sharing b (asyncMul(si64Matrix, sbMatrix))."""
+        return self._id(lib.sh3h_mul_bit(self.h, a, b, 0, 0))
+
+    def mul_bit_pub(self, a_const, b):
+        """c = b * a for a public constant a (asyncMul(i64, sbMatrix))."""
+        return self._id(lib.sh3h_mul_bit(self.h, 0, b, 1, int(a_const)))
 
     def add(self, a, b):
         return self._id(lib.sh3h_addsub(self.h, a, b, 0))

@@ -179,13 +179,107 @@ Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64Matrix& A, const si
     }).getClosure();
 }
 
-Sh3Task Sh3Evaluator::asyncMul(Sh3Task, const si64Matrix&, const sbMatrix&, si64Matrix&) {
-    throw std::runtime_error("asyncMul(si64Matrix, sbMatrix): bit x arithmetic product (SharedOT) is scheduled after the "
-                             "hot path (SURVEY 8f-1) " LOCATION);
+// ---- arithmetic x one shared bit -- Sh3Evaluator.cpp:119-263 ----------------------
+// c = b * a.  P1 is the OT receiver twice: from P0 it learns b*(a0+a2) - c0 - c2 - z (helper P2),
+// from P2 it learns b*a1 + z (helper P0).  Draw order from the common PRNGs is per element and
+// interleaved exactly as in the reference (it decides every party's share values).
+Sh3Task Sh3Evaluator::asyncMul(Sh3Task dep, const si64Matrix& A, const sbMatrix& B, si64Matrix& c) {
+    return dep.then([&](CommPkg& comm, Sh3Task self) {
+        if (B.rows() != A.rows() || A.cols() != 1 || B.bitCount() != 1) throw std::runtime_error(LOCATION);
+        gpu::Context* ctx = gpu::current();
+        const u64 n = A.rows();
+        auto& g = mShareGen;
+        // results are built aside so that c may alias A (Sh3Piecewise passes the same matrix)
+        eMatrix<i64> c0(n, 1), c1(n, 1);
+        const block seedPrev = g.mPrevCommon.getSeed(), seedNext = g.mNextCommon.getSeed();
+        switch (mPartyIdx) {
+        case 0: {
+            gpu::Buffer msgs(ctx, std::max<size_t>(16 * n, 16));
+            gpu::check(aby3cu_bitmul_msgs_p0(ctx->h(), A.mShares[0].dev(), A.mShares[1].dev(), B.mShares[0].dev(), B.mShares[1].dev(),
+                                             seedPrev.data(), streamElem(g.mPrevCommon), seedNext.data(), streamElem(g.mNextCommon),
+                                             c0.devOut(), c1.devOut(), (i64*)msgs.ptr(), n));
+            g.mPrevCommon.skip(16 * n);          // z and c[1] per element
+            g.mNextCommon.skip(8 * n);           // c[0]
+            mOtNextRecver.send(comm.mNext, (const i64*)msgs.ptr(), n);        // sender, receiver P1, helper P2
+            mOtNextRecver.help(comm.mNext, B.mShares[0].dev(), n);           // helper for P2 -> P1, choice b0
+            c.mShares[0] = std::move(c0);
+            c.mShares[1] = std::move(c1);
+            break;
+        }
+        case 1: {
+            g.mPrevCommon.getDevice(ctx, c1.devOut(), 8 * n);                // c[1]
+            auto f0 = SharedOT::asyncRecv(comm.mPrev, comm.mNext, n);        // sender P0, helper P2
+            auto f1 = SharedOT::asyncRecv(comm.mNext, comm.mPrev, n);        // sender P2, helper P0
+            c.mShares[1] = std::move(c1);
+            self.then([&, f0, f1, n](CommPkg& comm, Sh3Task) {
+                eMatrix<i64> r(n, 1);
+                f1.finish(B.mShares[1].dev(), r.devOut(), false);             // b*a1 + z
+                f0.finish(B.mShares[0].dev(), r.devMut(), true);              // + b*(a0+a2) - c0 - c2 - z
+                c.mShares[0] = std::move(r);
+                comm.mNext.asyncSendDevice(c.mShares[0].dev(), 8 * n);
+            });
+            break;
+        }
+        case 2: {
+            gpu::Buffer msgs(ctx, std::max<size_t>(16 * n, 16));
+            gpu::check(aby3cu_bitmul_msgs_p2(ctx->h(), A.mShares[1].dev(), B.mShares[0].dev(), B.mShares[1].dev(), seedNext.data(),
+                                             streamElem(g.mNextCommon), c0.devOut(), (i64*)msgs.ptr(), n));
+            g.mNextCommon.skip(16 * n);          // z and c[0] per element
+            mOtPrevRecver.help(comm.mPrev, B.mShares[1].dev(), n);           // helper for P0 -> P1, choice b1
+            mOtPrevRecver.send(comm.mPrev, (const i64*)msgs.ptr(), n);        // sender, receiver P1, helper P0
+            c.mShares[0] = std::move(c0);
+            c.mShares[1].resize(n, 1);
+            self.then([&, n](CommPkg& comm, Sh3Task self) {
+                auto f = comm.mPrev.asyncRecvDevice(c.mShares[1].devOut(), 8 * n).share();
+                self.then([f](CommPkg&, Sh3Task) { f.get(); });
+            });
+            break;
+        }
+        default: throw RTE_LOC;
+        }
+    }).getClosure();
 }
-Sh3Task Sh3Evaluator::asyncMul(Sh3Task, const i64&, const sbMatrix&, si64Matrix&) {
-    throw std::runtime_error("asyncMul(i64, sbMatrix): bit x arithmetic product (SharedOT) is scheduled after the "
-                             "hot path (SURVEY 8f-1) " LOCATION);
+
+// ---- public constant x one shared bit -- Sh3Evaluator.cpp:418-501 -------------------
+Sh3Task Sh3Evaluator::asyncMul(Sh3Task dep, const i64& a, const sbMatrix& b, si64Matrix& c) {
+    return dep.then([&, a](CommPkg& comm, Sh3Task self) {
+        if (b.bitCount() != 1) throw RTE_LOC;
+        gpu::Context* ctx = gpu::current();
+        const u64 n = b.rows();
+        if (c.rows() != n || c.cols() != 1) c.resize(n, 1);
+        auto& g = mShareGen;
+        switch (mPartyIdx) {
+        case 0: {
+            gpu::Buffer msgs(ctx, std::max<size_t>(16 * n, 16));
+            gpu::check(aby3cu_bitmul_pub_msgs(ctx->h(), a, b.mShares[0].dev(), b.mShares[1].dev(), g.mShareGen[0].key().data(),
+                                              g.mShareGen[1].key().data(), g.mShareElemIdx, (i64*)msgs.ptr(), n));
+            g.mShareElemIdx += n;
+            mOtNextRecver.send(comm.mNext, (const i64*)msgs.ptr(), n);
+            mOtPrevRecver.send(comm.mPrev, (const i64*)msgs.ptr(), n);
+            auto fu1 = comm.mNext.asyncRecvDevice(c.mShares[0].devOut(), 8 * n).share();
+            auto fu2 = comm.mPrev.asyncRecvDevice(c.mShares[1].devOut(), 8 * n).share();
+            self.then([fu1, fu2](CommPkg&, Sh3Task) { fu1.get(); fu2.get(); });
+            break;
+        }
+        case 1: {
+            g.getShares(ctx, nullptr, c.mShares[1].devOut(), n, false);
+            mOtNextRecver.help(comm.mNext, b.mShares[0].dev(), n);
+            comm.mPrev.asyncSendDevice(c.mShares[1].dev(), 8 * n);
+            auto f = SharedOT::asyncRecv(comm.mPrev, comm.mNext, n);
+            self.then([&, f](CommPkg&, Sh3Task) { f.finish(b.mShares[0].dev(), c.mShares[0].devOut(), false); });
+            break;
+        }
+        case 2: {
+            g.getShares(ctx, nullptr, c.mShares[0].devOut(), n, false);
+            mOtPrevRecver.help(comm.mPrev, b.mShares[1].dev(), n);
+            comm.mNext.asyncSendDevice(c.mShares[0].dev(), 8 * n);
+            auto f = SharedOT::asyncRecv(comm.mNext, comm.mPrev, n);
+            self.then([&, f](CommPkg&, Sh3Task) { f.finish(b.mShares[1].dev(), c.mShares[1].devOut(), false); });
+            break;
+        }
+        default: throw std::runtime_error(LOCATION);
+        }
+    }).getClosure();
 }
 
 }  // namespace aby3

@@ -21,13 +21,52 @@ struct TruncationPair {
     si64Matrix mRTrunc;    // replicated share of ~ r >> d, added back after truncation
 };
 
-// 3-party shared OT endpoint (aby3/OT/SharedOT.h); only its seed is part of this
-// round's path (it consumes one block of each common PRNG in init), the OT
-// protocol itself belongs to the bit x arithmetic multiplication.
-struct SharedOT {
-    void setSeed(const block& s) { mKey = s; mIdx = 0; }
+// 3-party "shared OT" (aby3/OT/SharedOT.{h,cpp}): sender and helper hold the same AES key
+// and block counter; the receiver learns m[choice].  All buffers are device buffers; the
+// masks are generated inside the kernels (aby3cu_ot_send / _help / _recv).
+class SharedOT {
+public:
+    void setSeed(const block& seed, u64 seedIdx = 0) { mKey = seed; mIdx = seedIdx; }
+    // masks n message pairs (d_msgs: n x 2 int64) and sends them to `recver`
+    void send(oc::Channel& recver, const i64* d_msgs, u64 n) {
+        gpu::Context* ctx = gpu::current();
+        gpu::Buffer masked(ctx, std::max<size_t>(16 * n, 16));
+        gpu::check(aby3cu_ot_send(ctx->h(), mKey.data(), mIdx, d_msgs, (i64*)masked.ptr(), n));
+        mIdx += n;
+        recver.asyncSendDevice(masked.ptr(), 16 * n);
+    }
+    // sends pad_i[choice_i] for the receiver's choice bits (bit 0 of each word of d_choice)
+    void help(oc::Channel& recver, const i64* d_choice, u64 n) {
+        gpu::Context* ctx = gpu::current();
+        gpu::Buffer mc(ctx, std::max<size_t>(8 * n, 16));
+        gpu::check(aby3cu_ot_help(ctx->h(), mKey.data(), mIdx, d_choice, (i64*)mc.ptr(), n));
+        mIdx += n;
+        recver.asyncSendDevice(mc.ptr(), 8 * n);
+    }
+    // receiver side: post both receives now, combine later with finish()
+    struct AsyncRecv {
+        std::shared_future<void> fMsgs, fHelp;
+        std::shared_ptr<gpu::Buffer> msgs, help;
+        u64 n = 0;
+        // out[i] (+)= msgs[i][choice_i] ^ help[i]
+        void finish(const i64* d_choice, i64* d_out, bool accumulate) const {
+            fMsgs.get(); fHelp.get();
+            gpu::Context* ctx = gpu::current();
+            gpu::check(aby3cu_ot_recv(ctx->h(), (const i64*)msgs->ptr(), (const i64*)help->ptr(), d_choice, d_out, n, accumulate ? 1 : 0));
+        }
+    };
+    static AsyncRecv asyncRecv(oc::Channel& sender, oc::Channel& helper, u64 n) {
+        gpu::Context* ctx = gpu::current();
+        AsyncRecv r;
+        r.n = n;
+        r.msgs = std::make_shared<gpu::Buffer>(ctx, std::max<size_t>(16 * n, 16));
+        r.help = std::make_shared<gpu::Buffer>(ctx, std::max<size_t>(8 * n, 16));
+        r.fMsgs = sender.asyncRecvDevice(r.msgs->ptr(), 16 * n).share();
+        r.fHelp = helper.asyncRecvDevice(r.help->ptr(), 8 * n).share();
+        return r;
+    }
     block mKey;
-    u64 mIdx = 0;
+    u64 mIdx = (u64)-1;
 };
 
 class Sh3Evaluator {
@@ -57,7 +96,7 @@ public:
         return asyncMul(dependency, A.i64Cast(), B.i64Cast(), C.i64Cast(), D);
     }
 
-    // bit x arithmetic products need SharedOT -- SURVEY 8(f) item 1, not in this round
+    // bit x arithmetic products over SharedOT (Sh3Evaluator.cpp:119-263, 418-501); B holds one bit per row
     Sh3Task asyncMul(Sh3Task dep, const si64Matrix& A, const sbMatrix& B, si64Matrix& C);
     Sh3Task asyncMul(Sh3Task dep, const i64& a, const sbMatrix& B, si64Matrix& C);
 

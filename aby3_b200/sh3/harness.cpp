@@ -304,6 +304,19 @@ int sh3h_mul(sh3h* h, int a, int b, int64_t shift, int out_id) {
     return rc ? -1 : id;
 }
 
+// c = b * a: eval.asyncMul(rt, si64Matrix, sbMatrix, c) (pub != 0: the public constant `a_pub`)
+int sh3h_mul_bit(sh3h* h, int a_id, int b_id, int pub, int64_t a_pub) {
+    const int id = h->next_handle++;
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        auto m = std::make_unique<si64Matrix>();
+        if (pub) P.eval.asyncMul(P.rt, (const i64&)a_pub, *P.bins.at(b_id), *m).get();
+        else P.eval.asyncMul(P.rt, *P.ints.at(a_id), *P.bins.at(b_id), *m).get();
+        P.ints[id] = std::move(m);
+    });
+    return rc ? -1 : id;
+}
+
 // C = A + B / A - B on shares (local)
 int sh3h_addsub(sh3h* h, int a, int b, int sub) {
     const int id = h->next_handle++;

@@ -126,6 +126,28 @@ int aby3cu_gemm_last_algo(const aby3cu_ctx* ctx);
  * single main-kernel launch (it synchronises on the closing event). */
 int aby3cu_gemm_last_main_kernel_ms(aby3cu_ctx* ctx, float* ms);
 
+/* ---- 3-party shared OT and the bit x arithmetic product ---------------- */
+/* aby3/OT/SharedOT.cpp:6-28: out[i][h] = msgs[i][h] ^ pad_i[h], pad_i = AES_key(toBlock(idx0+i)),
+ * h = 0 low 8 bytes, h = 1 high 8 bytes.  d_msgs / d_out: n pairs of int64, 16-byte aligned. */
+int aby3cu_ot_send(aby3cu_ctx* ctx, const uint8_t key[16], uint64_t idx0, const int64_t* d_msgs, int64_t* d_out, size_t n);
+/* SharedOT::help (:30-94): out[i] = pad_i[choice[i] & 1] */
+int aby3cu_ot_help(aby3cu_ctx* ctx, const uint8_t key[16], uint64_t idx0, const int64_t* d_choice, int64_t* d_out, size_t n);
+/* SharedOT::recv (:102-126): out[i] (+)= masked[i][choice[i] & 1] ^ help[i] */
+int aby3cu_ot_recv(aby3cu_ctx* ctx, const int64_t* d_masked, const int64_t* d_help, const int64_t* d_choice,
+                   int64_t* d_out, size_t n, int accumulate);
+/* Message pairs of asyncMul(si64Matrix, sbMatrix) (Sh3Evaluator.cpp:133-160): party 0 draws
+ * z, c1 from mPrevCommon (elements elem_prev+2i, +2i+1) and c0 from mNextCommon (elem_next+i). */
+int aby3cu_bitmul_msgs_p0(aby3cu_ctx* ctx, const int64_t* d_A0, const int64_t* d_A1, const int64_t* d_B0, const int64_t* d_B1,
+                          const uint8_t key_prev_common[16], uint64_t elem_prev,
+                          const uint8_t key_next_common[16], uint64_t elem_next,
+                          int64_t* d_C0, int64_t* d_C1, int64_t* d_msgs, size_t n);
+/* party 2 (:212-240): z, c0 from mNextCommon (elements elem_next+2i, +2i+1) */
+int aby3cu_bitmul_msgs_p2(aby3cu_ctx* ctx, const int64_t* d_A1, const int64_t* d_B0, const int64_t* d_B1,
+                          const uint8_t key_next_common[16], uint64_t elem_next, int64_t* d_C0, int64_t* d_msgs, size_t n);
+/* party 0 of asyncMul(i64 a, sbMatrix) (:430-447): pairs (z, a+z) ordered by b0^b1, z = getShare() */
+int aby3cu_bitmul_pub_msgs(aby3cu_ctx* ctx, int64_t a, const int64_t* d_B0, const int64_t* d_B1,
+                           const uint8_t key_prev[16], const uint8_t key_next[16], uint64_t elem0, int64_t* d_msgs, size_t n);
+
 /* ---- local share arithmetic / reveal ------------------------------------------- */
 enum { ABY3CU_OP_ADD = 0, ABY3CU_OP_SUB = 1, ABY3CU_OP_XOR = 2 };
 /* out = x op y  (sMatrix +,-: Sh3Types.h:805-820) */

@@ -330,9 +330,35 @@ void cross_term(const u64* A0, const u64* A1, const u64* B0, const u64* B1, u64*
     });
 }
 
+/* SharedOT restatement -- aby3/OT/SharedOT.cpp:6-126.  Sender and helper share (key, idx). */
+struct SharedOT {
+    Aes128 aes;
+    u64 idx = 0;
+    void setSeed(const u8 k[16]) { aes.setKey(k); idx = 0; }
+    /* send: masked[i][h] = m[i][h] ^ AES(idx+i)[h]   (:6-28) */
+    void send(const u64* m, u64* masked, u64 n) {
+        std::vector<u64> pad(2 * n);
+        aes.ctr(idx, n, (u8*)pad.data());
+        idx += n;
+        for (u64 i = 0; i < 2 * n; ++i) masked[i] = m[i] ^ pad[i];
+    }
+    /* help: mc[i] = AES(idx+i)[choice_i]   (:30-94; the 128-block stepping does not change the counters) */
+    void help(const u8* choice, u64* mc, u64 n) {
+        std::vector<u64> pad(2 * n);
+        aes.ctr(idx, n, (u8*)pad.data());
+        idx += n;
+        for (u64 i = 0; i < n; ++i) mc[i] = pad[2 * i + choice[i]];
+    }
+    /* recv: out[i] = masked[i][choice_i] ^ mc[i]   (:102-126) */
+    static void recv(const u64* masked, const u64* mc, const u8* choice, u64* out, u64 n) {
+        for (u64 i = 0; i < n; ++i) out[i] = masked[2 * i + choice[i]] ^ mc[i];
+    }
+};
+
 struct Party {
     int idx;
     ShareGen enc, eval;
+    SharedOT otPrevRecver, otNextRecver;     /* Sh3Evaluator.h:118-124 */
 };
 
 }  // namespace
@@ -409,7 +435,9 @@ orc_session* orc_session_new(const u8 enc_seeds[3][2][16], const u8 eval_seeds[3
         s->p[i].eval.init(eval_seeds[i][0], eval_seeds[i][1]);   /* Sh3Evaluator.cpp:9-15 */
         u8 k[16];
         s->p[i].eval.nextCommon.getBlock(k);   /* mOtPrevRecver.setSeed(mNextCommon.get<block>()) :13 */
+        s->p[i].otPrevRecver.setSeed(k);
         s->p[i].eval.prevCommon.getBlock(k);   /* mOtNextRecver.setSeed(mPrevCommon.get<block>()) :14 */
+        s->p[i].otNextRecver.setSeed(k);
     }
     return s;
 }
@@ -521,6 +549,95 @@ void orc_mul_trunc(orc_session* s, const i64* A, const i64* B, i64* C, u64 M, u6
             dst[i] = (i64)((u64)dst[i] + (u64)(sum >> shift));
         }
     }
+}
+
+/* Sh3Evaluator::asyncMul(si64Matrix A, sbMatrix B, si64Matrix C) -- Sh3Evaluator.cpp:119-263.
+ * A: n x 1 arithmetic shares, B: n x 1 binary shares of ONE bit (bit 0 of each word; the
+ * reference asserts the words are 0/1, here bit 0 is taken), C = b * a. */
+void orc_mul_bit(orc_session* s, const i64* A, const i64* B, i64* C, u64 n) {
+    auto a = [&](int p, int pl) { return (const u64*)plane(A, n, p, pl); };
+    auto b = [&](int p, int pl) { return (const u64*)plane(B, n, p, pl); };
+    auto c = [&](int p, int pl) { return (u64*)plane(C, n, p, pl); };
+    std::vector<u64> s0(2 * n), s1(2 * n), m0(2 * n), m2(2 * n), h0(n), h2(n), r0(n), r1(n);
+    std::vector<u8> ch(n), ch2(n);
+    /* party 0 (:133-170) */
+    {
+        ShareGen& g = s->p[0].eval;
+        for (u64 i = 0; i < n; ++i) {
+            const u64 bb0 = (b(0, 0)[i] ^ b(0, 1)[i]) & 1;
+            u64 z, c0, c1;
+            g.prevCommon.get((u8*)&z, 8);
+            g.nextCommon.get((u8*)&c0, 8);
+            g.prevCommon.get((u8*)&c1, 8);
+            c(0, 0)[i] = c0; c(0, 1)[i] = c1;
+            ch[i] = (u8)(b(0, 0)[i] & 1);
+            z = 0 - (c0 + c1) - z;
+            s0[2 * i + bb0] = z;
+            s0[2 * i + (bb0 ^ 1)] = a(0, 0)[i] + a(0, 1)[i] + z;
+        }
+        s->p[0].otNextRecver.send(s0.data(), m0.data(), n);       /* sender for the OT to P1 */
+        s->p[0].otNextRecver.help(ch.data(), h0.data(), n);       /* helper for P2 -> P1 */
+    }
+    /* party 2 (:212-258) */
+    {
+        ShareGen& g = s->p[2].eval;
+        for (u64 i = 0; i < n; ++i) {
+            const u64 bb1 = (b(2, 0)[i] ^ b(2, 1)[i]) & 1;
+            u64 z, c0;
+            g.nextCommon.get((u8*)&z, 8);
+            g.nextCommon.get((u8*)&c0, 8);
+            c(2, 0)[i] = c0;
+            ch2[i] = (u8)(b(2, 1)[i] & 1);
+            s1[2 * i + bb1] = z;
+            s1[2 * i + (bb1 ^ 1)] = a(2, 1)[i] + z;
+        }
+        s->p[2].otPrevRecver.help(ch2.data(), h2.data(), n);      /* helper for P0 -> P1 */
+        s->p[2].otPrevRecver.send(s1.data(), m2.data(), n);       /* sender for the OT to P1 */
+    }
+    /* party 1 (:171-211) */
+    {
+        ShareGen& g = s->p[1].eval;
+        std::vector<u8> b0(n), b1(n);
+        for (u64 i = 0; i < n; ++i) {
+            g.prevCommon.get((u8*)&c(1, 1)[i], 8);
+            b0[i] = (u8)(b(1, 0)[i] & 1);
+            b1[i] = (u8)(b(1, 1)[i] & 1);
+        }
+        SharedOT::recv(m0.data(), h2.data(), b0.data(), r0.data(), n);   /* b*(a0+a2) - c0 - c2 - z */
+        SharedOT::recv(m2.data(), h0.data(), b1.data(), r1.data(), n);   /* b*a1 + z */
+        for (u64 i = 0; i < n; ++i) c(1, 0)[i] = r1[i] + r0[i];
+        memcpy(c(2, 1), c(1, 0), n * 8);                                  /* send c[0] to P2 */
+    }
+}
+
+/* Sh3Evaluator::asyncMul(i64 a, sbMatrix B, si64Matrix C) -- Sh3Evaluator.cpp:418-501 */
+void orc_mul_bit_pub(orc_session* s, i64 aa, const i64* B, i64* C, u64 n) {
+    auto b = [&](int p, int pl) { return (const u64*)plane(B, n, p, pl); };
+    auto c = [&](int p, int pl) { return (u64*)plane(C, n, p, pl); };
+    std::vector<u64> s0(2 * n), mToP1(2 * n), mToP2(2 * n), h1(n), h2(n);
+    std::vector<u8> c1(n), c2(n);
+    for (u64 i = 0; i < n; ++i) {                                         /* party 0 :430-441 */
+        const u64 bb = (b(0, 0)[i] ^ b(0, 1)[i]) & 1;
+        const u64 z = (u64)s->p[0].eval.getShare();
+        s0[2 * i + bb] = z;
+        s0[2 * i + (bb ^ 1)] = (u64)aa + z;
+    }
+    s->p[0].otNextRecver.send(s0.data(), mToP1.data(), n);
+    s->p[0].otPrevRecver.send(s0.data(), mToP2.data(), n);
+    for (u64 i = 0; i < n; ++i) {                                         /* party 1 :455-470 */
+        c(1, 1)[i] = (u64)s->p[1].eval.getShare();
+        c1[i] = (u8)(b(1, 0)[i] & 1);
+    }
+    s->p[1].otNextRecver.help(c1.data(), h1.data(), n);                   /* helps P0 -> P2 */
+    for (u64 i = 0; i < n; ++i) {                                         /* party 2 :476-491 */
+        c(2, 0)[i] = (u64)s->p[2].eval.getShare();
+        c2[i] = (u8)(b(2, 1)[i] & 1);
+    }
+    s->p[2].otPrevRecver.help(c2.data(), h2.data(), n);                   /* helps P0 -> P1 */
+    memcpy(c(0, 0), c(1, 1), n * 8);                                      /* P1 -> P0 */
+    memcpy(c(0, 1), c(2, 0), n * 8);                                      /* P2 -> P0 */
+    SharedOT::recv(mToP1.data(), h2.data(), c1.data(), c(1, 0), n);
+    SharedOT::recv(mToP2.data(), h1.data(), c2.data(), c(2, 1), n);
 }
 
 /* ------------------------------------------------------------------------ */

@@ -77,6 +77,11 @@ void orc_mul_trunc(orc_session*, const int64_t* A, const int64_t* B, int64_t* C,
 void orc_trunc_tuple(orc_session*, int party, uint64_t n, uint64_t d,
                      int64_t* R, int64_t* RT0, int64_t* RT1);
 
+/* Sh3Evaluator::asyncMul(si64Matrix, sbMatrix) / asyncMul(i64, sbMatrix) with SharedOT
+ * (Sh3Evaluator.cpp:119-263, 418-501; aby3/OT/SharedOT.cpp).  B holds ONE bit per row. */
+void orc_mul_bit(orc_session*, const int64_t* A, const int64_t* B, int64_t* C, uint64_t n);
+void orc_mul_bit_pub(orc_session*, int64_t a, const int64_t* B, int64_t* C, uint64_t n);
+
 /* local share arithmetic (Sh3Types.h:805-820): op 0 add, 1 sub, 2 xor */
 void orc_share_op(const int64_t* X, const int64_t* Y, int64_t* Z, uint64_t n, int op);
 

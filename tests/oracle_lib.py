@@ -36,6 +36,8 @@ def _load():
     l.orc_mul.argtypes = [_p, _p, _p, _p, _u64, _u64, _u64, _int, _int]
     l.orc_mul_trunc.argtypes = [_p, _p, _p, _p, _u64, _u64, _u64, _int, _u64, _int]
     l.orc_trunc_tuple.argtypes = [_p, _int, _u64, _u64, _p, _p, _p]
+    l.orc_mul_bit.argtypes = [_p, _p, _p, _p, _u64]
+    l.orc_mul_bit_pub.argtypes = [_p, C.c_int64, _p, _p, _u64]
     l.orc_share_op.argtypes = [_p, _p, _p, _u64, _int]
     l.orc_plain_mul.argtypes = [_p, _p, _p, _u64, _u64, _u64, _int, _int]
     l.orc_cross_term.argtypes = [_p, _p, _p, _p, _p, _u64, _u64, _u64, _int, _int]
@@ -129,6 +131,18 @@ class Session:
         M, K, N = _dims(A, B, mode)
         Cc = np.empty((3, 2, M, N), dtype=np.int64)
         lib.orc_mul_trunc(self.h, ptr(A), ptr(B), ptr(Cc), M, K, N, mode, shift, nthreads)
+        return Cc
+
+    def mul_bit(self, A, B):
+        n = A[0, 0].size
+        Cc = np.empty((3, 2, n, 1), dtype=np.int64)
+        lib.orc_mul_bit(self.h, ptr(np.ascontiguousarray(A)), ptr(np.ascontiguousarray(B)), ptr(Cc), n)
+        return Cc
+
+    def mul_bit_pub(self, a, B):
+        n = B[0, 0].size
+        Cc = np.empty((3, 2, n, 1), dtype=np.int64)
+        lib.orc_mul_bit_pub(self.h, int(a), ptr(np.ascontiguousarray(B)), ptr(Cc), n)
         return Cc
 
     def trunc_tuple(self, party, n, d):

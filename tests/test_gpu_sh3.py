@@ -278,3 +278,27 @@ def test_binary_engine_packed_io_matches_oracle(pair, name, bits, width):
     om = np.int64(-1) if obits == 64 else np.int64((1 << obits) - 1)
     assert np.array_equal(s.get_shares(outs[0], binary=True) & om, outs_o[0] & om)
     assert_cursors(s, r)
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 70001])
+def test_arith_times_shared_bit_matches_oracle(pair, n):
+    """sh3_asyncArithBinMul_test / asyncPubArithBinMul (Sh3EvaluatorTests.cpp:780-1032): c = b*a
+    exactly; every share plane and PRNG / OT cursor position equal to the oracle's."""
+    s, r = pair
+    rng = np.random.default_rng(n)
+    a = rng.integers(-2**63, 2**63, (n, 1), dtype=np.int64)
+    b = rng.integers(0, 2, (n, 1)).astype(np.int64)
+    Bo = r.share_bin(0, b) & 1                       # one-bit sbMatrix: only bit 0 carries data
+    _ = s.share_bin(0, b, 1)                          # keep the encryptor cursors of both sides aligned
+    B = s.set_shares(Bo, binary=True, bit_count=1)
+    A, Ao = s.share_int(1, a), r.share_int(1, a)
+    for _ in range(2):                                # twice: the OT counters and PRNG cursors carry over
+        C = s.mul_bit(A, B)
+        Co = r.mul_bit(Ao, Bo)
+        assert np.array_equal(s.get_shares(C), Co)
+        assert np.array_equal(s.reveal(C, 0), a * b)
+    P = s.mul_bit_pub(-12345, B)
+    Po = r.mul_bit_pub(-12345, Bo)
+    assert np.array_equal(s.get_shares(P), Po)
+    assert np.array_equal(s.reveal(P, 2), -12345 * b)
+    assert_cursors(s, r)

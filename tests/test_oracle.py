@@ -242,3 +242,35 @@ def test_bit_transpose_definition():
         bits_in = np.unpackbits(m.reshape(rows, ins), axis=1, bitorder="little")[:, :cols]
         bits_out = np.unpackbits(t.reshape(cols, outs), axis=1, bitorder="little")[:, :rows]
         assert np.array_equal(bits_out, bits_in.T)
+
+
+def _bit_shares(s, bits):
+    """a one-bit sbMatrix the way the binary engine hands it out: only bit 0 carries data"""
+    sh = s.share_bin(0, bits.reshape(-1, 1).astype(np.int64))
+    return sh & 1
+
+
+def test_sh3_asyncArithBinMul_test():
+    """aby3_tests/Sh3EvaluatorTests.cpp:780-900: c = b * a exactly, and a consistent sharing."""
+    s = o.Session()
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 128, 1000):
+        a = rng.integers(-2**63, 2**63, (n, 1), dtype=np.int64)
+        b = rng.integers(0, 2, n)
+        A, B = s.share_int(0, a), _bit_shares(s, b)
+        Cs = s.mul_bit(A, B)
+        for p in range(3):
+            assert np.array_equal(o.reveal(Cs, p), a * b.reshape(n, 1))
+            assert np.array_equal(Cs[(p + 1) % 3, 1], Cs[p, 0])
+
+
+def test_sh3_asyncPubArithBinMul_test():
+    """Sh3EvaluatorTests.cpp:903-1032: c = b * a for a public constant a."""
+    s = o.Session()
+    rng = np.random.default_rng(4)
+    for n, a in ((5, 3), (300, -77), (64, 1 << 40)):
+        b = rng.integers(0, 2, n)
+        Cs = s.mul_bit_pub(a, _bit_shares(s, b))
+        for p in range(3):
+            assert np.array_equal(o.reveal(Cs, p).reshape(n), a * b)
+            assert np.array_equal(Cs[(p + 1) % 3, 1], Cs[p, 0])
