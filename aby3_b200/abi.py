@@ -78,6 +78,7 @@ PROTOTYPES = {
     "aby3cu_bitmul_pub_msgs": (_int, [_p, C.c_int64, _p, _p, _key, _key, _u64, _p, _sz]),
     "aby3cu_share_op": (_int, [_p, _int, _p, _p, _p, _sz]),
     "aby3cu_combine3": (_int, [_p, _int, _p, _p, _p, _p, _sz]),
+    "aby3cu_axpb": (_int, [_p, C.c_int64, _p, C.c_int64, _p, _sz]),
     "aby3cu_transpose_i64": (_int, [_p, _p, _u64, _u64, _p]),
     "aby3cu_gather_rows": (_int, [_p, _p, _u64, _p, _u64, _p]),
     "aby3cu_bin_row_bytes": (_u64, [_u64]),

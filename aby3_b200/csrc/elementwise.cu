@@ -192,6 +192,19 @@ __global__ void __launch_bounds__(kThreads) k_combine3(const i64* __restrict__ x
     }
 }
 
+// out = a * x + b (wrapping); x may be NULL (constant fill)
+__global__ void __launch_bounds__(kThreads) k_axpb(u64 a, const i64* __restrict__ x, u64 b, i64* __restrict__ out, size_t n, int vec) {
+    const size_t pairs = (n + 1) / 2;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = 2 * p;
+        const bool v2 = vec && i + 1 < n;
+        U64x2 v = {0, 0};
+        if (x) v = ld2(x, i, n, v2);
+        U64x2 o = {a * v.a + b, a * v.b + b};
+        st2(out, i, n, v2, o);
+    }
+}
+
 // 32x32 tile transpose of 8-byte elements through padded shared memory
 __global__ void __launch_bounds__(256) k_transpose(const i64* __restrict__ in, u64 rows, u64 cols, i64* __restrict__ out) {
     __shared__ i64 tile[32][33];
@@ -380,6 +393,16 @@ int aby3cu_combine3(aby3cu_ctx* ctx, int op, const i64* x0, const i64* x1, const
     if (op == ABY3CU_OP_ADD) k_combine3<ABY3CU_OP_ADD><<<grid, kThreads, 0, ctx->stream>>>(x0, x1, x2, out, n, vec);
     else k_combine3<ABY3CU_OP_XOR><<<grid, kThreads, 0, ctx->stream>>>(x0, x1, x2, out, n, vec);
     return post_launch(ctx, "k_combine3");
+}
+
+int aby3cu_axpb(aby3cu_ctx* ctx, i64 a, const i64* x, i64 b, i64* out, size_t n) {
+    ABY3CU_REQUIRE(ctx && (out || !n), "axpb: null argument");
+    if (!n) return 0;
+    DeviceGuard g(ctx->device);
+    const int vec = al16(out) && (!x || al16(x));
+    const unsigned grid = ew_grid(ctx, (n + 1) / 2, kThreads, 8);
+    k_axpb<<<grid, kThreads, 0, ctx->stream>>>((u64)a, x, (u64)b, out, n, vec);
+    return post_launch(ctx, "k_axpb");
 }
 
 int aby3cu_transpose_i64(aby3cu_ctx* ctx, const i64* in, u64 rows, u64 cols, i64* out) {

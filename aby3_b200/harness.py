@@ -38,6 +38,7 @@ def _load():
     l.sh3h_free.argtypes = [p, i32]
     l.sh3h_mul.argtypes = [p, i32, i32, i64, i32]
     l.sh3h_addsub.argtypes = [p, i32, i32, i32]
+    l.sh3h_piecewise.argtypes = [p, i32, p, i32, p, p, p, p, u64]
     l.sh3h_mul_bit.argtypes = [p, i32, i32, i32, i64]
     l.sh3h_reveal.argtypes = [p, i32, i32, i32, p]
     l.sh3h_trunc_tuple.argtypes = [p, i32, u64, u64, u64, p, p, p]
@@ -173,6 +174,18 @@ class Session:
     def mul_bit_pub(self, a_const, b):
         """c = b * a for a public constant a (asyncMul(i64, sbMatrix))."""
         return self._id(lib.sh3h_mul_bit(self.h, 0, b, 1, int(a_const)))
+
+    def piecewise(self, x, thresholds, coefficients, D=16):
+        """Sh3Piecewise::eval.  coefficients: one list per region, constant term first; python ints are
+        integer coefficients, floats fixed-point ones (aby3ML::logisticFunc uses
+        thresholds [-0.5, 0.5], coefficients [[], [0.5, 1], [1]])."""
+        th = np.asarray(thresholds, dtype=np.float64)
+        counts = np.asarray([len(c) for c in coefficients], dtype=np.int32)
+        flat = [v for c in coefficients for v in c]
+        is_int = np.asarray([isinstance(v, (int, np.integer)) for v in flat] or [0], dtype=np.int32)
+        ints = np.asarray([int(v) if isinstance(v, (int, np.integer)) else 0 for v in flat] or [0], dtype=np.int64)
+        dbl = np.asarray([float(v) for v in flat] or [0.0], dtype=np.float64)
+        return self._id(lib.sh3h_piecewise(self.h, x, _ptr(th), len(th), _ptr(counts), _ptr(is_int), _ptr(ints), _ptr(dbl), D))
 
     def add(self, a, b):
         return self._id(lib.sh3h_addsub(self.h, a, b, 0))

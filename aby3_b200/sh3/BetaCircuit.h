@@ -90,6 +90,11 @@ public:
         else if (mWireFlags[w] == BetaWireFlag::InvWire) mWireFlags[w] = BetaWireFlag::Wire;
         else throw RTE_LOC;
     }
+    // dst = NOT src: a copy whose reader must complement it (BetaCircuit::addInvert(in, out))
+    void addInvert(BetaWire src, BetaWire dst) {
+        addCopy(src, dst);
+        mWireFlags[dst] = BetaWireFlag::InvWire;
+    }
     bool isInvert(BetaWire w) const { return mWireFlags[w] == BetaWireFlag::InvWire; }
 
     // Order gates by AND depth.  level(g) = max over inputs of (level of the gate
@@ -244,6 +249,31 @@ public:
             cd.addCopy(e[0], c[0]);
         });
     }
+
+    // aby3/Circuit/CircuitLibrary.cpp:38-137: inputs a_0..a_{T-1} (x0+x1 minus threshold t) and b (x2);
+    // region bits: c_0 = [a_0+b < 0], c_t = NOT[a_{t-1}+b < 0] AND [a_t+b < 0], c_T = NOT[a_{T-1}+b < 0].
+    BetaCircuit* int_Sh3Piecewise_helper(u64 size, u64 numThresholds) {
+        return cached("pw" + std::to_string(size) + "_" + std::to_string(numThresholds), [&](BetaCircuit& cd) {
+            std::vector<BetaBundle> aa(numThresholds, BetaBundle(size));
+            for (auto& a : aa) cd.addInputBundle(a);
+            BetaBundle b(size);
+            cd.addInputBundle(b);
+            std::vector<BetaBundle> cc(numThresholds + 1, BetaBundle(1));
+            for (auto& c : cc) cd.addOutputBundle(c);
+            std::vector<BetaWire> th(numThresholds);
+            for (u64 t = 0; t < numThresholds; ++t) {
+                BetaBundle sum(size);
+                cd.addTempWireBundle(sum);
+                prefixAdd(cd, aa[t], b, sum, false);
+                th[t] = sum[size - 1];                        // sign bit of a_t + b
+            }
+            cd.addCopy(th[0], cc[0][0]);
+            for (u64 t = 1; t < numThresholds; ++t) cd.addGate(th[t - 1], th[t], GateType::na_And, cc[t][0]);
+            cd.addInvert(th[numThresholds - 1], cc[numThresholds][0]);
+        });
+    }
+    // aby3/Circuit/CircuitLibrary.cpp:350-394 (int_comp_helper): MSB of a + b
+    BetaCircuit* int_comp_helper(u64 size) { return int_int_add_msb(size); }
 
 private:
     std::map<std::string, BetaCircuit*> mCache;

@@ -14,6 +14,7 @@
 #include "Sh3BinaryEvaluator.h"
 #include "Sh3Encryptor.h"
 #include "Sh3Evaluator.h"
+#include "Sh3Piecewise.h"
 #include "../ml/Regression.h"
 
 using namespace aby3;
@@ -317,6 +318,31 @@ int sh3h_mul_bit(sh3h* h, int a_id, int b_id, int pub, int64_t a_pub) {
     return rc ? -1 : id;
 }
 
+// Sh3Piecewise::eval on an n x 1 fixed-point sharing.  Region r has coef_counts[r] coefficients
+// (constant first); coefficient k is the integer coef_int[k] when coef_is_int[k], else coef_dbl[k].
+int sh3h_piecewise(sh3h* h, int in_id, const double* thresholds, int n_thresholds, const int* coef_counts,
+                   const int* coef_is_int, const int64_t* coef_int, const double* coef_dbl, uint64_t D) {
+    const int id = h->next_handle++;
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        Sh3Piecewise pw;
+        for (int t = 0; t < n_thresholds; ++t) pw.mThresholds.emplace_back(thresholds[t]);
+        int k = 0;
+        pw.mCoefficients.resize(n_thresholds + 1);
+        for (int r = 0; r <= n_thresholds; ++r)
+            for (int c = 0; c < coef_counts[r]; ++c, ++k) {
+                if (coef_is_int[k]) pw.mCoefficients[r].emplace_back((i64)coef_int[k]);
+                else pw.mCoefficients[r].emplace_back(coef_dbl[k]);
+            }
+        auto& in = *P.ints.at(in_id);
+        auto out = std::make_unique<si64Matrix>(in.rows(), 1);
+        pw.eval(P.rt.noDependencies(), in, *out, D, P.eval).get();
+        P.ints[id] = std::move(out);
+        P.ctx->sync();
+    });
+    return rc ? -1 : id;
+}
+
 // C = A + B / A - B on shares (local)
 int sh3h_addsub(sh3h* h, int a, int b, int sub) {
     const int id = h->next_handle++;
@@ -525,6 +551,7 @@ sh3h_circuit* sh3h_circuit_build(const char* name, uint32_t bits) {
         else if (n == "add_msb") c->cir = c->lib.int_int_add_msb(bits);
         else if (n == "lt") c->cir = c->lib.int_int_lt(bits, bits);
         else if (n == "eq") c->cir = c->lib.int_eq(bits);
+        else if (n.rfind("piecewise", 0) == 0) c->cir = c->lib.int_Sh3Piecewise_helper(bits, std::stoul(n.substr(9)));
         else { g_err = "unknown circuit " + n; return nullptr; }
         return c.release();
     } catch (const std::exception& e) { g_err = e.what(); return nullptr; }

@@ -155,6 +155,9 @@ int aby3cu_share_op(aby3cu_ctx* ctx, int op, const int64_t* d_x, const int64_t* 
 /* out = x0 op x1 op x2 (reveal: Sh3Encryptor.cpp:497-536), op ADD or XOR */
 int aby3cu_combine3(aby3cu_ctx* ctx, int op, const int64_t* d_x0, const int64_t* d_x1, const int64_t* d_x2,
                     int64_t* d_out, size_t n);
+/* out = a * x + b element-wise (wrapping); x == NULL fills out with b.  Local affine maps of
+ * Sh3Piecewise::getFunctionValues / threshold shifts (Sh3Piecewise.cpp:441-451, 541-563). */
+int aby3cu_axpb(aby3cu_ctx* ctx, int64_t a, const int64_t* d_x, int64_t b, int64_t* d_out, size_t n);
 /* row-major transpose of an int64 matrix (sMatrix::transpose, Sh3Types.h:822-838) */
 int aby3cu_transpose_i64(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t rows, uint64_t cols, int64_t* d_out);
 /* gather rows: out[r,:] = in[idx[r],:]  (extractBatch, aby3-ML/Regression.h:43-58) */

@@ -302,3 +302,20 @@ def test_arith_times_shared_bit_matches_oracle(pair, n):
     assert np.array_equal(s.get_shares(P), Po)
     assert np.array_equal(s.reveal(P, 2), -12345 * b)
     assert_cursors(s, r)
+
+
+def test_piecewise_logistic_matches_oracle(pair):
+    """aby3ML::logisticFunc (aby3ML.h:121-139) through Sh3Piecewise on the device: every share plane
+    equal to the oracle's, reveal equal to the plaintext piecewise function."""
+    import piecewise_ref as pw
+    s, r = pair
+    D, n = 16, 5000
+    rng = np.random.default_rng(2)
+    x = (rng.uniform(-2, 2, (n, 1)) * (1 << D)).astype(np.int64)
+    th, coef = [-0.5, 0.5], [[], [0.5, 1], [1]]
+    X, Xo = s.share_int(0, x), r.share_int(0, x)
+    out = s.piecewise(X, th, coef, D)
+    outo = pw.shared(r, Xo, th, coef, D, harness.library_circuit("piecewise2", 64))
+    assert np.array_equal(s.get_shares(out), outo)
+    assert np.array_equal(s.reveal(out, 1), pw.plain(x, th, coef, D))
+    assert_cursors(s, r)

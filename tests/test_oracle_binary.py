@@ -99,3 +99,34 @@ def test_and_gate_mask_is_the_documented_keystream():
             out_wire = int(cir["gates"][4 * g + 2])
             exp = o.keystream(kp, g * rb, rb) ^ o.keystream(kn, g * rb, rb)
             assert np.array_equal(mem[p, 0, out_wire], exp)
+
+
+def test_piecewise_logistic_on_oracle():
+    """aby3-ML's logistic approximation (aby3ML.h:121-139): f(x) = 0 | x + 0.5 | 1 on the oracle,
+    exact against the plaintext evaluator (Sh3_Piecewise_plain_test semantics)."""
+    import piecewise_ref as pw
+    D, n = 16, 300
+    rng = np.random.default_rng(0)
+    x = (rng.uniform(-2, 2, (n, 1)) * (1 << D)).astype(np.int64)
+    x[:4, 0] = [-(1 << 15), (1 << 15), -(1 << 15) - 1, (1 << 15) - 1]      # on and next to the thresholds
+    th, coef = [-0.5, 0.5], [[], [0.5, 1], [1]]
+    s = o.Session()
+    X = s.share_int(0, x)
+    cir = harness.library_circuit("piecewise2", 64)
+    out = pw.shared(s, X, th, coef, D, cir)
+    exp = pw.plain(x, th, coef, D)
+    xf = x.astype(np.float64) / (1 << D)
+    assert np.array_equal(exp.reshape(-1), (np.clip(xf + 0.5, 0, 1) * (1 << D)).astype(np.int64).reshape(-1))
+    for p in range(3):
+        assert np.array_equal(o.reveal(out, p), exp)
+        assert np.array_equal(out[(p + 1) % 3, 1], out[p, 0])
+
+
+def test_piecewise_relu_on_oracle():
+    """Sh3PiecewiseTests.cpp:13-80: max(0, x) as a one-threshold piecewise function."""
+    import piecewise_ref as pw
+    D, n = 16, 100
+    x = (np.random.default_rng(1).uniform(-5, 5, (n, 1)) * (1 << D)).astype(np.int64)
+    s = o.Session()
+    out = pw.shared(s, s.share_int(1, x), [0], [[], [0, 1]], D, harness.library_circuit("piecewise1", 64))
+    assert np.array_equal(o.reveal(out, 0), np.maximum(x, 0))
