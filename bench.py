@@ -210,6 +210,53 @@ def linreg_bench(sess, samples, features=1024, batch=128, iters=300, lr=2.0 ** -
     return out
 
 
+def logistic_bench(sess, rows, features=512, reps=3):
+    """BASELINE configs[3]: aby3-ML logistic-regression inference with the piecewise sigmoid:
+    y = logisticFunc(X * W), X rows x 512, sf64<D16> (aby3-ML/aby3ML.h:102-139).  One pass =
+    the truncating 3-party product (skinny GEMV, HBM-bound on X), the region circuit
+    (two 64-bit MSB-of-sum adders + one na_And, bit-sliced), two bit x arithmetic products."""
+    rng = np.random.default_rng(13)
+    pid, xv = sess.plain(0, rows, features)
+    step = 1 << 14
+    for r0 in range(0, rows, step):
+        xv[r0:r0 + step] = (rng.uniform(-1.0, 1.0, (min(step, rows - r0), features)) * (1 << SHIFT)).astype(np.int64)
+    w = (rng.uniform(-0.1, 0.1, (features, 1)) * (1 << SHIFT)).astype(np.int64)
+    X = sess.share_plain(0, pid, rows, features)
+    sess.free(pid)
+    W = sess.share_int(0, w)
+    th, coef = [-0.5, 0.5], [[], [0.5, 1], [1]]
+
+    def once():
+        z = sess.mul(X, W, shift=SHIFT)
+        y = sess.piecewise(z, th, coef, SHIFT)
+        return z, y
+
+    z, y = once()
+    # sanity on a sample of rows: exact piecewise function of the revealed linear part
+    zr, yr = sess.reveal(z, 0), sess.reveal(y, 0)
+    exp = np.where(zr < -(1 << (SHIFT - 1)), 0, np.where(zr < (1 << (SHIFT - 1)), zr + (1 << (SHIFT - 1)), 1 << SHIFT))
+    ok = bool(np.array_equal(yr, exp))
+    for h in (z, y):
+        sess.free(h)
+    sess.sync()
+    l0 = sess.launches
+    sess.timer_begin()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        z, y = once()
+        sess.free(z)
+        sess.free(y)
+    ms = sess.timer_end()
+    wall = time.perf_counter() - t0
+    out = {"rows_per_s": rows * reps / (ms * 1e-3), "rows": rows, "features": features, "ms_per_pass": ms / reps,
+           "wall_ms_per_pass": wall * 1e3 / reps, "kernel_launches_per_pass": (sess.launches - l0) / reps,
+           "output_matches_plain_piecewise": ok, "decimal": "D16",
+           "timing": "CUDA events across the three party streams"}
+    for h in (X, W):
+        sess.free(h)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -220,6 +267,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--linreg-samples", type=int, default=1 << 20)
     ap.add_argument("--no-linreg", action="store_true")
+    ap.add_argument("--logistic-rows", type=int, default=1 << 21)
+    ap.add_argument("--no-logistic", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -313,6 +362,12 @@ def main():
             linreg = linreg_bench(sess, args.linreg_samples)
         except Exception as e:
             linreg = {"error": str(e)}
+    logistic = None
+    if rank == 0 and not args.no_logistic:
+        try:
+            logistic = logistic_bench(sess, args.logistic_rows)
+        except Exception as e:
+            logistic = {"error": str(e)}
     sess.close()
 
     if rank == 0:
@@ -332,6 +387,7 @@ def main():
                     "path": "enc.localIntMatrix(host a,b) -> eval.asyncMul(..., shift) -> enc.revealAll -> host c"},
             "gpu_launches": launches,
             "linreg": linreg,
+            "logistic_inference": logistic,
         }
         try:
             line["roofline"] = gemm_roofline(local)
