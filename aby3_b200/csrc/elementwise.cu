@@ -236,6 +236,21 @@ __global__ void __launch_bounds__(256) k_gather_rows(const i64* __restrict__ in,
     }
 }
 
+// out[idx[r],:] = in[r,:]
+__global__ void __launch_bounds__(256) k_scatter_rows(const i64* __restrict__ in, u64 cols, const u64* __restrict__ idx, u64 nrows, i64* __restrict__ out) {
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (cols == 1) {
+        for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (u64)gridDim.x * blockDim.x) out[idx[r]] = in[r];
+        return;
+    }
+    for (u64 r = warp; r < nrows; r += nwarps) {
+        const i64* src = in + r * cols;
+        i64* dst = out + idx[r] * cols;
+        for (u64 c = lane; c < cols; c += 32) dst[c] = src[c];
+    }
+}
+
 }  // namespace
 
 int upload_aes_constants() {
@@ -413,6 +428,15 @@ int aby3cu_transpose_i64(aby3cu_ctx* ctx, const i64* in, u64 rows, u64 cols, i64
     const unsigned grid = (unsigned)(tiles < (u64)ctx->sm_count * 8 ? tiles : (u64)ctx->sm_count * 8);
     k_transpose<<<grid, 256, 0, ctx->stream>>>(in, rows, cols, out);
     return post_launch(ctx, "k_transpose");
+}
+
+int aby3cu_scatter_rows(aby3cu_ctx* ctx, const i64* in, u64 cols, const u64* idx, u64 nrows, i64* out) {
+    ABY3CU_REQUIRE(ctx && ((in && idx && out) || !(nrows * cols)), "scatter_rows: null argument");
+    if (!(nrows * cols)) return 0;
+    DeviceGuard g(ctx->device);
+    const unsigned grid = ew_grid(ctx, cols == 1 ? nrows : nrows * 32, 256, 8);
+    k_scatter_rows<<<grid, 256, 0, ctx->stream>>>(in, cols, idx, nrows, out);
+    return post_launch(ctx, "k_scatter_rows");
 }
 
 int aby3cu_gather_rows(aby3cu_ctx* ctx, const i64* in, u64 cols, const u64* idx, u64 nrows, i64* out) {

@@ -38,6 +38,9 @@ def _load():
     l.sh3h_free.argtypes = [p, i32]
     l.sh3h_mul.argtypes = [p, i32, i32, i64, i32]
     l.sh3h_addsub.argtypes = [p, i32, i32, i32]
+    l.sh3h_cipher_gt.argtypes = [p, i32, i32]
+    l.sh3h_max_min_split.argtypes = [p, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    l.sh3h_odd_even_merge.argtypes = [p, i32, i32]
     l.sh3h_piecewise.argtypes = [p, i32, p, i32, p, p, p, p, u64]
     l.sh3h_mul_bit.argtypes = [p, i32, i32, i32, i64]
     l.sh3h_reveal.argtypes = [p, i32, i32, i32, p]
@@ -186,6 +189,20 @@ class Session:
         ints = np.asarray([int(v) if isinstance(v, (int, np.integer)) else 0 for v in flat] or [0], dtype=np.int64)
         dbl = np.asarray([float(v) for v in flat] or [0.0], dtype=np.float64)
         return self._id(lib.sh3h_piecewise(self.h, x, _ptr(th), len(th), _ptr(counts), _ptr(is_int), _ptr(ints), _ptr(dbl), D))
+
+    def cipher_gt(self, a, b):
+        """aby3-Basic cipher_gt: one-bit binary sharing of (a > b) for arithmetic sharings a, b."""
+        return self._id(lib.sh3h_cipher_gt(self.h, a, b))
+
+    def max_min_split(self, a, b):
+        """aby3-Basic bool_cipher_max_min_split on binary sharings of 64-bit values -> (max, min)."""
+        mx, mn = C.c_int(0), C.c_int(0)
+        self._chk(lib.sh3h_max_min_split(self.h, a, b, C.byref(mx), C.byref(mn)))
+        return mx.value, mn.value
+
+    def odd_even_merge(self, a, b):
+        """aby3-Basic odd_even_merge of two sorted binary sharings."""
+        return self._id(lib.sh3h_odd_even_merge(self.h, a, b))
 
     def add(self, a, b):
         return self._id(lib.sh3h_addsub(self.h, a, b, 0))

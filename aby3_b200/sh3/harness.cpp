@@ -15,6 +15,7 @@
 #include "Sh3Encryptor.h"
 #include "Sh3Evaluator.h"
 #include "Sh3Piecewise.h"
+#include "../basic/Basics.h"
 #include "../ml/Regression.h"
 
 using namespace aby3;
@@ -339,6 +340,42 @@ int sh3h_piecewise(sh3h* h, int in_id, const double* thresholds, int n_threshold
         pw.eval(P.rt.noDependencies(), in, *out, D, P.eval).get();
         P.ints[id] = std::move(out);
         P.ctx->sync();
+    });
+    return rc ? -1 : id;
+}
+
+// ---- aby3-Basic building blocks (basic/Basics.h) -----------------------------------
+// res = (A > B) on arithmetic sharings: cipher_gt (BuildingBlocks.cpp:525-532)
+int sh3h_cipher_gt(sh3h* h, int a_id, int b_id) {
+    const int id = h->next_handle++;
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        auto m = std::make_unique<sbMatrix>();
+        basic::cipher_gt(i, *P.ints.at(a_id), *P.ints.at(b_id), *m, P.eval, P.rt);
+        P.bins[id] = std::move(m);
+    });
+    return rc ? -1 : id;
+}
+// (max, min) of two binary sharings of 64-bit values: bool_cipher_max_min_split (BoolBasic.cpp:275-312)
+int sh3h_max_min_split(sh3h* h, int a_id, int b_id, int* max_id, int* min_id) {
+    *max_id = h->next_handle++;
+    *min_id = h->next_handle++;
+    return h->run([&](int i) {
+        Party& P = h->p[i];
+        auto mx = std::make_unique<sbMatrix>(), mn = std::make_unique<sbMatrix>();
+        basic::bool_cipher_max_min_split(i, *P.bins.at(a_id), *P.bins.at(b_id), *mx, *mn, P.enc, P.eval, P.rt);
+        P.bins[*max_id] = std::move(mx);
+        P.bins[*min_id] = std::move(mn);
+    });
+}
+// odd_even_merge of two sorted binary sharings (Sort.cpp:327-406)
+int sh3h_odd_even_merge(sh3h* h, int a_id, int b_id) {
+    const int id = h->next_handle++;
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        auto m = std::make_unique<sbMatrix>();
+        basic::odd_even_merge(*P.bins.at(a_id), *P.bins.at(b_id), *m, i, P.enc, P.eval, P.rt);
+        P.bins[id] = std::move(m);
     });
     return rc ? -1 : id;
 }

@@ -257,6 +257,49 @@ def logistic_bench(sess, rows, features=512, reps=3):
     return out
 
 
+def basic_bench(sess, n):
+    """BASELINE configs[4]: aby3-Basic greater-than and odd-even merge over secret-shared int64
+    elements (Sh3BinaryEvaluator AND-layer throughput).  (i) cipher_gt on two vectors of n elements
+    (MSB-of-sum circuit, 64-bit prefix adder); (ii) odd_even_merge of two sorted runs of n/2
+    elements: ceil(log2(n/2)) + 1 compare-exchange stages, each one int_int_lt(64) circuit plus two
+    bitwiseAnd(64) circuits (BoolBasic.cpp:275-312, Sort.cpp:327-406)."""
+    rng = np.random.default_rng(17)
+    a = rng.integers(-2**62, 2**62, (n, 1), dtype=np.int64)
+    b = rng.integers(-2**62, 2**62, (n, 1), dtype=np.int64)
+    A, B = sess.share_int(0, a), sess.share_int(0, b)
+    gt = sess.cipher_gt(A, B)
+    ok_gt = bool(np.array_equal(sess.reveal(gt, 0, binary=True) & 1, (a > b).astype(np.int64)))
+    sess.free(gt)
+    sess.sync()
+    l0 = sess.launches
+    sess.timer_begin()
+    gt = sess.cipher_gt(A, B)
+    ms_gt = sess.timer_end()
+    l_gt = sess.launches - l0
+    for h in (gt, A, B):
+        sess.free(h)
+    half = n // 2
+    d1 = np.sort(a[:half, 0]).reshape(-1, 1)
+    d2 = np.sort(b[:half, 0]).reshape(-1, 1)
+    D1, D2 = sess.share_bin(0, d1, 64), sess.share_bin(0, d2, 64)
+    sess.sync()
+    l0 = sess.launches
+    sess.timer_begin()
+    t0 = time.perf_counter()
+    m = sess.odd_even_merge(D1, D2)
+    ms_merge = sess.timer_end()
+    wall = time.perf_counter() - t0
+    l_merge = sess.launches - l0
+    merged = sess.reveal(m, 0, binary=True).reshape(-1)
+    ok_merge = bool(np.all(np.diff(merged) >= 0)) and merged.size == 2 * half
+    for h in (m, D1, D2):
+        sess.free(h)
+    return {"elements": n, "gt_elements_per_s": n / (ms_gt * 1e-3), "gt_ms": ms_gt, "gt_kernel_launches": l_gt, "gt_correct": ok_gt,
+            "merge_elements_per_s": 2 * half / (ms_merge * 1e-3), "merge_ms": ms_merge, "merge_wall_ms": wall * 1e3,
+            "merge_kernel_launches": l_merge, "merge_sorted": ok_merge,
+            "timing": "CUDA events across the three party streams"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -269,6 +312,8 @@ def main():
     ap.add_argument("--no-linreg", action="store_true")
     ap.add_argument("--logistic-rows", type=int, default=1 << 21)
     ap.add_argument("--no-logistic", action="store_true")
+    ap.add_argument("--basic-elements", type=int, default=1 << 22)
+    ap.add_argument("--no-basic", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -368,6 +413,12 @@ def main():
             logistic = logistic_bench(sess, args.logistic_rows)
         except Exception as e:
             logistic = {"error": str(e)}
+    basic = None
+    if rank == 0 and not args.no_basic:
+        try:
+            basic = basic_bench(sess, args.basic_elements)
+        except Exception as e:
+            basic = {"error": str(e)}
     sess.close()
 
     if rank == 0:
@@ -388,6 +439,7 @@ def main():
             "gpu_launches": launches,
             "linreg": linreg,
             "logistic_inference": logistic,
+            "gt_and_merge": basic,
         }
         try:
             line["roofline"] = gemm_roofline(local)

@@ -164,6 +164,11 @@ int aby3cu_transpose_i64(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t rows, ui
 int aby3cu_gather_rows(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t cols, const uint64_t* d_idx,
                        uint64_t nrows, int64_t* d_out);
 
+/* scatter rows: out[idx[r],:] = in[r,:]  (compare-exchange write-back of aby3-Basic's
+ * odd_even_merge, aby3-Basic/Sort.cpp:388-393) */
+int aby3cu_scatter_rows(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t cols, const uint64_t* d_idx,
+                        uint64_t nrows, int64_t* d_out);
+
 /* ---- binary engine: Sh3BinaryEvaluator ----------------------------------------- */
 /* row stride (bytes) of the bit-sliced wire memory for `width` instances
  * (mMem.reset(width, wires, 8) with 256-bit blocks, Sh3BinaryEvaluator.cpp:84). */

@@ -319,3 +319,37 @@ def test_piecewise_logistic_matches_oracle(pair):
     assert np.array_equal(s.get_shares(out), outo)
     assert np.array_equal(s.reveal(out, 1), pw.plain(x, th, coef, D))
     assert_cursors(s, r)
+
+
+def test_basic_blocks_match_oracle(pair):
+    """aby3-Basic on the device (basic/Basics.h): cipher_gt, bool_cipher_max_min_split and
+    odd_even_merge (50 + 98 elements, SortTest.cpp:363) -- shares bit-exact against the same
+    compositions on the oracle, reveals against plaintext."""
+    import basic_ref as br
+    s, r = pair
+    rng = np.random.default_rng(0)
+    n = 1000
+    a, b = rng.integers(-2**62, 2**62, (n, 1), dtype=np.int64), rng.integers(-2**62, 2**62, (n, 1), dtype=np.int64)
+    A, B = s.share_int(0, a), s.share_int(1, b)
+    Ao, Bo = r.share_int(0, a), r.share_int(1, b)
+    gt = s.cipher_gt(A, B)
+    gto = br.cipher_gt(r, Ao, Bo)
+    assert np.array_equal(s.get_shares(gt, binary=True) & 1, gto & 1)
+    assert np.array_equal(s.reveal(gt, 0, binary=True) & 1, (a > b).astype(np.int64))
+    X, Y = s.share_bin(0, a, 64), s.share_bin(2, b, 64)
+    Xo, Yo = r.share_bin(0, a), r.share_bin(2, b)
+    mx, mn = s.max_min_split(X, Y)
+    mxo, mno = br.max_min_split(r, Xo, Yo)
+    assert np.array_equal(s.get_shares(mx, binary=True), mxo)
+    assert np.array_equal(s.get_shares(mn, binary=True), mno)
+    assert np.array_equal(s.reveal(mx, 1, binary=True), np.maximum(a, b))
+    d1 = np.sort(rng.integers(-2**40, 2**40, 50)).reshape(-1, 1).astype(np.int64)
+    d2 = np.sort(rng.integers(-2**40, 2**40, 98)).reshape(-1, 1).astype(np.int64)
+    D1, D2 = s.share_bin(0, d1, 64), s.share_bin(0, d2, 64)
+    D1o, D2o = r.share_bin(0, d1), r.share_bin(0, d2)
+    m = s.odd_even_merge(D1, D2)
+    mo = br.odd_even_merge(r, D1o, D2o)
+    assert np.array_equal(s.get_shares(m, binary=True), mo)
+    got = s.reveal(m, 0, binary=True).reshape(-1)
+    assert np.array_equal(got, np.sort(np.concatenate([d1, d2]).reshape(-1)))
+    assert_cursors(s, r)

@@ -130,3 +130,27 @@ def test_piecewise_relu_on_oracle():
     s = o.Session()
     out = pw.shared(s, s.share_int(1, x), [0], [[], [0, 1]], D, harness.library_circuit("piecewise1", 64))
     assert np.array_equal(o.reveal(out, 0), np.maximum(x, 0))
+
+
+def test_basic_blocks_on_oracle():
+    """aby3_tests/Test.cpp / BoolTest.cpp / SortTest.cpp semantics on the oracle: gt, max/min split,
+    odd-even merge of two sorted runs (50 + 98 elements as in SortTest.cpp:363)."""
+    import basic_ref as br
+    rng = np.random.default_rng(0)
+    s = o.Session()
+    n = 16
+    a = np.arange(n, dtype=np.int64).reshape(n, 1)
+    b = (n - np.arange(n, dtype=np.int64)).reshape(n, 1)
+    gt = br.cipher_gt(s, s.share_int(0, a), s.share_int(0, b))
+    assert np.array_equal(o.reveal(gt, 0, binary=True) & 1, (a > b).astype(np.int64))
+    x = rng.integers(-2**62, 2**62, (40, 1), dtype=np.int64)
+    y = rng.integers(-2**62, 2**62, (40, 1), dtype=np.int64)
+    mx, mn = br.max_min_split(s, s.share_bin(0, x), s.share_bin(1, y))
+    assert np.array_equal(o.reveal(mx, 0, binary=True), np.maximum(x, y))
+    assert np.array_equal(o.reveal(mn, 2, binary=True), np.minimum(x, y))
+    d1 = np.sort(rng.integers(-2**40, 2**40, 50)).reshape(-1, 1).astype(np.int64)
+    d2 = np.sort(rng.integers(-2**40, 2**40, 98)).reshape(-1, 1).astype(np.int64)
+    merged = br.odd_even_merge(s, s.share_bin(0, d1), s.share_bin(0, d2))
+    got = o.reveal(merged, 1, binary=True).reshape(-1)
+    assert sorted(got.tolist()) == sorted(np.concatenate([d1, d2]).reshape(-1).tolist())
+    assert np.all(np.diff(got) >= 0), "the merge network of Sort.cpp:327-406 must sort two sorted runs"
