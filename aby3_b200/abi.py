@@ -81,6 +81,7 @@ PROTOTYPES = {
     "aby3cu_axpb": (_int, [_p, C.c_int64, _p, C.c_int64, _p, _sz]),
     "aby3cu_transpose_i64": (_int, [_p, _p, _u64, _u64, _p]),
     "aby3cu_gather_rows": (_int, [_p, _p, _u64, _p, _u64, _p]),
+    "aby3cu_iota_u64": (_int, [_p, _u64, _u64, _p, _sz]),
     "aby3cu_scatter_rows": (_int, [_p, _p, _u64, _p, _u64, _p]),
     "aby3cu_bin_row_bytes": (_u64, [_u64]),
     "aby3cu_bit_transpose": (_int, [_p, _p, _u64, _u64, _u64, _p, _u64, _p]),

@@ -150,16 +150,13 @@ inline int odd_even_merge(sbMatrix& data1, sbMatrix& data2, sbMatrix& res, int p
         gpu::check(aby3cu_d2d(ctx->h(), max2.mShares[s].devOut(), ctx->device(), data2.mShares[s].dev() + (l2 - 1), ctx->device(), 8));
     }
     bool_cipher_max(pIdx, max1, max2, maxEle, enc, eval, rt);
-    auto upload = [&](const std::vector<u64>& v) {
-        gpu::Buffer b(ctx, std::max<size_t>(v.size() * 8, 16));
-        gpu::check(aby3cu_h2d(ctx->h(), b.ptr(), v.data(), v.size() * 8));
-        ctx->sync();
+    // index vectors are arithmetic progressions: built on the device
+    auto iota = [&](u64 start, u64 step, u64 n) {
+        gpu::Buffer b(ctx, std::max<size_t>(n * 8, 16));
+        gpu::check(aby3cu_iota_u64(ctx->h(), start, step, (u64*)b.ptr(), n));
         return b;
     };
-    std::vector<u64> even(l1), odd(l2);
-    for (u64 i = 0; i < l1; ++i) even[i] = 2 * i;
-    for (u64 i = 0; i < l2; ++i) odd[i] = 2 * i + 1;
-    gpu::Buffer dEven = upload(even), dOdd = upload(odd);
+    gpu::Buffer dEven = iota(0, 2, l1), dOdd = iota(1, 2, l2);
     for (int s = 0; s < 2; ++s) {
         const i64 pad = maxEle.mShares[s](0, 0);
         i64* r = result.mShares[s].devOut();
@@ -170,11 +167,10 @@ inline int odd_even_merge(sbMatrix& data1, sbMatrix& data2, sbMatrix& res, int p
     u64 t = (u64)std::ceil(std::log2((double)length) + 1);
     u64 q = (u64)1 << (t - 1), d = 1, r0 = 0;
     while (d > 0) {
-        std::vector<u64> xm, ym;
-        for (u64 i = r0; i + d < length * 2; i += 2) { xm.push_back(i); ym.push_back(i + d); }
-        if (!xm.empty()) {
-            gpu::Buffer dX = upload(xm), dY = upload(ym);
-            const u64 m = xm.size();
+        // compare positions i and i + d for i = r0, r0 + 2, ... < 2*length - d   (:366-371)
+        const u64 m = (length * 2 > r0 + d) ? (length * 2 - d - r0 + 1) / 2 : 0;
+        if (m) {
+            gpu::Buffer dX = iota(r0, 2, m), dY = iota(r0 + d, 2, m);
             sbMatrix X(m, BITSIZE), Y(m, BITSIZE), mx, mn;
             for (int s = 0; s < 2; ++s) {
                 gpu::check(aby3cu_gather_rows(ctx->h(), result.mShares[s].dev(), 1, (const u64*)dX.ptr(), m, X.mShares[s].devOut()));

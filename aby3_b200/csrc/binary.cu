@@ -230,23 +230,27 @@ __global__ void __launch_bounds__(256) k_bin_level(const uint4* __restrict__ gat
 template <int VEC, bool PACK>
 __global__ void __launch_bounds__(256) k_bin_rows(u8* mem, u64 row_bytes, const u32* __restrict__ locs, u32 n_locs, u64 nbytes, u8* buf,
                                                   const u8* __restrict__ invert) {
-    const u64 per = nbytes / VEC, total = per * n_locs;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
-        const u64 j = i / per, o = (i % per) * VEC;
-        u8* m = mem + (u64)locs[j] * row_bytes + o;
-        u8* b = buf + j * nbytes + o;
+    // blockIdx.y walks the rows, blockIdx.x / threadIdx.x the row's VEC-byte pieces (no 64-bit divisions)
+    const u64 per = nbytes / VEC;
+    for (u32 j = blockIdx.y; j < n_locs; j += gridDim.y) {
+        u8* mrow = mem + (u64)locs[j] * row_bytes;
+        u8* brow = buf + (u64)j * nbytes;
         const bool inv = PACK && invert && invert[j];
-        if (VEC == 16) {
-            if (PACK) {
-                uint4 v = *reinterpret_cast<const uint4*>(m);
-                if (inv) { v.x = ~v.x; v.y = ~v.y; v.z = ~v.z; v.w = ~v.w; }
-                *reinterpret_cast<uint4*>(b) = v;
-            } else *reinterpret_cast<uint4*>(m) = *reinterpret_cast<const uint4*>(b);
-        } else if (VEC == 8) {
-            if (PACK) { u64 v = *reinterpret_cast<const u64*>(m); *reinterpret_cast<u64*>(b) = inv ? ~v : v; }
-            else *reinterpret_cast<u64*>(m) = *reinterpret_cast<const u64*>(b);
-        } else {
-            if (PACK) *b = inv ? (u8)~*m : *m; else *m = *b;
+        for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < per; c += (u64)gridDim.x * blockDim.x) {
+            u8* m = mrow + c * VEC;
+            u8* b = brow + c * VEC;
+            if (VEC == 16) {
+                if (PACK) {
+                    uint4 v = *reinterpret_cast<const uint4*>(m);
+                    if (inv) { v.x = ~v.x; v.y = ~v.y; v.z = ~v.z; v.w = ~v.w; }
+                    *reinterpret_cast<uint4*>(b) = v;
+                } else *reinterpret_cast<uint4*>(m) = *reinterpret_cast<const uint4*>(b);
+            } else if (VEC == 8) {
+                if (PACK) { u64 v = *reinterpret_cast<const u64*>(m); *reinterpret_cast<u64*>(b) = inv ? ~v : v; }
+                else *reinterpret_cast<u64*>(m) = *reinterpret_cast<const u64*>(b);
+            } else {
+                if (PACK) *b = inv ? (u8)~*m : *m; else *m = *b;
+            }
         }
     }
 }
@@ -342,8 +346,10 @@ static int rows_copy(aby3cu_ctx* ctx, bool pack, void* mem, u64 row_bytes, const
     DeviceGuard g(ctx->device);
     const uintptr_t bits = reinterpret_cast<uintptr_t>(mem) | reinterpret_cast<uintptr_t>(buf) | nbytes | row_bytes;
     const int vec = (bits & 15) == 0 ? 16 : (bits & 7) == 0 ? 8 : 1;
-    const u64 items = (nbytes / vec) * n_locs;
-    const unsigned grid = ew_grid(ctx, items, 256, 8);
+    const u64 per = nbytes / vec;
+    const unsigned gx = (unsigned)((per + 255) / 256 < 64 ? (per + 255) / 256 : 64);
+    const u64 want_y = ((u64)ctx->sm_count * 8 + gx - 1) / gx;
+    const dim3 grid(gx ? gx : 1, (unsigned)(n_locs < want_y ? n_locs : (want_y ? want_y : 1)));
 #define ABY3CU_ROWS(V, P) k_bin_rows<V, P><<<grid, 256, 0, ctx->stream>>>((u8*)mem, row_bytes, locs, n_locs, nbytes, (u8*)buf, invert)
     if (vec == 16) { if (pack) ABY3CU_ROWS(16, true); else ABY3CU_ROWS(16, false); }
     else if (vec == 8) { if (pack) ABY3CU_ROWS(8, true); else ABY3CU_ROWS(8, false); }

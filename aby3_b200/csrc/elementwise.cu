@@ -229,11 +229,19 @@ __global__ void __launch_bounds__(256) k_transpose(const i64* __restrict__ in, u
 __global__ void __launch_bounds__(256) k_gather_rows(const i64* __restrict__ in, u64 cols, const u64* __restrict__ idx, u64 nrows, i64* __restrict__ out) {
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
+    if (cols == 1) {
+        for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (u64)gridDim.x * blockDim.x) out[r] = in[idx[r]];
+        return;
+    }
     for (u64 r = warp; r < nrows; r += nwarps) {
         const i64* src = in + idx[r] * cols;
         i64* dst = out + r * cols;
         for (u64 c = lane; c < cols; c += 32) dst[c] = src[c];
     }
+}
+
+__global__ void __launch_bounds__(256) k_iota(u64 start, u64 step, u64* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = start + step * i;
 }
 
 // out[idx[r],:] = in[r,:]
@@ -430,6 +438,14 @@ int aby3cu_transpose_i64(aby3cu_ctx* ctx, const i64* in, u64 rows, u64 cols, i64
     return post_launch(ctx, "k_transpose");
 }
 
+int aby3cu_iota_u64(aby3cu_ctx* ctx, u64 start, u64 step, u64* out, size_t n) {
+    ABY3CU_REQUIRE(ctx && (out || !n), "iota: null argument");
+    if (!n) return 0;
+    DeviceGuard g(ctx->device);
+    k_iota<<<ew_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(start, step, out, n);
+    return post_launch(ctx, "k_iota");
+}
+
 int aby3cu_scatter_rows(aby3cu_ctx* ctx, const i64* in, u64 cols, const u64* idx, u64 nrows, i64* out) {
     ABY3CU_REQUIRE(ctx && ((in && idx && out) || !(nrows * cols)), "scatter_rows: null argument");
     if (!(nrows * cols)) return 0;
@@ -443,7 +459,7 @@ int aby3cu_gather_rows(aby3cu_ctx* ctx, const i64* in, u64 cols, const u64* idx,
     ABY3CU_REQUIRE(ctx && ((in && idx && out) || !(nrows * cols)), "gather_rows: null argument");
     if (!(nrows * cols)) return 0;
     DeviceGuard g(ctx->device);
-    const unsigned grid = ew_grid(ctx, nrows * 32, 256, 8);
+    const unsigned grid = ew_grid(ctx, cols == 1 ? nrows : nrows * 32, 256, 8);
     k_gather_rows<<<grid, 256, 0, ctx->stream>>>(in, cols, idx, nrows, out);
     return post_launch(ctx, "k_gather_rows");
 }

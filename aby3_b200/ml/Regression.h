@@ -41,7 +41,6 @@ void SGD_Linear(RegressionParam& params, Engine& engine, sf64Matrix<D>& X, sf64M
     gpu::Context* ctx = gpu::current();
     gpu::Buffer dIdx(ctx, std::max<size_t>(batchIndices.size() * 8, 16));
     gpu::check(aby3cu_h2d(ctx->h(), dIdx.ptr(), batchIndices.data(), batchIndices.size() * 8));
-    ctx->sync();
 
     sf64Matrix<D> XX(params.mBatchSize, X.cols()), YY(params.mBatchSize, 1);
     // the learning rate in log2 form: this many extra bits are truncated (:139)

@@ -56,6 +56,7 @@ public:
             if (it != mFree.end() && !it->second.empty()) {
                 e = it->second.back();
                 it->second.pop_back();
+                mCached -= bytes;
             }
         }
         if (e.ptr) {
@@ -72,11 +73,29 @@ public:
     // `after` (may be null): an event recorded on ANOTHER stream that still reads the buffer
     void release(void* p, size_t bytes, void* after = nullptr) {
         if (!p) return;
-        std::lock_guard<std::mutex> g(mMtx);
-        mFree[roundSize(bytes)].push_back(Entry{p, after});
+        bytes = roundSize(bytes);
+        {
+            std::lock_guard<std::mutex> g(mMtx);
+            if (mCached + bytes <= kCacheCap) {
+                mFree[bytes].push_back(Entry{p, after});
+                mCached += bytes;
+                return;
+            }
+        }
+        // the cache is full: give the block back to the driver (workloads whose buffer sizes keep
+        // changing -- e.g. the shrinking stages of a merge network -- must not hoard HBM)
+        if (after) { aby3cu_event_sync(after); aby3cu_event_destroy(after); }
+        aby3cu_free(mCtx, p);
     }
 
-    static size_t roundSize(size_t b) { return (b + 511) & ~size_t(511); }
+    // Size classes: multiples of 512 B up to 1 MiB, then 1/8-octave steps, so that buffers whose
+    // sizes drift (stage after stage of a merge network) still recycle each other's memory.
+    static size_t roundSize(size_t b) {
+        if (b <= (size_t(1) << 20)) return (b + 511) & ~size_t(511);
+        size_t step = size_t(1) << 17;
+        while ((step << 4) < b) step <<= 1;          // step = 2^k with 8*step < b <= 16*step
+        return (b + step - 1) / step * step;
+    }
 
 private:
     struct Entry { void* ptr; void* event; };
@@ -84,6 +103,8 @@ private:
     int mDevice = 0;
     std::mutex mMtx;
     std::map<size_t, std::vector<Entry>> mFree;
+    size_t mCached = 0;
+    static constexpr size_t kCacheCap = size_t(24) << 30;
 };
 
 // The context of the calling thread (one thread per party, as in the reference:

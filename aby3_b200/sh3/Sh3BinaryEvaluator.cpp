@@ -45,7 +45,7 @@ void Sh3BinaryEvaluator::setCir(oc::BetaCircuit* cir, u64 width, block prevSeed,
     mAndLocsDev.reset(mCtx, std::max<size_t>(locs.size() * 4, 16));
     if (!flat.empty()) gpu::check(aby3cu_h2d(mCtx->h(), mGatesDev.ptr(), flat.data(), flat.size() * 4));
     if (!locs.empty()) gpu::check(aby3cu_h2d(mCtx->h(), mAndLocsDev.ptr(), locs.data(), locs.size() * 4));
-    mCtx->sync();          // `flat` / `locs` are pageable temporaries
+    // (h2d from pageable memory is staged before the call returns: `flat` / `locs` may die now)
 }
 
 void Sh3BinaryEvaluator::setInput(u64 i, const sbMatrix& in) {
@@ -82,7 +82,6 @@ void Sh3BinaryEvaluator::setInput(u64 idx, const sPackedBin& in) {
     for (int s = 0; s < 2; ++s)
         gpu::check(aby3cu_bin_scatter_rows(mCtx->h(), mMem[s].ptr(), mRowBytes, (const u32*)dIdx.ptr(), (u32)idxs.size(),
                                            in.simdWidth() * 8, in.mShares[s].dev()));
-    mCtx->sync();
 }
 
 Sh3Task Sh3BinaryEvaluator::asyncEvaluate(Sh3Task dependency) {
@@ -112,7 +111,9 @@ Sh3Task Sh3BinaryEvaluator::asyncEvaluate(Sh3Task dependency, oc::BetaCircuit* c
 void Sh3BinaryEvaluator::roundCallback(CommPkg& comm, Sh3Task task) {
     const u64 levels = mCir->mLevelCounts.size();
     if (mLevel > levels) throw std::runtime_error("evaluateRound() was called but no rounds remain... " LOCATION);
-    const u64 sendBytes = (mWidth + 7) / 8;
+    // each AND output row travels as ceil(width/8) bytes (.cpp:795-796), padded to 16 so that the
+    // pack / scatter kernels move whole 128-bit words (the pad carries bits beyond `width` only)
+    const u64 sendBytes = (((mWidth + 7) / 8) + 15) & ~15ull;
 
     if (mLevel) {                                                     // :555-573
         const u64 prev = mLevel - 1;
@@ -178,7 +179,6 @@ void Sh3BinaryEvaluator::getOutput(const std::vector<oc::BetaWire>& outWires, sb
         gpu::check(aby3cu_bit_transpose_gather(mCtx->h(), mMem[s].ptr(), (const u32*)dIdx.ptr(), bits, mWidth, mRowBytes,
                                                dst, out.i64Cols() * 8, anyInv ? (const u8*)dInv.ptr() : nullptr));
     }
-    mCtx->sync();          // idx / inv are pageable temporaries
 }
 
 void Sh3BinaryEvaluator::getOutput(u64 i, sPackedBin& out, bool allowUninitialized) {
@@ -204,7 +204,6 @@ void Sh3BinaryEvaluator::getOutput(const std::vector<oc::BetaWire>& outWires, sP
     for (int s = 0; s < 2; ++s)
         gpu::check(aby3cu_bin_pack_rows(mCtx->h(), mMem[s].ptr(), mRowBytes, (const u32*)dIdx.ptr(), (u32)n, out.simdWidth() * 8,
                                         out.mShares[s].devOut(), anyInv ? (const u8*)dInv.ptr() : nullptr));
-    mCtx->sync();
 }
 
 }  // namespace aby3

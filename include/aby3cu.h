@@ -164,6 +164,8 @@ int aby3cu_transpose_i64(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t rows, ui
 int aby3cu_gather_rows(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t cols, const uint64_t* d_idx,
                        uint64_t nrows, int64_t* d_out);
 
+/* out[i] = start + step * i: index vectors of the merge network (Sort.cpp:366-371) */
+int aby3cu_iota_u64(aby3cu_ctx* ctx, uint64_t start, uint64_t step, uint64_t* d_out, size_t n);
 /* scatter rows: out[idx[r],:] = in[r,:]  (compare-exchange write-back of aby3-Basic's
  * odd_even_merge, aby3-Basic/Sort.cpp:388-393) */
 int aby3cu_scatter_rows(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t cols, const uint64_t* d_idx,

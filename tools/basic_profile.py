@@ -1,0 +1,43 @@
+"""Where does a compare-exchange stage spend its time?  Times the pieces of
+bool_cipher_max_min_split at merge scale through the harness (wall clock + device)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from aby3_b200 import harness  # noqa: E402
+
+
+def timed(sess, name, fn, reps=3):
+    fn()
+    sess.sync()
+    l0 = sess.launches
+    sess.timer_begin()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = fn()
+    ms = sess.timer_end()
+    wall = (time.perf_counter() - t0) * 1e3
+    print("%-34s device %9.3f ms  wall %9.3f ms  launches %5d" % (name, ms / reps, wall / reps, (sess.launches - l0) // reps), flush=True)
+    return out
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else (1 << 21) - 3
+    s = harness.Session()
+    rng = np.random.default_rng(0)
+    a = rng.integers(-2**62, 2**62, (n, 1), dtype=np.int64)
+    b = rng.integers(-2**62, 2**62, (n, 1), dtype=np.int64)
+    A, B = s.share_bin(0, a, 64), s.share_bin(0, b, 64)
+    for name in ("and", "lt", "add_msb", "eq"):
+        cir = harness.library_circuit(name, 64)
+        print(name, "gates", len(cir["gates"]) // 4, "nonlinear", cir["nonlinear"], "levels", len(cir["level_gates"]), "wires", cir["wire_count"])
+        timed(s, "bin_eval %s n=%d" % (name, n), lambda: [s.free(h) for h in s.bin_eval(cir, [A, B])])
+    timed(s, "max_min_split n=%d" % n, lambda: [s.free(h) for h in s.max_min_split(A, B)])
+    s.close()
+
+
+if __name__ == "__main__":
+    main()
