@@ -225,6 +225,40 @@ __global__ void __launch_bounds__(256) k_bin_level(const uint4* __restrict__ gat
     }
 }
 
+// All gates of the list are NONLINEAR and mutually independent (the nonlinear gates of one
+// AND-depth level, whose linear producers have already run): gate x column parallel, gate g uses
+// the zero-share block range of nonlinear gate and0 + g.  Fills the machine even when the number
+// of instances is small compared with the number of gates.
+__global__ void __launch_bounds__(256) k_bin_and_layer(const uint4* __restrict__ gates, u32 n_gates, u64* mem0, const u64* mem1, u64 rw,
+                                                       const __grid_constant__ AesKey kp, const __grid_constant__ AesKey kn, u64 and0) {
+    aes_table_init();
+    __syncthreads();
+    const u32 Tl = (threadIdx.x & 31) * 4;
+    const u64 chunks = rw / 2;
+    for (u32 g = blockIdx.y; g < n_gates; g += gridDim.y) {
+        const uint4 G = gates[g];
+        const u32 type = G.w;
+        for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (u64)gridDim.x * blockDim.x) {
+            const W2 a0 = ldw(mem0, G.x, rw, c), a1 = ldw(mem1, G.x, rw, c);
+            const W2 b0 = ldw(mem0, G.y, rw, c), b1 = ldw(mem1, G.y, rw, c);
+            W2 x0 = a0, x1 = a1, y0 = b0, y1 = b1;
+            if (type == 1) { x0 = {~a0.a, ~a0.b}; x1 = {~a1.a, ~a1.b}; y0 = {~b0.a, ~b0.b}; y1 = {~b1.a, ~b1.b}; }
+            else if (type == 4) { x0 = {~a0.a, ~a0.b}; x1 = {~a1.a, ~a1.b}; }
+            W2 o0;
+            o0.a = (x0.a & y0.a) ^ (x0.a & y1.a) ^ (x1.a & y0.a);
+            o0.b = (x0.b & y0.b) ^ (x0.b & y1.b) ^ (x1.b & y0.b);
+            if (type == 14) { o0.a ^= a0.a ^ b0.a; o0.b ^= a0.b ^ b0.b; }
+            u32 p[4], q[4];
+            const u64 ctr = (and0 + g) * chunks + c;
+            aes_encrypt_ctr(Tl, kp, ctr, p);
+            aes_encrypt_ctr(Tl, kn, ctr, q);
+            o0.a ^= (((u64)(p[1] ^ q[1])) << 32) | (u64)(p[0] ^ q[0]);
+            o0.b ^= (((u64)(p[3] ^ q[3])) << 32) | (u64)(p[2] ^ q[2]);
+            stw(mem0, G.z, rw, c, o0);
+        }
+    }
+}
+
 // rows <-> contiguous message; VEC = bytes moved per thread step (16, 8 or 1).  PACK may
 // complement the rows flagged in `invert` (inverted output wires, getOutput :1252-1258).
 template <int VEC, bool PACK>
@@ -336,6 +370,23 @@ int aby3cu_bin_level(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void* d_m
         k_bin_level<false><<<grid, 256, 0, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0, (u64*)d_mem1, rw, zero, zero, and_index0);
     }
     return post_launch(ctx, "k_bin_level");
+}
+
+int aby3cu_bin_and_layer(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void* d_mem0, const void* d_mem1, u64 row_bytes,
+                         const u8 key_prev[16], const u8 key_next[16], u64 and_index0) {
+    ABY3CU_REQUIRE(ctx && key_prev && key_next && ((d_gates && d_mem0 && d_mem1) || !n_gates), "bin_and_layer: null argument");
+    ABY3CU_REQUIRE(row_bytes % 16 == 0, "bin_and_layer: row_bytes must be a multiple of 16");
+    if (!n_gates || !row_bytes) return 0;
+    DeviceGuard g(ctx->device);
+    AesKey kp, kn; host_expand_key(key_prev, &kp); host_expand_key(key_next, &kn);
+    ABY3CU_CHECK(cudaFuncSetAttribute(k_bin_and_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
+    const u64 chunks = row_bytes / 16;
+    const u64 gx = (chunks + 255) / 256 < 32 ? (chunks + 255) / 256 : 32;
+    u64 gy = ((u64)ctx->sm_count * 3 + gx - 1) / gx;
+    if (gy > n_gates) gy = n_gates;
+    k_bin_and_layer<<<dim3((unsigned)gx, (unsigned)gy), 256, kAesTableBytes, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0,
+                                                                                            (const u64*)d_mem1, row_bytes / 8, kp, kn, and_index0);
+    return post_launch(ctx, "k_bin_and_layer");
 }
 
 static int rows_copy(aby3cu_ctx* ctx, bool pack, void* mem, u64 row_bytes, const u32* locs, u32 n_locs, u64 nbytes, void* buf,

@@ -100,7 +100,9 @@ public:
     // Order gates by AND depth.  level(g) = max over inputs of (level of the gate
     // that produced it + 1 if that gate is nonlinear); a nonlinear gate's output
     // is only usable one communication round later (Sh3BinaryEvaluator.cpp:555-573).
-    // Gate order inside a level keeps the construction order (stable).
+    // Inside a level the linear gates come first (construction order), then the nonlinear ones
+    // (construction order): a nonlinear gate may read same-level linear outputs but nothing reads a
+    // nonlinear output before the next level, so the nonlinear gates of a level are independent.
     void levelByAndDepth() {
         std::vector<u32> ready(mWireCount, 0);     // first level at which the wire's value is usable
         std::vector<u32> lvl(mGates.size());
@@ -114,7 +116,10 @@ public:
         }
         std::vector<u64> order(mGates.size());
         for (u64 g = 0; g < order.size(); ++g) order[g] = g;
-        std::stable_sort(order.begin(), order.end(), [&](u64 x, u64 y) { return lvl[x] < lvl[y]; });
+        std::stable_sort(order.begin(), order.end(), [&](u64 x, u64 y) {
+            if (lvl[x] != lvl[y]) return lvl[x] < lvl[y];
+            return isLinear(mGates[x].mType) && !isLinear(mGates[y].mType);
+        });
         std::vector<BetaGate> sorted(mGates.size());
         mLevelCounts.assign(mGates.empty() ? 0 : maxLevel + 1, 0);
         mLevelAndCounts.assign(mLevelCounts.size(), 0);

@@ -41,6 +41,15 @@ void Sh3BinaryEvaluator::setCir(oc::BetaCircuit* cir, u64 width, block prevSeed,
         mLevelGateOff.push_back(mLevelGateOff.back() + cir->mLevelCounts[l]);
         mLevelAndOff.push_back(mLevelAndOff.back() + cir->mLevelAndCounts[l]);
     }
+    mLevelLinear.clear();
+    for (u64 l = 0; l < cir->mLevelCounts.size(); ++l) {
+        u64 g = mLevelGateOff[l];
+        const u64 end = mLevelGateOff[l + 1];
+        while (g < end && oc::isLinear(cir->mGates[g].mType)) ++g;
+        const u64 nLinear = g - mLevelGateOff[l];
+        while (g < end && !oc::isLinear(cir->mGates[g].mType)) ++g;
+        mLevelLinear.push_back(g == end ? (i64)nLinear : -1);
+    }
     mGatesDev.reset(mCtx, std::max<size_t>(flat.size() * 4, 16));
     mAndLocsDev.reset(mCtx, std::max<size_t>(locs.size() * 4, 16));
     if (!flat.empty()) gpu::check(aby3cu_h2d(mCtx->h(), mGatesDev.ptr(), flat.data(), flat.size() * 4));
@@ -131,9 +140,18 @@ void Sh3BinaryEvaluator::roundCallback(CommPkg& comm, Sh3Task task) {
         const u64 g0 = mLevelGateOff[mLevel], ng = mLevelGateOff[mLevel + 1] - g0;
         const u64 a0 = mLevelAndOff[mLevel], nAnd = mLevelAndOff[mLevel + 1] - a0;
         if (a0 != mShareIdx) throw RTE_LOC;
-        gpu::check(aby3cu_bin_level(mCtx->h(), (const u32*)mGatesDev.ptr() + 4 * g0, (u32)ng, mMem[0].ptr(),
-                                    mMem[1].ptr(), mRowBytes, nAnd ? mShareAES[0].key().data() : nullptr,
-                                    nAnd ? mShareAES[1].key().data() : nullptr, mShareIdx));
+        const i64 nLin = mLevelLinear[mLevel];
+        if (nLin >= 0 && nAnd) {
+            // linear gates column-parallel (in order), then the level's nonlinear gates gate x column parallel
+            gpu::check(aby3cu_bin_level(mCtx->h(), (const u32*)mGatesDev.ptr() + 4 * g0, (u32)nLin, mMem[0].ptr(), mMem[1].ptr(),
+                                        mRowBytes, nullptr, nullptr, mShareIdx));
+            gpu::check(aby3cu_bin_and_layer(mCtx->h(), (const u32*)mGatesDev.ptr() + 4 * (g0 + nLin), (u32)nAnd, mMem[0].ptr(),
+                                            mMem[1].ptr(), mRowBytes, mShareAES[0].key().data(), mShareAES[1].key().data(), mShareIdx));
+        } else {
+            gpu::check(aby3cu_bin_level(mCtx->h(), (const u32*)mGatesDev.ptr() + 4 * g0, (u32)ng, mMem[0].ptr(),
+                                        mMem[1].ptr(), mRowBytes, nAnd ? mShareAES[0].key().data() : nullptr,
+                                        nAnd ? mShareAES[1].key().data() : nullptr, mShareIdx));
+        }
         mShareIdx += nAnd;
         if (nAnd) {                                                   // :795-796, :1161-1171
             const size_t bytes = nAnd * sendBytes;

@@ -58,6 +58,7 @@ private:
     gpu::Buffer mGatesDev;              // [gates][4] u32
     gpu::Buffer mAndLocsDev;            // output wires of the nonlinear gates, in gate order
     std::vector<u64> mLevelGateOff, mLevelAndOff;
+    std::vector<i64> mLevelLinear;      // leading linear gates of the level when the rest is all nonlinear, else -1
     gpu::Buffer mRecvBuf;
     std::vector<std::future<void>> mRecvFutr;
     u64 mRecvLevel = 0;

@@ -197,6 +197,11 @@ int aby3cu_bit_transpose_gather(aby3cu_ctx* ctx, const void* d_in, const uint32_
 int aby3cu_bin_level(aby3cu_ctx* ctx, const uint32_t* d_gates, uint32_t n_gates,
                      void* d_mem0, void* d_mem1, uint64_t row_bytes,
                      const uint8_t key_prev[16], const uint8_t key_next[16], uint64_t and_index0);
+/* The nonlinear gates of one level when they are listed AFTER the level's linear gates (they are
+ * then mutually independent): gate x instance parallel.  Gate g of the list uses the zero-share
+ * block range of nonlinear gate and_index0 + g, exactly as aby3cu_bin_level would. */
+int aby3cu_bin_and_layer(aby3cu_ctx* ctx, const uint32_t* d_gates, uint32_t n_gates, void* d_mem0, const void* d_mem1,
+                         uint64_t row_bytes, const uint8_t key_prev[16], const uint8_t key_next[16], uint64_t and_index0);
 /* sendBuff packing (:795-796) and getOutput(sPackedBin) (:1213-1283):
  * out[j*nbytes .. ) = first nbytes of row locs[j] of mem, complemented where d_invert[j] != 0
  * (d_invert may be NULL). */
