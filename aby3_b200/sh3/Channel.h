@@ -20,6 +20,7 @@
 #pragma once
 #include <dlfcn.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -45,16 +46,26 @@ struct Pipe {
     std::mutex mtx;
     std::condition_variable cv;
     std::deque<Message> q;
+    std::atomic<u64> count{0};
     void push(Message&& m) {
         {
             std::lock_guard<std::mutex> g(mtx);
             q.push_back(std::move(m));
+            count.fetch_add(1, std::memory_order_release);
         }
         cv.notify_all();
     }
     Message pop() {
+        // latency-bound protocols (SGD: two rounds per iteration) wait for a peer thread that is
+        // microseconds away: poll briefly before paying for a futex sleep / wake-up
+        for (int spin = 0; spin < 20000 && count.load(std::memory_order_acquire) == 0; ++spin) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
         std::unique_lock<std::mutex> l(mtx);
         cv.wait(l, [&] { return !q.empty(); });
+        count.fetch_sub(1, std::memory_order_relaxed);
         Message m = std::move(q.front());
         q.pop_front();
         return m;
