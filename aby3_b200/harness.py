@@ -44,6 +44,7 @@ def _load():
     l.sh3h_piecewise.argtypes = [p, i32, p, i32, p, p, p, p, u64]
     l.sh3h_mul_bit.argtypes = [p, i32, i32, i32, i64]
     l.sh3h_reveal.argtypes = [p, i32, i32, i32, p]
+    l.sh3h_reveal_plain.argtypes = [p, i32, i32, i32]
     l.sh3h_trunc_tuple.argtypes = [p, i32, u64, u64, u64, p, p, p]
     l.sh3h_bin_eval.argtypes = [p, p, C.c_uint32, C.c_uint32, p, C.c_uint32, p, p, C.c_uint32, p, p, p, p, C.c_uint32, p, p]
     l.sh3h_linreg.argtypes = [p, i32, i32, i32, p, u64, u64, C.c_double]
@@ -216,6 +217,11 @@ class Session:
             out = np.empty((r, c), dtype=np.int64)
         self._chk(lib.sh3h_reveal(self.h, hid, int(binary), party, _ptr(out)))
         return out
+
+    def reveal_plain(self, hid, party, plain_id):
+        """revealAll; `party`'s result lands in its page-locked plaintext matrix `plain_id`
+        (the numpy view returned by plain() stays valid when the shape matches)."""
+        self._chk(lib.sh3h_reveal_plain(self.h, hid, party, plain_id))
 
     def trunc_tuple(self, party, rows, cols, d):
         n = rows * cols

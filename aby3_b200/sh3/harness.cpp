@@ -404,6 +404,23 @@ int sh3h_reveal(sh3h* h, int id, int binary, int who, int64_t* out) {
     });
 }
 
+// enc.revealAll on every party; party `who` reveals straight into its page-locked plaintext
+// matrix `plain_id` (the d2h copy lands in the buffer the caller reads: no host-side copy)
+int sh3h_reveal_plain(sh3h* h, int id, int who, int plain_id) {
+    return h->run([&](int i) {
+        Party& P = h->p[i];
+        if (i == who) {
+            i64Matrix& dest = *P.plains.at(plain_id);
+            P.enc.revealAll(P.comm, *P.ints.at(id), dest);
+            (void)dest.hostData();
+        } else {
+            i64Matrix dest;
+            P.enc.revealAll(P.comm, *P.ints.at(id), dest);
+            P.ctx->sync();
+        }
+    });
+}
+
 // getTruncationTuple on one party (advances its cursors): R, RT0, RT1 of n = rows*cols
 int sh3h_trunc_tuple(sh3h* h, int party, uint64_t rows, uint64_t cols, uint64_t d, int64_t* R, int64_t* RT0, int64_t* RT1) {
     return h->run([&](int i) {

@@ -54,57 +54,94 @@ def synth_inputs(M, K, N, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): an NVML
+    polling thread in this process (a sample every ~2 ms; nvidia-smi -lms takes longer to start
+    than a short run lasts and is only the fallback)."""
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.path = gpu_index, None, None
+        self.gpu, self.rows, self.stop_flag, self.th, self.smi = gpu_index, [], False, None, None
+
+    def _nvml_loop(self, nv, h):
+        bad = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+               "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append((float(sm), pw, [k for k, v in bad.items() if mask & v]))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.th.start()
+        except Exception:
+            self.th = None
+            self._start_smi()
+
+    def _start_smi(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            self.smi = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                         "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
-            self.proc = None
+            self.smi = None
+
+    def mark(self):
+        """Start of the timed region: earlier samples (warm-up) are dropped."""
+        self.rows_from = len(self.rows)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if not self.proc:
-            return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        try:
-            rows = [l.strip().split(", ") for l in open(self.path) if l.strip()]
-            os.unlink(self.path)
-        except Exception:
-            rows = []
-        sm, reasons = [], set()
-        for r in rows:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvml"}
+        if self.th is not None:
+            self.stop_flag = True
+            self.th.join(timeout=2)
+            rows = self.rows[getattr(self, "rows_from", 0):] or self.rows
+            out["sm_max_mhz"] = self.sm_max
+        elif self.smi is not None:
+            out["source"] = "nvidia-smi"
             try:
-                sm.append(float(r[1]))
-                out["sm_max_mhz"] = float(r[2])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.strip().lower().startswith("active"):
-                        reasons.add(name)
+                self.smi.terminate()
+                self.smi.wait(timeout=5)
             except Exception:
                 pass
-        if sm:
-            # "under load": the upper half of the samples by power draw
+            rows = []
             try:
-                pw = [float(r[3]) for r in rows][:len(sm)]
-                order = np.argsort(pw)[len(pw) // 2:]
-                out["sm_mhz"] = float(np.median(np.array(sm)[order]))
-                out["power_w_max"] = float(np.max(pw))
+                for l in open(self.path):
+                    r = l.strip().split(", ")
+                    if len(r) >= 8:
+                        out["sm_max_mhz"] = float(r[2])
+                        rows.append((float(r[1]), float(r[3]), [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                                                    "sw_power_cap"), r[4:8]) if v.strip().lower().startswith("active")]))
+                os.unlink(self.path)
             except Exception:
-                out["sm_mhz"] = float(np.median(sm))
-        out["reasons"] = sorted(reasons)
-        out["samples"] = len(sm)
+                pass
+        else:
+            return out
+        if rows:
+            sm = np.array([r[0] for r in rows])
+            pw = np.array([r[1] for r in rows])
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_min_mhz"] = float(np.min(sm))
+            out["power_w_max"] = float(np.max(pw))
+            out["reasons"] = sorted({x for r in rows for x in r[2]})
+            out["samples"] = len(rows)
         return out
 
 
@@ -351,6 +388,7 @@ def main():
     barrier()
     sess.sync()
     launches0 = sess.launches
+    sampler.mark()
     sess.timer_begin()
     for _ in range(args.steps):
         sess.mul(A, B, shift=SHIFT, out=Cid)
@@ -369,7 +407,7 @@ def main():
     e2e_steps = max(1, min(args.steps, 3))
     pa, va = sess.plain(0, M, K)
     pb, vb = sess.plain(0, K, N)
-    out = np.empty((M, N), dtype=np.int64)
+    pc, out = sess.plain(0, M, N)          # page-locked: the reveal's d2h copy lands here
     va[...] = a
     vb[...] = b
 
@@ -379,7 +417,7 @@ def main():
         ha = sess.share_plain(0, pa, M, K)
         hb = sess.share_plain(0, pb, K, N)
         hc = sess.mul(ha, hb, shift=SHIFT)
-        sess.reveal(hc, 0, out=out)
+        sess.reveal_plain(hc, 0, pc)
         for h in (ha, hb, hc):
             sess.free(h)
 
@@ -432,10 +470,10 @@ def main():
                        "l2": "inputs larger than L2 (per party 4 x %d MiB share planes + %d MiB limb planes)" % (8 * M * K >> 20, 2 * 16 * M * K >> 20),
                        "timing": "CUDA events across the three party streams (fork/join on one start and one end event), max over ranks",
                        "executed_u64_mac_per_s": 6.0 * value, "max_abs_err_ulp_vs_plain": max_err},
-            "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "power_w_max", "samples")},
+            "clocks": clocks,
             "e2e": {"value": world * step_macs / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * (M * K + K * N), "d2h_bytes_per_step": 8 * M * N,
                     "ms_per_step": e2e_t * 1e3, "steps": e2e_steps,
-                    "path": "enc.localIntMatrix(host a,b) -> eval.asyncMul(..., shift) -> enc.revealAll -> host c"},
+                    "path": "enc.localIntMatrix(page-locked host a,b) -> eval.asyncMul(..., shift) -> enc.revealAll -> page-locked host c"},
             "gpu_launches": launches,
             "linreg": linreg,
             "logistic_inference": logistic,
