@@ -1,6 +1,12 @@
 #pragma once
 // shim of cryptoTools/Common/Defines.h (absent third-party header; see ../../README.md)
+#include <algorithm>
 #include <array>
+#include <cassert>
+#include <functional>
+#include <future>
+#include <list>
+#include <utility>
 #include <cstdint>
 #include <cstring>
 #include <iomanip>
@@ -18,6 +24,7 @@
 #define OC_STRINGIZE(x) OC_STRINGIZE_DETAIL(x)
 #define LOCATION __FILE__ ":" OC_STRINGIZE(__LINE__)
 #define RTE_LOC std::runtime_error(LOCATION)
+#define TODO(x)
 
 namespace osuCrypto {
 typedef uint64_t u64;

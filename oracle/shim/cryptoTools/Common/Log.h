@@ -16,14 +16,14 @@ struct ostreamLock {
     std::unique_lock<std::mutex> mLock;
     explicit ostreamLock(std::ostream& o) : out(o), mLock(gIoStreamMtx) {}
     template <typename T>
-    ostreamLock& operator<<(const T& v) { out << v; return *this; }
+    ostreamLock& operator<<(T&& v) { out << std::forward<T>(v); return *this; }
     ostreamLock& operator<<(std::ostream& (*v)(std::ostream&)) { out << v; return *this; }
 };
 struct ostreamLocker {
     std::ostream& out;
     explicit ostreamLocker(std::ostream& o) : out(o) {}
     template <typename T>
-    ostreamLocker& operator<<(const T& v) { std::lock_guard<std::mutex> g(gIoStreamMtx); out << v; return *this; }
+    ostreamLocker& operator<<(T&& v) { std::lock_guard<std::mutex> g(gIoStreamMtx); out << std::forward<T>(v); return *this; }
     ostreamLocker& operator<<(std::ostream& (*v)(std::ostream&)) { std::lock_guard<std::mutex> g(gIoStreamMtx); out << v; return *this; }
 };
 extern ostreamLocker lout;

@@ -3,7 +3,13 @@
 // (Sh3_Runtime_schedule_test).  Host only: no device is needed or touched.
 #include <cstdio>
 
+// -DREF_RUNTIME: the SAME assertions against the reference's own Sh3Runtime / Scheduler, compiled from
+// /root/reference with the stand-in headers of oracle/shim (tests/test_ref_parity.py)
+#ifdef REF_RUNTIME
+#include <aby3/sh3/Sh3Runtime.h>
+#else
 #include "aby3_b200/sh3/Sh3Runtime.h"
+#endif
 
 using namespace aby3;
 

@@ -1,0 +1,193 @@
+"""ctypes binding of oracle/_ref/libaby3ref.so: the REFERENCE's own sh3 sources (Sh3Runtime, Sh3Encryptor,
+Sh3Evaluator, SharedOT, Sh3BinaryEvaluator, Sh3Piecewise, CircuitLibrary) compiled unmodified from
+/root/reference against the stand-in third-party headers of oracle/shim (oracle/Makefile target `_ref`,
+driver oracle/ref_driver.cpp).  Test infrastructure: used to pin oracle/oracle.cpp, never by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATH = os.path.join(ROOT, "oracle", "_ref", "libaby3ref.so")
+REFERENCE = os.environ.get("ABY3_REFERENCE", "/root/reference")
+
+_p, _u64, _int = C.c_void_p, C.c_uint64, C.c_int
+
+
+def available():
+    """Build when the reference tree is present (this container); otherwise use the prebuilt library
+    that travelled with the snapshot (GPU box); otherwise report unavailable."""
+    if os.path.isdir(os.path.join(REFERENCE, "aby3", "sh3")):
+        r = subprocess.run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "oracle"), "_ref", "REF=" + REFERENCE],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building oracle/_ref failed:\n" + r.stdout[-4000:])
+    return os.path.exists(PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libaby3ref.so is missing and %s is absent" % REFERENCE)
+        l = C.CDLL(PATH)
+        l.ref_last_error.restype = C.c_char_p
+        l.ref_session_new.restype = _p
+        l.ref_session_new.argtypes = [_p, _p]
+        l.ref_session_free.argtypes = [_p]
+        l.ref_session_set_disable_randomization.argtypes = [_p, _int]
+        l.ref_share_int.argtypes = [_p, _int, _p, _p, _u64, _u64]
+        l.ref_share_bin.argtypes = [_p, _int, _p, _p, _u64, _u64]
+        l.ref_reveal_all.argtypes = [_p, _p, _u64, _u64, _int, _p]
+        l.ref_mul.argtypes = [_p, _p, _p, _p, _u64, _u64]
+        l.ref_mul_trunc.argtypes = [_p, _p, _p, _p, _u64, _u64, _u64]
+        l.ref_trunc_tuple.argtypes = [_p, _int, _u64, _u64, _u64, _p, _p, _p]
+        l.ref_mul_bit.argtypes = [_p, _p, _p, _p, _u64]
+        l.ref_mul_bit_pub.argtypes = [_p, C.c_int64, _p, _p, _u64]
+        l.ref_bin_eval.argtypes = [_p, _p, _u64, _p, _p]
+        l.ref_piecewise.argtypes = [_p, _p, _u64, _p, _int, _p, _p, _p, _p, _u64, _p]
+        l.ref_piecewise_plain.argtypes = [_p, _u64, _p, _int, _p, _p, _p, _p, _u64, _p]
+        l.ref_time_mul_trunc.restype = C.c_double
+        l.ref_time_mul_trunc.argtypes = [_p, _u64, _u64, _u64, _u64, _int]
+        _lib = l
+    return _lib
+
+
+def ptr(a):
+    return a.ctypes.data_as(_p)
+
+
+def _chk(rc):
+    if rc != 0:
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+
+
+def _coefs(thresholds, coefficients):
+    th = np.asarray(thresholds, dtype=np.float64)
+    counts = np.asarray([len(c) for c in coefficients], dtype=np.int32)
+    flat = [v for c in coefficients for v in c]
+    is_int = np.asarray([isinstance(v, (int, np.integer)) for v in flat] or [0], dtype=np.int32)
+    ints = np.asarray([int(v) if isinstance(v, (int, np.integer)) else 0 for v in flat] or [0], dtype=np.int64)
+    dbl = np.asarray([float(v) for v in flat] or [0.0], dtype=np.float64)
+    return th, counts, is_int, ints, dbl
+
+
+class Session:
+    """Three reference parties (threads) with the seeds of aby3_tests/Sh3EvaluatorTests.cpp:41-47 by default."""
+
+    def __init__(self, enc_seeds, eval_seeds):
+        self._e = C.create_string_buffer(enc_seeds, 96)
+        self._v = C.create_string_buffer(eval_seeds, 96)
+        self.h = lib().ref_session_new(C.cast(self._e, _p), C.cast(self._v, _p))
+        if not self.h:
+            raise RuntimeError("reference: " + lib().ref_last_error().decode())
+
+    def close(self):
+        if self.h:
+            lib().ref_session_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def disable_randomization(self, on=True):
+        lib().ref_session_set_disable_randomization(self.h, int(on))
+
+    def share_int(self, owner, plain):
+        plain = np.ascontiguousarray(plain, dtype=np.int64)
+        sh = np.empty((3, 2) + plain.shape, dtype=np.int64)
+        _chk(lib().ref_share_int(self.h, owner, ptr(plain), ptr(sh), plain.shape[0], plain.shape[1]))
+        return sh
+
+    def share_bin(self, owner, plain):
+        plain = np.ascontiguousarray(plain, dtype=np.int64)
+        sh = np.empty((3, 2) + plain.shape, dtype=np.int64)
+        _chk(lib().ref_share_bin(self.h, owner, ptr(plain), ptr(sh), plain.shape[0], plain.shape[1]))
+        return sh
+
+    def reveal_all(self, shares, binary=False):
+        shares = np.ascontiguousarray(shares, dtype=np.int64)
+        r, c = shares.shape[2], shares.shape[3]
+        out = np.empty((3, r, c), dtype=np.int64)
+        _chk(lib().ref_reveal_all(self.h, ptr(shares), r, c, int(binary), ptr(out)))
+        return out
+
+    def mul(self, A, B):
+        A, B = np.ascontiguousarray(A), np.ascontiguousarray(B)
+        Cc = np.empty_like(A)
+        _chk(lib().ref_mul(self.h, ptr(A), ptr(B), ptr(Cc), A.shape[2], A.shape[3]))
+        return Cc
+
+    def mul_trunc(self, A, B, shift):
+        A, B = np.ascontiguousarray(A), np.ascontiguousarray(B)
+        Cc = np.empty_like(A)
+        _chk(lib().ref_mul_trunc(self.h, ptr(A), ptr(B), ptr(Cc), A.shape[2], A.shape[3], shift))
+        return Cc
+
+    def trunc_tuple(self, party, rows, cols, d):
+        n = rows * cols
+        R, T0, T1 = (np.empty(n, dtype=np.int64) for _ in range(3))
+        _chk(lib().ref_trunc_tuple(self.h, party, rows, cols, d, ptr(R), ptr(T0), ptr(T1)))
+        return R, T0, T1
+
+    def mul_bit(self, A, B):
+        A, B = np.ascontiguousarray(A), np.ascontiguousarray(B)
+        n = A[0, 0].size
+        Cc = np.empty((3, 2, n, 1), dtype=np.int64)
+        _chk(lib().ref_mul_bit(self.h, ptr(A), ptr(B), ptr(Cc), n))
+        return Cc
+
+    def mul_bit_pub(self, a, B):
+        B = np.ascontiguousarray(B)
+        n = B[0, 0].size
+        Cc = np.empty((3, 2, n, 1), dtype=np.int64)
+        _chk(lib().ref_mul_bit_pub(self.h, int(a), ptr(B), ptr(Cc), n))
+        return Cc
+
+    def bin_eval(self, cir, width, inputs):
+        import oracle_lib as o
+        c = o.Circuit()
+        keep = []
+
+        def arr(a):
+            keep.append(a)
+            return a.ctypes.data_as(_p)
+
+        c.wire_count, c.gate_count = cir["wire_count"], len(cir["gates"]) // 4
+        c.gates, c.level_count, c.level_gates = arr(cir["gates"]), len(cir["level_gates"]), arr(cir["level_gates"])
+        c.num_inputs, c.input_first, c.input_bits = len(cir["input_bits"]), arr(cir["input_first"]), arr(cir["input_bits"])
+        c.num_outputs, c.output_off, c.output_bits = len(cir["output_bits"]), arr(cir["output_off"]), arr(cir["output_bits"])
+        c.output_wires, c.output_invert = arr(cir["output_wires"]), arr(cir["output_invert"])
+        ins = [np.ascontiguousarray(x, dtype=np.int64) for x in inputs]
+        outs = [np.zeros((3, 2, width, (int(b) + 63) // 64), dtype=np.int64) for b in cir["output_bits"]]
+        in_ptrs = (_p * len(ins))(*[x.ctypes.data_as(_p) for x in ins])
+        out_ptrs = (_p * len(outs))(*[x.ctypes.data_as(_p) for x in outs])
+        _chk(lib().ref_bin_eval(self.h, C.byref(c), width, in_ptrs, out_ptrs))
+        return outs
+
+    def piecewise(self, X, thresholds, coefficients, D):
+        X = np.ascontiguousarray(X, dtype=np.int64)
+        n = X[0, 0].size
+        th, counts, is_int, ints, dbl = _coefs(thresholds, coefficients)
+        Y = np.empty((3, 2, n, 1), dtype=np.int64)
+        _chk(lib().ref_piecewise(self.h, ptr(X), n, ptr(th), len(th), ptr(counts), ptr(is_int), ptr(ints), ptr(dbl), D, ptr(Y)))
+        return Y
+
+    def time_mul_trunc(self, M, K, N, shift, reps=1):
+        """seconds per asyncMul(A (M x K), B (K x N), C, shift).get() over three party threads"""
+        t = lib().ref_time_mul_trunc(self.h, M, K, N, shift, reps)
+        if t < 0:
+            raise RuntimeError("reference: " + lib().ref_last_error().decode())
+        return t
+
+
+def piecewise_plain(x, thresholds, coefficients, D):
+    x = np.ascontiguousarray(x, dtype=np.int64).reshape(-1)
+    th, counts, is_int, ints, dbl = _coefs(thresholds, coefficients)
+    y = np.empty_like(x)
+    _chk(lib().ref_piecewise_plain(ptr(x), x.size, ptr(th), len(th), ptr(counts), ptr(is_int), ptr(ints), ptr(dbl), D, ptr(y)))
+    return y

@@ -1,0 +1,260 @@
+"""Pins the oracle (oracle/oracle.cpp, the CPU restatement every GPU parity test compares with) against
+the REFERENCE ITSELF: oracle/_ref/libaby3ref.so is the reference's own sh3 sources (Sh3Runtime,
+Sh3Encryptor, Sh3ShareGen, Sh3Evaluator, SharedOT, Sh3BinaryEvaluator, Sh3Piecewise, CircuitLibrary)
+compiled UNMODIFIED from /root/reference against stand-in headers for the absent third-party libraries
+(oracle/shim/README.md).  Same seeds, same inputs -> every party's two share planes must be identical.
+
+What this does NOT pin (restated in oracle/shim, not inspectable here): the cryptoTools primitives
+(oc::PRNG / oc::AES keystream layout, oc::transpose bit order beyond what Sh3ConverterTests fixes,
+BetaLibrary gate order).  Runs on CPU; on a box without /root/reference the prebuilt library is used."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as o
+import ref_lib as r
+
+pytestmark = pytest.mark.skipif(not r.available(), reason="oracle/_ref not built and /root/reference absent")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def pair(enc=None, ev=None):
+    e, v = o.default_seeds()
+    return o.Session(enc or e, ev or v), r.Session(enc or e, ev or v)
+
+
+def other_seeds():
+    rng = np.random.default_rng(99)
+    return bytes(rng.integers(0, 256, 96, dtype=np.uint8)), bytes(rng.integers(0, 256, 96, dtype=np.uint8))
+
+
+def consistent_seeds():
+    """party i's next seed == party i+1's prev seed, as a real deployment has them"""
+    rng = np.random.default_rng(5)
+    k = [bytes(rng.integers(0, 256, 16, dtype=np.uint8)) for _ in range(6)]
+    enc = b"".join(k[i] + k[(i + 1) % 3] for i in range(3))
+    ev = b"".join(k[3 + i] + k[3 + (i + 1) % 3] for i in range(3))
+    return enc, ev
+
+
+@pytest.mark.parametrize("seeds", ["default", "random"])
+def test_share_and_reveal_int(seeds):
+    so, sr = pair() if seeds == "default" else pair(*consistent_seeds())
+    rng = np.random.default_rng(1)
+    for owner, shape in ((0, (1, 1)), (1, (7, 5)), (2, (33, 17)), (0, (300, 3))):      # crosses the 256-block refill
+        a = rng.integers(-2**63, 2**63, shape, dtype=np.int64)
+        Ao, Ar = so.share_int(owner, a), sr.share_int(owner, a)
+        assert np.array_equal(Ao, Ar)
+        rev = sr.reveal_all(Ar)
+        for p in range(3):
+            assert np.array_equal(rev[p], a)
+            assert np.array_equal(o.reveal(Ao, p), a)
+
+
+def test_share_and_reveal_bin():
+    so, sr = pair()
+    rng = np.random.default_rng(2)
+    for owner, shape in ((0, (5, 1)), (1, (64, 2)), (2, (700, 1))):
+        a = rng.integers(-2**63, 2**63, shape, dtype=np.int64)
+        Ao, Ar = so.share_bin(owner, a), sr.share_bin(owner, a)
+        assert np.array_equal(Ao, Ar)
+        rev = sr.reveal_all(Ar, binary=True)
+        for p in range(3):
+            assert np.array_equal(rev[p], a)
+            assert np.array_equal(o.reveal(Ao, p, binary=True), a)
+
+
+def test_asyncMul_si64Matrix_shares():
+    """Sh3Evaluator.cpp:92-116 (this fork's element-wise cross term + zero share + reshare); chained
+    products keep the zero-share cursor in step (Sh3EvaluatorTests.cpp: 10 chained rounds)."""
+    so, sr = pair()
+    rng = np.random.default_rng(3)
+    a = rng.integers(-2**63, 2**63, (10, 10), dtype=np.int64)
+    b = rng.integers(-2**63, 2**63, (10, 10), dtype=np.int64)
+    Ao, Ar = so.share_int(0, a), sr.share_int(0, a)
+    Bo, Br = so.share_int(1, b), sr.share_int(1, b)
+    exp = a.copy()
+    for _ in range(10):
+        Ao, Ar = so.mul(Ao, Bo, mode=1), sr.mul(Ar, Br)
+        assert np.array_equal(Ao, Ar)
+        exp = exp * b
+    assert np.array_equal(sr.reveal_all(Ar)[2], exp)
+    # a size that needs several refills of the 256-block share buffer
+    x = rng.integers(-2**63, 2**63, (40, 40), dtype=np.int64)
+    Xo, Xr = so.share_int(2, x), sr.share_int(2, x)
+    assert np.array_equal(so.mul(Xo, Xo, mode=1), sr.mul(Xr, Xr))
+
+
+def test_getTruncationTuple_shares():
+    """Sh3Evaluator.cpp:503-566, every party, several shifts; the draws advance the common PRNGs"""
+    so, sr = pair()
+    for d in (8, 16, 33):
+        for p in range(3):
+            for rows, cols in ((1, 1), (7, 5), (64, 33)):
+                to, tr = so.trunc_tuple(p, rows * cols, d), sr.trunc_tuple(p, rows, cols, d)
+                for x, y in zip(to, tr):
+                    assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("disable", [False, True])
+def test_asyncMul_truncating_shares(disable):
+    """Sh3Evaluator.cpp:651-730 on square operands (the fork's element-wise overwrite, :664-665)"""
+    so, sr = pair()
+    so.disable_randomization(disable)
+    sr.disable_randomization(disable)
+    rng = np.random.default_rng(4)
+    for n, d in ((6, 16), (24, 8), (40, 16)):
+        a = (rng.normal(0, 100, (n, n)) * (1 << d)).astype(np.int64)
+        b = (rng.normal(0, 100, (n, n)) * (1 << d)).astype(np.int64)
+        Ao, Ar = so.share_int(2, a), sr.share_int(2, a)
+        Bo, Br = so.share_int(0, b), sr.share_int(0, b)
+        Co, Cr = so.mul_trunc(Ao, Bo, d, mode=1), sr.mul_trunc(Ar, Br, d)
+        assert np.array_equal(Co, Cr)
+        assert np.max(np.abs(sr.reveal_all(Cr)[0] - ((a * b) >> d))) <= (1 if disable else 4)
+
+
+def _bits(s, b):
+    return s.share_bin(0, b.reshape(-1, 1).astype(np.int64)) & 1          # Sh3EvaluatorTests.cpp:846-854
+
+
+def test_asyncMul_bit_times_arithmetic_shares():
+    """Sh3Evaluator.cpp:119-263 + aby3/OT/SharedOT.cpp; pinned by sh3_asyncArithBinMul_test (:780-900)"""
+    so, sr = pair()
+    rng = np.random.default_rng(5)
+    for n in (1, 100, 300):
+        a = rng.integers(-2**31, 2**31, (n, 1), dtype=np.int64)
+        b = rng.integers(0, 2, n)
+        Ao, Ar = so.share_int(0, a), sr.share_int(0, a)
+        Bo, Br = _bits(so, b), _bits(sr, b)
+        assert np.array_equal(Bo, Br)
+        Co, Cr = so.mul_bit(Ao, Bo), sr.mul_bit(Ar, Br)
+        assert np.array_equal(Co, Cr)
+        assert np.array_equal(sr.reveal_all(Cr)[1], a * b.reshape(n, 1))
+
+
+def test_asyncMul_bit_times_public_shares():
+    """Sh3Evaluator.cpp:418-501; pinned by sh3_asyncPubArithBinMul_test (:903-1032)"""
+    so, sr = pair()
+    rng = np.random.default_rng(6)
+    for n, a in ((5, 3), (300, -77), (64, 1 << 40)):
+        b = rng.integers(0, 2, n)
+        Bo, Br = _bits(so, b), _bits(sr, b)
+        Co, Cr = so.mul_bit_pub(a, Bo), sr.mul_bit_pub(a, Br)
+        assert np.array_equal(Co, Cr)
+        assert np.array_equal(sr.reveal_all(Cr)[0].reshape(n), a * b)
+
+
+def _lib_circuit(name, bits):
+    from aby3_b200 import harness          # host-only use: the facade's circuit library as DATA for both engines
+    return harness.library_circuit(name, bits)
+
+
+@pytest.mark.parametrize("name,bits,width", [("and", 64, 1), ("and", 64, 300), ("or", 64, 77), ("xor", 33, 65), ("add", 16, 100),
+                                             ("add_depth", 64, 257), ("add_msb", 64, 2049), ("lt", 64, 130), ("eq", 64, 64),
+                                             ("piecewise2", 64, 96)])
+def test_binary_engine_shares(name, bits, width):
+    """Sh3BinaryEvaluator.cpp setCir / setInput / roundCallback / getShares / getOutput on the same
+    levelised circuit: output share planes identical (AND masks, reshare order, transposes, inversion flags)."""
+    so, sr = pair()
+    cir = _lib_circuit(name, bits)
+    rng = np.random.default_rng(7)
+    ins_o, ins_r, plain = [], [], []
+    for k, nb in enumerate(cir["input_bits"]):
+        nb = int(nb)
+        words = (nb + 63) // 64
+        v = rng.integers(-2**63, 2**63, (width, words), dtype=np.int64)
+        if nb % 64:
+            v[:, -1] &= (1 << (nb % 64)) - 1
+        plain.append(v)
+        ins_o.append(so.share_bin(k % 3, v))
+        ins_r.append(sr.share_bin(k % 3, v))
+    outs_o, _ = o.bin_eval(so, cir, width, ins_o)
+    outs_r = sr.bin_eval(cir, width, ins_r)
+    for k, (x, y) in enumerate(zip(outs_o, outs_r)):
+        nb = int(cir["output_bits"][k])
+        mask = np.int64(-1) if nb % 64 == 0 else np.int64((1 << (nb % 64)) - 1)
+        x, y = x.copy(), y.copy()
+        x[..., -1] &= mask                    # bits beyond bitCount are unspecified in both (sbMatrix::trim)
+        y[..., -1] &= mask
+        assert np.array_equal(x, y), "output %d of %s" % (k, name)
+    if name == "and":
+        assert np.array_equal(sr.reveal_all(outs_r[0], binary=True)[0], plain[0] & plain[1])
+    if name == "add_depth":
+        assert np.array_equal(sr.reveal_all(outs_r[0], binary=True)[0], plain[0] + plain[1])
+    # both engines consumed the same number of bytes from the common PRNGs (one key block each)
+    to, tr = so.trunc_tuple(0, 4, 16), sr.trunc_tuple(0, 4, 1, 16)
+    assert all(np.array_equal(a, b) for a, b in zip(to, tr))
+
+
+def test_piecewise_plain_matches_reference():
+    """Sh3Piecewise::eval(i64Matrix) -- the plaintext evaluator aby3_tests/Sh3PiecewiseTests.cpp:13-80 pins"""
+    import piecewise_ref as pw
+    rng = np.random.default_rng(8)
+    D = 16
+    x = (rng.uniform(-2, 2, 500) * (1 << D)).astype(np.int64)
+    for th, coef in (([-0.5, 0.5], [[], [0.5, 1], [1]]), ([0.0], [[], [0, 1]]), ([-1.0, 0.0, 1.0], [[1], [0.25, 2], [], [3, -1]])):
+        assert np.array_equal(pw.plain(x, th, coef, D).reshape(-1), r.piecewise_plain(x, th, coef, D))
+
+
+def test_piecewise_step_function_reveals_like_reference():
+    """The reference's three-party Sh3Piecewise::eval (Sh3Piecewise.cpp:184-567: getInputRegions, the region
+    circuit from its own CircuitLibrary, asyncMul(i64, sbMatrix) per region) against the oracle-side composition,
+    on piecewise-CONSTANT functions.  The region circuit comes from each side's own circuit library, so share
+    planes may differ; reconstructed outputs may not.
+
+    Degree-1 regions cannot be checked this way: the reference passes functionOutputs[c] as both A and C of
+    asyncMul(si64Matrix, sbMatrix) (Sh3Piecewise.cpp:296-300) and party 0 overwrites c[0](i), c[1](i) before it
+    reads A[0](i) + A[1](i) (Sh3Evaluator.cpp:155-162), so its three-party result is garbage there (its own
+    three-party test is skipped, aby3_tests/Sh3PiecewiseTests.cpp:129).  For those the pinned semantics are the
+    plaintext evaluator's (test above), which the oracle and the device path reproduce."""
+    import piecewise_ref as pw
+    so, sr = pair()
+    rng = np.random.default_rng(9)
+    D, n = 16, 200
+    x = (rng.uniform(-1.5, 1.5, (n, 1)) * (1 << D)).astype(np.int64)
+    cir2, cir3 = _lib_circuit("piecewise2", 64), _lib_circuit("piecewise3", 64)
+    for th, coef, cir in (([-0.5, 0.5], [[], [0.25], [1]], cir2), ([0.0, 1.0], [[3], [], [-2]], cir2),
+                          ([-1.0, 0.0, 1.0], [[1], [2], [], [7]], cir3)):
+        Xo, Xr = so.share_int(0, x), sr.share_int(0, x)
+        Yr = sr.piecewise(Xr, th, coef, D)
+        Yo = pw.shared(so, Xo, th, coef, D, cir)
+        exp = pw.plain(x, th, coef, D)
+        assert np.array_equal(sr.reveal_all(Yr)[0], exp)
+        assert np.array_equal(o.reveal(Yo, 0), exp)
+        for p in range(3):
+            assert np.array_equal(Yr[(p + 1) % 3, 1], Yr[p, 0])          # a consistent replicated sharing
+
+
+def test_reference_piecewise_aliasing_is_what_breaks_degree_one_regions():
+    """Documents the finding above: same inputs, logisticFunc coefficients -- the reference's three-party
+    result differs from its own plaintext evaluator exactly on the rows of the degree-1 region."""
+    import piecewise_ref as pw
+    _, sr = pair()
+    rng = np.random.default_rng(10)
+    D, n = 16, 64
+    x = (rng.uniform(-1.5, 1.5, (n, 1)) * (1 << D)).astype(np.int64)
+    th, coef = [-0.5, 0.5], [[], [0.5, 1], [1]]
+    got = sr.reveal_all(sr.piecewise(sr.share_int(0, x), th, coef, D))[0]
+    exp = r.piecewise_plain(x, th, coef, D).reshape(n, 1)
+    middle = (x >= -(1 << (D - 1))) & (x < (1 << (D - 1)))
+    assert np.array_equal(got[~middle], exp[~middle])
+    assert middle.any() and not np.array_equal(got[middle], exp[middle])
+
+
+def test_scheduler_orders_hold_for_the_reference_runtime(tmp_path):
+    """tests/cpp/test_runtime.cpp (the assertions of aby3_tests/Sh3RuntimeTests.cpp, which the facade's
+    Sh3Runtime passes in test_cpp_runtime.py) compiled against the reference's own Sh3Runtime."""
+    if not os.path.isdir(os.path.join(r.REFERENCE, "aby3", "sh3")):
+        pytest.skip("needs the reference headers")
+    exe = str(tmp_path / "test_runtime_ref")
+    orc = os.path.join(ROOT, "oracle")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-w", "-maes", "-msse4.1", "-mavx2", "-DREF_RUNTIME",
+                           "-I", os.path.join(orc, "shim"), "-I", r.REFERENCE, "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "test_runtime.cpp"), os.path.join(orc, "shim", "shim.cpp"),
+                           os.path.join(orc, "_ref", "Sh3Runtime.o"), os.path.join(orc, "_ref", "Sh3Types.o")])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "ALL OK" in out.stdout
