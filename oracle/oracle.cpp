@@ -3,11 +3,13 @@
  * hot path.  TEST INFRASTRUCTURE ONLY (see oracle.h): never linked or loaded
  * by anything under aby3_b200/.
  *
- * "parity unpinned" at the raw PRNG / share level: the reference holds no
- * golden vectors for it and its PRNG comes from cryptoTools (libOTe @
- * cf537295c47a3924c13030a9b796cee9d6ebeace), absent here.  AES itself is
- * pinned by FIPS-197; reconstruction-level behaviour is pinned by
- * re-expressing the reference's unit tests (tests/test_oracle_*.py).
+ * Pinned share-for-share against the reference's own sources compiled from
+ * /root/reference (oracle/_ref, tests/test_ref_parity.py).  Still "parity
+ * unpinned": the cryptoTools primitives under them (PRNG keystream layout,
+ * toBlock byte order, bit transpose; libOTe @
+ * cf537295c47a3924c13030a9b796cee9d6ebeace is absent here and restated in
+ * oracle/shim).  AES itself is pinned by FIPS-197; reconstruction-level
+ * behaviour by re-expressing the reference's unit tests (tests/test_oracle_*.py).
  *
  * Every function cites the reference lines it restates (paths relative to
  * /root/reference).  Written from the algorithm, not copied: the reference

@@ -7,14 +7,23 @@
  * cpu_baseline / --impl reference legs of bench.py may load it.  Nothing under
  * aby3_b200/ links, imports or calls it.
  *
- * PARITY STATUS: "parity unpinned" at the raw keystream / per-party share
- * level.  The reference contains no golden vectors for AES, PRNG output or
- * share values and its PRNG/AES live in
- * osu-crypto/libOTe @ cf537295c47a3924c13030a9b796cee9d6ebeace (cryptoTools
- * submodule), which is absent from /root/reference and from this image.  What
- * IS pinned: AES-128 against FIPS-197 Appendix B/C.1 and SP 800-38A F.5.1,
- * and every reconstruction-level check of the reference's own unit tests
- * (tests/test_oracle_*.py re-express aby3_tests/Sh3EvaluatorTests.cpp etc.).
+ * PARITY STATUS: pinned against the REFERENCE'S OWN CODE at the protocol level:
+ * oracle/_ref/libaby3ref.so is the reference's sh3 sources (Sh3Runtime,
+ * Sh3Encryptor, Sh3ShareGen, Sh3Evaluator, SharedOT, Sh3BinaryEvaluator,
+ * Sh3Piecewise, CircuitLibrary) compiled unmodified from /root/reference by
+ * oracle/Makefile (target _ref), and tests/test_ref_parity.py checks this
+ * restatement against it share plane for share plane on the same seeds
+ * (sharing, reveal, asyncMul, getTruncationTuple, truncating asyncMul,
+ * bit x arithmetic products over SharedOT, the binary engine, scheduler order).
+ * Still "parity unpinned": the third-party PRIMITIVES under that code.  The
+ * reference's PRNG/AES/transpose live in osu-crypto/libOTe @
+ * cf537295c47a3924c13030a9b796cee9d6ebeace (cryptoTools submodule), absent from
+ * /root/reference and this image; oracle/shim/ restates them from their public
+ * interface (oc::PRNG = one contiguous AES-128-CTR keystream over toBlock(ctr),
+ * toBlock(hi, lo) byte order, LSB-first bit transpose) and both sides of the
+ * comparison share those assumptions.  AES-128 itself is pinned by FIPS-197
+ * Appendix B/C.1 and SP 800-38A F.5.1; the reference's own reconstruction-level
+ * test assertions are re-expressed in tests/test_oracle_*.py.
  *
  * Conventions: party i holds (x_i, x_{i-1}); plane 0 is
  * the party's own share, plane 1 the previous party's.  All "shares" arrays
