@@ -55,6 +55,7 @@ PROTOTYPES = {
     "aby3cu_d2h": (_int, [_p, _p, _p, _sz]),
     "aby3cu_d2d": (_int, [_p, _p, _int, _p, _int, _sz]),
     "aby3cu_event_create": (_int, [_p, C.POINTER(_p)]),
+    "aby3cu_event_create_sync": (_int, [_p, C.POINTER(_p)]),
     "aby3cu_event_destroy": (_int, [_p]),
     "aby3cu_event_record": (_int, [_p, _p]),
     "aby3cu_event_wait": (_int, [_p, _p]),
@@ -77,9 +78,12 @@ PROTOTYPES = {
     "aby3cu_bitmul_msgs_p2": (_int, [_p, _p, _p, _p, _key, _u64, _p, _p, _sz]),
     "aby3cu_bitmul_pub_msgs": (_int, [_p, C.c_int64, _p, _p, _key, _key, _u64, _p, _sz]),
     "aby3cu_share_op": (_int, [_p, _int, _p, _p, _p, _sz]),
+    "aby3cu_share_op2": (_int, [_p, _int, _p, _p, _p, _p, _p, _p, _sz]),
     "aby3cu_combine3": (_int, [_p, _int, _p, _p, _p, _p, _sz]),
     "aby3cu_axpb": (_int, [_p, C.c_int64, _p, C.c_int64, _p, _sz]),
     "aby3cu_transpose_i64": (_int, [_p, _p, _u64, _u64, _p]),
+    "aby3cu_transpose_i64_2": (_int, [_p, _p, _p, _u64, _u64, _p, _p]),
+    "aby3cu_gather_rows_multi": (_int, [_p, _int, _p, _p, _p, _p, _u64]),
     "aby3cu_gather_rows": (_int, [_p, _p, _u64, _p, _u64, _p]),
     "aby3cu_iota_u64": (_int, [_p, _u64, _u64, _p, _sz]),
     "aby3cu_scatter_rows": (_int, [_p, _p, _u64, _p, _u64, _p]),

@@ -55,6 +55,8 @@ def build_sh3(force=False):
         return None
     srcs = _sources(d, (".cpp", ".h")) + [os.path.join(ROOT, "include", "aby3cu.h")]
     cpps = [s for s in srcs if s.endswith(".cpp")]
+    # headers of the app layers the harness instantiates (aby3-ML, aby3-Basic)
+    srcs += _sources(os.path.join(PKG, "ml"), (".h",)) + _sources(os.path.join(PKG, "basic"), (".h",))
     if not cpps:
         return None
     if force or _newer(so, srcs + [os.path.join(PKG, "libaby3cu.so")]):

@@ -241,6 +241,14 @@ int aby3cu_event_create(aby3cu_ctx* ctx, void** event) {
     *event = ev;
     return 0;
 }
+int aby3cu_event_create_sync(aby3cu_ctx* ctx, void** event) {
+    ABY3CU_REQUIRE(ctx && event, "event_create_sync: null argument");
+    DeviceGuard g(ctx->device);
+    cudaEvent_t ev;
+    ABY3CU_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    *event = ev;
+    return 0;
+}
 int aby3cu_event_destroy(void* event) {
     if (event) ABY3CU_CHECK(cudaEventDestroy((cudaEvent_t)event));
     return 0;

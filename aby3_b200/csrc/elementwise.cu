@@ -36,7 +36,7 @@ __device__ __forceinline__ void st2(i64* p, size_t i, size_t n, bool vec, U64x2 
     }
 }
 
-__host__ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__host__ __device__ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---------------------------------------------------------------------------------
 // keystream fill: out[i] = KS[e0 + i]
@@ -178,6 +178,25 @@ __global__ void __launch_bounds__(kThreads) k_share_op(const i64* __restrict__ x
     }
 }
 
+// both share planes of a replicated sharing in one launch (blockIdx.y = plane)
+struct Planes2 { const i64* x[2]; const i64* y[2]; i64* out[2]; };
+template <int OP>
+__global__ void __launch_bounds__(kThreads) k_share_op2(Planes2 p, size_t n, int vec) {
+    const i64* __restrict__ x = p.x[blockIdx.y];
+    const i64* __restrict__ y = p.y[blockIdx.y];
+    i64* __restrict__ out = p.out[blockIdx.y];
+    const size_t pairs = (n + 1) / 2;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < pairs; q += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = 2 * q;
+        const bool v2 = vec && i + 1 < n;
+        U64x2 a = ld2(x, i, n, v2), b = ld2(y, i, n, v2), o;
+        if (OP == ABY3CU_OP_ADD) { o.a = a.a + b.a; o.b = a.b + b.b; }
+        else if (OP == ABY3CU_OP_SUB) { o.a = a.a - b.a; o.b = a.b - b.b; }
+        else { o.a = a.a ^ b.a; o.b = a.b ^ b.b; }
+        st2(out, i, n, v2, o);
+    }
+}
+
 template <int OP>
 __global__ void __launch_bounds__(kThreads) k_combine3(const i64* __restrict__ x0, const i64* __restrict__ x1, const i64* __restrict__ x2,
                                                        i64* __restrict__ out, size_t n, int vec) {
@@ -222,6 +241,56 @@ __global__ void __launch_bounds__(256) k_transpose(const i64* __restrict__ in, u
             if (r < rows && c < cols) out[c * rows + r] = tile[lx][j];
         }
         __syncthreads();
+    }
+}
+
+// 32x32 tile transpose of both share planes (blockIdx.y = plane)
+__global__ void __launch_bounds__(256) k_transpose2(const i64* __restrict__ in0, const i64* __restrict__ in1, u64 rows, u64 cols,
+                                                    i64* __restrict__ out0, i64* __restrict__ out1) {
+    __shared__ i64 tile[32][33];
+    const i64* __restrict__ in = blockIdx.y ? in1 : in0;
+    i64* __restrict__ out = blockIdx.y ? out1 : out0;
+    const u64 tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+    for (u64 t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+        const u64 tr = t / tiles_c, tc = t % tiles_c;
+        const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+        for (int j = ly; j < 32; j += 8) {
+            u64 r = tr * 32 + j, c = tc * 32 + lx;
+            if (r < rows && c < cols) tile[j][lx] = in[r * cols + c];
+        }
+        __syncthreads();
+        for (int j = ly; j < 32; j += 8) {
+            u64 c = tc * 32 + j, r = tr * 32 + lx;
+            if (r < rows && c < cols) out[c * rows + r] = tile[lx][j];
+        }
+        __syncthreads();
+    }
+}
+
+// several row gathers that share one index vector, in one launch (blockIdx.y = job): the mini-batch
+// extraction of SGD takes the same rows of X and Y, both share planes
+struct GatherJobs { const i64* in[ABY3CU_MAX_GATHER_JOBS]; i64* out[ABY3CU_MAX_GATHER_JOBS]; u64 cols[ABY3CU_MAX_GATHER_JOBS]; };
+__global__ void __launch_bounds__(256) k_gather_rows_multi(GatherJobs jobs, const u64* __restrict__ idx, u64 nrows) {
+    const i64* __restrict__ in = jobs.in[blockIdx.y];
+    i64* __restrict__ out = jobs.out[blockIdx.y];
+    const u64 cols = jobs.cols[blockIdx.y];
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (cols == 1) {
+        for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (u64)gridDim.x * blockDim.x) out[r] = in[idx[r]];
+        return;
+    }
+    const bool v2 = (cols & 1) == 0 && al16(in) && al16(out);
+    for (u64 r = warp; r < nrows; r += nwarps) {
+        const i64* src = in + idx[r] * cols;
+        i64* dst = out + r * cols;
+        if (v2) {
+            const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);
+            ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst);
+            for (u64 c = lane; c < cols / 2; c += 32) d2[c] = s2[c];
+        } else {
+            for (u64 c = lane; c < cols; c += 32) dst[c] = src[c];
+        }
     }
 }
 
@@ -406,6 +475,21 @@ int aby3cu_share_op(aby3cu_ctx* ctx, int op, const i64* x, const i64* y, i64* ou
     return post_launch(ctx, "k_share_op");
 }
 
+int aby3cu_share_op2(aby3cu_ctx* ctx, int op, const i64* x0, const i64* y0, i64* out0, const i64* x1, const i64* y1, i64* out1, size_t n) {
+    ABY3CU_REQUIRE(ctx && ((x0 && y0 && out0 && x1 && y1 && out1) || !n), "share_op2: null argument");
+    ABY3CU_REQUIRE(op >= 0 && op <= 2, "share_op2: bad op");
+    if (!n) return 0;
+    DeviceGuard g(ctx->device);
+    const int vec = al16(x0) && al16(y0) && al16(out0) && al16(x1) && al16(y1) && al16(out1);
+    unsigned gx = ew_grid(ctx, (n + 1) / 2, kThreads, 4);
+    const dim3 grid(gx, 2);
+    Planes2 p{{x0, x1}, {y0, y1}, {out0, out1}};
+    if (op == ABY3CU_OP_ADD) k_share_op2<ABY3CU_OP_ADD><<<grid, kThreads, 0, ctx->stream>>>(p, n, vec);
+    else if (op == ABY3CU_OP_SUB) k_share_op2<ABY3CU_OP_SUB><<<grid, kThreads, 0, ctx->stream>>>(p, n, vec);
+    else k_share_op2<ABY3CU_OP_XOR><<<grid, kThreads, 0, ctx->stream>>>(p, n, vec);
+    return post_launch(ctx, "k_share_op2");
+}
+
 int aby3cu_combine3(aby3cu_ctx* ctx, int op, const i64* x0, const i64* x1, const i64* x2, i64* out, size_t n) {
     ABY3CU_REQUIRE(ctx && ((x0 && x1 && x2 && out) || !n), "combine3: null argument");
     ABY3CU_REQUIRE(op == ABY3CU_OP_ADD || op == ABY3CU_OP_XOR, "combine3: bad op");
@@ -436,6 +520,35 @@ int aby3cu_transpose_i64(aby3cu_ctx* ctx, const i64* in, u64 rows, u64 cols, i64
     const unsigned grid = (unsigned)(tiles < (u64)ctx->sm_count * 8 ? tiles : (u64)ctx->sm_count * 8);
     k_transpose<<<grid, 256, 0, ctx->stream>>>(in, rows, cols, out);
     return post_launch(ctx, "k_transpose");
+}
+
+int aby3cu_transpose_i64_2(aby3cu_ctx* ctx, const i64* in0, const i64* in1, u64 rows, u64 cols, i64* out0, i64* out1) {
+    ABY3CU_REQUIRE(ctx && ((in0 && in1 && out0 && out1) || !(rows * cols)), "transpose2: null argument");
+    if (!(rows * cols)) return 0;
+    DeviceGuard g(ctx->device);
+    const u64 tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+    const unsigned gx = (unsigned)(tiles < (u64)ctx->sm_count * 4 ? tiles : (u64)ctx->sm_count * 4);
+    k_transpose2<<<dim3(gx, 2), 256, 0, ctx->stream>>>(in0, in1, rows, cols, out0, out1);
+    return post_launch(ctx, "k_transpose2");
+}
+
+int aby3cu_gather_rows_multi(aby3cu_ctx* ctx, int njobs, const i64* const* in, const u64* cols, i64* const* out, const u64* idx, u64 nrows) {
+    ABY3CU_REQUIRE(ctx && in && cols && out, "gather_rows_multi: null argument");
+    ABY3CU_REQUIRE(njobs >= 1 && njobs <= ABY3CU_MAX_GATHER_JOBS, "gather_rows_multi: bad job count");
+    if (!nrows) return 0;
+    ABY3CU_REQUIRE(idx, "gather_rows_multi: null index vector");
+    GatherJobs jobs;
+    u64 maxc = 1;
+    for (int j = 0; j < ABY3CU_MAX_GATHER_JOBS; ++j) {
+        const int k = j < njobs ? j : 0;
+        ABY3CU_REQUIRE(in[k] && out[k] && cols[k], "gather_rows_multi: null / empty job");
+        jobs.in[j] = in[k]; jobs.out[j] = out[k]; jobs.cols[j] = cols[k];
+        if (cols[k] > maxc) maxc = cols[k];
+    }
+    DeviceGuard g(ctx->device);
+    const unsigned gx = ew_grid(ctx, maxc == 1 ? nrows : nrows * 32, 256, 4);
+    k_gather_rows_multi<<<dim3(gx, (unsigned)njobs), 256, 0, ctx->stream>>>(jobs, idx, nrows);
+    return post_launch(ctx, "k_gather_rows_multi");
 }
 
 int aby3cu_iota_u64(aby3cu_ctx* ctx, u64 start, u64 step, u64* out, size_t n) {

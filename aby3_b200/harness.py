@@ -25,6 +25,8 @@ def _load():
     l.sh3h_create.argtypes = [i32, i32, i32, C.c_char_p, C.c_char_p]
     l.sh3h_create_nccl.restype = p
     l.sh3h_create_nccl.argtypes = [i32, i32, i32, C.c_char_p, C.c_char_p]
+    l.sh3h_create_shared_stream.restype = p
+    l.sh3h_create_shared_stream.argtypes = [i32, C.c_char_p, C.c_char_p]
     l.sh3h_destroy.argtypes = [p]
     l.sh3h_set_disable_randomization.argtypes = [p, i32]
     l.sh3h_set_gemm_algo.argtypes = [p, i32]
@@ -84,8 +86,13 @@ class Session:
         """transport "local": in-process hand-off (same GPU: D2D, other GPU: NVLink peer copy);
         "nccl": three different GPUs, ncclSend/ncclRecv over NVLink."""
         e, v = default_seeds()
-        create = lib.sh3h_create_nccl if transport == "nccl" else lib.sh3h_create
-        self.h = create(devices[0], devices[1], devices[2], enc_seeds or e, eval_seeds or v)
+        if transport == "shared_stream":
+            # co-located parties on one stream: ordering by enqueue order, no events per message
+            assert devices[0] == devices[1] == devices[2]
+            self.h = lib.sh3h_create_shared_stream(devices[0], enc_seeds or e, eval_seeds or v)
+        else:
+            create = lib.sh3h_create_nccl if transport == "nccl" else lib.sh3h_create
+            self.h = create(devices[0], devices[1], devices[2], enc_seeds or e, eval_seeds or v)
         if not self.h:
             raise Sh3Error(lib.sh3h_last_error().decode())
 

@@ -35,10 +35,34 @@ namespace oc {
 namespace detail {
 
 struct Message {
-    std::vector<u8> host;                 // host payload (when dev is empty)
+    std::vector<u8> host;                 // host payload (when dev / shared are empty)
     aby3::gpu::Buffer dev;                // device payload (staging buffer owned by the sender's pool)
-    void* ready = nullptr;                // event: payload complete on the sender's stream
+    std::shared_ptr<aby3::gpu::SharedBuffer> shared;   // device payload sent without a copy
+    void* ready = nullptr;                // event: payload complete on the sender's stream (null: same stream)
+    int readyDevice = 0;
     size_t bytes = 0;
+};
+
+// What a zero-copy receive hands to the protocol: a pointer that is valid (in stream order) on the
+// receiver's stream, and the object keeping it alive.  release() after the last kernel reading it
+// has been enqueued.
+struct Borrowed {
+    const void* ptr = nullptr;
+    size_t bytes = 0;
+    aby3::gpu::Buffer own;                                  // staging buffer taken over from the message, or an own copy
+    std::shared_ptr<aby3::gpu::SharedBuffer> shared;        // sender-shared buffer
+    bool ownedByPeer = false;                               // `own` belongs to the sender's pool
+    void release(aby3::gpu::Context* reader) {
+        if (shared) {
+            if (shared->ctx()->stream() != reader->stream()) shared->addReader(reader->device(), reader->recordEvent());
+            shared.reset();
+        }
+        if (own) {
+            if (ownedByPeer && own.ctx()->stream() != reader->stream()) own.free(reader->recordEvent());
+            else own.free();
+        }
+        ptr = nullptr;
+    }
 };
 
 // one direction of a local channel
@@ -113,6 +137,14 @@ struct Transport {
     // which blocks the host until the bytes are in p / ordered on the stream for d.
     virtual std::function<void()> postRecvHost(u8* p, size_t n) = 0;
     virtual std::function<void()> postRecvDevice(void* d, size_t n) = 0;
+    // zero-copy forms; the defaults fall back to the copying ones
+    virtual void sendDeviceShared(const std::shared_ptr<aby3::gpu::SharedBuffer>& b, size_t n) { sendDevice(b->ptr(), n); }
+    virtual std::function<void()> postRecvDeviceBorrow(size_t n, Borrowed* out) {
+        out->own.reset(context(), std::max<size_t>(n, 16));
+        out->ptr = out->own.ptr();
+        out->bytes = n;
+        return postRecvDevice(out->own.ptr(), n);
+    }
     virtual void flush() {}
     virtual aby3::gpu::Context* context() const = 0;
 };
@@ -120,6 +152,7 @@ struct Transport {
 struct LocalTransport : Transport {
     std::shared_ptr<Pipe> out, in;
     aby3::gpu::Context* ctx = nullptr;
+    void* peerStream = nullptr;           // the stream of the context at the other end
     aby3::gpu::Context* context() const override { return ctx; }
     void requireCtx() const {
         if (!ctx) throw std::runtime_error("Channel: device transfer on a channel without a device context " LOCATION);
@@ -135,14 +168,14 @@ struct LocalTransport : Transport {
     void recvHost(u8* p, size_t n) {
         Message m = in->pop();
         if (m.bytes != n) throw std::runtime_error("Channel: message size mismatch " LOCATION);
-        if (m.dev) {
+        if (m.dev || m.shared) {
             // device message consumed on the host (e.g. reveal into an i64Matrix)
             requireCtx();
-            aby3::gpu::check(aby3cu_event_wait(ctx->h(), m.ready));
-            if (n) aby3::gpu::check(aby3cu_d2h(ctx->h(), p, m.dev.ptr(), n));
+            waitReady(m);
+            if (n) aby3::gpu::check(aby3cu_d2h(ctx->h(), p, m.dev ? m.dev.ptr() : m.shared->ptr(), n));
             ctx->sync();
-            aby3cu_event_destroy(m.ready);
             m.dev.free();
+            m.shared.reset();
         } else if (n) {
             memcpy(p, m.host.data(), n);
         }
@@ -153,23 +186,70 @@ struct LocalTransport : Transport {
         m.bytes = n;
         m.dev.reset(ctx, std::max<size_t>(n, 16));
         if (n) aby3::gpu::check(aby3cu_d2d(ctx->h(), m.dev.ptr(), ctx->device(), d, ctx->device(), n));
-        aby3::gpu::check(aby3cu_event_create(ctx->h(), &m.ready));
-        aby3::gpu::check(aby3cu_event_record(ctx->h(), m.ready));
+        markReady(m);
         out->push(std::move(m));
+    }
+    void sendDeviceShared(const std::shared_ptr<aby3::gpu::SharedBuffer>& b, size_t n) override {
+        requireCtx();
+        if (b->ctx() != ctx) throw std::runtime_error("Channel: a shared buffer must come from the sender's own context " LOCATION);
+        Message m;
+        m.bytes = n;
+        m.shared = b;
+        markReady(m);
+        out->push(std::move(m));
+    }
+    // Parties whose contexts share ONE stream are ordered by enqueue order alone: the receiver's host thread
+    // only learns of a message after the sender has enqueued its producer, so no event is needed.
+    bool sameStream() const { return peerStream && peerStream == ctx->stream(); }
+    void markReady(Message& m) {
+        if (sameStream()) return;
+        m.ready = ctx->recordEvent();
+        m.readyDevice = ctx->device();
+    }
+    void waitReady(Message& m) {
+        if (!m.ready) return;
+        aby3::gpu::check(aby3cu_event_wait(ctx->h(), m.ready));
+        aby3::gpu::EventPool::put(m.readyDevice, m.ready);
+        m.ready = nullptr;
+    }
+    std::function<void()> postRecvDeviceBorrow(size_t n, Borrowed* b) override {
+        return [this, n, b] {
+            requireCtx();
+            Message m = in->pop();
+            if (m.bytes != n) throw std::runtime_error("Channel: message size mismatch " LOCATION);
+            b->bytes = n;
+            aby3::gpu::Context* owner = m.shared ? m.shared->ctx() : (m.dev ? m.dev.ctx() : nullptr);
+            if (owner && owner->device() == ctx->device()) {
+                waitReady(m);
+                if (m.shared) { b->shared = std::move(m.shared); b->ptr = b->shared->ptr(); }
+                else { b->own = std::move(m.dev); b->ownedByPeer = true; b->ptr = b->own.ptr(); }
+                return;
+            }
+            // another GPU (NVLink peer copy) or a host payload: land it in a buffer of our own
+            b->own.reset(ctx, std::max<size_t>(n, 16));
+            b->ptr = b->own.ptr();
+            deliver(m, b->own.ptr(), n);
+        };
     }
     void recvDevice(void* d, size_t n) {
         requireCtx();
         Message m = in->pop();
         if (m.bytes != n) throw std::runtime_error("Channel: message size mismatch " LOCATION);
-        if (m.dev) {
-            aby3::gpu::check(aby3cu_event_wait(ctx->h(), m.ready));
-            if (n) aby3::gpu::check(aby3cu_d2d(ctx->h(), d, ctx->device(), m.dev.ptr(), m.dev.ctx()->device(), n));
-            aby3cu_event_destroy(m.ready);
-            // the staging buffer returns to the sender's pool once OUR copy has run
-            void* done = nullptr;
-            aby3::gpu::check(aby3cu_event_create(ctx->h(), &done));
-            aby3::gpu::check(aby3cu_event_record(ctx->h(), done));
-            m.dev.free(done);
+        deliver(m, d, n);
+    }
+    void deliver(Message& m, void* d, size_t n) {
+        if (m.dev || m.shared) {
+            aby3::gpu::Context* owner = m.dev ? m.dev.ctx() : m.shared->ctx();
+            const void* src = m.dev ? m.dev.ptr() : m.shared->ptr();
+            const bool same = !m.ready;
+            waitReady(m);
+            if (n) aby3::gpu::check(aby3cu_d2d(ctx->h(), d, ctx->device(), src, owner->device(), n));
+            // the payload returns to the sender's pool once OUR copy has run
+            if (m.dev) m.dev.free(same ? nullptr : ctx->recordEvent());
+            else {
+                if (!same) m.shared->addReader(ctx->device(), ctx->recordEvent());
+                m.shared.reset();
+            }
         } else if (n) {
             aby3::gpu::check(aby3cu_h2d(ctx->h(), d, m.host.data(), n));
             ctx->sync();   // m.host dies with this scope
@@ -274,6 +354,8 @@ struct NcclTransport : Transport {
 
 }  // namespace detail
 
+using Borrowed = detail::Borrowed;
+
 class Channel {
 public:
     Channel() = default;
@@ -287,6 +369,7 @@ public:
         auto tb = std::make_shared<detail::LocalTransport>();
         ta->out = ab; ta->in = ba; ta->ctx = ctxA;
         tb->out = ba; tb->in = ab; tb->ctx = ctxB;
+        if (ctxA && ctxB && ctxA->device() == ctxB->device()) { ta->peerStream = ctxB->stream(); tb->peerStream = ctxA->stream(); }
         return {Channel(ta), Channel(tb)};
     }
     // NCCL endpoint towards rank `peer` of the party's communicator
@@ -372,6 +455,18 @@ public:
     std::future<void> asyncRecvDevice(void* d_dst, size_t bytes) {
         require();
         return post(mT->postRecvDevice(d_dst, bytes));
+    }
+    // Zero-copy forms for buffers the protocol never writes again (the opened xy - r of the truncating
+    // product, Sh3Evaluator.cpp:676-700).  Local transport on one GPU: no staging copy on either side;
+    // other transports copy as above.
+    void asyncSendDeviceShared(const std::shared_ptr<aby3::gpu::SharedBuffer>& buf, size_t bytes) {
+        require();
+        mBytesSent += bytes;
+        mT->sendDeviceShared(buf, bytes);
+    }
+    std::future<void> asyncRecvDeviceBorrow(size_t bytes, Borrowed* out) {
+        require();
+        return post(mT->postRecvDeviceBorrow(bytes, out));
     }
 
     // ------------------------------------------------------------------ stats -

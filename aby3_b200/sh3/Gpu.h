@@ -16,6 +16,38 @@ inline void check(int rc) {
     if (rc != 0) throw std::runtime_error(std::string("aby3cu: ") + aby3cu_last_error());
 }
 
+// Ordering-only CUDA events, recycled per device: a message hand-over between parties must not pay
+// for cudaEventCreate / cudaEventDestroy.  An event may be re-recorded as soon as every wait on it
+// has been ISSUED (cudaStreamWaitEvent captures the record that precedes the call).
+class EventPool {
+public:
+    static void* get(aby3cu_ctx* ctx, int device) {
+        auto& p = inst();
+        {
+            std::lock_guard<std::mutex> g(p.mMtx);
+            auto& v = p.mFree[device];
+            if (!v.empty()) { void* e = v.back(); v.pop_back(); return e; }
+        }
+        void* e = nullptr;
+        check(aby3cu_event_create_sync(ctx, &e));
+        return e;
+    }
+    static void put(int device, void* e) {
+        if (!e) return;
+        auto& p = inst();
+        {
+            std::lock_guard<std::mutex> g(p.mMtx);
+            auto& v = p.mFree[device];
+            if (v.size() < 8192) { v.push_back(e); return; }
+        }
+        aby3cu_event_destroy(e);
+    }
+private:
+    static EventPool& inst() { static EventPool* p = new EventPool; return *p; }   // leaked on purpose: outlives every context
+    std::mutex mMtx;
+    std::map<int, std::vector<void*>> mFree;
+};
+
 // One party's device, stream and buffer pool.  Buffers released to the pool are
 // reused in stream order; a buffer another party's stream may still be reading
 // is parked together with the event that marks the end of that read.
@@ -36,7 +68,7 @@ public:
         aby3cu_sync(mCtx);
         for (auto& kv : mFree)
             for (auto& e : kv.second) {
-                if (e.event) aby3cu_event_destroy(e.event);
+                if (e.event) EventPool::put(mDevice, e.event);
                 aby3cu_free(mCtx, e.ptr);
             }
         aby3cu_ctx_destroy(mCtx);
@@ -62,7 +94,7 @@ public:
         if (e.ptr) {
             if (e.event) {
                 check(aby3cu_event_wait(mCtx, e.event));
-                aby3cu_event_destroy(e.event);
+                EventPool::put(mDevice, e.event);
             }
             return e.ptr;
         }
@@ -84,9 +116,14 @@ public:
         }
         // the cache is full: give the block back to the driver (workloads whose buffer sizes keep
         // changing -- e.g. the shrinking stages of a merge network -- must not hoard HBM)
-        if (after) { aby3cu_event_sync(after); aby3cu_event_destroy(after); }
+        if (after) { aby3cu_event_sync(after); EventPool::put(mDevice, after); }
         aby3cu_free(mCtx, p);
     }
+    // a recycled ordering event for this context's device / recorded on this context's stream
+    void* newEvent() { return EventPool::get(mCtx, mDevice); }
+    void* recordEvent() { void* e = newEvent(); check(aby3cu_event_record(mCtx, e)); return e; }
+    void recycleEvent(void* e) { EventPool::put(mDevice, e); }
+    void* stream() const { return aby3cu_ctx_stream(mCtx); }
 
     // Size classes: multiples of 512 B up to 1 MiB, then 1/8-octave steps, so that buffers whose
     // sizes drift (stage after stage of a merge network) still recycle each other's memory.
@@ -142,7 +179,7 @@ public:
     }
     void free(void* after = nullptr) {
         if (mPtr && mCtx) mCtx->release(mPtr, mBytes, after);
-        else if (after) aby3cu_event_destroy(after);
+        else if (after) aby3cu_event_destroy(after);        // no owner to hand it to
         mPtr = nullptr; mBytes = 0; mCtx = nullptr;
     }
     void* ptr() const { return mPtr; }
@@ -153,6 +190,36 @@ private:
     Context* mCtx = nullptr;
     void* mPtr = nullptr;
     size_t mBytes = 0;
+};
+
+// A device buffer several parties read: the producer sends it WITHOUT a staging copy, every reader
+// reports the event after its last read, and the block returns to the producer's pool once the
+// producer's stream has been ordered behind all of them.  Contents are immutable once shared.
+class SharedBuffer {
+public:
+    SharedBuffer(Context* c, size_t bytes) : mBuf(c, bytes) {}
+    SharedBuffer(const SharedBuffer&) = delete;
+    SharedBuffer& operator=(const SharedBuffer&) = delete;
+    ~SharedBuffer() {
+        Context* c = mBuf.ctx();
+        std::lock_guard<std::mutex> g(mMtx);
+        for (auto& r : mReaders) {
+            if (c) aby3cu_event_wait(c->h(), r.second);
+            EventPool::put(r.first, r.second);
+        }
+    }
+    void* ptr() const { return mBuf.ptr(); }
+    size_t bytes() const { return mBuf.bytes(); }
+    Context* ctx() const { return mBuf.ctx(); }
+    // `event` (from reader's device pool) marks the end of a reader's last access
+    void addReader(int device, void* event) {
+        std::lock_guard<std::mutex> g(mMtx);
+        mReaders.emplace_back(device, event);
+    }
+private:
+    Buffer mBuf;
+    std::mutex mMtx;
+    std::vector<std::pair<int, void*>> mReaders;
 };
 
 // Page-locked host blocks are expensive to create (cudaHostAlloc is a syscall-heavy

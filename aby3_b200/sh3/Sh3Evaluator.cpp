@@ -133,12 +133,13 @@ Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64Matrix& A, const si
         const u8* kp = rnd ? seedPrev.data() : nullptr;
         const u64 en = rnd ? streamElem(g.mNextCommon) : 0, ep = rnd ? streamElem(g.mPrevCommon) : 0;
 
-        // abMinusR and the two receive buffers live until the continuation has run
-        struct Scratch { gpu::Buffer v, s0, s1; };
+        // abMinusR is written once and then only read -- by this party's continuation and by the parties it is
+        // opened to -- so it is sent without a staging copy and received without one (SharedBuffer / Borrowed)
+        struct Scratch { std::shared_ptr<gpu::SharedBuffer> v; oc::Borrowed s0, s1; };
         auto sc = std::make_shared<Scratch>();
         const size_t bytes = std::max<size_t>(n * sizeof(i64), 16);
-        sc->v.reset(ctx, bytes);
-        i64* V = (i64*)sc->v.ptr();
+        sc->v = std::make_shared<gpu::SharedBuffer>(ctx, bytes);
+        i64* V = (i64*)sc->v->ptr();
 
         // RTrunc is produced into fresh matrices and moved into C only after the
         // cross term has been enqueued, so C may alias A or B (as in the reference,
@@ -162,18 +163,18 @@ Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64Matrix& A, const si
         // open xy - r to parties 0 and 1 (:676-684)
         auto& rt = self.getRuntime();
         const u64 next = (rt.mPartyIdx + 1) % 3, prev = (rt.mPartyIdx + 2) % 3;
-        if (next < 2) comm.mNext.asyncSendDevice(V, n * sizeof(i64));
-        if (prev < 2) comm.mPrev.asyncSendDevice(V, n * sizeof(i64));
+        if (next < 2) comm.mNext.asyncSendDeviceShared(sc->v, n * sizeof(i64));
+        if (prev < 2) comm.mPrev.asyncSendDeviceShared(sc->v, n * sizeof(i64));
         if (rt.mPartyIdx < 2) {
-            sc->s0.reset(ctx, bytes);
-            sc->s1.reset(ctx, bytes);
-            auto fu0 = comm.mNext.asyncRecvDevice(sc->s0.ptr(), n * sizeof(i64)).share();
-            auto fu1 = comm.mPrev.asyncRecvDevice(sc->s1.ptr(), n * sizeof(i64)).share();
+            auto fu0 = comm.mNext.asyncRecvDeviceBorrow(n * sizeof(i64), &sc->s0).share();
+            auto fu1 = comm.mPrev.asyncRecvDeviceBorrow(n * sizeof(i64), &sc->s1).share();
             self.then([fu0, fu1, sc, &C, shift, n, ctx, this](CommPkg&, Sh3Task&) mutable {
                 fu0.get(); fu1.get();
                 // C[mPartyIdx] += (s0 + s1 + v) >> shift   (:712-718)
-                gpu::check(aby3cu_trunc_finish(ctx->h(), (const i64*)sc->s0.ptr(), (const i64*)sc->s1.ptr(),
-                                               (const i64*)sc->v.ptr(), C.mShares[mPartyIdx].devMut(), n, shift));
+                gpu::check(aby3cu_trunc_finish(ctx->h(), (const i64*)sc->s0.ptr, (const i64*)sc->s1.ptr,
+                                               (const i64*)sc->v->ptr(), C.mShares[mPartyIdx].devMut(), n, shift));
+                sc->s0.release(ctx);
+                sc->s1.release(ctx);
             });
         }
     }).getClosure();

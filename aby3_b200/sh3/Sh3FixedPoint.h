@@ -134,12 +134,17 @@ struct sf64Matrix : private si64Matrix {
     u64 size() const { return mShares[0].size(); }
     Ref<sf64<D>> operator()(u64 x, u64 y) { return Ref<sf64<D>>(mShares[0](x, y), mShares[1](x, y)); }
     Ref<sf64<D>> operator()(u64 xy) { return Ref<sf64<D>>(mShares[0](xy), mShares[1](xy)); }
-    sf64Matrix& operator+=(const sf64Matrix& B) { mShares[0] += B.mShares[0]; mShares[1] += B.mShares[1]; return *this; }
-    sf64Matrix& operator-=(const sf64Matrix& B) { mShares[0] -= B.mShares[0]; mShares[1] -= B.mShares[1]; return *this; }
-    sf64Matrix operator+(const sf64Matrix& B) const { sf64Matrix r = *this; r += B; return r; }
-    sf64Matrix operator-(const sf64Matrix& B) const { sf64Matrix r = *this; r -= B; return r; }
-    sf64Matrix transpose() const { sf64Matrix r = *this; r.transposeInPlace(); return r; }
-    void transposeInPlace() { mShares[0].transposeInPlace(); mShares[1].transposeInPlace(); }
+    // both share planes as one kernel launch (eMatrix::binary2)
+    static sf64Matrix& op2(const sf64Matrix& A, const sf64Matrix& B, sf64Matrix& out, int op) {
+        eMatrix<i64>::binary2(A.mShares[0], B.mShares[0], out.mShares[0], A.mShares[1], B.mShares[1], out.mShares[1], op);
+        return out;
+    }
+    sf64Matrix& operator+=(const sf64Matrix& B) { return op2(*this, B, *this, ABY3CU_OP_ADD); }
+    sf64Matrix& operator-=(const sf64Matrix& B) { return op2(*this, B, *this, ABY3CU_OP_SUB); }
+    sf64Matrix operator+(const sf64Matrix& B) const { sf64Matrix r; op2(*this, B, r, ABY3CU_OP_ADD); return r; }
+    sf64Matrix operator-(const sf64Matrix& B) const { sf64Matrix r; op2(*this, B, r, ABY3CU_OP_SUB); return r; }
+    sf64Matrix transpose() const { sf64Matrix r; eMatrix<i64>::transpose2(mShares[0], mShares[1], r.mShares[0], r.mShares[1]); return r; }
+    void transposeInPlace() { eMatrix<i64>::transpose2(mShares[0], mShares[1], mShares[0], mShares[1]); }
     Row row(u64 i) { return Row{*this, i}; }
     Col col(u64 i) { return Col{*this, i}; }
     ConstRow row(u64 i) const { return ConstRow{*this, i}; }

@@ -110,25 +110,23 @@ struct sMatrix {
     void operator()(u64 x, u64 y, Share<T> v) { mShares[0](x, y) = v[0]; mShares[1](x, y) = v[1]; }
 
     // local (communication-free) share arithmetic -- Sh3Types.h:805-820; on device
+    // (both planes go out as one kernel launch)
     sMatrix operator+(const sMatrix& B) const {
         sMatrix r;
-        r.mShares[0] = mShares[0] + B.mShares[0];
-        r.mShares[1] = mShares[1] + B.mShares[1];
+        eMatrix<T>::binary2(mShares[0], B.mShares[0], r.mShares[0], mShares[1], B.mShares[1], r.mShares[1], ABY3CU_OP_ADD);
         return r;
     }
     sMatrix operator-(const sMatrix& B) const {
         sMatrix r;
-        r.mShares[0] = mShares[0] - B.mShares[0];
-        r.mShares[1] = mShares[1] - B.mShares[1];
+        eMatrix<T>::binary2(mShares[0], B.mShares[0], r.mShares[0], mShares[1], B.mShares[1], r.mShares[1], ABY3CU_OP_SUB);
         return r;
     }
     sMatrix transpose() const {
         sMatrix r;
-        r.mShares[0] = mShares[0].transpose();
-        r.mShares[1] = mShares[1].transpose();
+        eMatrix<T>::transpose2(mShares[0], mShares[1], r.mShares[0], r.mShares[1]);
         return r;
     }
-    void transposeInPlace() { mShares[0].transposeInPlace(); mShares[1].transposeInPlace(); }
+    void transposeInPlace() { eMatrix<T>::transpose2(mShares[0], mShares[1], mShares[0], mShares[1]); }
 
     Row row(u64 i) { return Row{*this, i}; }
     Col col(u64 i) { return Col{*this, i}; }

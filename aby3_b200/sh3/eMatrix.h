@@ -155,6 +155,52 @@ public:
     }
     void transposeInPlace() { *this = transpose(); }
 
+    // Both share planes of a replicated sharing at once: (o0, o1) = (a0 op b0, a1 op b1) as ONE kernel
+    // launch when the operands live on the device (latency-bound protocol loops count launches).
+    // o may be the same object as a (in-place) but not as b.
+    static void binary2(const eMatrix& a0, const eMatrix& b0, eMatrix& o0, const eMatrix& a1, const eMatrix& b1, eMatrix& o1, int op) {
+        if (a0.mRows != b0.mRows || a0.mCols != b0.mCols || a1.mRows != b1.mRows || a1.mCols != b1.mCols ||
+            a0.mRows != a1.mRows || a0.mCols != a1.mCols)
+            throw std::runtime_error("eMatrix: shape mismatch " LOCATION);
+        if constexpr (kDeviceOps) {
+            if ((a0.mDevValid || b0.mDevValid) && (a1.mDevValid || b1.mDevValid) && a0.size()) {
+                const int64_t* x0 = (const int64_t*)a0.dev();
+                const int64_t* y0 = (const int64_t*)b0.dev();
+                const int64_t* x1 = (const int64_t*)a1.dev();
+                const int64_t* y1 = (const int64_t*)b1.dev();
+                auto outPtr = [](eMatrix& o, const eMatrix& a) -> int64_t* {
+                    if (&o == &a) return (int64_t*)o.devMut();
+                    o.resize(a.mRows, a.mCols);
+                    return (int64_t*)o.devOut();
+                };
+                int64_t* z0 = outPtr(o0, a0);
+                int64_t* z1 = outPtr(o1, a1);
+                gpu::check(aby3cu_share_op2(a0.ctx()->h(), op, x0, y0, z0, x1, y1, z1, a0.size()));
+                return;
+            }
+        }
+        if (&o0 == &a0) o0.inplace(b0, op); else o0 = a0.binary(b0, op);
+        if (&o1 == &a1) o1.inplace(b1, op); else o1 = a1.binary(b1, op);
+    }
+    // (t0, t1) = (a0^T, a1^T) in one launch; t may be the same object as a
+    static void transpose2(const eMatrix& a0, const eMatrix& a1, eMatrix& t0, eMatrix& t1) {
+        if constexpr (kDeviceOps) {
+            if (a0.mDevValid && a1.mDevValid && a0.size() && a0.mRows == a1.mRows && a0.mCols == a1.mCols) {
+                eMatrix r0, r1;
+                r0.mRows = a0.mCols; r0.mCols = a0.mRows;
+                r1.mRows = a1.mCols; r1.mCols = a1.mRows;
+                gpu::check(aby3cu_transpose_i64_2(a0.ctx()->h(), (const int64_t*)a0.dev(), (const int64_t*)a1.dev(), a0.mRows, a0.mCols,
+                                                  (int64_t*)r0.devOut(), (int64_t*)r1.devOut()));
+                t0 = std::move(r0);
+                t1 = std::move(r1);
+                return;
+            }
+        }
+        eMatrix r0 = a0.transpose(), r1 = a1.transpose();
+        t0 = std::move(r0);
+        t1 = std::move(r1);
+    }
+
     bool operator==(const eMatrix& b) const {
         if (mRows != b.mRows || mCols != b.mCols) return false;
         return size() == 0 || memcmp(hostData(), b.hostData(), size() * sizeof(T)) == 0;

@@ -115,6 +115,11 @@ static sh3h* create_impl(int dev0, int dev1, int dev2, const uint8_t* enc_seeds,
 sh3h* sh3h_create(int dev0, int dev1, int dev2, const uint8_t* enc_seeds, const uint8_t* eval_seeds) {
     return create_impl(dev0, dev1, dev2, enc_seeds, eval_seeds, 0);
 }
+// three parties on ONE GPU sharing ONE stream: enqueue order alone orders the parties' kernels, so a
+// message hand-over needs no CUDA event (latency-bound protocols such as SGD count driver calls)
+sh3h* sh3h_create_shared_stream(int dev, const uint8_t* enc_seeds, const uint8_t* eval_seeds) {
+    return create_impl(dev, dev, dev, enc_seeds, eval_seeds, 2);
+}
 // parties on three DIFFERENT GPUs, reshare by ncclSend/ncclRecv over NVLink
 sh3h* sh3h_create_nccl(int dev0, int dev1, int dev2, const uint8_t* enc_seeds, const uint8_t* eval_seeds) {
     return create_impl(dev0, dev1, dev2, enc_seeds, eval_seeds, 1);
@@ -124,8 +129,11 @@ static sh3h* create_impl(int dev0, int dev1, int dev2, const uint8_t* enc_seeds,
     try {
         std::unique_ptr<sh3h> h(new sh3h);
         const int dev[3] = {dev0, dev1, dev2};
-        for (int i = 0; i < 3; ++i) h->p[i].ctx.reset(new gpu::Context(dev[i]));
-        if (use_nccl) {
+        for (int i = 0; i < 3; ++i) {
+            if (use_nccl == 2 && i > 0) h->p[i].ctx.reset(new gpu::Context(dev[i], h->p[0].ctx->stream()));
+            else h->p[i].ctx.reset(new gpu::Context(dev[i]));
+        }
+        if (use_nccl == 1) {
             if (dev0 == dev1 || dev1 == dev2 || dev0 == dev2)
                 throw std::runtime_error("NCCL transport needs three different GPUs (kernels that wait on each other must not share a device)");
             auto& api = oc::detail::NcclApi::get();

@@ -60,6 +60,7 @@ int aby3cu_d2h(aby3cu_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 /* device-to-device; dst_device/src_device may differ (NVLink peer copy) */
 int aby3cu_d2d(aby3cu_ctx* ctx, void* d_dst, int dst_device, const void* d_src, int src_device, size_t bytes);
 int aby3cu_event_create(aby3cu_ctx* ctx, void** event);
+int aby3cu_event_create_sync(aby3cu_ctx* ctx, void** event);  /* ordering only (no timing): cheaper to record */
 int aby3cu_event_destroy(void* event);
 int aby3cu_event_record(aby3cu_ctx* ctx, void* event);       /* on ctx's stream */
 int aby3cu_event_wait(aby3cu_ctx* ctx, void* event);         /* ctx's stream waits */
@@ -152,6 +153,10 @@ int aby3cu_bitmul_pub_msgs(aby3cu_ctx* ctx, int64_t a, const int64_t* d_B0, cons
 enum { ABY3CU_OP_ADD = 0, ABY3CU_OP_SUB = 1, ABY3CU_OP_XOR = 2 };
 /* out = x op y  (sMatrix +,-: Sh3Types.h:805-820) */
 int aby3cu_share_op(aby3cu_ctx* ctx, int op, const int64_t* d_x, const int64_t* d_y, int64_t* d_out, size_t n);
+/* the same on BOTH share planes of a replicated sharing in one launch (sMatrix::operator+/-, Sh3Types.h:805-820
+ * touch mShares[0] and mShares[1]); latency-bound callers (SGD) halve their launches */
+int aby3cu_share_op2(aby3cu_ctx* ctx, int op, const int64_t* d_x0, const int64_t* d_y0, int64_t* d_out0,
+                     const int64_t* d_x1, const int64_t* d_y1, int64_t* d_out1, size_t n);
 /* out = x0 op x1 op x2 (reveal: Sh3Encryptor.cpp:497-536), op ADD or XOR */
 int aby3cu_combine3(aby3cu_ctx* ctx, int op, const int64_t* d_x0, const int64_t* d_x1, const int64_t* d_x2,
                     int64_t* d_out, size_t n);
@@ -160,6 +165,14 @@ int aby3cu_combine3(aby3cu_ctx* ctx, int op, const int64_t* d_x0, const int64_t*
 int aby3cu_axpb(aby3cu_ctx* ctx, int64_t a, const int64_t* d_x, int64_t b, int64_t* d_out, size_t n);
 /* row-major transpose of an int64 matrix (sMatrix::transpose, Sh3Types.h:822-838) */
 int aby3cu_transpose_i64(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t rows, uint64_t cols, int64_t* d_out);
+/* both share planes in one launch (sMatrix::transpose, Sh3Types.h:822-838) */
+int aby3cu_transpose_i64_2(aby3cu_ctx* ctx, const int64_t* d_in0, const int64_t* d_in1, uint64_t rows, uint64_t cols,
+                           int64_t* d_out0, int64_t* d_out1);
+/* up to ABY3CU_MAX_GATHER_JOBS row gathers sharing one index vector in one launch: job j copies rows
+ * idx[0..nrows) of in[j] (cols[j] wide) to out[j]  (extractBatch takes the same rows of X and Y, both planes) */
+#define ABY3CU_MAX_GATHER_JOBS 4
+int aby3cu_gather_rows_multi(aby3cu_ctx* ctx, int njobs, const int64_t* const* d_in, const uint64_t* cols,
+                             int64_t* const* d_out, const uint64_t* d_idx, uint64_t nrows);
 /* gather rows: out[r,:] = in[idx[r],:]  (extractBatch, aby3-ML/Regression.h:43-58) */
 int aby3cu_gather_rows(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t cols, const uint64_t* d_idx,
                        uint64_t nrows, int64_t* d_out);

@@ -203,3 +203,46 @@ def test_bit_transpose_round_trip_full_size(ctx):
     abi.check(lib.aby3cu_bit_transpose(ctx.h, d_x.p, width, bits, 8, d_m.p, rb, None))
     abi.check(lib.aby3cu_bit_transpose(ctx.h, d_m.p, bits, width, rb, d_y.p, 8, None))
     assert np.array_equal(ctx.download(d_y, width), x)
+
+
+def test_two_plane_ops_and_multi_gather(ctx):
+    """share_op2 / transpose_i64_2 / gather_rows_multi: both share planes (and X with Y) in one launch"""
+    for n in (1, 2, 3, 513, 100003):
+        x0, y0, x1, y1 = (rnd(50 + k, n) for k in range(4))
+        d = [ctx.upload(a) for a in (x0, y0, x1, y1)]
+        o0, o1 = ctx.alloc(8 * n), ctx.alloc(8 * n)
+        for op, f in ((0, lambda a, b: a.view(U64) + b.view(U64)), (1, lambda a, b: a.view(U64) - b.view(U64)),
+                      (2, lambda a, b: a.view(U64) ^ b.view(U64))):
+            abi.check(lib.aby3cu_share_op2(ctx.h, op, d[0].p, d[1].p, o0.p, d[2].p, d[3].p, o1.p, n))
+            assert np.array_equal(ctx.download(o0, n, U64), f(x0, y0))
+            assert np.array_equal(ctx.download(o1, n, U64), f(x1, y1))
+        # in place on the first operand (sf64Matrix::operator-=)
+        abi.check(lib.aby3cu_share_op2(ctx.h, 1, d[0].p, d[1].p, d[0].p, d[2].p, d[3].p, d[2].p, n))
+        assert np.array_equal(ctx.download(d[0], n, U64), x0.view(U64) - y0.view(U64))
+        assert np.array_equal(ctx.download(d[2], n, U64), x1.view(U64) - y1.view(U64))
+    for r, c in ((1, 1), (128, 1024), (33, 65), (1000, 7)):
+        m0, m1 = rnd(60, r * c).reshape(r, c), rnd(61, r * c).reshape(r, c)
+        d0, d1 = ctx.upload(m0), ctx.upload(m1)
+        t0, t1 = ctx.alloc(8 * r * c), ctx.alloc(8 * r * c)
+        abi.check(lib.aby3cu_transpose_i64_2(ctx.h, d0.p, d1.p, r, c, t0.p, t1.p))
+        assert np.array_equal(ctx.download(t0, (c, r)), m0.T)
+        assert np.array_equal(ctx.download(t1, (c, r)), m1.T)
+    rows, cols = 500, 38
+    X0, X1 = rnd(70, rows * cols).reshape(rows, cols), rnd(71, rows * cols).reshape(rows, cols)
+    Y0, Y1 = rnd(72, rows).reshape(rows, 1), rnd(73, rows).reshape(rows, 1)
+    idx = np.random.default_rng(74).integers(0, rows, 128).astype(np.uint64)
+    srcs = [ctx.upload(a) for a in (X0, X1, Y0, Y1)]
+    outs = [ctx.alloc(8 * 128 * cols), ctx.alloc(8 * 128 * cols), ctx.alloc(8 * 128), ctx.alloc(8 * 128)]
+    di = ctx.upload(idx)
+    in_p = (C.c_void_p * 4)(*[b.p for b in srcs])
+    out_p = (C.c_void_p * 4)(*[b.p for b in outs])
+    cols_a = (C.c_uint64 * 4)(cols, cols, 1, 1)
+    abi.check(lib.aby3cu_gather_rows_multi(ctx.h, 4, in_p, cols_a, out_p, di.p, 128))
+    for src, out, w in zip((X0, X1, Y0, Y1), outs, (cols, cols, 1, 1)):
+        assert np.array_equal(ctx.download(out, (128, w)), src[idx.astype(np.int64)])
+    # odd column count (no 16-byte rows) and fewer jobs
+    Z = rnd(75, rows * 37).reshape(rows, 37)
+    dz, oz = ctx.upload(Z), ctx.alloc(8 * 128 * 37)
+    in1, out1, c1 = (C.c_void_p * 1)(dz.p), (C.c_void_p * 1)(oz.p), (C.c_uint64 * 1)(37)
+    abi.check(lib.aby3cu_gather_rows_multi(ctx.h, 1, in1, c1, out1, di.p, 128))
+    assert np.array_equal(ctx.download(oz, (128, 37)), Z[idx.astype(np.int64)])

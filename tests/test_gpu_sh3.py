@@ -353,3 +353,39 @@ def test_basic_blocks_match_oracle(pair):
     got = s.reveal(m, 0, binary=True).reshape(-1)
     assert np.array_equal(got, np.sort(np.concatenate([d1, d2]).reshape(-1)))
     assert_cursors(s, r)
+
+
+def test_shared_stream_session_matches_oracle():
+    """Co-located parties on ONE stream (no event per message): truncating matmul, SGD and a binary
+    circuit give the same share planes as the oracle."""
+    s, r = harness.Session(transport="shared_stream"), o.Session()
+    try:
+        rng = np.random.default_rng(21)
+        a = (rng.normal(0, 20, (130, 70)) * (1 << 16)).astype(np.int64)
+        b = (rng.normal(0, 20, (70, 50)) * (1 << 16)).astype(np.int64)
+        A, B = s.share_int(0, a), s.share_int(1, b)
+        Ao, Bo = r.share_int(0, a), r.share_int(1, b)
+        for _ in range(3):
+            Cs = s.mul(A, B, shift=16)
+            assert np.array_equal(s.get_shares(Cs), r.mul_trunc(Ao, Bo, 16))
+        assert np.array_equal(s.get_shares(s.mul(A, B)), r.mul(Ao, Bo))
+        N, F, Bt, iters, lr, D = 256, 16, 8, 40, 2.0 ** -6, 16
+        x = rng.normal(1, 1, (N, F))
+        y = x[:, :1] * 2.0
+        fx, fy, fw = fixed(x, D), fixed(y, D), np.zeros((F, 1), dtype=np.int64)
+        idx = rng.integers(0, N, iters * Bt).astype(np.uint64)
+        X, Y, W = s.share_int(0, fx), s.share_int(0, fy), s.share_int(0, fw)
+        Xo, Yo, Wo = r.share_int(0, fx), r.share_int(0, fy), r.share_int(0, fw)
+        s.linreg(X, Y, W, idx, iters, Bt, lr)
+        assert np.array_equal(s.get_shares(W), oracle_linreg(r, Xo, Yo, Wo, idx, iters, Bt, lr, D))
+        cir = harness.library_circuit("lt", 64)
+        u, v = rnd(22, (700, 1)), rnd(23, (700, 1))
+        U, V = s.share_bin(0, u, 64), s.share_bin(2, v, 64)
+        Uo, Vo = r.share_bin(0, u), r.share_bin(2, v)
+        out = s.bin_eval(cir, [U, V])[0]
+        outo, _ = o.bin_eval(r, cir, 700, [Uo, Vo])
+        assert np.array_equal(s.get_shares(out, binary=True) & 1, outo[0] & 1)
+        assert_cursors(s, r)
+    finally:
+        s.close()
+        r.close()
