@@ -77,6 +77,8 @@ PROTOTYPES = {
     "aby3cu_bitmul_msgs_p0": (_int, [_p, _p, _p, _p, _p, _key, _u64, _key, _u64, _p, _p, _p, _sz]),
     "aby3cu_bitmul_msgs_p2": (_int, [_p, _p, _p, _p, _key, _u64, _p, _p, _sz]),
     "aby3cu_bitmul_pub_msgs": (_int, [_p, C.c_int64, _p, _p, _key, _key, _u64, _p, _sz]),
+    "aby3cu_bits_expand": (_int, [_p, _p, _u64, _u64, _u64, _p]),
+    "aby3cu_bitinj_msgs": (_int, [_p, _p, _p, _u64, _u64, _u64, _key, _u64, _key, _u64, _p, _p, _p]),
     "aby3cu_share_op": (_int, [_p, _int, _p, _p, _p, _sz]),
     "aby3cu_share_op2": (_int, [_p, _int, _p, _p, _p, _p, _p, _p, _sz]),
     "aby3cu_combine3": (_int, [_p, _int, _p, _p, _p, _p, _sz]),

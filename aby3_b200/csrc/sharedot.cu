@@ -107,6 +107,34 @@ __global__ void __launch_bounds__(kOtThreads) k_bitmul_pub(u64 a, const u64* __r
     }
 }
 
+// Sh3Converter::bitInjection, choice vectors (Sh3Converter.cpp:244-247, 282-285): bit j of row i of a
+// binary share matrix -> word i*bitCount + j (value 0 / 1), the layout the OT kernels index
+__global__ void __launch_bounds__(kOtThreads) k_bits_expand(const u64* __restrict__ in, u64 words, u64 bit_count, u64* __restrict__ out, size_t total) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const u64 i = k / bit_count, j = k - i * bit_count;
+        out[k] = (in[i * words + (j >> 6)] >> (j & 63)) & 1;
+    }
+}
+
+// Sh3Converter::bitInjection, party 2 (sender, Sh3Converter.cpp:318-347): d0 / d1 = the next words of the
+// nextCommon / prevCommon streams; m[k][c] = -d0[k] - d1[k] + (c ^ b_k), b_k = bit k of in0 ^ in1
+__global__ void __launch_bounds__(kOtThreads) k_bitinj_msgs(const u64* __restrict__ in0, const u64* __restrict__ in1, u64 words, u64 bit_count,
+                                                            const __grid_constant__ AesKey knext, u64 en, const __grid_constant__ AesKey kprev, u64 ep,
+                                                            u64* __restrict__ d0, u64* __restrict__ d1, u64* __restrict__ msgs, size_t total) {
+    aes_table_init();
+    __syncthreads();
+    const u32 lane4 = (threadIdx.x & 31) * 4;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const u64 i = k / bit_count, j = k - i * bit_count;
+        const u64 w = i * words + (j >> 6);
+        const u64 b = ((in0[w] ^ in1[w]) >> (j & 63)) & 1;
+        const u64 x0 = stream_elem(lane4, knext, en + k), x1 = stream_elem(lane4, kprev, ep + k);
+        const u64 base = 0 - x0 - x1;
+        d0[k] = x0; d1[k] = x1;
+        *reinterpret_cast<ulonglong2*>(msgs + 2 * k) = b ? make_ulonglong2(base + 1, base) : make_ulonglong2(base, base + 1);
+    }
+}
+
 template <class K>
 int big_smem(K kernel) {
     ABY3CU_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
@@ -190,6 +218,34 @@ int aby3cu_bitmul_pub_msgs(aby3cu_ctx* ctx, i64 a, const i64* B0, const i64* B1,
     k_bitmul_pub<<<ew_grid(ctx, n, kOtThreads, 3), kOtThreads, kAesTableBytes, ctx->stream>>>((u64)a, (const u64*)B0, (const u64*)B1, kp, kn, elem0,
                                                                                              (u64*)d_msgs, n);
     return post_launch(ctx, "k_bitmul_pub");
+}
+
+int aby3cu_bits_expand(aby3cu_ctx* ctx, const i64* d_in, u64 rows, u64 words, u64 bit_count, i64* d_out) {
+    ABY3CU_REQUIRE(ctx, "bits_expand: null context");
+    ABY3CU_REQUIRE(bit_count <= 64 * words, "bits_expand: bit count exceeds the row width");
+    const size_t total = (size_t)rows * bit_count;
+    if (!total) return 0;
+    ABY3CU_REQUIRE(d_in && d_out, "bits_expand: null argument");
+    DeviceGuard g(ctx->device);
+    k_bits_expand<<<ew_grid(ctx, total, kOtThreads, 8), kOtThreads, 0, ctx->stream>>>((const u64*)d_in, words, bit_count, (u64*)d_out, total);
+    return post_launch(ctx, "k_bits_expand");
+}
+
+int aby3cu_bitinj_msgs(aby3cu_ctx* ctx, const i64* d_in0, const i64* d_in1, u64 rows, u64 words, u64 bit_count,
+                       const u8 key_next_common[16], u64 elem_next, const u8 key_prev_common[16], u64 elem_prev,
+                       i64* d_d0, i64* d_d1, i64* d_msgs) {
+    ABY3CU_REQUIRE(ctx && key_next_common && key_prev_common, "bitinj_msgs: null argument");
+    ABY3CU_REQUIRE(bit_count <= 64 * words, "bitinj_msgs: bit count exceeds the row width");
+    const size_t total = (size_t)rows * bit_count;
+    if (!total) return 0;
+    ABY3CU_REQUIRE(d_in0 && d_in1 && d_d0 && d_d1 && d_msgs, "bitinj_msgs: null argument");
+    ABY3CU_REQUIRE(al16p(d_msgs), "bitinj_msgs: message pairs must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    AesKey kn, kp; host_expand_key(key_next_common, &kn); host_expand_key(key_prev_common, &kp);
+    if (big_smem(k_bitinj_msgs)) return 1;
+    k_bitinj_msgs<<<ew_grid(ctx, total, kOtThreads, 3), kOtThreads, kAesTableBytes, ctx->stream>>>(
+        (const u64*)d_in0, (const u64*)d_in1, words, bit_count, kn, elem_next, kp, elem_prev, (u64*)d_d0, (u64*)d_d1, (u64*)d_msgs, total);
+    return post_launch(ctx, "k_bitinj_msgs");
 }
 
 }  // extern "C"

@@ -45,6 +45,10 @@ def _load():
     l.sh3h_odd_even_merge.argtypes = [p, i32, i32]
     l.sh3h_piecewise.argtypes = [p, i32, p, i32, p, p, p, p, u64]
     l.sh3h_mul_bit.argtypes = [p, i32, i32, i32, i64]
+    l.sh3h_conv_init.argtypes = [p]
+    l.sh3h_conv_a2b.argtypes = [p, i32]
+    l.sh3h_conv_bit_injection.argtypes = [p, i32, i32]
+    l.sh3h_conv_packed_roundtrip.argtypes = [p, i32, p, C.POINTER(u64)]
     l.sh3h_reveal.argtypes = [p, i32, i32, i32, p]
     l.sh3h_reveal_plain.argtypes = [p, i32, i32, i32]
     l.sh3h_trunc_tuple.argtypes = [p, i32, u64, u64, u64, p, p, p]
@@ -56,6 +60,7 @@ def _load():
     l.sh3h_sync.argtypes = [p]
     l.sh3h_launch_count.restype = u64
     l.sh3h_launch_count.argtypes = [p]
+    l.sh3h_pool_stats.argtypes = [p, p]
     l.sh3h_bytes_sent.restype = u64
     l.sh3h_bytes_sent.argtypes = [p]
     return l
@@ -198,6 +203,28 @@ class Session:
         dbl = np.asarray([float(v) for v in flat] or [0.0], dtype=np.float64)
         return self._id(lib.sh3h_piecewise(self.h, x, _ptr(th), len(th), _ptr(counts), _ptr(is_int), _ptr(ints), _ptr(dbl), D))
 
+    def conv_init(self):
+        """Sh3Converter::init(rt, eval.mShareGen) on every party"""
+        self._chk(lib.sh3h_conv_init(self.h))
+
+    def conv_a2b(self, x):
+        """Sh3Converter::toBinaryMatrix(si64Matrix): arithmetic sharing -> binary sharing (64 bits per word)"""
+        return self._id(lib.sh3h_conv_a2b(self.h, x))
+
+    def conv_bit_injection(self, b, two_rounds=False):
+        """Sh3Converter::bitInjection: binary sharing (rows x bits) -> arithmetic sharing, one element per bit"""
+        return self._id(lib.sh3h_conv_bit_injection(self.h, b, int(two_rounds)))
+
+    def conv_packed_roundtrip(self, b, bit_count):
+        """toPackedBin then toBinaryMatrix(sPackedBin); returns (new handle, packed planes [3][2][bit_count][simd])"""
+        rows, _ = self.shape(b, binary=True)
+        simd = (rows + 63) // 64
+        packed = np.zeros((3, 2, bit_count, simd), dtype=np.int64)
+        sw = C.c_uint64(0)
+        hid = self._id(lib.sh3h_conv_packed_roundtrip(self.h, b, _ptr(packed), C.byref(sw)))
+        assert sw.value == simd
+        return hid, packed
+
     def cipher_gt(self, a, b):
         """aby3-Basic cipher_gt: one-bit binary sharing of (a > b) for arithmetic sharings a, b."""
         return self._id(lib.sh3h_cipher_gt(self.h, a, b))
@@ -270,6 +297,13 @@ class Session:
     @property
     def launches(self):
         return int(lib.sh3h_launch_count(self.h))
+
+    @property
+    def pool_stats(self):
+        """(driver mallocs, bytes, driver frees) behind the three parties' buffer pools"""
+        a = np.zeros(3, dtype=np.uint64)
+        lib.sh3h_pool_stats(self.h, _ptr(a))
+        return tuple(int(x) for x in a)
 
     @property
     def bytes_sent(self):

@@ -177,7 +177,18 @@ private:
 class BetaLibrary {
 public:
     enum class Optimized { Size, Depth };
+    enum class IntType { TwosComplement, Unsigned };
+    enum class AdderType { Addition, Subtraction };
     ~BetaLibrary() { for (auto& kv : mCache) delete kv.second; }
+
+    // c = a + b on the given (already allocated) bundles, c.size() bits, operands sign-extended
+    // (BetaLibrary::add_build as called by Sh3Converter.cpp:403-406 and CircuitLibrary.cpp)
+    static void add_build(BetaCircuit& cd, const BetaBundle& a, const BetaBundle& b, const BetaBundle& c, const BetaBundle& /*temps*/,
+                          IntType it, Optimized op) {
+        if (it != IntType::TwosComplement) throw std::runtime_error("add_build: only two's complement operands are used on this path " LOCATION);
+        if (op == Optimized::Depth) prefixAdd(cd, a, b, c, false);
+        else rippleAdd(cd, a, b, c);
+    }
 
     BetaCircuit* int_int_bitwiseAnd(u64 a, u64 b, u64 c) { return bitwise("and", GateType::And, a, b, c); }
     BetaCircuit* int_int_bitwiseOr(u64 a, u64 b, u64 c) { return bitwise("or", GateType::Or, a, b, c); }

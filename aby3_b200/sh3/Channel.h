@@ -58,7 +58,7 @@ struct Borrowed {
             shared.reset();
         }
         if (own) {
-            if (ownedByPeer && own.ctx()->stream() != reader->stream()) own.free(reader->recordEvent());
+            if (ownedByPeer && own.ctx()->stream() != reader->stream()) own.free(reader->recordEvent(), reader->device());
             else own.free();
         }
         ptr = nullptr;
@@ -245,7 +245,7 @@ struct LocalTransport : Transport {
             waitReady(m);
             if (n) aby3::gpu::check(aby3cu_d2d(ctx->h(), d, ctx->device(), src, owner->device(), n));
             // the payload returns to the sender's pool once OUR copy has run
-            if (m.dev) m.dev.free(same ? nullptr : ctx->recordEvent());
+            if (m.dev) m.dev.free(same ? nullptr : ctx->recordEvent(), ctx->device());
             else {
                 if (!same) m.shared->addReader(ctx->device(), ctx->recordEvent());
                 m.shared.reset();

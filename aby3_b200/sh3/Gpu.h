@@ -68,7 +68,7 @@ public:
         aby3cu_sync(mCtx);
         for (auto& kv : mFree)
             for (auto& e : kv.second) {
-                if (e.event) EventPool::put(mDevice, e.event);
+                if (e.event) EventPool::put(e.eventDevice, e.event);
                 aby3cu_free(mCtx, e.ptr);
             }
         aby3cu_ctx_destroy(mCtx);
@@ -81,7 +81,7 @@ public:
     void* alloc(size_t bytes) {
         if (bytes == 0) return nullptr;
         bytes = roundSize(bytes);
-        Entry e{nullptr, nullptr};
+        Entry e{nullptr, nullptr, -1};
         {
             std::lock_guard<std::mutex> g(mMtx);
             auto it = mFree.find(bytes);
@@ -94,30 +94,38 @@ public:
         if (e.ptr) {
             if (e.event) {
                 check(aby3cu_event_wait(mCtx, e.event));
-                EventPool::put(mDevice, e.event);
+                EventPool::put(e.eventDevice, e.event);
             }
             return e.ptr;
         }
         void* p = nullptr;
         check(aby3cu_malloc(mCtx, &p, bytes));
+        ++mMallocs; mMallocBytes += bytes;
         return p;
     }
-    // `after` (may be null): an event recorded on ANOTHER stream that still reads the buffer
-    void release(void* p, size_t bytes, void* after = nullptr) {
+    // pool misses (driver allocations) since creation: a steady-state loop should show none
+    u64 mallocCount() const { return mMallocs; }
+    u64 mallocBytes() const { return mMallocBytes; }
+    u64 freeCount() const { return mFrees; }
+    // `after` (may be null): a pooled event recorded on ANOTHER stream (of device `afterDevice`) that still
+    // reads the buffer
+    void release(void* p, size_t bytes, void* after = nullptr, int afterDevice = -1) {
         if (!p) return;
         bytes = roundSize(bytes);
+        if (after && afterDevice < 0) afterDevice = mDevice;
         {
             std::lock_guard<std::mutex> g(mMtx);
             if (mCached + bytes <= kCacheCap) {
-                mFree[bytes].push_back(Entry{p, after});
+                mFree[bytes].push_back(Entry{p, after, afterDevice});
                 mCached += bytes;
                 return;
             }
         }
         // the cache is full: give the block back to the driver (workloads whose buffer sizes keep
         // changing -- e.g. the shrinking stages of a merge network -- must not hoard HBM)
-        if (after) { aby3cu_event_sync(after); EventPool::put(mDevice, after); }
+        if (after) { aby3cu_event_sync(after); EventPool::put(afterDevice, after); }
         aby3cu_free(mCtx, p);
+        ++mFrees;
     }
     // a recycled ordering event for this context's device / recorded on this context's stream
     void* newEvent() { return EventPool::get(mCtx, mDevice); }
@@ -135,12 +143,13 @@ public:
     }
 
 private:
-    struct Entry { void* ptr; void* event; };
+    struct Entry { void* ptr; void* event; int eventDevice; };
     aby3cu_ctx* mCtx = nullptr;
     int mDevice = 0;
     std::mutex mMtx;
     std::map<size_t, std::vector<Entry>> mFree;
     size_t mCached = 0;
+    u64 mMallocs = 0, mMallocBytes = 0, mFrees = 0;
     static constexpr size_t kCacheCap = size_t(24) << 30;
 };
 
@@ -177,8 +186,9 @@ public:
         free();
         mCtx = c; mBytes = bytes; mPtr = c->alloc(bytes);
     }
-    void free(void* after = nullptr) {
-        if (mPtr && mCtx) mCtx->release(mPtr, mBytes, after);
+    // `after`: a pooled ordering event of device `afterDevice` marking the last foreign read
+    void free(void* after = nullptr, int afterDevice = -1) {
+        if (mPtr && mCtx) mCtx->release(mPtr, mBytes, after, afterDevice);
         else if (after) aby3cu_event_destroy(after);        // no owner to hand it to
         mPtr = nullptr; mBytes = 0; mCtx = nullptr;
     }

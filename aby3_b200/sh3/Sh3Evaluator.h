@@ -107,10 +107,12 @@ public:
     SharedOT mOtPrevRecver;   // seed shared with the next party
     SharedOT mOtNextRecver;   // seed shared with the previous party
 
+    // index of the next 8-byte element of a common PRNG's keystream (what the fused device kernels are addressed by)
+    static u64 streamElem(const oc::PRNG& p);
+
 private:
     enum class MulMode { Matmul, Hadamard };
     static MulMode mulMode(const si64Matrix& A, const si64Matrix& B);
-    static u64 streamElem(const oc::PRNG& p);
 };
 
 }  // namespace aby3

@@ -14,6 +14,7 @@
 #include "Sh3BinaryEvaluator.h"
 #include "Sh3Encryptor.h"
 #include "Sh3Evaluator.h"
+#include "Sh3Converter.h"
 #include "Sh3Piecewise.h"
 #include "../basic/Basics.h"
 #include "../ml/Regression.h"
@@ -71,6 +72,8 @@ struct Party {
     Sh3Runtime rt;
     Sh3Encryptor enc;
     Sh3Evaluator eval;
+    Sh3Converter conv;
+    bool convInit = false;
     std::map<int, std::unique_ptr<si64Matrix>> ints;
     std::map<int, std::unique_ptr<sbMatrix>> bins;
     std::map<int, std::unique_ptr<i64Matrix>> plains;
@@ -352,6 +355,59 @@ int sh3h_piecewise(sh3h* h, int in_id, const double* thresholds, int n_threshold
     return rc ? -1 : id;
 }
 
+// ---- Sh3Converter --------------------------------------------------------------------
+static Sh3Converter& converter(Party& P) {
+    if (!P.convInit) { P.conv.init(P.rt, P.eval.mShareGen); P.convInit = true; }
+    return P.conv;
+}
+// conv.init(rt, eval.mShareGen) on every party (idempotent; the conversions below call it on first use)
+int sh3h_conv_init(sh3h* h) {
+    return h->run([&](int i) { (void)converter(h->p[i]); });
+}
+// conv.toBinaryMatrix(rt, si64Matrix in, sbMatrix dest).get(): arithmetic -> binary, 64 bits per word
+int sh3h_conv_a2b(sh3h* h, int in_id) {
+    const int id = h->next_handle++;
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        auto m = std::make_unique<sbMatrix>();
+        converter(P).toBinaryMatrix(P.rt.noDependencies(), *P.ints.at(in_id), *m).get();
+        P.bins[id] = std::move(m);
+        P.ctx->sync();
+    });
+    return rc ? -1 : id;
+}
+// conv.bitInjection(rt, sbMatrix in, si64Matrix dest, twoRounds).get(): one arithmetic element per input bit
+int sh3h_conv_bit_injection(sh3h* h, int in_id, int two_rounds) {
+    const int id = h->next_handle++;
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        auto m = std::make_unique<si64Matrix>();
+        converter(P).bitInjection(P.rt.noDependencies(), *P.bins.at(in_id), *m, two_rounds != 0).get();
+        P.ints[id] = std::move(m);
+        P.ctx->sync();
+    });
+    return rc ? -1 : id;
+}
+// toPackedBin followed by toBinaryMatrix(sPackedBin); the packed planes ([3][2][bitCount * simd] words) are copied
+// to packed_out (may be null) for comparison with the oracle's bit transpose
+int sh3h_conv_packed_roundtrip(sh3h* h, int in_id, int64_t* packed_out, uint64_t* simd_width) {
+    const int id = h->next_handle++;
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        sPackedBin pk;
+        converter(P).toPackedBin(*P.bins.at(in_id), pk);
+        if (i == 0 && simd_width) *simd_width = pk.simdWidth();
+        if (packed_out)
+            for (int s = 0; s < 2; ++s)
+                memcpy(packed_out + ((uint64_t)i * 2 + s) * pk.size(), pk.mShares[s].hostData(), pk.size() * 8);
+        auto m = std::make_unique<sbMatrix>();
+        converter(P).toBinaryMatrix(pk, *m);
+        P.bins[id] = std::move(m);
+        P.ctx->sync();
+    });
+    return rc ? -1 : id;
+}
+
 // ---- aby3-Basic building blocks (basic/Basics.h) -----------------------------------
 // res = (A > B) on arithmetic sharings: cipher_gt (BuildingBlocks.cpp:525-532)
 int sh3h_cipher_gt(sh3h* h, int a_id, int b_id) {
@@ -584,6 +640,11 @@ uint64_t sh3h_launch_count(sh3h* h) {
     for (int i = 0; i < 3; ++i) n += aby3cu_launch_count(h->p[i].ctx->h());
     return n;
 }
+// driver allocations / frees behind the parties' buffer pools: [0] mallocs, [1] bytes, [2] frees
+void sh3h_pool_stats(sh3h* h, uint64_t out[3]) {
+    out[0] = out[1] = out[2] = 0;
+    for (int i = 0; i < 3; ++i) { out[0] += h->p[i].ctx->mallocCount(); out[1] += h->p[i].ctx->mallocBytes(); out[2] += h->p[i].ctx->freeCount(); }
+}
 uint64_t sh3h_bytes_sent(sh3h* h) {
     uint64_t n = 0;
     for (int i = 0; i < 3; ++i) n += h->p[i].comm.mNext.getTotalDataSent() + h->p[i].comm.mPrev.getTotalDataSent();
@@ -598,6 +659,7 @@ extern "C" {
 
 struct sh3h_circuit {
     oc::BetaLibrary lib;
+    oc::BetaCircuit own;
     oc::BetaCircuit* cir = nullptr;
 };
 
@@ -614,6 +676,12 @@ sh3h_circuit* sh3h_circuit_build(const char* name, uint32_t bits) {
         else if (n == "lt") c->cir = c->lib.int_int_lt(bits, bits);
         else if (n == "eq") c->cir = c->lib.int_eq(bits);
         else if (n.rfind("piecewise", 0) == 0) c->cir = c->lib.int_Sh3Piecewise_helper(bits, std::stoul(n.substr(9)));
+        else if (n == "a2b") {            // Sh3Converter::getArithToBinCircuit(64, bits), levelised as setCir does
+            Sh3Converter conv;
+            c->own = conv.getArithToBinCircuit(64, bits);
+            c->own.levelByAndDepth();
+            c->cir = &c->own;
+        }
         else { g_err = "unknown circuit " + n; return nullptr; }
         return c.release();
     } catch (const std::exception& e) { g_err = e.what(); return nullptr; }

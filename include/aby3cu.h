@@ -149,6 +149,16 @@ int aby3cu_bitmul_msgs_p2(aby3cu_ctx* ctx, const int64_t* d_A1, const int64_t* d
 int aby3cu_bitmul_pub_msgs(aby3cu_ctx* ctx, int64_t a, const int64_t* d_B0, const int64_t* d_B1,
                            const uint8_t key_prev[16], const uint8_t key_next[16], uint64_t elem0, int64_t* d_msgs, size_t n);
 
+/* ---- Sh3Converter::bitInjection (aby3/sh3/Sh3Converter.cpp:211-370) ------------------------ */
+/* choice vectors (:244-247, 282-285): out[i*bit_count + j] = bit j of row i of a rows x words binary share plane */
+int aby3cu_bits_expand(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t rows, uint64_t words, uint64_t bit_count, int64_t* d_out);
+/* party 2, the OT sender (:318-347): d0 / d1 = the next rows*bit_count words of the nextCommon / prevCommon
+ * streams (its output share planes); message pair k = (m, m) with m = -d0[k] - d1[k], plus 1 in slot b_k ^ 1,
+ * b_k = bit k of in0 ^ in1 */
+int aby3cu_bitinj_msgs(aby3cu_ctx* ctx, const int64_t* d_in0, const int64_t* d_in1, uint64_t rows, uint64_t words, uint64_t bit_count,
+                       const uint8_t key_next_common[16], uint64_t elem_next, const uint8_t key_prev_common[16], uint64_t elem_prev,
+                       int64_t* d_d0, int64_t* d_d1, int64_t* d_msgs);
+
 /* ---- local share arithmetic / reveal ------------------------------------------- */
 enum { ABY3CU_OP_ADD = 0, ABY3CU_OP_SUB = 1, ABY3CU_OP_XOR = 2 };
 /* out = x op y  (sMatrix +,-: Sh3Types.h:805-820) */

@@ -361,6 +361,8 @@ struct Party {
     int idx;
     ShareGen enc, eval;
     SharedOT otPrevRecver, otNextRecver;     /* Sh3Evaluator.h:118-124 */
+    SharedOT convOT12, convOT02;             /* Sh3Converter.h:19 */
+    bool convInit = false;
 };
 
 }  // namespace
@@ -791,6 +793,73 @@ void orc_bin_eval(orc_session* s, const orc_circuit* cir, u64 width,
             for (int pl = 0; pl < 2; ++pl)
                 memcpy(mem_dump + ((u64)p * 2 + pl) * W * rb, mem[p][pl].data(), W * rb);
     }
+}
+
+/* ---- Sh3Converter restatement -- aby3/sh3/Sh3Converter.h:24-41, Sh3Converter.cpp:63-411 -------- */
+/* conv.init(rt, eval.mShareGen) on every party: the OT seeds are the next block of the common PRNGs */
+void orc_conv_init(orc_session* s) {
+    u8 k[16];
+    s->p[0].eval.prevCommon.getBlock(k); s->p[0].convOT02.setSeed(k);
+    s->p[1].eval.nextCommon.getBlock(k); s->p[1].convOT12.setSeed(k);
+    s->p[2].eval.prevCommon.getBlock(k); s->p[2].convOT12.setSeed(k);
+    s->p[2].eval.nextCommon.getBlock(k); s->p[2].convOT02.setSeed(k);
+    for (auto& p : s->p) p.convInit = true;
+}
+
+/* toBinaryMatrix(dep, si64Matrix in, sbMatrix dest) up to the circuit: the two adder inputs.
+ * X: arithmetic shares [3][2][n]; x0 / x1: binary shares [3][2][n] of (in.0 + in.2) and in.1
+ * (Sh3Converter.cpp:73-196).  dest = adder(x0, x1) is then orc_bin_eval on getArithToBinCircuit. */
+void orc_conv_a2b_inputs(orc_session* s, const i64* X, u64 n, i64* x0, i64* x1) {
+    memset(x0, 0, 6 * n * 8);
+    memset(x1, 0, 6 * n * 8);
+    std::vector<i64> r0(n), r2(n);
+    s->p[0].eval.prevCommon.get((u8*)r0.data(), n * 8);      /* :90 */
+    s->p[2].eval.nextCommon.get((u8*)r2.data(), n * 8);      /* :182 */
+    const i64* a0 = plane(X, n, 0, 0);
+    const i64* a1 = plane(X, n, 0, 1);
+    for (u64 i = 0; i < n; ++i) {
+        const i64 v = (i64)((u64)a0[i] + (u64)a1[i]) ^ r0[i];        /* :91 */
+        plane(x0, n, 0, 0)[i] = v;
+        plane(x0, n, 0, 1)[i] = r0[i];
+        plane(x0, n, 1, 1)[i] = v;                                   /* received from party 0, :109/:150 */
+        plane(x0, n, 2, 0)[i] = r2[i];
+        plane(x1, n, 1, 0)[i] = plane(X, n, 1, 0)[i];                /* :139 */
+        plane(x1, n, 2, 1)[i] = plane(X, n, 2, 1)[i];                /* :183 */
+    }
+}
+
+/* bitInjection(dep, sbMatrix in, si64Matrix dest, twoRounds = false) -- Sh3Converter.cpp:211-370.
+ * B: binary shares [3][2][rows * words]; Y: arithmetic shares [3][2][rows * bits], one element per bit. */
+void orc_conv_bit_injection(orc_session* s, const i64* B, u64 rows, u64 words, u64 bits, i64* Y) {
+    const u64 nin = rows * words, n = rows * bits;
+    std::vector<u64> d0(n), d1(n), m(2 * n), masked0(2 * n), masked1(2 * n), mc0(n), mc1(n), out0(n), out1(n);
+    std::vector<u8> c0(n), c1(n);
+    auto bit = [&](const i64* pl, u64 k) { const u64 i = k / bits, j = k % bits; return (u8)(((u64)pl[i * words + j / 64] >> (j % 64)) & 1); };
+    /* party 2, the sender (:318-357) */
+    s->p[2].eval.nextCommon.get((u8*)d0.data(), n * 8);
+    s->p[2].eval.prevCommon.get((u8*)d1.data(), n * 8);
+    for (u64 k = 0; k < n; ++k) {
+        const u8 b = bit(plane(B, nin, 2, 0), k) ^ bit(plane(B, nin, 2, 1), k);
+        const u64 base = 0 - d0[k] - d1[k];
+        m[2 * k] = base; m[2 * k + 1] = base;
+        m[2 * k + (b ^ 1)] += 1;
+    }
+    s->p[2].convOT12.send(m.data(), masked0.data(), n);          /* to receiver 0 */
+    s->p[2].convOT02.send(m.data(), masked1.data(), n);          /* to receiver 1 */
+    /* party 0: receiver 0 (choices = its own share), helper for receiver 1 (:232-271) */
+    for (u64 k = 0; k < n; ++k) c0[k] = bit(plane(B, nin, 0, 0), k);
+    s->p[0].convOT02.help(c0.data(), mc1.data(), n);
+    s->p[0].eval.prevCommon.get((u8*)plane(Y, n, 0, 1), n * 8);
+    /* party 1: helper for receiver 0 with x0 (its prev share), then receiver 1 (:273-314) */
+    for (u64 k = 0; k < n; ++k) c1[k] = bit(plane(B, nin, 1, 1), k);
+    s->p[1].convOT12.help(c1.data(), mc0.data(), n);
+    s->p[1].eval.nextCommon.get((u8*)plane(Y, n, 1, 0), n * 8);
+    SharedOT::recv(masked0.data(), mc0.data(), c0.data(), out0.data(), n);
+    SharedOT::recv(masked1.data(), mc1.data(), c1.data(), out1.data(), n);
+    memcpy(plane(Y, n, 0, 0), out0.data(), n * 8);
+    memcpy(plane(Y, n, 1, 1), out1.data(), n * 8);
+    memcpy(plane(Y, n, 2, 0), d0.data(), n * 8);
+    memcpy(plane(Y, n, 2, 1), d1.data(), n * 8);
 }
 
 int orc_selftest(void) {

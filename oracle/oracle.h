@@ -136,6 +136,14 @@ uint64_t orc_bin_row_bytes(uint64_t width);
 void orc_bin_eval(orc_session*, const orc_circuit* cir, uint64_t width,
                   const int64_t* const* inputs, int64_t* const* outputs, uint8_t* mem_dump);
 
+/* ---- Sh3Converter restatement (aby3/sh3/Sh3Converter.h:24-41, Sh3Converter.cpp:63-411) ---- */
+/* conv.init(rt, eval.mShareGen) on every party (draws the OT seeds from the common PRNGs) */
+void orc_conv_init(orc_session*);
+/* toBinaryMatrix(si64Matrix): the two inputs of the adder circuit, binary shares [3][2][n] */
+void orc_conv_a2b_inputs(orc_session*, const int64_t* X, uint64_t n, int64_t* x0, int64_t* x1);
+/* bitInjection (one round form): B binary shares [3][2][rows*words] -> Y arithmetic shares [3][2][rows*bits] */
+void orc_conv_bit_injection(orc_session*, const int64_t* B, uint64_t rows, uint64_t words, uint64_t bits, int64_t* Y);
+
 /* self test: FIPS-197 vectors, soft == AES-NI, PRNG == keystream.  0 = ok */
 int orc_selftest(void);
 int orc_has_aesni(void);

@@ -14,6 +14,7 @@
 //
 // Share arrays: int64 [party(3)][plane(2)][n], plane 0 = own share, as oracle.h.
 #include <aby3/sh3/Sh3BinaryEvaluator.h>
+#include <aby3/sh3/Sh3Converter.h>
 #include <aby3/sh3/Sh3Encryptor.h>
 #include <aby3/sh3/Sh3Evaluator.h>
 #include <aby3/sh3/Sh3Piecewise.h>
@@ -32,6 +33,7 @@ struct RefParty {
     Sh3Runtime rt;
     Sh3Encryptor enc;
     Sh3Evaluator eval;
+    Sh3Converter conv;
 };
 }  // namespace
 
@@ -308,6 +310,55 @@ int ref_piecewise_plain(const int64_t* x, uint64_t n, const double* thresholds, 
         memcpy(in.data(), x, n * 8);
         pw.eval(in, out, D);
         memcpy(y, out.data(), n * 8);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// ---- Sh3Converter (aby3/sh3/Sh3Converter.cpp) -----------------------------------------------------
+// conv.init(rt, eval.mShareGen) on every party
+int ref_conv_init(ref_session* s) {
+    try {
+        for (auto& P : s->p) P.conv.init(P.rt, P.eval.mShareGen);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+// conv.toBinaryMatrix(rt, si64Matrix in, sbMatrix dest).get(); dest left empty -> 64 bits per input word
+int ref_conv_a2b(ref_session* s, const int64_t* X, uint64_t rows, uint64_t cols, int64_t* Y) {
+    return s->run([&](int i) {
+        RefParty& P = s->p[i];
+        si64Matrix in;
+        loadInt(in, X, i, rows, cols);
+        sbMatrix dest;
+        P.conv.toBinaryMatrix(P.rt.noDependencies(), in, dest).get();
+        P.rt.runAll();                       // the trailing state-keeping continuations (Sh3Converter.cpp:112)
+        if (dest.rows() != rows || dest.i64Cols() != cols) throw std::runtime_error("unexpected a2b output shape");
+        storeBin(dest, Y, i);
+    });
+}
+// conv.bitInjection(rt, sbMatrix in (rows x bits), si64Matrix dest).get(); Y: [3][2][rows * bits]
+int ref_conv_bit_injection(ref_session* s, const int64_t* B, uint64_t rows, uint64_t bits, int64_t* Y) {
+    return s->run([&](int i) {
+        RefParty& P = s->p[i];
+        sbMatrix in;
+        loadBin(in, B, i, rows, bits);
+        si64Matrix dest;
+        P.conv.bitInjection(P.rt.noDependencies(), in, dest).get();
+        storeInt(dest, Y, i);
+    });
+}
+// conv.toPackedBin(in, pk) then conv.toBinaryMatrix(pk, out) on one share plane pair; packed: [2][bits * simd] words
+int ref_conv_packed_roundtrip(const int64_t* in2, uint64_t rows, uint64_t bits, int64_t* packed2, uint64_t simd, int64_t* out2) {
+    try {
+        Sh3Converter conv;
+        sbMatrix in(rows, bits), out;
+        const u64 n = in.i64Size();
+        for (int p = 0; p < 2; ++p) memcpy(in.mShares[p].data(), in2 + p * n, n * 8);
+        sPackedBin pk;
+        conv.toPackedBin(in, pk);
+        if (pk.simdWidth() != simd || pk.bitCount() != bits) throw std::runtime_error("unexpected packed shape");
+        for (int p = 0; p < 2; ++p) memcpy(packed2 + p * bits * simd, pk.mShares[p].data(), bits * simd * 8);
+        conv.toBinaryMatrix(pk, out);
+        for (int p = 0; p < 2; ++p) memcpy(out2 + p * n, out.mShares[p].data(), n * 8);
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }

@@ -1,5 +1,8 @@
 #pragma once
-// shim of cryptoTools/Common/Matrix.h: an owning row-major matrix (zero-initialised unless asked otherwise)
+// shim of cryptoTools/Common/Matrix.h: an owning row-major matrix.  NEW storage is always zero-filled, also
+// for AllocType::Uninitialized: the reference relies on fresh allocations reading as zero (e.g. the "x1 = 0"
+// operands of Sh3Converter::toBinaryMatrix, Sh3Converter.cpp:82-85, are resized but never written), which holds
+// for the untouched pages a real run gets from the OS and must hold here for recycled heap blocks too.
 #include "cryptoTools/Common/MatrixView.h"
 namespace osuCrypto {
 template <typename T>
@@ -31,6 +34,7 @@ public:
         const u64 n = rows * cols, old = this->size();
         if (n > mCapacity) {
             T* p = n ? static_cast<T*>(::operator new(n * sizeof(T), std::align_val_t(64))) : nullptr;
+            if (p) std::memset((void*)p, 0, n * sizeof(T));
             const u64 keep = std::min(old, n);
             if (keep) std::memcpy(p, this->mData, keep * sizeof(T));
             release();

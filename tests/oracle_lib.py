@@ -45,6 +45,9 @@ def _load():
     l.orc_bin_row_bytes.restype = _u64
     l.orc_bin_row_bytes.argtypes = [_u64]
     l.orc_bin_eval.argtypes = [_p, _p, _u64, _p, _p, _p]
+    l.orc_conv_init.argtypes = [_p]
+    l.orc_conv_a2b_inputs.argtypes = [_p, _p, _u64, _p, _p]
+    l.orc_conv_bit_injection.argtypes = [_p, _p, _u64, _u64, _u64, _p]
     return l
 
 
@@ -149,6 +152,28 @@ class Session:
         R, T0, T1 = (np.empty(n, dtype=np.int64) for _ in range(3))
         lib.orc_trunc_tuple(self.h, party, n, d, ptr(R), ptr(T0), ptr(T1))
         return R, T0, T1
+
+    def conv_init(self):
+        """Sh3Converter::init(rt, eval.mShareGen) on every party"""
+        lib.orc_conv_init(self.h)
+
+    def conv_a2b(self, X, cir):
+        """Sh3Converter::toBinaryMatrix(si64Matrix): X arithmetic shares [3][2][rows][cols] -> binary shares of the
+        same values; cir = the flat adder circuit (harness.library_circuit("a2b", 64 * cols))."""
+        X = np.ascontiguousarray(X, dtype=np.int64)
+        rows = X.shape[2]
+        x0, x1 = np.empty_like(X), np.empty_like(X)
+        lib.orc_conv_a2b_inputs(self.h, ptr(X), X[0, 0].size, ptr(x0), ptr(x1))
+        outs, _ = bin_eval(self, cir, rows, [x0, x1])
+        return outs[0]
+
+    def conv_bit_injection(self, B, bits):
+        """Sh3Converter::bitInjection: B binary shares [3][2][rows][words] -> arithmetic shares [3][2][rows][bits]"""
+        B = np.ascontiguousarray(B, dtype=np.int64)
+        rows, words = B.shape[2], B.shape[3]
+        Y = np.empty((3, 2, rows, bits), dtype=np.int64)
+        lib.orc_conv_bit_injection(self.h, ptr(B), rows, words, bits, ptr(Y))
+        return Y
 
 
 def _dims(A, B, mode):

@@ -51,6 +51,10 @@ def lib():
         l.ref_bin_eval.argtypes = [_p, _p, _u64, _p, _p]
         l.ref_piecewise.argtypes = [_p, _p, _u64, _p, _int, _p, _p, _p, _p, _u64, _p]
         l.ref_piecewise_plain.argtypes = [_p, _u64, _p, _int, _p, _p, _p, _p, _u64, _p]
+        l.ref_conv_init.argtypes = [_p]
+        l.ref_conv_a2b.argtypes = [_p, _p, _u64, _u64, _p]
+        l.ref_conv_bit_injection.argtypes = [_p, _p, _u64, _u64, _p]
+        l.ref_conv_packed_roundtrip.argtypes = [_p, _u64, _u64, _p, _u64, _p]
         l.ref_time_mul_trunc.restype = C.c_double
         l.ref_time_mul_trunc.argtypes = [_p, _u64, _u64, _u64, _u64, _int]
         _lib = l
@@ -177,6 +181,22 @@ class Session:
         _chk(lib().ref_piecewise(self.h, ptr(X), n, ptr(th), len(th), ptr(counts), ptr(is_int), ptr(ints), ptr(dbl), D, ptr(Y)))
         return Y
 
+    def conv_init(self):
+        _chk(lib().ref_conv_init(self.h))
+
+    def conv_a2b(self, X):
+        X = np.ascontiguousarray(X, dtype=np.int64)
+        Y = np.empty_like(X)
+        _chk(lib().ref_conv_a2b(self.h, ptr(X), X.shape[2], X.shape[3], ptr(Y)))
+        return Y
+
+    def conv_bit_injection(self, B, bits):
+        B = np.ascontiguousarray(B, dtype=np.int64)
+        rows = B.shape[2]
+        Y = np.empty((3, 2, rows, bits), dtype=np.int64)
+        _chk(lib().ref_conv_bit_injection(self.h, ptr(B), rows, bits, ptr(Y)))
+        return Y
+
     def time_mul_trunc(self, M, K, N, shift, reps=1):
         """seconds per asyncMul(A (M x K), B (K x N), C, shift).get() over three party threads"""
         t = lib().ref_time_mul_trunc(self.h, M, K, N, shift, reps)
@@ -191,3 +211,15 @@ def piecewise_plain(x, thresholds, coefficients, D):
     y = np.empty_like(x)
     _chk(lib().ref_piecewise_plain(ptr(x), x.size, ptr(th), len(th), ptr(counts), ptr(is_int), ptr(ints), ptr(dbl), D, ptr(y)))
     return y
+
+
+def conv_packed_roundtrip(planes, bits):
+    """Sh3Converter::toPackedBin + toBinaryMatrix(sPackedBin) of the reference on one pair of share planes
+    [2][rows][words] -> (packed [2][bits][simd], unpacked [2][rows][words])"""
+    planes = np.ascontiguousarray(planes, dtype=np.int64)
+    rows = planes.shape[1]
+    simd = (rows + 63) // 64
+    packed = np.zeros((2, bits, simd), dtype=np.int64)
+    out = np.zeros_like(planes)
+    _chk(lib().ref_conv_packed_roundtrip(ptr(planes), rows, bits, ptr(packed), simd, ptr(out)))
+    return packed, out

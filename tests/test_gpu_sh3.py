@@ -389,3 +389,58 @@ def test_shared_stream_session_matches_oracle():
     finally:
         s.close()
         r.close()
+
+
+def test_converter_matches_oracle(pair):
+    """Sh3Converter on the device (toBinaryMatrix(si64Matrix), bitInjection, toPackedBin / toBinaryMatrix(sPackedBin))
+    against the oracle restatement, which tests/test_ref_parity.py pins against the reference's own code."""
+    s, r = pair
+    s.conv_init()
+    r.conv_init()
+    rng = np.random.default_rng(31)
+    for rows, cols in ((43, 2), (1, 1), (1000, 1)):
+        x = rnd(32 + rows, (rows, cols))
+        X, Xo = s.share_int(0, x), r.share_int(0, x)
+        Y = s.conv_a2b(X)
+        Yo = r.conv_a2b(Xo, harness.library_circuit("a2b", 64 * cols))
+        assert np.array_equal(s.get_shares(Y, binary=True), Yo)
+        assert np.array_equal(s.reveal(Y, 2, binary=True), x)
+    for rows, bits in ((43, 17), (5, 64), (20, 91), (3000, 1)):
+        words = (bits + 63) // 64
+        x = rnd(40 + bits, (rows, words))
+        if bits % 64:
+            x[:, -1] &= (1 << (bits % 64)) - 1
+        B, Bo = s.share_bin(1, x, bits), r.share_bin(1, x)
+        Y = s.conv_bit_injection(B)
+        Yo = r.conv_bit_injection(Bo, bits)
+        assert np.array_equal(s.get_shares(Y), Yo)
+        exp = np.stack([(x[:, j // 64] >> (j % 64)) & 1 for j in range(bits)], axis=1)
+        assert np.array_equal(s.reveal(Y, 0), exp)
+    assert_cursors(s, r)
+    for rows, bits in ((1, 1), (65, 63), (200, 130), (5000, 64)):
+        words = (bits + 63) // 64
+        x = rnd(50 + rows, (rows, words))
+        if bits % 64:
+            x[:, -1] &= (1 << (bits % 64)) - 1
+        B = s.share_bin(0, x, bits)
+        sh = s.get_shares(B, binary=True)
+        back, packed = s.conv_packed_roundtrip(B, bits)
+        assert np.array_equal(s.get_shares(back, binary=True), sh)
+        simd = (rows + 63) // 64
+        for p in range(3):
+            for pl in range(2):
+                t = o.bit_transpose(sh[p, pl].view(np.uint8).reshape(-1), rows, bits, words * 8, simd * 8)
+                assert np.array_equal(t.view(np.int64).reshape(bits, simd), packed[p, pl])
+
+
+def test_converter_two_round_bit_injection(pair):
+    """bitInjection(twoRounds = true): party 1 receives its copy from party 0 instead of a second OT"""
+    s, _ = pair
+    x = rnd(60, (100, 1)) & 0x1FFFF
+    B = s.share_bin(2, x, 17)
+    Y = s.conv_bit_injection(B, two_rounds=True)
+    exp = np.stack([(x[:, 0] >> j) & 1 for j in range(17)], axis=1)
+    sh = s.get_shares(Y)
+    for p in range(3):
+        assert np.array_equal(s.reveal(Y, p), exp)
+        assert np.array_equal(sh[(p + 1) % 3, 1], sh[p, 0])

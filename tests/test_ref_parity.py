@@ -244,6 +244,63 @@ def test_reference_piecewise_aliasing_is_what_breaks_degree_one_regions():
     assert middle.any() and not np.array_equal(got[middle], exp[middle])
 
 
+def test_converter_arith_to_binary_shares():
+    """Sh3Converter::toBinaryMatrix(si64Matrix) (Sh3Converter.cpp:63-209; Sh3_convert_arithToBinaryMatrix_test):
+    oracle restatement vs the reference's code, share planes and reveals."""
+    so, sr = pair()
+    so.conv_init()
+    sr.conv_init()
+    rng = np.random.default_rng(11)
+    for rows, cols in ((43, 2), (1, 1), (130, 1)):
+        x = rng.integers(-2**63, 2**63, (rows, cols), dtype=np.int64)
+        Xo, Xr = so.share_int(0, x), sr.share_int(0, x)
+        cir = _lib_circuit("a2b", 64 * cols)
+        Yo, Yr = so.conv_a2b(Xo, cir), sr.conv_a2b(Xr)
+        assert np.array_equal(sr.reveal_all(Yr, binary=True)[0], x)
+        assert np.array_equal(o.reveal(Yo, 1, binary=True), x)
+        assert np.array_equal(Yo, Yr)
+
+
+def test_converter_bit_injection_shares():
+    """Sh3Converter::bitInjection (Sh3Converter.cpp:211-370; Sh3_convert_BitInjection_test: n = 43, m = 17)"""
+    so, sr = pair()
+    so.conv_init()
+    sr.conv_init()
+    rng = np.random.default_rng(12)
+    for rows, bits in ((43, 17), (5, 64), (20, 91), (300, 1)):
+        words = (bits + 63) // 64
+        x = rng.integers(-2**63, 2**63, (rows, words), dtype=np.int64)
+        if bits % 64:
+            x[:, -1] &= (1 << (bits % 64)) - 1
+        Bo, Br = so.share_bin(1, x), sr.share_bin(1, x)
+        Yo, Yr = so.conv_bit_injection(Bo, bits), sr.conv_bit_injection(Br, bits)
+        exp = np.zeros((rows, bits), dtype=np.int64)
+        for j in range(bits):
+            exp[:, j] = (x[:, j // 64] >> (j % 64)) & 1
+        assert np.array_equal(sr.reveal_all(Yr)[2], exp)
+        assert np.array_equal(o.reveal(Yo, 0), exp)
+        assert np.array_equal(Yo, Yr)
+    # the common PRNGs advanced identically
+    assert all(np.array_equal(a, b) for a, b in zip(so.trunc_tuple(2, 3, 16), sr.trunc_tuple(2, 3, 1, 16)))
+
+
+def test_converter_packed_layout():
+    """toPackedBin / toBinaryMatrix(sPackedBin) (Sh3Converter.cpp:12-61; Sh3_convert_b64Matrix_PackedBin_test):
+    the reference's packed layout equals the oracle's bit transpose, and the round trip is the identity."""
+    rng = np.random.default_rng(13)
+    for rows, bits in ((1, 1), (64, 64), (65, 63), (200, 130), (256, 256)):
+        words = (bits + 63) // 64
+        planes = rng.integers(-2**63, 2**63, (2, rows, words), dtype=np.int64)
+        if bits % 64:
+            planes[:, :, -1] &= (1 << (bits % 64)) - 1
+        packed, back = r.conv_packed_roundtrip(planes, bits)
+        assert np.array_equal(back, planes)
+        simd = (rows + 63) // 64
+        for p in range(2):
+            t = o.bit_transpose(planes[p].view(np.uint8).reshape(-1), rows, bits, words * 8, simd * 8)
+            assert np.array_equal(t.view(np.int64).reshape(bits, simd), packed[p])
+
+
 def test_scheduler_orders_hold_for_the_reference_runtime(tmp_path):
     """tests/cpp/test_runtime.cpp (the assertions of aby3_tests/Sh3RuntimeTests.cpp, which the facade's
     Sh3Runtime passes in test_cpp_runtime.py) compiled against the reference's own Sh3Runtime."""

@@ -36,6 +36,30 @@ def main():
         print(name, "gates", len(cir["gates"]) // 4, "nonlinear", cir["nonlinear"], "levels", len(cir["level_gates"]), "wires", cir["wire_count"])
         timed(s, "bin_eval %s n=%d" % (name, n), lambda: [s.free(h) for h in s.bin_eval(cir, [A, B])])
     timed(s, "max_min_split n=%d" % n, lambda: [s.free(h) for h in s.max_min_split(A, B)])
+    # one merge of two sorted halves of n elements each: where do the stages spend their time?
+    d1 = np.sort(a[:, 0]).reshape(-1, 1)
+    d2 = np.sort(b[:, 0]).reshape(-1, 1)
+    D1, D2 = s.share_bin(0, d1, 64), s.share_bin(0, d2, 64)
+    s.sync()
+    p0 = s.pool_stats
+    l0 = s.launches
+    s.timer_begin()
+    t0 = time.perf_counter()
+    m = s.odd_even_merge(D1, D2)
+    ms = s.timer_end()
+    wall = (time.perf_counter() - t0) * 1e3
+    p1 = s.pool_stats
+    print("odd_even_merge 2 x %d: device %.1f ms wall %.1f ms launches %d; pool: %d mallocs (%.1f GiB), %d frees"
+          % (n, ms, wall, s.launches - l0, p1[0] - p0[0], (p1[1] - p0[1]) / 2**30, p1[2] - p0[2]), flush=True)
+    s.free(m)
+    s.sync()
+    p0 = s.pool_stats
+    s.timer_begin()
+    m = s.odd_even_merge(D1, D2)
+    ms = s.timer_end()
+    p1 = s.pool_stats
+    print("odd_even_merge again:       device %.1f ms; pool: %d mallocs (%.1f GiB), %d frees"
+          % (ms, p1[0] - p0[0], (p1[1] - p0[1]) / 2**30, p1[2] - p0[2]), flush=True)
     s.close()
 
 
