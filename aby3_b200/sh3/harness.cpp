@@ -371,6 +371,10 @@ int sh3h_conv_a2b(sh3h* h, int in_id) {
         Party& P = h->p[i];
         auto m = std::make_unique<sbMatrix>();
         converter(P).toBinaryMatrix(P.rt.noDependencies(), *P.ints.at(in_id), *m).get();
+        // the closure completes with the last circuit round; getOutput and the state-keeping continuation hang
+        // off the inner closure (Sh3BinaryEvaluator.cpp:467-473, Sh3Converter.cpp:112) and run with the queue,
+        // as in the reference's test (run(t0, t1, t2), aby3_tests/Sh3ConverterTests.cpp:336)
+        P.rt.runAll();
         P.bins[id] = std::move(m);
         P.ctx->sync();
     });
