@@ -45,6 +45,8 @@ def _load():
     l.sh3h_odd_even_merge.argtypes = [p, i32, i32]
     l.sh3h_piecewise.argtypes = [p, i32, p, i32, p, p, p, p, u64]
     l.sh3h_mul_bit.argtypes = [p, i32, i32, i32, i64]
+    l.sh3h_share_packed.argtypes = [p, i32, i32, u64, u64, i32, p]
+    l.sh3h_reveal_packed.argtypes = [p, i32, i32, p]
     l.sh3h_conv_init.argtypes = [p]
     l.sh3h_conv_a2b.argtypes = [p, i32]
     l.sh3h_conv_bit_injection.argtypes = [p, i32, i32]
@@ -202,6 +204,23 @@ class Session:
         ints = np.asarray([int(v) if isinstance(v, (int, np.integer)) else 0 for v in flat] or [0], dtype=np.int64)
         dbl = np.asarray([float(v) for v in flat] or [0.0], dtype=np.float64)
         return self._id(lib.sh3h_piecewise(self.h, x, _ptr(th), len(th), _ptr(counts), _ptr(is_int), _ptr(ints), _ptr(dbl), D))
+
+    def share_packed(self, owner, values, use_task=False):
+        """Sh3Encryptor::localPackedBinary / remotePackedBinary: rows secrets of 64 * cols bits, bit-sliced.
+        Returns (handle, share planes [3][2][bits][simd])."""
+        values = np.ascontiguousarray(values, dtype=np.int64)
+        rows, cols = values.shape
+        pid, view = self.plain(owner, rows, cols)
+        view[...] = values
+        sh = np.zeros((3, 2, 64 * cols, (rows + 63) // 64), dtype=np.int64)
+        hid = self._id(lib.sh3h_share_packed(self.h, owner, pid, rows, cols, int(use_task), _ptr(sh)))
+        self.free(pid)
+        return hid, sh
+
+    def reveal_packed(self, hid, party, rows, cols):
+        out = np.empty((rows, cols), dtype=np.int64)
+        self._chk(lib.sh3h_reveal_packed(self.h, hid, party, _ptr(out)))
+        return out
 
     def conv_init(self):
         """Sh3Converter::init(rt, eval.mShareGen) on every party"""

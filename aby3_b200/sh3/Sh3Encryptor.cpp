@@ -216,11 +216,88 @@ Sh3Task Sh3Encryptor::reveal(Sh3Task dep, u64 partyIdx, const sbMatrix& x) {
     });
 }
 
+// ------------------------------------------------------- bit-sliced sharings ----
+// dest.mShares[0] = transpose(m) ^ z (or z alone at the other parties), -> next, <- prev   (Sh3Encryptor.cpp:342-425)
+std::future<void> Sh3Encryptor::sharePacked(CommPkg& comm, const i64Matrix* m, sPackedBin& dest) {
+    gpu::Context* ctx = gpu::current();
+    const u64 n = dest.mShares[0].size();
+    if (m) {
+        if (dest.bitCount() != m->cols() * 64) throw std::runtime_error(LOCATION);          // :344-347
+        if (dest.shareCount() != m->rows()) throw std::runtime_error(LOCATION);
+        gpu::Buffer t(ctx, std::max<size_t>(n * 8, 16));
+        gpu::check(aby3cu_memset(ctx->h(), t.ptr(), 0, std::max<size_t>(n * 8, 16)));
+        if (n) gpu::check(aby3cu_bit_transpose(ctx->h(), m->dev(), m->rows(), dest.bitCount(), m->cols() * 8, t.ptr(),
+                                               dest.simdWidth() * 8, nullptr));
+        mShareGen.getShares(ctx, (const i64*)t.ptr(), dest.mShares[0].devOut(), n, true);   // :356-357
+    } else {
+        mShareGen.getShares(ctx, nullptr, dest.mShares[0].devOut(), n, true);               // :403-404
+    }
+    comm.mNext.asyncSendDevice(dest.mShares[0].dev(), n * sizeof(i64));
+    return comm.mPrev.asyncRecvDevice(dest.mShares[1].devOut(), n * sizeof(i64));
+}
+void Sh3Encryptor::localPackedBinary(CommPkg& comm, const i64Matrix& m, sPackedBin& dest) { sharePacked(comm, &m, dest).get(); }
+Sh3Task Sh3Encryptor::localPackedBinary(Sh3Task dep, const i64Matrix& m, sPackedBin& dest) {
+    return dep.then([this, &m, &dest](CommPkg& comm, Sh3Task& self) {
+        auto fu = sharePacked(comm, &m, dest);
+        self.then([fu = std::move(fu)](CommPkg&, Sh3Task&) mutable { fu.get(); });
+    }).getClosure();
+}
+void Sh3Encryptor::remotePackedBinary(CommPkg& comm, sPackedBin& dest) { sharePacked(comm, nullptr, dest).get(); }
+Sh3Task Sh3Encryptor::remotePackedBinary(Sh3Task dep, sPackedBin& dest) {
+    return dep.then([this, &dest](CommPkg& comm, Sh3Task& self) {
+        auto fu = sharePacked(comm, nullptr, dest);
+        self.then([fu = std::move(fu)](CommPkg&, Sh3Task&) mutable { fu.get(); });
+    }).getClosure();
+}
+// r = transpose(next.x0 ^ x0 ^ x1): one row per secret, ceil(bitCount / 64) words   (Sh3Encryptor.cpp:627-651, 672-691)
+void Sh3Encryptor::revealPacked(CommPkg& comm, const sPackedBin& A, i64Matrix& r) {
+    gpu::Context* ctx = gpu::current();
+    const u64 n = A.mShares[0].size(), wordWidth = (A.bitCount() + 63) / 64;
+    r.resize(A.shareCount(), wordWidth);
+    gpu::Buffer buff(ctx, std::max<size_t>(n * 8, 16));
+    comm.mNext.recvDevice(buff.ptr(), n * sizeof(i64));
+    gpu::check(aby3cu_combine3(ctx->h(), ABY3CU_OP_XOR, (const i64*)buff.ptr(), A.mShares[0].dev(), A.mShares[1].dev(), (i64*)buff.ptr(), n));
+    i64* out = r.devOut();
+    gpu::check(aby3cu_memset(ctx->h(), out, 0, std::max<size_t>(r.size() * 8, 16)));
+    if (n) gpu::check(aby3cu_bit_transpose(ctx->h(), buff.ptr(), A.bitCount(), A.shareCount(), A.simdWidth() * 8, out, wordWidth * 8, nullptr));
+}
+void Sh3Encryptor::reveal(CommPkg& comm, const sPackedBin& x, i64Matrix& dest) { revealPacked(comm, x, dest); }
+void Sh3Encryptor::reveal(CommPkg& comm, u64 partyIdx, const sPackedBin& x) {
+    if ((mPartyIdx + 2) % 3 == partyIdx) {
+        comm.mPrev.asyncSendDevice(x.mShares[0].dev(), x.mShares[0].size() * sizeof(i64));
+        comm.mPrev.flush();
+    }
+}
+void Sh3Encryptor::revealAll(CommPkg& comm, const sPackedBin& x, i64Matrix& dest) {
+    comm.mPrev.asyncSendDevice(x.mShares[0].dev(), x.mShares[0].size() * sizeof(i64));
+    revealPacked(comm, x, dest);
+}
+Sh3Task Sh3Encryptor::reveal(Sh3Task dep, const sPackedBin& x, i64Matrix& dest) {
+    return dep.then([this, &x, &dest](CommPkg& comm, Sh3Task&) { revealPacked(comm, x, dest); });
+}
+Sh3Task Sh3Encryptor::reveal(Sh3Task dep, u64 partyIdx, const sPackedBin& x) {
+    const bool send = ((mPartyIdx + 2) % 3) == partyIdx;
+    return dep.then([send, &x](CommPkg& comm, Sh3Task&) {
+        if (send) comm.mPrev.asyncSendDevice(x.mShares[0].dev(), x.mShares[0].size() * sizeof(i64));
+    });
+}
+Sh3Task Sh3Encryptor::revealAll(Sh3Task dep, const sPackedBin& x, i64Matrix& dest) {
+    reveal(dep, (mPartyIdx + 2) % 3, x);
+    return reveal(dep, x, dest);
+}
+
 // Sh3Encryptor::rand (Sh3Encryptor.cpp:726-758): a fresh random sharing, plane 0 from
 // the next-key stream and plane 1 from the prev-key stream (getRandIntShare).
 void Sh3Encryptor::rand(si64Matrix& dest) {
     gpu::Context* ctx = gpu::current();
     const u64 n = dest.size();
+    gpu::check(aby3cu_aes_ctr_fill(ctx->h(), mShareGen.mShareGen[1].key().data(), 8 * mShareGen.mShareElemIdx, dest.mShares[0].devOut(), 8 * n));
+    gpu::check(aby3cu_aes_ctr_fill(ctx->h(), mShareGen.mShareGen[0].key().data(), 8 * mShareGen.mShareElemIdx, dest.mShares[1].devOut(), 8 * n));
+    mShareGen.mShareElemIdx += n;
+}
+void Sh3Encryptor::rand(sPackedBin& dest) {
+    gpu::Context* ctx = gpu::current();
+    const u64 n = dest.mShares[0].size();
     gpu::check(aby3cu_aes_ctr_fill(ctx->h(), mShareGen.mShareGen[1].key().data(), 8 * mShareGen.mShareElemIdx, dest.mShares[0].devOut(), 8 * n));
     gpu::check(aby3cu_aes_ctr_fill(ctx->h(), mShareGen.mShareGen[0].key().data(), 8 * mShareGen.mShareElemIdx, dest.mShares[1].devOut(), 8 * n));
     mShareGen.mShareElemIdx += n;

@@ -2,7 +2,7 @@
 // Sh3Encryptor.cpp:15-340, 430-560).  Same entry points, same message pattern
 // (share: x0 -> next, recv x1 <- prev; reveal: x0 -> prev, recv <- next); the
 // per-element loops run as aby3cu kernels and the messages are device buffers.
-// sPackedBin forms are not part of this round.
+// sPackedBin forms: localPackedBinary / remotePackedBinary / reveal.
 #pragma once
 #include "Sh3FixedPoint.h"
 #include "Sh3Runtime.h"
@@ -93,8 +93,22 @@ public:
     template <Decimal D>
     Sh3Task reveal(Sh3Task dep, u64 partyIdx, const sf64Matrix<D>& x) { return reveal(dep, partyIdx, x.i64Cast()); }
 
+    // bit-sliced (sPackedBin) forms -- Sh3Encryptor.cpp:342-425, 627-724: the plaintext rows are transposed
+    // into bit-slices before masking; reveal transposes back to one row per secret
+    void localPackedBinary(CommPkg& comm, const i64Matrix& m, sPackedBin& dest);
+    Sh3Task localPackedBinary(Sh3Task dep, const i64Matrix& m, sPackedBin& dest);
+    void remotePackedBinary(CommPkg& comm, sPackedBin& dest);
+    Sh3Task remotePackedBinary(Sh3Task dep, sPackedBin& dest);
+    void reveal(CommPkg& comm, const sPackedBin& x, i64Matrix& dest);
+    void revealAll(CommPkg& comm, const sPackedBin& x, i64Matrix& dest);
+    void reveal(CommPkg& comm, u64 partyIdx, const sPackedBin& x);
+    Sh3Task reveal(Sh3Task dep, const sPackedBin& x, i64Matrix& dest);
+    Sh3Task revealAll(Sh3Task dep, const sPackedBin& x, i64Matrix& dest);
+    Sh3Task reveal(Sh3Task dep, u64 partyIdx, const sPackedBin& x);
+
     void rand(si64Matrix& dest);
     void rand(sbMatrix& dest);
+    void rand(sPackedBin& dest);
 
     u64 mPartyIdx = (u64)-1;
     Sh3ShareGen mShareGen;
@@ -103,6 +117,8 @@ private:
     // x0 = m (+|^) z on the device, x0 -> next, post the receive of x1 <- prev
     std::future<void> shareMatrix(CommPkg& comm, const i64Matrix* m, eMatrix<i64>& x0, eMatrix<i64>& x1, bool binary);
     void revealMatrix(CommPkg& comm, const eMatrix<i64>& x0, const eMatrix<i64>& x1, i64Matrix& dest, bool binary);
+    std::future<void> sharePacked(CommPkg& comm, const i64Matrix* m, sPackedBin& dest);
+    void revealPacked(CommPkg& comm, const sPackedBin& x, i64Matrix& dest);
 };
 
 }  // namespace aby3

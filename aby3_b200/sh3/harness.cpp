@@ -77,6 +77,7 @@ struct Party {
     std::map<int, std::unique_ptr<si64Matrix>> ints;
     std::map<int, std::unique_ptr<sbMatrix>> bins;
     std::map<int, std::unique_ptr<i64Matrix>> plains;
+    std::map<int, std::unique_ptr<sPackedBin>> packs;
     void* ev_start = nullptr;
     void* ev_stop = nullptr;
 };
@@ -181,7 +182,7 @@ void sh3h_destroy(sh3h* h) {
     if (!h) return;
     h->run([&](int i) {
         Party& P = h->p[i];
-        P.ints.clear(); P.bins.clear(); P.plains.clear();
+        P.ints.clear(); P.bins.clear(); P.plains.clear(); P.packs.clear();
         P.ctx->sync();
     });
     for (int i = 0; i < 3; ++i) {
@@ -298,7 +299,7 @@ int sh3h_shape(sh3h* h, int id, int binary, uint64_t* rows, uint64_t* cols) {
 }
 
 int sh3h_free(sh3h* h, int id) {
-    return h->run([&](int i) { h->p[i].ints.erase(id); h->p[i].bins.erase(id); h->p[i].plains.erase(id); });
+    return h->run([&](int i) { h->p[i].ints.erase(id); h->p[i].bins.erase(id); h->p[i].plains.erase(id); h->p[i].packs.erase(id); });
 }
 
 // eval.asyncMul(rt, A, B, C [, shift]).get() on every party.  shift < 0: no truncation.
@@ -353,6 +354,38 @@ int sh3h_piecewise(sh3h* h, int in_id, const double* thresholds, int n_threshold
         P.ctx->sync();
     });
     return rc ? -1 : id;
+}
+
+// ---- bit-sliced sharings (Sh3Encryptor::localPackedBinary / remotePackedBinary / revealAll) ----------
+// rows secrets of 64 * cols bits from `owner`'s plaintext matrix; shares_out (may be null): [3][2][bits * simd] words
+int sh3h_share_packed(sh3h* h, int owner, int plain_id, uint64_t rows, uint64_t cols, int use_task, int64_t* shares_out) {
+    const int id = h->next_handle++;
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        auto m = std::make_unique<sPackedBin>(rows, 64 * cols);
+        if (use_task) {
+            if (i == owner) P.enc.localPackedBinary(P.rt.noDependencies(), *P.plains.at(plain_id), *m).get();
+            else P.enc.remotePackedBinary(P.rt.noDependencies(), *m).get();
+        } else {
+            if (i == owner) P.enc.localPackedBinary(P.comm, *P.plains.at(plain_id), *m);
+            else P.enc.remotePackedBinary(P.comm, *m);
+        }
+        if (shares_out)
+            for (int s = 0; s < 2; ++s)
+                memcpy(shares_out + ((uint64_t)i * 2 + s) * m->size(), m->mShares[s].hostData(), m->size() * 8);
+        P.packs[id] = std::move(m);
+    });
+    return rc ? -1 : id;
+}
+// enc.revealAll(comm, sPackedBin, dest) on every party; party `who`'s rows x words result is copied out
+int sh3h_reveal_packed(sh3h* h, int id, int who, int64_t* out) {
+    return h->run([&](int i) {
+        Party& P = h->p[i];
+        i64Matrix dest;
+        P.enc.revealAll(P.comm, *P.packs.at(id), dest);
+        if (i == who) memcpy(out, dest.hostData(), dest.size() * 8);
+        else P.ctx->sync();
+    });
 }
 
 // ---- Sh3Converter --------------------------------------------------------------------

@@ -363,6 +363,25 @@ int ref_conv_packed_roundtrip(const int64_t* in2, uint64_t rows, uint64_t bits, 
     } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }
 
+// Sh3Encryptor::localPackedBinary (owner) / remotePackedBinary, then revealAll(comm, sPackedBin, dest) on every party.
+// plain: rows x cols words; shares: [3][2][64*cols * simd] words; revealed: [3][rows * cols]
+int ref_share_reveal_packed(ref_session* s, int owner, const int64_t* plain, uint64_t rows, uint64_t cols, int64_t* shares, int64_t* revealed) {
+    return s->run([&](int i) {
+        RefParty& P = s->p[i];
+        sPackedBin pk(rows, 64 * cols);
+        if (i == owner) {
+            i64Matrix pl(rows, cols);
+            memcpy(pl.data(), plain, rows * cols * 8);
+            P.enc.localPackedBinary(P.comm, pl, pk);
+        } else P.enc.remotePackedBinary(P.comm, pk);
+        const u64 n = pk.mShares[0].size();
+        for (int p = 0; p < 2; ++p) memcpy(shares + (u64(i) * 2 + p) * n, pk.mShares[p].data(), n * 8);
+        i64Matrix dest;
+        P.enc.revealAll(P.comm, pk, dest);
+        memcpy(revealed + u64(i) * rows * cols, dest.data(), rows * cols * 8);
+    });
+}
+
 // Time the reference's three-party truncating product on this host (bench.py --impl reference / cpu_baseline):
 // asyncMul(dep, A (M x K), B (K x N), C, shift).get() on three party threads -- the three Eigen-form products
 // of Sh3Evaluator.cpp:662-665 (here: the shim's blocked loop), the fork's element-wise overwrite (:667-668,

@@ -153,6 +153,15 @@ class Session:
         lib.orc_trunc_tuple(self.h, party, n, d, ptr(R), ptr(T0), ptr(T1))
         return R, T0, T1
 
+    def share_packed(self, owner, plain):
+        """Sh3Encryptor::localPackedBinary / remotePackedBinary (Sh3Encryptor.cpp:342-425): the plaintext rows are
+        bit-transposed (one row per bit, one bit per secret) and then shared exactly like localBinMatrix."""
+        plain = np.ascontiguousarray(plain, dtype=np.int64)
+        rows, cols = plain.shape
+        simd = (rows + 63) // 64
+        t = bit_transpose(plain.view(np.uint8).reshape(-1), rows, 64 * cols, cols * 8, simd * 8)
+        return self.share_bin(owner, t.view(np.int64).reshape(64 * cols, simd))
+
     def conv_init(self):
         """Sh3Converter::init(rt, eval.mShareGen) on every party"""
         lib.orc_conv_init(self.h)

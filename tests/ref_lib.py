@@ -55,6 +55,7 @@ def lib():
         l.ref_conv_a2b.argtypes = [_p, _p, _u64, _u64, _p]
         l.ref_conv_bit_injection.argtypes = [_p, _p, _u64, _u64, _p]
         l.ref_conv_packed_roundtrip.argtypes = [_p, _u64, _u64, _p, _u64, _p]
+        l.ref_share_reveal_packed.argtypes = [_p, _int, _p, _u64, _u64, _p, _p]
         l.ref_time_mul_trunc.restype = C.c_double
         l.ref_time_mul_trunc.argtypes = [_p, _u64, _u64, _u64, _u64, _int]
         _lib = l
@@ -196,6 +197,15 @@ class Session:
         Y = np.empty((3, 2, rows, bits), dtype=np.int64)
         _chk(lib().ref_conv_bit_injection(self.h, ptr(B), rows, bits, ptr(Y)))
         return Y
+
+    def share_reveal_packed(self, owner, plain):
+        """localPackedBinary / remotePackedBinary then revealAll(sPackedBin): (shares [3][2][bits][simd], revealed [3][rows][cols])"""
+        plain = np.ascontiguousarray(plain, dtype=np.int64)
+        rows, cols = plain.shape
+        sh = np.zeros((3, 2, 64 * cols, (rows + 63) // 64), dtype=np.int64)
+        rev = np.zeros((3, rows, cols), dtype=np.int64)
+        _chk(lib().ref_share_reveal_packed(self.h, owner, ptr(plain), rows, cols, ptr(sh), ptr(rev)))
+        return sh, rev
 
     def time_mul_trunc(self, M, K, N, shift, reps=1):
         """seconds per asyncMul(A (M x K), B (K x N), C, shift).get() over three party threads"""

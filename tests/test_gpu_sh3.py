@@ -446,3 +446,17 @@ def test_converter_two_round_bit_injection(pair):
     for p in range(3):
         assert np.array_equal(s.reveal(Y, p), exp)
         assert np.array_equal(sh[(p + 1) % 3, 1], sh[p, 0])
+
+
+@pytest.mark.parametrize("use_task", [False, True])
+def test_packed_binary_sharing_matches_oracle(pair, use_task):
+    """localPackedBinary / remotePackedBinary / revealAll(sPackedBin) on the device vs the oracle (pinned against
+    the reference in tests/test_ref_parity.py)"""
+    s, r = pair
+    for owner, (rows, cols) in ((0, (1, 1)), (1, (65, 1)), (2, (200, 2)), (0, (5000, 1))):
+        x = rnd(70 + rows, (rows, cols))
+        hid, sh = s.share_packed(owner, x, use_task=use_task)
+        assert np.array_equal(sh, r.share_packed(owner, x))
+        for p in range(3):
+            assert np.array_equal(s.reveal_packed(hid, p, rows, cols), x)
+    assert_cursors(s, r)

@@ -301,6 +301,19 @@ def test_converter_packed_layout():
             assert np.array_equal(t.view(np.int64).reshape(bits, simd), packed[p])
 
 
+def test_packed_binary_sharing_and_reveal():
+    """Sh3Encryptor::localPackedBinary / remotePackedBinary / revealAll(sPackedBin) (Sh3Encryptor.cpp:342-425, 627-724)"""
+    so, sr = pair()
+    rng = np.random.default_rng(14)
+    for owner, (rows, cols) in ((0, (1, 1)), (1, (65, 1)), (2, (200, 2)), (0, (64, 3))):
+        x = rng.integers(-2**63, 2**63, (rows, cols), dtype=np.int64)
+        sh_r, rev = sr.share_reveal_packed(owner, x)
+        sh_o = so.share_packed(owner, x)
+        assert np.array_equal(sh_o, sh_r)
+        for p in range(3):
+            assert np.array_equal(rev[p], x)
+
+
 def test_scheduler_orders_hold_for_the_reference_runtime(tmp_path):
     """tests/cpp/test_runtime.cpp (the assertions of aby3_tests/Sh3RuntimeTests.cpp, which the facade's
     Sh3Runtime passes in test_cpp_runtime.py) compiled against the reference's own Sh3Runtime."""
