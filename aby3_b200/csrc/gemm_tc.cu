@@ -267,12 +267,34 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         u32 tile_iter = 0;
         for (u32 t = blockIdx.x; t < ntiles_total; t += gridDim.x, ++tile_iter) {
             const u32 mt = t / p.ntiles, nt = t % p.ntiles;
-            mbar_wait(tmem_full, tile_iter & 1);
-            tc_fence_after();
             const u64 grow = p.row0 + (u64)mt * TM + row_in_tile;
             const u64 gcol0 = (u64)nt * TN;
+            const bool rowok = grow < p.rows_end;
+            const bool fast = gcol0 + TN <= p.N && ((p.N & 1) == 0);
+            u64* dst = p.C + grow * p.N + gcol0;
+            // The tile's C values (z or -r pre-loaded by the caller, or an earlier K chunk) are fetched into
+            // registers WHILE the MMAs of this tile still run: one thread owns one row, so these loads are 64-byte
+            // pieces 8*N bytes apart -- latency-bound, and otherwise exposed after the accumulators complete.
+            u64 cpre[TN];
+            if (p.accumulate && rowok) {
+                if (fast) {
+#pragma unroll
+                    for (int j = 0; j < TN; j += 2) {
+                        const ulonglong2 o = __ldcs(reinterpret_cast<const ulonglong2*>(dst + j));
+                        cpre[j] = o.x; cpre[j + 1] = o.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) cpre[j] = (gcol0 + j < p.N) ? dst[j] : 0;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) cpre[j] = 0;
+            }
+            mbar_wait(tmem_full, tile_iter & 1);
+            tc_fence_after();
             const u32 tlane = tmem + ((quarter * 32u) << 16);
-#pragma unroll 1
+#pragma unroll
             for (int c0 = 0; c0 < TN; c0 += 8) {
                 u32 d[8][8];
 #pragma unroll
@@ -281,27 +303,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
                 u64 out[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    u64 acc = 0;
+                    u64 acc = cpre[c0 + j];
 #pragma unroll
                     for (int s = 0; s < 8; ++s) acc += (u64)d[s][j] << (8 * s);
                     out[j] = acc;
                 }
-                if (grow < p.rows_end) {
-                    u64* dst = p.C + grow * p.N + gcol0 + c0;
-                    if (gcol0 + c0 + 8 <= p.N && ((p.N & 1) == 0)) {
+                if (rowok) {
+                    if (fast) {
 #pragma unroll
-                        for (int j = 0; j < 8; j += 2) {
-                            ulonglong2 v = make_ulonglong2(out[j], out[j + 1]);
-                            if (p.accumulate) {
-                                const ulonglong2 o = *reinterpret_cast<const ulonglong2*>(dst + j);
-                                v.x += o.x; v.y += o.y;
-                            }
-                            *reinterpret_cast<ulonglong2*>(dst + j) = v;
-                        }
+                        for (int j = 0; j < 8; j += 2)
+                            __stcs(reinterpret_cast<ulonglong2*>(dst + c0 + j), make_ulonglong2(out[j], out[j + 1]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            if (gcol0 + c0 + j < p.N) dst[j] = p.accumulate ? dst[j] + out[j] : out[j];
+                            if (gcol0 + c0 + j < p.N) dst[c0 + j] = out[j];
                     }
                 }
             }
