@@ -45,6 +45,7 @@ constexpr u32 STAGE_BYTES = A_CHUNK + B_CHUNK;
 constexpr u32 SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // + barriers, tmem slot, alignment slack
 constexpr int THREADS = 192;
 constexpr u64 K_MAX = 8192;        // per launch, see the exactness bound above
+constexpr u32 RASTER_M = 8;        // tile rows per rasterisation group
 
 // ------------------------------------------------------------------ PTX wrappers --
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -208,13 +209,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     const u32 tmem = *tmem_slot;
 
     const u32 ntiles_total = p.mtiles * p.ntiles;
+    // Tile order: groups of RASTER_M tile rows, column-major inside a group, so that the ~148 tiles in flight share
+    // 8 A panels and ~19 B panels through L2 instead of streaming all of B for every wave.
+    auto tile_coords = [&](u32 t, u32& mt, u32& nt) {
+        const u32 group = RASTER_M * p.ntiles, g = t / group, r = t - g * group;
+        const u32 gm = (p.mtiles - g * RASTER_M < RASTER_M) ? (p.mtiles - g * RASTER_M) : RASTER_M;
+        mt = g * RASTER_M + r % gm;
+        nt = r / gm;
+    };
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             u32 stage = 0, phase = 0;
             for (u32 t = blockIdx.x; t < ntiles_total; t += gridDim.x) {
-                const u32 mt = t / p.ntiles, nt = t % p.ntiles;
+                u32 mt, nt;
+                tile_coords(t, mt, nt);
                 const u8* a = p.pa + (u64)mt * p.kblocks * A_CHUNK;
                 const u8* b = p.pb + (u64)nt * p.kblocks * B_CHUNK;
                 for (u32 kb = 0; kb < p.kblocks; ++kb) {
@@ -266,7 +276,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         const u32 row_in_tile = quarter * 32 + lane;
         u32 tile_iter = 0;
         for (u32 t = blockIdx.x; t < ntiles_total; t += gridDim.x, ++tile_iter) {
-            const u32 mt = t / p.ntiles, nt = t % p.ntiles;
+            u32 mt, nt;
+            tile_coords(t, mt, nt);
             const u64 grow = p.row0 + (u64)mt * TM + row_in_tile;
             const u64 gcol0 = (u64)nt * TN;
             const bool rowok = grow < p.rows_end;
