@@ -38,7 +38,7 @@ namespace tc {
 constexpr int TM = 128;            // tile rows  (= MMA M, TMEM lanes)
 constexpr int TN = 64;             // tile cols  (per limb accumulator)
 constexpr int TK = 32;             // k per stage (= MMA K for 8-bit operands)
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr u32 A_CHUNK = 8 * TM * TK;      // 32768 B
 constexpr u32 B_CHUNK = 8 * TN * TK;      // 16384 B
 constexpr u32 STAGE_BYTES = A_CHUNK + B_CHUNK;

@@ -399,7 +399,7 @@ def main():
     ap.add_argument("--no-linreg", action="store_true")
     ap.add_argument("--logistic-rows", type=int, default=1 << 21)
     ap.add_argument("--no-logistic", action="store_true")
-    ap.add_argument("--basic-elements", type=int, default=1 << 22)
+    ap.add_argument("--basic-elements", type=int, default=1 << 24)
     ap.add_argument("--no-basic", action="store_true")
     args = ap.parse_args()
 
