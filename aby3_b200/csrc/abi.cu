@@ -181,7 +181,12 @@ int aby3cu_malloc(aby3cu_ctx* ctx, void** d_ptr, size_t bytes) {
     DeviceGuard g(ctx->device);
     *d_ptr = nullptr;
     if (!bytes) return 0;
-    ABY3CU_CHECK(cudaMalloc(d_ptr, bytes));
+    const cudaError_t e = cudaMalloc(d_ptr, bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();        // an allocation failure is not sticky: clear it so that the caller may trim and retry
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return 1;
+    }
     return 0;
 }
 int aby3cu_free(aby3cu_ctx* ctx, void* d_ptr) {

@@ -62,6 +62,7 @@ def _load():
     l.sh3h_sync.argtypes = [p]
     l.sh3h_launch_count.restype = u64
     l.sh3h_launch_count.argtypes = [p]
+    l.sh3h_trim.argtypes = [p]
     l.sh3h_pool_stats.argtypes = [p, p]
     l.sh3h_bytes_sent.restype = u64
     l.sh3h_bytes_sent.argtypes = [p]
@@ -316,6 +317,11 @@ class Session:
     @property
     def launches(self):
         return int(lib.sh3h_launch_count(self.h))
+
+    def trim(self):
+        """Return the cached device blocks of the three buffer pools to the driver (call between workloads
+        whose buffer sizes differ, so that one workload's cache is not the next one's memory pressure)."""
+        self._chk(lib.sh3h_trim(self.h))
 
     @property
     def pool_stats(self):

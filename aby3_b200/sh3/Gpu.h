@@ -99,9 +99,29 @@ public:
             return e.ptr;
         }
         void* p = nullptr;
-        check(aby3cu_malloc(mCtx, &p, bytes));
+        if (aby3cu_malloc(mCtx, &p, bytes) != 0) {
+            // HBM is exhausted by blocks this pool keeps for reuse: hand them back and try once more
+            trim();
+            check(aby3cu_malloc(mCtx, &p, bytes));
+        }
         ++mMallocs; mMallocBytes += bytes;
         return p;
+    }
+    // give every cached block back to the driver (between workloads with different buffer sizes)
+    void trim() {
+        std::map<size_t, std::vector<Entry>> drop;
+        {
+            std::lock_guard<std::mutex> g(mMtx);
+            drop.swap(mFree);
+            mCached = 0;
+        }
+        aby3cu_sync(mCtx);
+        for (auto& kv : drop)
+            for (auto& e : kv.second) {
+                if (e.event) { aby3cu_event_sync(e.event); EventPool::put(e.eventDevice, e.event); }
+                aby3cu_free(mCtx, e.ptr);
+                ++mFrees;
+            }
     }
     // pool misses (driver allocations) since creation: a steady-state loop should show none
     u64 mallocCount() const { return mMallocs; }

@@ -677,6 +677,8 @@ uint64_t sh3h_launch_count(sh3h* h) {
     for (int i = 0; i < 3; ++i) n += aby3cu_launch_count(h->p[i].ctx->h());
     return n;
 }
+// return every cached device block of the parties' pools to the driver
+int sh3h_trim(sh3h* h) { return h->run([&](int i) { h->p[i].ctx->trim(); }); }
 // driver allocations / frees behind the parties' buffer pools: [0] mallocs, [1] bytes, [2] frees
 void sh3h_pool_stats(sh3h* h, uint64_t out[3]) {
     out[0] = out[1] = out[2] = 0;

@@ -490,18 +490,21 @@ def main():
     if max_err > 4:
         raise SystemExit("bench: revealed product is off by %d ulp (> 4) from the plaintext product" % max_err)
     linreg = None
+    sess.trim()          # each side workload starts with empty buffer pools
     if rank == 0 and not args.no_linreg:
         try:
             linreg = linreg_bench(sess, args.linreg_samples)
         except Exception as e:
             linreg = {"error": str(e)}
     logistic = None
+    sess.trim()
     if rank == 0 and not args.no_logistic:
         try:
             logistic = logistic_bench(sess, args.logistic_rows)
         except Exception as e:
             logistic = {"error": str(e)}
     basic = None
+    sess.trim()
     if rank == 0 and not args.no_basic:
         try:
             basic = basic_bench(sess, args.basic_elements)
