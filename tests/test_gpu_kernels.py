@@ -246,3 +246,24 @@ def test_two_plane_ops_and_multi_gather(ctx):
     in1, out1, c1 = (C.c_void_p * 1)(dz.p), (C.c_void_p * 1)(oz.p), (C.c_uint64 * 1)(37)
     abi.check(lib.aby3cu_gather_rows_multi(ctx.h, 1, in1, c1, out1, di.p, 128))
     assert np.array_equal(ctx.download(oz, (128, 37)), Z[idx.astype(np.int64)])
+
+
+def test_gemm_skinny_shapes(ctx):
+    """GEMV-like shapes (N <= 8) of the CUDA-core path: odd K (scalar loads), K beyond one shared-memory chunk
+    (accumulation across launches), every N bucket, unaligned A planes."""
+    for (M, K, N) in [(1, 1, 1), (37, 513, 1), (300, 4100, 1), (64, 2048, 2), (33, 1500, 3), (129, 700, 5), (17, 300, 8), (5000, 512, 1)]:
+        a0, a1 = rnd(11, M * K + 1), rnd(12, M * K + 1)
+        b0, b1 = rnd(13, K * N).reshape(K, N), rnd(14, K * N).reshape(K, N)
+        c0 = rnd(15, M * N).reshape(M, N)
+        d = [ctx.upload(x) for x in (a0, a1, b0, b1)]
+        for off in (0, 1):                       # off = 1: planes start 8 bytes off a 16-byte boundary
+            A0, A1 = a0[off:off + M * K].reshape(M, K), a1[off:off + M * K].reshape(M, K)
+            exp = o.cross_term(np.ascontiguousarray(A0), np.ascontiguousarray(A1), b0, b1).view(U64)
+            dc = ctx.upload(c0)
+            abi.check(lib.aby3cu_gemm_cross(ctx.h, abi.GEMM_IMAD, d[0].at(8 * off), d[1].at(8 * off), d[2].p, d[3].p, M, K, N, dc.p, 1))
+            assert np.array_equal(ctx.download(dc, (M, N), U64), exp + c0.view(U64)), (M, K, N, off, "acc")
+            abi.check(lib.aby3cu_gemm_cross(ctx.h, abi.GEMM_AUTO, d[0].at(8 * off), d[1].at(8 * off), d[2].p, d[3].p, M, K, N, dc.p, 0))
+            assert np.array_equal(ctx.download(dc, (M, N), U64), exp), (M, K, N, off)
+            dc.free()
+        for x in d:
+            x.free()

@@ -70,6 +70,11 @@ def main():
     report("trunc_tuple(negr)", timeit(ctx, lambda: abi.check(lib.aby3cu_trunc_tuple(ctx.h, KA, 4, KB, 4, 16, None, p[4], p[5], p[6], n))), 24)
     report("trunc_finish", timeit(ctx, lambda: abi.check(lib.aby3cu_trunc_finish(ctx.h, p[0], p[1], p[2], p[3], n, 16))), 40)
     report("share_add", timeit(ctx, lambda: abi.check(lib.aby3cu_share_op(ctx.h, 0, p[0], p[1], p[2], n))), 24)
+    # GEMV-like cross term (logistic inference / SGD shapes): A planes streamed once, 16 B per (m, k)
+    for (Mv, Kv) in ((n // 512, 512), (n // 1024, 1024)):
+        ms = timeit(ctx, lambda: abi.check(lib.aby3cu_gemm_cross(ctx.h, abi.GEMM_IMAD, p[0], p[1], p[2], p[3], Mv, Kv, 1, p[4], 1)))
+        print(json.dumps({"kernel": "gemm_skinny %dx%dx1" % (Mv, Kv), "ms": round(ms, 4), "GBps": round(16 * Mv * Kv / ms / 1e6, 1),
+                          "frac_of_measured_hbm": round(16 * Mv * Kv / ms / 1e6 / PEAK, 3), "bytes_per_mk": 16}), flush=True)
     # binary: transpose 2^24 x 64 and one 64-gate AND level over 2^24 instances
     width = 1 << 24
     rb = lib.aby3cu_bin_row_bytes(width)
