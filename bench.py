@@ -47,9 +47,9 @@ def synth_inputs(M, K, N, seed):
     `(u32 >> 8) / 100.0`, aby3_tests/Sh3EvaluatorTests.cpp:469-470, overflows 64 bits once K = 4096
     products are summed at D16, and the truncation protocol needs |x*y| << 2^63; the kernels' run
     time does not depend on the values.)"""
-    rng = np.random.default_rng(seed)
-    a = (rng.uniform(-4.0, 4.0, (M, K)) * (1 << SHIFT)).astype(np.int64)
-    b = (rng.uniform(-4.0, 4.0, (K, N)) * (1 << SHIFT)).astype(np.int64)
+    # a: this rank's row block (seeded per rank); b: the same on every rank (B is replicated, SURVEY 8e)
+    a = (np.random.default_rng(seed).uniform(-4.0, 4.0, (M, K)) * (1 << SHIFT)).astype(np.int64)
+    b = (np.random.default_rng(999).uniform(-4.0, 4.0, (K, N)) * (1 << SHIFT)).astype(np.int64)
     return a, b
 
 

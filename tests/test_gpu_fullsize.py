@@ -154,3 +154,73 @@ print("ROWBLOCK OK", ctx.launches)
     assert out.returncode == 0 and "ROWBLOCK OK" in out.stdout, out.stdout
     launches = int(out.stdout.strip().split()[-1])
     assert launches >= 1 + 2 * 3          # pack_b + several (pack_a, gemm) pairs
+
+
+def test_linreg_config3_shapes_match_oracle():
+    """config 3 shapes (batch 128 x 1024 features): a few SGD_Linear iterations, w shares bit-exact vs the oracle's
+    composition of the same products (the full 2^20-sample run differs only in which rows are gathered)."""
+    import test_gpu_sh3 as t
+    s, r = harness.Session(), o.Session()
+    try:
+        N, F, B, iters, lr, D = 2048, 1024, 128, 4, 2.0 ** -10, 16
+        rng = np.random.default_rng(9)
+        x = (rng.normal(1, 1, (N, F)) * (1 << D)).astype(np.int64)
+        y = (rng.normal(1, 1, (N, 1)) * (1 << D)).astype(np.int64)
+        w = np.zeros((F, 1), dtype=np.int64)
+        idx = rng.integers(0, N, iters * B).astype(np.uint64)
+        X, Y, W = s.share_int(0, x), s.share_int(0, y), s.share_int(0, w)
+        Xo, Yo, Wo = r.share_int(0, x), r.share_int(0, y), r.share_int(0, w)
+        s.linreg(X, Y, W, idx, iters, B, lr)
+        assert np.array_equal(s.get_shares(W), t.oracle_linreg(r, Xo, Yo, Wo, idx, iters, B, lr, D))
+    finally:
+        s.close()
+        r.close()
+
+
+def test_logistic_inference_config4_shape_property():
+    """config 4 shape (rows x 512 features, piecewise sigmoid): the revealed output is EXACTLY the plaintext piecewise
+    function of the revealed linear part (the truncation noise sits in z, f(z) is deterministic given z)."""
+    s = harness.Session()
+    try:
+        rows, F, D = 1 << 17, 512, 16
+        rng = np.random.default_rng(10)
+        x = (rng.uniform(-1, 1, (rows, F)) * (1 << D)).astype(np.int64)
+        w = (rng.uniform(-0.1, 0.1, (F, 1)) * (1 << D)).astype(np.int64)
+        X, W = s.share_int(0, x), s.share_int(1, w)
+        z = s.mul(X, W, shift=D)
+        yv = s.piecewise(z, [-0.5, 0.5], [[], [0.5, 1], [1]], D)
+        zr, yr = s.reveal(z, 0), s.reveal(yv, 2)
+        half = 1 << (D - 1)
+        exp = np.where(zr < -half, 0, np.where(zr < half, zr + half, 1 << D))
+        assert np.array_equal(yr, exp)
+        assert np.max(np.abs(zr - ((x @ w) >> D))) <= 4
+        sh = s.get_shares(yv)
+        for p in range(3):
+            assert np.array_equal(sh[(p + 1) % 3, 1], sh[p, 0])
+    finally:
+        s.close()
+
+
+def test_cipher_gt_and_merge_config5_properties():
+    """config 5: cipher_gt over 2^22 pairs equals the plaintext comparison; odd_even_merge of two sorted runs of 2^19
+    keys (odd sizes too) returns a sorted permutation of the inputs."""
+    s = harness.Session()
+    try:
+        n = 1 << 22
+        rng = np.random.default_rng(11)
+        a = rng.integers(-2**62, 2**62, (n, 1), dtype=np.int64)
+        b = rng.integers(-2**62, 2**62, (n, 1), dtype=np.int64)
+        b[:1000] = a[:1000]                                   # ties
+        A, B = s.share_int(0, a), s.share_int(2, b)
+        gt = s.cipher_gt(A, B)
+        assert np.array_equal(s.reveal(gt, 1, binary=True) & 1, (a > b).astype(np.int64))
+        for h in (gt, A, B):
+            s.free(h)
+        for l1, l2 in (((1 << 19), (1 << 19)), (1000, 777), (1, 1)):
+            d1 = np.sort(rng.integers(-2**62, 2**62, l1)).reshape(-1, 1)
+            d2 = np.sort(rng.integers(-2**62, 2**62, l2)).reshape(-1, 1)
+            D1, D2 = s.share_bin(0, d1, 64), s.share_bin(1, d2, 64)
+            m = s.reveal(s.odd_even_merge(D1, D2), 0, binary=True).reshape(-1)
+            assert np.array_equal(m, np.sort(np.concatenate([d1[:, 0], d2[:, 0]])))
+    finally:
+        s.close()
