@@ -81,4 +81,27 @@ void SGD_Linear(RegressionParam& params, Engine& engine, sf64Matrix<D>& X, sf64M
                      acc[3] / params.mIterations, acc[4] / params.mIterations, acc[5] / params.mIterations);
 }
 
+// Logistic regression (aby3-ML/Regression.h:218-295): the same loop with the piecewise sigmoid between the two
+// products: error = logisticFunc(XX * w) - YY.
+template <typename Engine, Decimal D>
+void SGD_Logistic(RegressionParam& params, Engine& engine, sf64Matrix<D>& X, sf64Matrix<D>& Y, sf64Matrix<D>& w,
+                  const std::vector<u64>& batchIndices) {
+    if (X.rows() != Y.rows() || Y.cols() != 1) throw std::runtime_error(LOCATION);
+    if (batchIndices.size() != params.mIterations * params.mBatchSize) throw std::runtime_error(LOCATION);
+    gpu::Context* ctx = gpu::current();
+    gpu::Buffer dIdx(ctx, std::max<size_t>(batchIndices.size() * 8, 16));
+    gpu::check(aby3cu_h2d(ctx->h(), dIdx.ptr(), batchIndices.data(), batchIndices.size() * 8));
+    sf64Matrix<D> XX(params.mBatchSize, X.cols()), YY(params.mBatchSize, 1);
+    const u64 aB = (u64)std::log2(1 / (params.mLearningRate / params.mBatchSize));
+    for (u64 i = 0; i < params.mIterations; ++i) {
+        extractBatch(XX, YY, X, Y, (const u64*)dIdx.ptr() + i * params.mBatchSize, params.mBatchSize);
+        sf64Matrix<D> xw = engine.mul(XX, w);                       // :263
+        sf64Matrix<D> fxw = engine.logisticFunc(xw);                // :264
+        sf64Matrix<D> error = fxw - YY;                             // :269
+        XX.transposeInPlace();                                      // :274
+        sf64Matrix<D> update = engine.mulTruncate(XX, error, aB);   // :277
+        w = w - update;
+    }
+}
+
 }  // namespace aby3

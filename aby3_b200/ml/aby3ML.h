@@ -6,6 +6,7 @@
 #pragma once
 #include "../sh3/Sh3Encryptor.h"
 #include "../sh3/Sh3Evaluator.h"
+#include "../sh3/Sh3Piecewise.h"
 
 namespace aby3 {
 
@@ -79,6 +80,28 @@ public:
         sf64Matrix<D> dest;
         mEval.asyncMul(mRt.noDependencies(), left, right, dest, shift).get();
         return dest;
+    }
+
+    // aby3ML.h:119-139: the piecewise approximation f(x) = 0 | x + 0.5 | 1 with cuts at -0.5 and 0.5
+    Sh3Piecewise mLogistic;
+    static void setLogistic(Sh3Piecewise& pw) {
+        if (pw.mThresholds.size()) return;
+        pw.mThresholds.resize(2);
+        pw.mThresholds[0] = -0.5;
+        pw.mThresholds[1] = 0.5;
+        pw.mCoefficients.resize(3);
+        pw.mCoefficients[1].resize(2);
+        pw.mCoefficients[1][0] = 0.5;
+        pw.mCoefficients[1][1] = 1;
+        pw.mCoefficients[2].resize(1);
+        pw.mCoefficients[2][0] = 1;
+    }
+    template <Decimal D>
+    sf64Matrix<D> logisticFunc(const sf64Matrix<D>& Y) {
+        setLogistic(mLogistic);
+        sf64Matrix<D> out(Y.rows(), Y.cols());
+        mLogistic.eval<D>(mRt.noDependencies(), Y, out, mEval).get();
+        return out;
     }
 };
 

@@ -553,6 +553,14 @@ struct PartyEngine {
         P.eval.asyncMul(P.rt, l, r, d, shift).get();
         return d;
     }
+    Sh3Piecewise mLogistic;
+    template <Decimal D>
+    sf64Matrix<D> logisticFunc(const sf64Matrix<D>& Y) {
+        aby3ML::setLogistic(mLogistic);
+        sf64Matrix<D> out(Y.rows(), Y.cols());
+        mLogistic.eval<D>(P.rt.noDependencies(), Y, out, P.eval).get();
+        return out;
+    }
 };
 }  // namespace
 
@@ -570,6 +578,19 @@ int sh3h_linreg(sh3h* h, int x_id, int y_id, int w_id, const uint64_t* batch_idx
         std::vector<u64> idx(batch_idx, batch_idx + iters * batch);
         PartyEngine eng{P};
         SGD_Linear(params, eng, X, Y, W, idx);
+    });
+}
+
+int sh3h_logreg(sh3h* h, int x_id, int y_id, int w_id, const uint64_t* batch_idx, uint64_t iters, uint64_t batch, double lr) {
+    return h->run([&](int i) {
+        Party& P = h->p[i];
+        auto& X = reinterpret_cast<sf64Matrix<D16>&>(*P.ints.at(x_id));
+        auto& Y = reinterpret_cast<sf64Matrix<D16>&>(*P.ints.at(y_id));
+        auto& W = reinterpret_cast<sf64Matrix<D16>&>(*P.ints.at(w_id));
+        RegressionParam params{iters, batch, lr};
+        std::vector<u64> idx(batch_idx, batch_idx + iters * batch);
+        PartyEngine eng{P};
+        SGD_Logistic(params, eng, X, Y, W, idx);
     });
 }
 

@@ -460,3 +460,44 @@ def test_packed_binary_sharing_matches_oracle(pair, use_task):
         for p in range(3):
             assert np.array_equal(s.reveal_packed(hid, p, rows, cols), x)
     assert_cursors(s, r)
+
+
+def oracle_logreg(r, X, Y, w, idx, iters, B, lr, D=16):
+    """aby3-ML/Regression.h:218-295 on the oracle's share arrays (piecewise sigmoid between the two products)."""
+    import math
+    import piecewise_ref as pw
+    aB = int(math.log2(1 / (lr / B)))
+    cir = harness.library_circuit("piecewise2", 64)
+    for i in range(iters):
+        bi = idx[i * B:(i + 1) * B].astype(np.int64)
+        XX = np.ascontiguousarray(X[:, :, bi, :])
+        YY = np.ascontiguousarray(Y[:, :, bi, :])
+        xw = r.mul_trunc(XX, w, D)
+        fxw = pw.shared(r, np.ascontiguousarray(xw), [-0.5, 0.5], [[], [0.5, 1], [1]], D, cir)
+        err = (fxw.view(U64) - YY.view(U64)).view(np.int64)
+        XXt = np.ascontiguousarray(np.swapaxes(XX, 2, 3))
+        upd = r.mul_trunc(XXt, np.ascontiguousarray(err), D + aB)
+        w = np.ascontiguousarray((w.view(U64) - upd.view(U64)).view(np.int64))
+    return w
+
+
+def test_logistic_regression_sgd_matches_oracle(pair):
+    """aby3-ML SGD_Logistic on sf64<D16>: w shares after k iterations bit-exact against the oracle-side composition,
+    and the learnt model separates the classes."""
+    s, r = pair
+    N, F, B, iters, lr, D = 512, 8, 32, 60, 2.0 ** -2, 16
+    rng = np.random.default_rng(41)
+    model = np.array([[1.5], [-2.0], [0.5], [0.0], [1.0], [-1.0], [0.0], [0.25]])
+    x = rng.normal(0, 1, (N, F))
+    y = ((x @ model) > 0).astype(np.float64)
+    fx, fy, fw = fixed(x, D), fixed(y, D), np.zeros((F, 1), dtype=np.int64)
+    idx = rng.integers(0, N, iters * B).astype(np.uint64)
+    X, Y, W = s.share_int(0, fx), s.share_int(0, fy), s.share_int(0, fw)
+    Xo, Yo, Wo = r.share_int(0, fx), r.share_int(0, fy), r.share_int(0, fw)
+    s.logreg(X, Y, W, idx, iters, B, lr)
+    Wo = oracle_logreg(r, Xo, Yo, Wo, idx, iters, B, lr, D)
+    assert np.array_equal(s.get_shares(W), Wo)
+    learnt = s.reveal(W, 0).astype(np.float64) / (1 << D)
+    acc = np.mean(((x @ learnt) > 0).astype(np.float64) == y)
+    assert acc > 0.85, acc
+    assert_cursors(s, r)
