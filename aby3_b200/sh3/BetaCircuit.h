@@ -193,6 +193,8 @@ public:
     BetaCircuit* int_int_bitwiseAnd(u64 a, u64 b, u64 c) { return bitwise("and", GateType::And, a, b, c); }
     BetaCircuit* int_int_bitwiseOr(u64 a, u64 b, u64 c) { return bitwise("or", GateType::Or, a, b, c); }
     BetaCircuit* int_int_bitwiseXor(u64 a, u64 b, u64 c) { return bitwise("xor", GateType::Xor, a, b, c); }
+    // c_i = NOR(a_i, b_i)  (aby3/Circuit/CircuitLibrary.cpp:397-428, bits_nor_helper)
+    BetaCircuit* bits_nor_helper(u64 size) { return bitwise("nor", GateType::Nor, size, size, size); }
 
     // c = a + b (two's complement, cBits low bits)
     BetaCircuit* int_int_add(u64 aBits, u64 bBits, u64 cBits, Optimized op = Optimized::Size) {

@@ -730,6 +730,7 @@ sh3h_circuit* sh3h_circuit_build(const char* name, uint32_t bits) {
         if (n == "and") c->cir = c->lib.int_int_bitwiseAnd(bits, bits, bits);
         else if (n == "or") c->cir = c->lib.int_int_bitwiseOr(bits, bits, bits);
         else if (n == "xor") c->cir = c->lib.int_int_bitwiseXor(bits, bits, bits);
+        else if (n == "nor") c->cir = c->lib.bits_nor_helper(bits);
         else if (n == "add") c->cir = c->lib.int_int_add(bits, bits, bits, oc::BetaLibrary::Optimized::Size);
         else if (n == "add_depth") c->cir = c->lib.int_int_add(bits, bits, bits, oc::BetaLibrary::Optimized::Depth);
         else if (n == "add_msb") c->cir = c->lib.int_int_add_msb(bits);

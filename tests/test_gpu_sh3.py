@@ -196,7 +196,7 @@ def test_bad_shapes_throw(pair):
         s.mul(A, B)
 
 
-BIN_CASES = [("and", 8, 256), ("and", 64, 5000), ("or", 64, 300), ("add", 8, 256), ("add_depth", 64, 3000),
+BIN_CASES = [("and", 8, 256), ("and", 64, 5000), ("or", 64, 300), ("nor", 64, 333), ("xor", 33, 65), ("add", 8, 256), ("add_depth", 64, 3000),
              ("add_msb", 64, 2049), ("lt", 64, 4097), ("eq", 64, 100)]
 
 

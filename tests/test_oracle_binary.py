@@ -28,6 +28,8 @@ def expected(name, a, b, bits):
         return a | b
     if name == "xor":
         return a ^ b
+    if name == "nor":
+        return ~(a | b) & m
     if name in ("add", "add_depth"):
         return (a + b) & m
     if name == "add_msb":
@@ -39,7 +41,7 @@ def expected(name, a, b, bits):
     raise KeyError(name)
 
 
-CASES = [("and", 8), ("and", 64), ("or", 64), ("xor", 17), ("add", 8), ("add", 64), ("add_depth", 8), ("add_depth", 64),
+CASES = [("and", 8), ("and", 64), ("or", 64), ("nor", 64), ("nor", 9), ("xor", 17), ("add", 8), ("add", 64), ("add_depth", 8), ("add_depth", 64),
          ("add_msb", 8), ("add_msb", 64), ("lt", 8), ("lt", 64), ("eq", 64), ("eq", 13)]
 
 

@@ -152,7 +152,7 @@ def _lib_circuit(name, bits):
     return harness.library_circuit(name, bits)
 
 
-@pytest.mark.parametrize("name,bits,width", [("and", 64, 1), ("and", 64, 300), ("or", 64, 77), ("xor", 33, 65), ("add", 16, 100),
+@pytest.mark.parametrize("name,bits,width", [("and", 64, 1), ("and", 64, 300), ("or", 64, 77), ("nor", 64, 91), ("xor", 33, 65), ("add", 16, 100),
                                              ("add_depth", 64, 257), ("add_msb", 64, 2049), ("lt", 64, 130), ("eq", 64, 64),
                                              ("piecewise2", 64, 96)])
 def test_binary_engine_shares(name, bits, width):
