@@ -418,6 +418,20 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    # Page-locked buffers and the party threads should live on the NUMA node this rank's GPU hangs off: with 8 ranks
+    # the h2d / d2h legs of the end-to-end number otherwise cross the socket interconnect.
+    numa = "unset"
+    if world > 1:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = int(vis.split(",")[local]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else local
+            nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(idx))
+            numa = "gpu-local cpus (%d)" % len(os.sched_getaffinity(0))
+        except Exception as e:
+            numa = "unchanged (%s)" % type(e).__name__
+
     from aby3_b200 import harness
     M = K = N = args.size
     sess = harness.Session(devices=(local, local, local))
@@ -522,7 +536,7 @@ def main():
                        "global_rows": M * world, "gemm": "tcgen05 u8-limb (kind::i8), 128x64 tiles, 12 MMA per 32-deep k-step",
                        "l2": "inputs larger than L2 (per party 4 x %d MiB share planes + %d MiB limb planes)" % (8 * M * K >> 20, 2 * 16 * M * K >> 20),
                        "timing": "CUDA events across the three party streams (fork/join on one start and one end event), max over ranks",
-                       "executed_u64_mac_per_s": 6.0 * value, "max_abs_err_ulp_vs_plain": max_err},
+                       "executed_u64_mac_per_s": 6.0 * value, "max_abs_err_ulp_vs_plain": max_err, "cpu_affinity": numa},
             "clocks": clocks,
             "e2e": {"value": world * step_macs / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * (M * K + K * N), "d2h_bytes_per_step": 8 * M * N,
                     "ms_per_step": e2e_t * 1e3, "steps": e2e_steps,
