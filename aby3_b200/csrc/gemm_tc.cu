@@ -106,6 +106,15 @@ __device__ __forceinline__ constexpr u32 make_idesc(u32 n) {
 }
 
 // ------------------------------------------------------------------ limb packing --
+// byte `limb` of four consecutive 64-bit values, packed into one word: three PRMT instead of shifts / masks / ors
+__device__ __forceinline__ u32 limb4(const u64* v, int limb) {
+    const int b = limb & 3;
+    const u32 x0 = limb < 4 ? (u32)v[0] : (u32)(v[0] >> 32), x1 = limb < 4 ? (u32)v[1] : (u32)(v[1] >> 32);
+    const u32 x2 = limb < 4 ? (u32)v[2] : (u32)(v[2] >> 32), x3 = limb < 4 ? (u32)v[3] : (u32)(v[3] >> 32);
+    const u32 sel = (u32)b | ((u32)(4 + b) << 4);                  // byte b of the first, byte b of the second operand
+    const u32 t01 = __byte_perm(x0, x1, sel), t23 = __byte_perm(x2, x3, sel);
+    return __byte_perm(t01, t23, 0x5410);
+}
 // A chunk (mt, kb): [limb 8][kc 2][row-group 16][row 8][16 B]; one thread = one
 // row x 16 k: reads 128 contiguous bytes, writes 8 x 16 bytes.
 __global__ void __launch_bounds__(256) k_pack_a(const u64* __restrict__ A0, const u64* __restrict__ A1,
@@ -126,11 +135,7 @@ __global__ void __launch_bounds__(256) k_pack_a(const u64* __restrict__ A0, cons
     for (int i = 0; i < 8; ++i) {
         u32 w[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            u32 b0 = (u32)(v[4 * q + 0] >> (8 * i)) & 0xFF, b1 = (u32)(v[4 * q + 1] >> (8 * i)) & 0xFF;
-            u32 b2 = (u32)(v[4 * q + 2] >> (8 * i)) & 0xFF, b3 = (u32)(v[4 * q + 3] >> (8 * i)) & 0xFF;
-            w[q] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-        }
+        for (int q = 0; q < 4; ++q) w[q] = limb4(v + 4 * q, i);
         *reinterpret_cast<uint4*>(chunk + i * 4096) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
@@ -160,11 +165,7 @@ __global__ void __launch_bounds__(128) k_pack_b(const u64* __restrict__ B0, cons
     for (int i = 0; i < 8; ++i) {
         u32 w[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            u32 b0 = (u32)(v[4 * q + 0] >> (8 * i)) & 0xFF, b1 = (u32)(v[4 * q + 1] >> (8 * i)) & 0xFF;
-            u32 b2 = (u32)(v[4 * q + 2] >> (8 * i)) & 0xFF, b3 = (u32)(v[4 * q + 3] >> (8 * i)) & 0xFF;
-            w[q] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-        }
+        for (int q = 0; q < 4; ++q) w[q] = limb4(v + 4 * q, i);
         *reinterpret_cast<uint4*>(chunk + i * 1024) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
