@@ -55,6 +55,10 @@ PROTOTYPES = {
     "aby3cu_d2h": (_int, [_p, _p, _p, _sz]),
     "aby3cu_d2d": (_int, [_p, _p, _int, _p, _int, _sz]),
     "aby3cu_event_create": (_int, [_p, C.POINTER(_p)]),
+    "aby3cu_capture_begin": (_int, [_p]),
+    "aby3cu_capture_end": (_int, [_p, C.POINTER(_p)]),
+    "aby3cu_graph_launch": (_int, [_p, _p, _u64]),
+    "aby3cu_graph_destroy": (_int, [_p]),
     "aby3cu_event_create_sync": (_int, [_p, C.POINTER(_p)]),
     "aby3cu_event_destroy": (_int, [_p]),
     "aby3cu_event_record": (_int, [_p, _p]),
@@ -67,6 +71,7 @@ PROTOTYPES = {
     "aby3cu_mul_hadamard": (_int, [_p, _p, _p, _p, _p, _key, _key, _u64, _p, _sz]),
     "aby3cu_mul_hadamard_trunc": (_int, [_p, _p, _p, _p, _p, _key, _u64, _key, _u64, _u64, _p, _p, _p, _sz]),
     "aby3cu_trunc_tuple": (_int, [_p, _key, _u64, _key, _u64, _u64, _p, _p, _p, _p, _sz]),
+    "aby3cu_trunc_tuple_at": (_int, [_p, _key, _u64, _key, _u64, _p, _u64, _u64, _p, _p, _p, _p, _sz]),
     "aby3cu_trunc_finish": (_int, [_p, _p, _p, _p, _p, _sz, _u64]),
     "aby3cu_gemm_cross": (_int, [_p, _int, _p, _p, _p, _p, _u64, _u64, _u64, _p, _int]),
     "aby3cu_gemm_last_algo": (_int, [_p]),
@@ -86,6 +91,8 @@ PROTOTYPES = {
     "aby3cu_transpose_i64": (_int, [_p, _p, _u64, _u64, _p]),
     "aby3cu_transpose_i64_2": (_int, [_p, _p, _p, _u64, _u64, _p, _p]),
     "aby3cu_gather_rows_multi": (_int, [_p, _int, _p, _p, _p, _p, _u64]),
+    "aby3cu_gather_rows_multi_at": (_int, [_p, _int, _p, _p, _p, _p, _u64, _p]),
+    "aby3cu_counter_add": (_int, [_p, _p, _u64]),
     "aby3cu_gather_rows": (_int, [_p, _p, _u64, _p, _u64, _p]),
     "aby3cu_iota_u64": (_int, [_p, _u64, _u64, _p, _sz]),
     "aby3cu_scatter_rows": (_int, [_p, _p, _u64, _p, _u64, _p]),

@@ -281,6 +281,38 @@ int aby3cu_event_elapsed_ms(void* start, void* stop, float* ms) {
     return 0;
 }
 
+// ---- CUDA graphs: capture the work enqueued on this context's stream (and on streams that join it through
+// events) and replay it with one launch -----------------------------------------------------------------
+int aby3cu_capture_begin(aby3cu_ctx* ctx) {
+    ABY3CU_REQUIRE(ctx, "capture_begin: null context");
+    DeviceGuard g(ctx->device);
+    ABY3CU_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    return 0;
+}
+int aby3cu_capture_end(aby3cu_ctx* ctx, void** graph_exec) {
+    ABY3CU_REQUIRE(ctx && graph_exec, "capture_end: null argument");
+    DeviceGuard g(ctx->device);
+    cudaGraph_t graph = nullptr;
+    ABY3CU_CHECK(cudaStreamEndCapture(ctx->stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return 1; }
+    *graph_exec = exec;
+    return 0;
+}
+int aby3cu_graph_launch(aby3cu_ctx* ctx, void* graph_exec, uint64_t kernel_nodes) {
+    ABY3CU_REQUIRE(ctx && graph_exec, "graph_launch: null argument");
+    DeviceGuard g(ctx->device);
+    ABY3CU_CHECK(cudaGraphLaunch((cudaGraphExec_t)graph_exec, ctx->stream));
+    ctx->launches += kernel_nodes;          // the kernels inside the graph still run: keep the launch count honest
+    return 0;
+}
+int aby3cu_graph_destroy(void* graph_exec) {
+    if (graph_exec) ABY3CU_CHECK(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    return 0;
+}
+
 int aby3cu_host_keystream(const u8 key[16], u64 byte_off, size_t nbytes, u8* out) {
     ABY3CU_REQUIRE(key && (out || !nbytes), "host_keystream: null argument");
     ABY3CU_REQUIRE(nbytes <= 4096, "host_keystream: only for small key draws (<= 4096 bytes); use aes_ctr_fill");

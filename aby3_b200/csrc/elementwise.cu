@@ -122,8 +122,11 @@ __global__ void __launch_bounds__(kThreads) k_trunc(const i64* __restrict__ A0, 
                                                     const __grid_constant__ AesKey knext, u64 en,
                                                     const __grid_constant__ AesKey kprev, u64 ep, unsigned d2,
                                                     i64* __restrict__ V, i64* __restrict__ R, i64* __restrict__ NEGR,
-                                                    i64* __restrict__ RT0, i64* __restrict__ RT1, size_t n, int vec) {
+                                                    i64* __restrict__ RT0, i64* __restrict__ RT1, size_t n, int vec,
+                                                    const u64* __restrict__ iter, u64 iter_stride) {
     if (RAND) { aes_table_init(); __syncthreads(); }
+    // replayed as a CUDA-graph node: the stream offsets advance with a device-resident iteration counter
+    if (iter) { const u64 it = *iter; en += it * iter_stride; ep += it * iter_stride; }
     const u32 Tl = (threadIdx.x & 31) * 4;
     const size_t pairs = (n + 1) / 2;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += (size_t)gridDim.x * blockDim.x) {
@@ -270,7 +273,8 @@ __global__ void __launch_bounds__(256) k_transpose2(const i64* __restrict__ in0,
 // several row gathers that share one index vector, in one launch (blockIdx.y = job): the mini-batch
 // extraction of SGD takes the same rows of X and Y, both share planes
 struct GatherJobs { const i64* in[ABY3CU_MAX_GATHER_JOBS]; i64* out[ABY3CU_MAX_GATHER_JOBS]; u64 cols[ABY3CU_MAX_GATHER_JOBS]; };
-__global__ void __launch_bounds__(256) k_gather_rows_multi(GatherJobs jobs, const u64* __restrict__ idx, u64 nrows) {
+__global__ void __launch_bounds__(256) k_gather_rows_multi(GatherJobs jobs, const u64* __restrict__ idx, u64 nrows, const u64* __restrict__ iter) {
+    if (iter) idx += *iter * nrows;            // graph replay: batch number `*iter` of a long index vector
     const i64* __restrict__ in = jobs.in[blockIdx.y];
     i64* __restrict__ out = jobs.out[blockIdx.y];
     const u64 cols = jobs.cols[blockIdx.y];
@@ -410,7 +414,8 @@ int aby3cu_mul_hadamard(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64
 
 static int launch_trunc(aby3cu_ctx* ctx, bool crossterm, const i64* A0, const i64* A1, const i64* B0, const i64* B1,
                         const u8* key_next, u64 en, const u8* key_prev, u64 ep, u64 d,
-                        i64* V, i64* R, i64* NEGR, i64* RT0, i64* RT1, size_t n) {
+                        i64* V, i64* R, i64* NEGR, i64* RT0, i64* RT1, size_t n,
+                        const u64* iter = nullptr, u64 iter_stride = 0) {
     ABY3CU_REQUIRE((key_prev == nullptr) == (key_next == nullptr), "trunc: give both keys or neither");
     ABY3CU_REQUIRE(d + 2 < 64, "trunc: shift too large");
     if (!n) return 0;
@@ -428,7 +433,7 @@ static int launch_trunc(aby3cu_ctx* ctx, bool crossterm, const i64* A0, const i6
     do {                                                                                                        \
         if (Rn && enable_big_smem(k_trunc<C, Rn>)) return 1;                                                    \
         k_trunc<C, Rn><<<grid, kThreads, smem, ctx->stream>>>(A0, A1, B0, B1, kn, en, kp, ep, d2, V, R, NEGR,   \
-                                                              RT0, RT1, n, vec);                                \
+                                                              RT0, RT1, n, vec, iter, iter_stride);             \
     } while (0)
     if (crossterm) { if (rnd) ABY3CU_LAUNCH_TRUNC(true, true); else ABY3CU_LAUNCH_TRUNC(true, false); }
     else           { if (rnd) ABY3CU_LAUNCH_TRUNC(false, true); else ABY3CU_LAUNCH_TRUNC(false, false); }
@@ -449,6 +454,14 @@ int aby3cu_trunc_tuple(aby3cu_ctx* ctx, const u8 key_next_common[16], u64 elem_n
     ABY3CU_REQUIRE(ctx && ((RT0 && RT1) || !n), "trunc_tuple: null argument");
     return launch_trunc(ctx, false, nullptr, nullptr, nullptr, nullptr, key_next_common, elem_next, key_prev_common,
                         elem_prev, d, nullptr, R, NEGR, RT0, RT1, n);
+}
+
+int aby3cu_trunc_tuple_at(aby3cu_ctx* ctx, const u8 key_next_common[16], u64 elem_next, const u8 key_prev_common[16],
+                          u64 elem_prev, const u64* d_iter, u64 iter_stride, u64 d, i64* R, i64* NEGR, i64* RT0, i64* RT1, size_t n) {
+    ABY3CU_REQUIRE(ctx && ((RT0 && RT1) || !n), "trunc_tuple_at: null argument");
+    ABY3CU_REQUIRE(key_next_common && key_prev_common && d_iter, "trunc_tuple_at: keys and the iteration counter are required");
+    return launch_trunc(ctx, false, nullptr, nullptr, nullptr, nullptr, key_next_common, elem_next, key_prev_common,
+                        elem_prev, d, nullptr, R, NEGR, RT0, RT1, n, d_iter, iter_stride);
 }
 
 int aby3cu_trunc_finish(aby3cu_ctx* ctx, const i64* s0, const i64* s1, const i64* s2, i64* C, size_t n, u64 shift) {
@@ -533,6 +546,20 @@ int aby3cu_transpose_i64_2(aby3cu_ctx* ctx, const i64* in0, const i64* in1, u64 
 }
 
 int aby3cu_gather_rows_multi(aby3cu_ctx* ctx, int njobs, const i64* const* in, const u64* cols, i64* const* out, const u64* idx, u64 nrows) {
+    return aby3cu_gather_rows_multi_at(ctx, njobs, in, cols, out, idx, nrows, nullptr);
+}
+
+__global__ void k_counter_add(u64* c, u64 inc) { *c += inc; }
+
+int aby3cu_counter_add(aby3cu_ctx* ctx, u64* d_counter, u64 inc) {
+    ABY3CU_REQUIRE(ctx && d_counter, "counter_add: null argument");
+    DeviceGuard g(ctx->device);
+    k_counter_add<<<1, 1, 0, ctx->stream>>>(d_counter, inc);
+    return post_launch(ctx, "k_counter_add");
+}
+
+int aby3cu_gather_rows_multi_at(aby3cu_ctx* ctx, int njobs, const i64* const* in, const u64* cols, i64* const* out, const u64* idx, u64 nrows,
+                                const u64* d_iter) {
     ABY3CU_REQUIRE(ctx && in && cols && out, "gather_rows_multi: null argument");
     ABY3CU_REQUIRE(njobs >= 1 && njobs <= ABY3CU_MAX_GATHER_JOBS, "gather_rows_multi: bad job count");
     if (!nrows) return 0;
@@ -547,7 +574,7 @@ int aby3cu_gather_rows_multi(aby3cu_ctx* ctx, int njobs, const i64* const* in, c
     }
     DeviceGuard g(ctx->device);
     const unsigned gx = ew_grid(ctx, maxc == 1 ? nrows : nrows * 32, 256, 4);
-    k_gather_rows_multi<<<dim3(gx, (unsigned)njobs), 256, 0, ctx->stream>>>(jobs, idx, nrows);
+    k_gather_rows_multi<<<dim3(gx, (unsigned)njobs), 256, 0, ctx->stream>>>(jobs, idx, nrows, d_iter);
     return post_launch(ctx, "k_gather_rows_multi");
 }
 

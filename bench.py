@@ -257,7 +257,7 @@ def gemm_roofline(device):
     bf16 = pk.get("bf16_tflops")
     peak = 2.0 * bf16 if bf16 else 2.0 * 1590.0
     return {"bound": "tensor", "kernel": "k_gemm_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": 4.47e9, "traffic_source": "profiles/r1_summary.md: dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full", "ms_per_launch": ms,
+            "traffic": 2.69e9, "traffic_source": "profiles/r1_gemm_tc_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full", "ms_per_launch": ms,
             "note": "int8 TOP/s; peak = 2 x %s dense bf16 (kind::i8 issues at twice the bf16 rate), %s"
                     % ("measured" if bf16 else "fallback", "of measured" if bf16 else "of fallback")}
 

@@ -60,6 +60,15 @@ int aby3cu_d2h(aby3cu_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 /* device-to-device; dst_device/src_device may differ (NVLink peer copy) */
 int aby3cu_d2d(aby3cu_ctx* ctx, void* d_dst, int dst_device, const void* d_src, int src_device, size_t bytes);
 int aby3cu_event_create(aby3cu_ctx* ctx, void** event);
+/* CUDA graphs for latency-bound protocol loops (one SGD iteration of aby3-ML/Regression.h:142-171 is ~28 small
+ * kernels): capture_begin starts recording the work enqueued on ctx's stream -- and on the streams of other contexts
+ * that join it through event_record / event_wait -- capture_end returns an executable graph, graph_launch replays it on
+ * ctx's stream (kernel_nodes = kernels inside, added to the launch count).  Kernel arguments are frozen at capture; the
+ * *_at entry points read the per-iteration offsets from a device counter instead. */
+int aby3cu_capture_begin(aby3cu_ctx* ctx);
+int aby3cu_capture_end(aby3cu_ctx* ctx, void** graph_exec);
+int aby3cu_graph_launch(aby3cu_ctx* ctx, void* graph_exec, uint64_t kernel_nodes);
+int aby3cu_graph_destroy(void* graph_exec);
 int aby3cu_event_create_sync(aby3cu_ctx* ctx, void** event);  /* ordering only (no timing): cheaper to record */
 int aby3cu_event_destroy(void* event);
 int aby3cu_event_record(aby3cu_ctx* ctx, void* event);       /* on ctx's stream */
@@ -106,6 +115,10 @@ int aby3cu_mul_hadamard_trunc(aby3cu_ctx* ctx, const int64_t* d_A0, const int64_
 int aby3cu_trunc_tuple(aby3cu_ctx* ctx, const uint8_t key_next_common[16], uint64_t elem_next,
                        const uint8_t key_prev_common[16], uint64_t elem_prev, uint64_t d,
                        int64_t* d_R, int64_t* d_NEGR, int64_t* d_RT0, int64_t* d_RT1, size_t n);
+/* getTruncationTuple replayable inside a CUDA graph: the stream offsets are elem_next / elem_prev + *d_iter * iter_stride */
+int aby3cu_trunc_tuple_at(aby3cu_ctx* ctx, const uint8_t key_next_common[16], uint64_t elem_next, const uint8_t key_prev_common[16],
+                          uint64_t elem_prev, const uint64_t* d_iter, uint64_t iter_stride, uint64_t d,
+                          int64_t* d_R, int64_t* d_negR, int64_t* d_RT0, int64_t* d_RT1, size_t n);
 /* Open-and-truncate continuation (Sh3Evaluator.cpp:712-718):
  * C[i] += (s0[i] + s1[i] + s2[i]) >> shift  (arithmetic). */
 int aby3cu_trunc_finish(aby3cu_ctx* ctx, const int64_t* d_s0, const int64_t* d_s1, const int64_t* d_s2,
@@ -183,6 +196,11 @@ int aby3cu_transpose_i64_2(aby3cu_ctx* ctx, const int64_t* d_in0, const int64_t*
 #define ABY3CU_MAX_GATHER_JOBS 4
 int aby3cu_gather_rows_multi(aby3cu_ctx* ctx, int njobs, const int64_t* const* d_in, const uint64_t* cols,
                              int64_t* const* d_out, const uint64_t* d_idx, uint64_t nrows);
+/* the same, replayable inside a CUDA graph: the batch is idx[*d_iter * nrows ...) (d_iter: device counter, may be NULL) */
+int aby3cu_gather_rows_multi_at(aby3cu_ctx* ctx, int njobs, const int64_t* const* d_in, const uint64_t* cols,
+                                int64_t* const* d_out, const uint64_t* d_idx, uint64_t nrows, const uint64_t* d_iter);
+/* *d_counter += inc on the context's stream (the iteration counter of a replayed graph) */
+int aby3cu_counter_add(aby3cu_ctx* ctx, uint64_t* d_counter, uint64_t inc);
 /* gather rows: out[r,:] = in[idx[r],:]  (extractBatch, aby3-ML/Regression.h:43-58) */
 int aby3cu_gather_rows(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t cols, const uint64_t* d_idx,
                        uint64_t nrows, int64_t* d_out);
