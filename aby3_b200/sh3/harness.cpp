@@ -18,6 +18,7 @@
 #include "Sh3Piecewise.h"
 #include "../basic/Basics.h"
 #include "../ml/Regression.h"
+#include "../ml/SgdGraph.h"
 
 using namespace aby3;
 
@@ -579,6 +580,23 @@ int sh3h_linreg(sh3h* h, int x_id, int y_id, int w_id, const uint64_t* batch_idx
         PartyEngine eng{P};
         SGD_Linear(params, eng, X, Y, W, idx);
     });
+}
+
+// The same training loop for parties that share one GPU, replayed as ONE CUDA graph per iteration (ml/SgdGraph.h).
+// Issued from the calling thread; the party threads stay idle.  Result and PRNG cursors are those of sh3h_linreg.
+int sh3h_linreg_graph(sh3h* h, int x_id, int y_id, int w_id, const uint64_t* batch_idx, uint64_t iters, uint64_t batch, double lr) {
+    try {
+        std::array<ColocatedSgdLinear<D16>::PartyRef, 3> P;
+        for (int i = 0; i < 3; ++i) {
+            Party& p = h->p[i];
+            P[i] = {p.ctx.get(), &p.eval, &reinterpret_cast<sf64Matrix<D16>&>(*p.ints.at(x_id)),
+                    &reinterpret_cast<sf64Matrix<D16>&>(*p.ints.at(y_id)), &reinterpret_cast<sf64Matrix<D16>&>(*p.ints.at(w_id))};
+        }
+        RegressionParam params{iters, batch, lr};
+        std::vector<u64> idx(batch_idx, batch_idx + iters * batch);
+        ColocatedSgdLinear<D16>::run(P, params, idx);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }
 
 int sh3h_logreg(sh3h* h, int x_id, int y_id, int w_id, const uint64_t* batch_idx, uint64_t iters, uint64_t batch, double lr) {

@@ -501,3 +501,32 @@ def test_logistic_regression_sgd_matches_oracle(pair):
     acc = np.mean(((x @ learnt) > 0).astype(np.float64) == y)
     assert acc > 0.85, acc
     assert_cursors(s, r)
+
+
+def test_graph_sgd_matches_facade_and_oracle(pair):
+    """ml/SgdGraph.h: SGD_Linear replayed as one CUDA graph per iteration gives the same w shares and PRNG cursors
+    as the facade loop (three party threads) and as the oracle; a second call continues from the advanced cursors."""
+    s, r = pair
+    N, F, B, iters, lr, D = 700, 40, 16, 37, 2.0 ** -6, 16
+    rng = np.random.default_rng(51)
+    x = rng.normal(1, 1, (N, F))
+    y = x[:, :3] @ np.array([[2.0], [-1.0], [0.5]])
+    fx, fy, fw = fixed(x, D), fixed(y, D), np.zeros((F, 1), dtype=np.int64)
+    idx = rng.integers(0, N, 2 * iters * B).astype(np.uint64)
+    X, Y, W = s.share_int(0, fx), s.share_int(0, fy), s.share_int(0, fw)
+    Xo, Yo, Wo = r.share_int(0, fx), r.share_int(0, fy), r.share_int(0, fw)
+    s.linreg_graph(X, Y, W, idx[:iters * B], iters, B, lr)
+    Wo = oracle_linreg(r, Xo, Yo, Wo, idx[:iters * B], iters, B, lr, D)
+    assert np.array_equal(s.get_shares(W), Wo)
+    assert_cursors(s, r)
+    # continue: one more stretch through the graph, then one through the facade loop
+    s.linreg_graph(X, Y, W, idx[iters * B:iters * B + 5 * B], 5, B, lr)
+    Wo = oracle_linreg(r, Xo, Yo, Wo, idx[iters * B:iters * B + 5 * B], 5, B, lr, D)
+    assert np.array_equal(s.get_shares(W), Wo)
+    s.linreg(X, Y, W, idx[-3 * B:], 3, B, lr)
+    Wo = oracle_linreg(r, Xo, Yo, Wo, idx[-3 * B:], 3, B, lr, D)
+    assert np.array_equal(s.get_shares(W), Wo)
+    s.linreg_graph(X, Y, W, idx[:B], 1, B, lr)                     # a single iteration: no graph at all
+    Wo = oracle_linreg(r, Xo, Yo, Wo, idx[:B], 1, B, lr, D)
+    assert np.array_equal(s.get_shares(W), Wo)
+    assert_cursors(s, r)

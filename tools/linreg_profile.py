@@ -34,6 +34,16 @@ def run(transport):
     wall = time.perf_counter() - t0
     ms = sess.timer_end()
     print("[%s] linreg: %.1f us/iter wall, %.1f us/iter device span, %.1f launches/iter" % (transport, wall * 1e6 / iters, ms * 1e3 / iters, (sess.launches - l0) / iters), flush=True)
+    # the graph-replayed trainer on the same data
+    W2 = sess.share_int(0, np.zeros((features, 1), dtype=np.int64))
+    sess.linreg_graph(X, Y, W2, idx[:20 * batch], 20, batch, 2.0 ** -10)
+    sess.sync()
+    l0 = sess.launches
+    t0 = time.perf_counter()
+    sess.linreg_graph(X, Y, W2, idx, iters, batch, 2.0 ** -10)
+    sess.sync()
+    wall = time.perf_counter() - t0
+    print("[%s] linreg_graph: %.1f us/iter wall, %.1f kernels/iter" % (transport, wall * 1e6 / iters, (sess.launches - l0) / iters), flush=True)
     sess.close()
 
 
