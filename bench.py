@@ -290,8 +290,9 @@ def gemm_roofline(device):
             "traffic": 2.69e9, "traffic_source": "profiles/r1_gemm_tc_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full", "ms_per_launch": ms,
             "peak_cublaslt_int8_8192": int8, "peak_twice_measured_bf16": twice_bf16, "frac_of_nominal_4500": achieved / 4500.0,
             "tensor_pipe_active_pct_ncu": 88.1,
-            "note": "int8 TOP/s (144*M*N*K ops per launch); peak = max(cuBLASLt int8 GEMM measured live on this GPU, 2 x %s dense bf16)"
-                    % ("measured" if bf16 else "fallback")}
+            "note": "int8 TOP/s (144*M*N*K ops per launch); frac is of %s: peak = max(cuBLASLt int8 GEMM measured live on this GPU, 2 x the %s dense "
+                    "bf16 rate of MEASURED_PEAKS.json -- kind::i8 issues at twice the bf16 rate); a library GEMM as denominator lets a good kernel read a little above 1"
+                    % (("measured", "measured") if bf16 else ("fallback", "fallback"))}
 
 
 def linreg_bench(sess, samples, features=1024, batch=128, iters=300, lr=2.0 ** -10):

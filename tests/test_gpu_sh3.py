@@ -530,3 +530,51 @@ def test_graph_sgd_matches_facade_and_oracle(pair):
     Wo = oracle_linreg(r, Xo, Yo, Wo, idx[:B], 1, B, lr, D)
     assert np.array_equal(s.get_shares(W), Wo)
     assert_cursors(s, r)
+
+
+@pytest.mark.parametrize("seed,width", [(0, 1), (1, 64), (2, 65), (3, 300), (4, 2049), (5, 77), (6, 100000), (7, 31)])
+def test_random_circuits_match_oracle(pair, seed, width):
+    """Random circuits over every supported gate type with inverted outputs, ragged widths: device == oracle share for
+    share (the oracle is pinned against the reference's evaluator on the same circuits in tests/test_ref_parity.py)."""
+    import circuits_random as cr
+    s, r = pair
+    cir = cr.random_circuit(seed, n_gates=100 + 20 * seed)
+    rng = np.random.default_rng(seed)
+    ins = [rng.integers(0, 2 ** int(b), width, dtype=np.uint64) for b in cir["input_bits"]]
+    S = [s.share_bin(k % 3, x.view(np.int64).reshape(width, 1), int(cir["input_bits"][k])) for k, x in enumerate(ins)]
+    So = [r.share_bin(k % 3, x.view(np.int64).reshape(width, 1)) for k, x in enumerate(ins)]
+    outs = s.bin_eval(cir, S)
+    oo, _ = o.bin_eval(r, cir, width, So)
+    exp = cr.plain_eval(cir, ins) if width <= 5000 else None
+    for k in range(len(oo)):
+        m = np.int64((1 << int(cir["output_bits"][k])) - 1)
+        assert np.array_equal(s.get_shares(outs[k], binary=True) & m, oo[k] & m), k
+        if exp is not None:
+            assert np.array_equal(s.reveal(outs[k], 1, binary=True).reshape(width).view(np.uint64) & np.uint64(m), exp[k]), k
+    assert_cursors(s, r)
+
+
+def test_random_shapes_products_match_oracle(pair):
+    """Ragged shapes through every product form (matrix / element-wise, with and without truncation, all GEMM paths
+    as AUTO picks them): shares bit-exact against the oracle."""
+    s, r = pair
+    rng = np.random.default_rng(77)
+    for _ in range(12):
+        M, K, N = (int(x) for x in rng.integers(1, 200, 3))
+        a, b = fixed(rng.normal(0, 30, (M, K)), 16), fixed(rng.normal(0, 30, (K, N)), 16)
+        A, B = s.share_int(int(rng.integers(0, 3)), a), s.share_int(int(rng.integers(0, 3)), b)
+        Ao, Bo = r.share_int(0, a), r.share_int(0, b)
+        Ao, Bo = s.get_shares(A), s.get_shares(B)            # same starting shares on both sides
+        if M == K and K == N:
+            continue
+        assert np.array_equal(s.get_shares(s.mul(A, B)), r.mul(Ao, Bo))
+        assert np.array_equal(s.get_shares(s.mul(A, B, shift=16)), r.mul_trunc(Ao, Bo, 16))
+    for n in (1, 3, 1000):
+        a, b = fixed(rng.normal(0, 30, (n, 1)), 16), fixed(rng.normal(0, 30, (n, 1)), 16)
+        A, B = s.share_int(0, a), s.share_int(1, b)
+        Ao, Bo = s.get_shares(A), s.get_shares(B)
+        r.share_int(0, a); r.share_int(1, b)                 # keep the encryptor cursors in step
+        if n == 1:
+            continue                                         # 1 x 1 is a (1 x 1) matrix product on both sides
+        assert np.array_equal(s.get_shares(s.mul(A, B)), r.mul(Ao, Bo, mode=1))
+        assert np.array_equal(s.get_shares(s.mul(A, B, shift=16)), r.mul_trunc(Ao, Bo, 16, mode=1))

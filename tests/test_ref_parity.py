@@ -189,6 +189,26 @@ def test_binary_engine_shares(name, bits, width):
     assert all(np.array_equal(a, b) for a, b in zip(to, tr))
 
 
+@pytest.mark.parametrize("seed,width", [(0, 1), (1, 64), (2, 65), (3, 300), (4, 2049), (5, 77), (6, 4096), (7, 31)])
+def test_random_circuits_all_gate_types(seed, width):
+    """Random circuits over every gate type the engine supports (Xor, And, Nor, Or, Nxor, copy, na_And) with random
+    inverted outputs: oracle == the reference's evaluator share for share, and both reveal the plaintext evaluation."""
+    import circuits_random as cr
+    so, sr = pair()
+    cir = cr.random_circuit(seed, n_gates=100 + 20 * seed)
+    rng = np.random.default_rng(seed)
+    ins = [rng.integers(0, 2 ** int(b), width, dtype=np.uint64) for b in cir["input_bits"]]
+    So = [so.share_bin(k % 3, x.view(np.int64).reshape(width, 1)) for k, x in enumerate(ins)]
+    Sr = [sr.share_bin(k % 3, x.view(np.int64).reshape(width, 1)) for k, x in enumerate(ins)]
+    oo, _ = o.bin_eval(so, cir, width, So)
+    rr = sr.bin_eval(cir, width, Sr)
+    exp = cr.plain_eval(cir, ins)
+    for k in range(len(oo)):
+        m = np.int64((1 << int(cir["output_bits"][k])) - 1)
+        assert np.array_equal(oo[k] & m, rr[k] & m), k
+        assert np.array_equal(o.reveal(oo[k], 0, binary=True).reshape(width).view(np.uint64) & np.uint64(m), exp[k]), k
+
+
 def test_piecewise_plain_matches_reference():
     """Sh3Piecewise::eval(i64Matrix) -- the plaintext evaluator aby3_tests/Sh3PiecewiseTests.cpp:13-80 pins"""
     import piecewise_ref as pw
