@@ -389,6 +389,41 @@ int aby3cu_bin_and_layer(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void*
     return post_launch(ctx, "k_bin_and_layer");
 }
 
+// The shadow evaluator of the reference's BINARY_ENGINE_DEBUG build (Sh3BinaryEvaluator.cpp:1469-1601), on the device:
+// with all three share planes of the wire memory at hand, every gate is re-evaluated on the reconstructed wire values
+// and compared with the reconstructed output wire; mismatching instances are counted.
+__global__ void __launch_bounds__(256) k_bin_check(const uint4* __restrict__ gates, const u8* __restrict__ skip, u32 n_gates,
+                                                   const u64* __restrict__ m0, const u64* __restrict__ m1, const u64* __restrict__ m2,
+                                                   u64 rw, u64 width, unsigned long long* __restrict__ bad, u32* __restrict__ first_bad) {
+    const u64 words = (width + 63) / 64;
+    for (u32 g = blockIdx.y; g < n_gates; g += gridDim.y) {
+        if (skip && skip[g]) continue;
+        const uint4 G = gates[g];
+        for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < words; c += (u64)gridDim.x * blockDim.x) {
+            const u64 a = m0[(u64)G.x * rw + c] ^ m1[(u64)G.x * rw + c] ^ m2[(u64)G.x * rw + c];
+            const u64 b = m0[(u64)G.y * rw + c] ^ m1[(u64)G.y * rw + c] ^ m2[(u64)G.y * rw + c];
+            const u64 o = m0[(u64)G.z * rw + c] ^ m1[(u64)G.z * rw + c] ^ m2[(u64)G.z * rw + c];
+            u64 e;
+            switch (G.w) {
+            case 6: e = a ^ b; break;
+            case 8: e = a & b; break;
+            case 1: e = ~(a | b); break;
+            case 14: e = a | b; break;
+            case 9: e = ~(a ^ b); break;
+            case 10: e = a; break;
+            case 4: e = ~a & b; break;
+            default: e = ~o; break;                 // unsupported type: always a mismatch
+            }
+            u64 diff = e ^ o;
+            if (c == words - 1 && (width & 63)) diff &= (1ull << (width & 63)) - 1;
+            if (diff) {
+                atomicAdd(bad, (unsigned long long)__popcll(diff));
+                atomicMin(first_bad, g);
+            }
+        }
+    }
+}
+
 static int rows_copy(aby3cu_ctx* ctx, bool pack, void* mem, u64 row_bytes, const u32* locs, u32 n_locs, u64 nbytes, void* buf,
                      const u8* invert) {
     ABY3CU_REQUIRE(ctx && ((mem && locs && buf) || !(n_locs * nbytes)), "bin rows: null argument");
@@ -416,6 +451,25 @@ int aby3cu_bin_pack_rows(aby3cu_ctx* ctx, const void* d_mem, u64 row_bytes, cons
 
 int aby3cu_bin_scatter_rows(aby3cu_ctx* ctx, void* d_mem, u64 row_bytes, const u32* d_locs, u32 n_locs, u64 nbytes, const void* d_in) {
     return rows_copy(ctx, false, d_mem, row_bytes, d_locs, n_locs, nbytes, const_cast<void*>(d_in), nullptr);
+}
+
+int aby3cu_bin_check_gates(aby3cu_ctx* ctx, const u32* d_gates, const u8* d_skip, u32 n_gates, const void* d_plane_a, const void* d_plane_b,
+                           const void* d_plane_c, u64 row_bytes, u64 width, u64* d_bad_count, u32* d_first_bad_gate) {
+    ABY3CU_REQUIRE(ctx && d_bad_count && d_first_bad_gate, "bin_check_gates: null argument");
+    ABY3CU_REQUIRE(row_bytes % 8 == 0, "bin_check_gates: row_bytes must be a multiple of 8");
+    DeviceGuard g(ctx->device);
+    ABY3CU_CHECK(cudaMemsetAsync(d_bad_count, 0, 8, ctx->stream));
+    ABY3CU_CHECK(cudaMemsetAsync(d_first_bad_gate, 0xFF, 4, ctx->stream));
+    if (!n_gates || !width) return 0;
+    ABY3CU_REQUIRE(d_gates && d_plane_a && d_plane_b && d_plane_c, "bin_check_gates: null argument");
+    const u64 words = (width + 63) / 64;
+    const unsigned gx = (unsigned)((words + 255) / 256 < 64 ? (words + 255) / 256 : 64);
+    u64 gy = ((u64)ctx->sm_count * 8 + gx - 1) / gx;
+    if (gy > n_gates) gy = n_gates;
+    k_bin_check<<<dim3(gx, (unsigned)gy), 256, 0, ctx->stream>>>((const uint4*)d_gates, d_skip, n_gates, (const u64*)d_plane_a, (const u64*)d_plane_b,
+                                                                   (const u64*)d_plane_c, row_bytes / 8, width, (unsigned long long*)d_bad_count,
+                                                                   d_first_bad_gate);
+    return post_launch(ctx, "k_bin_check");
 }
 
 }  // extern "C"

@@ -55,6 +55,7 @@ def _load():
     l.sh3h_reveal_plain.argtypes = [p, i32, i32, i32]
     l.sh3h_trunc_tuple.argtypes = [p, i32, u64, u64, u64, p, p, p]
     l.sh3h_bin_eval.argtypes = [p, p, C.c_uint32, C.c_uint32, p, C.c_uint32, p, p, C.c_uint32, p, p, p, p, C.c_uint32, p, p]
+    l.sh3h_bin_eval_check.argtypes = [p, p, C.c_uint32, C.c_uint32, p, C.c_uint32, p, p, C.c_uint32, p, p, p, p, C.c_uint32, p, i64, i32, C.POINTER(u64)]
     l.sh3h_linreg.argtypes = [p, i32, i32, i32, p, u64, u64, C.c_double]
     l.sh3h_logreg.argtypes = l.sh3h_linreg.argtypes
     l.sh3h_linreg_graph.argtypes = l.sh3h_linreg.argtypes
@@ -298,6 +299,20 @@ class Session:
             _ptr(cir["output_off"]), _ptr(cir["output_bits"]), _ptr(cir["output_wires"]),
             _ptr(inv) if inv is not None else None, len(cir["output_bits"]), _ptr(ins), _ptr(outs)))
         return [int(x) for x in outs]
+
+    def bin_eval_check(self, cir, input_ids, tamper_wire=-1, tamper_party=0):
+        """Evaluate `cir`, then the device-side shadow check of every gate on the reconstructed wires
+        (Sh3BinaryEvaluator::enableDebug / validateMemory).  Returns the number of disagreeing instance-gates summed over
+        the three parties; tamper_wire >= 0 injects a one-bit fault into that wire at `tamper_party` first."""
+        ins = np.asarray(input_ids, dtype=np.int32)
+        inv = cir.get("output_invert")
+        bad = C.c_uint64(0)
+        self._chk(lib.sh3h_bin_eval_check(
+            self.h, _ptr(cir["gates"]), len(cir["gates"]) // 4, cir["wire_count"], _ptr(cir["level_gates"]),
+            len(cir["level_gates"]), _ptr(cir["input_first"]), _ptr(cir["input_bits"]), len(cir["input_bits"]),
+            _ptr(cir["output_off"]), _ptr(cir["output_bits"]), _ptr(cir["output_wires"]),
+            _ptr(inv) if inv is not None else None, len(cir["output_bits"]), _ptr(ins), int(tamper_wire), int(tamper_party), C.byref(bad)))
+        return int(bad.value)
 
     def linreg(self, X, Y, w, batch_idx, iters, batch, lr):
         """aby3-ML SGD_Linear (ml/Regression.h) on sf64<D16> shares; w is updated in place."""

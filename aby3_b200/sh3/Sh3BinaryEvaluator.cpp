@@ -168,6 +168,51 @@ void Sh3BinaryEvaluator::roundCallback(CommPkg& comm, Sh3Task task) {
     if (hasMoreRounds()) {
         auto t = task.then([this](CommPkg& comm, Sh3Task& task) { roundCallback(comm, task); });
         t.name() = "callback";
+    } else if (mDebug) {
+        validateMemory();
+    }
+}
+
+// Shadow evaluation after the last round: fetch x_{i+1} (the next party's own plane) over the debug channels,
+// reconstruct every wire and re-evaluate every gate on the device.
+void Sh3BinaryEvaluator::validateMemory() {
+    if (!mDebug) return;
+    if (!mDebugPrev.isConnected() || !mDebugNext.isConnected()) throw std::runtime_error("enableDebug needs both debug channels " LOCATION);
+    const u64 planeBytes = (u64)mCir->mWireCount * mRowBytes;
+    gpu::Buffer third(mCtx, std::max<u64>(planeBytes, 16)), res(mCtx, 16);
+    mDebugPrev.asyncSendDevice(mMem[0].ptr(), planeBytes);              // our x_i is the previous party's x_{(i-1)+1}
+    mDebugNext.recvDevice(third.ptr(), planeBytes);
+    // a wire written by more than one gate holds only its last value: gates touching such wires are exempt
+    std::vector<u32> writes(mCir->mWireCount, 0);
+    for (auto& G : mCir->mGates) ++writes[G.mOutput];
+    std::vector<u8> skip(mCir->mGates.size(), 0);
+    bool anySkip = false;
+    for (u64 g = 0; g < mCir->mGates.size(); ++g) {
+        const auto& G = mCir->mGates[g];
+        if (writes[G.mOutput] > 1 || writes[G.mInput[0]] > 1 || writes[G.mInput[1]] > 1) { skip[g] = 1; anySkip = true; }
+        // an input bundle wire that is also written by a gate is overwritten as well
+    }
+    for (auto& in : mCir->mInputs)
+        for (auto w : in.mWires)
+            if (writes[w]) {
+                for (u64 g = 0; g < mCir->mGates.size(); ++g) {
+                    const auto& G = mCir->mGates[g];
+                    if (G.mOutput == w || G.mInput[0] == w || G.mInput[1] == w) { skip[g] = 1; anySkip = true; }
+                }
+            }
+    gpu::Buffer dSkip(mCtx, std::max<size_t>(skip.size(), 16));
+    if (anySkip) gpu::check(aby3cu_h2d(mCtx->h(), dSkip.ptr(), skip.data(), skip.size()));
+    gpu::check(aby3cu_bin_check_gates(mCtx->h(), (const u32*)mGatesDev.ptr(), anySkip ? (const u8*)dSkip.ptr() : nullptr,
+                                      (u32)mCir->mGates.size(), mMem[0].ptr(), mMem[1].ptr(), third.ptr(), mRowBytes, mWidth,
+                                      (u64*)res.ptr(), (u32*)((u8*)res.ptr() + 8)));
+    u64 host[2] = {0, 0};
+    gpu::check(aby3cu_d2h(mCtx->h(), host, res.ptr(), 16));
+    mCtx->sync();
+    mDebugMismatches = host[0];
+    if (host[0]) {
+        const u32 g = (u32)host[1];
+        throw std::runtime_error("binary engine shadow check failed: " + std::to_string(host[0]) + " instance-gates disagree, first at gate " +
+                                 std::to_string(g) + " (type " + std::to_string((u32)mCir->mGates[g].mType) + ") " LOCATION);
     }
 }
 

@@ -6,7 +6,7 @@
 // planes) lives in HBM; each AND-depth level is one gate-interpreter kernel with
 // in-register AES-CTR zero shares, followed by the reshare of the level's AND
 // outputs to the next party.  The BINARY_ENGINE_DEBUG shadow evaluator of the
-// reference is not part of this round.
+// reference is a run-time switch here (enableDebug): a device-side gate checker.
 #pragma once
 #include "BetaCircuit.h"
 #include "Sh3Runtime.h"
@@ -42,6 +42,23 @@ public:
     void getOutput(const std::vector<oc::BetaWire>& wires, sPackedBin& out, bool allowUninitialized = false);
 
     bool hasMoreRounds() const { return mLevel <= mCir->mLevelCounts.size(); }
+
+    // The reference's BINARY_ENGINE_DEBUG shadow evaluator as a run-time switch (Sh3BinaryEvaluator.h:29-47): with two
+    // extra channels to the neighbours, the parties exchange their third share plane after the last round and every gate
+    // is re-evaluated on the reconstructed wire values on the device; a mismatch throws.  (Gates touching a wire that is
+    // written more than once cannot be checked after the fact and are skipped.)
+    bool mDebug = false;
+    u64 mDebugPartyIdx = (u64)-1;
+    oc::Channel mDebugPrev, mDebugNext;
+    void enableDebug(u64 partyIdx, oc::Channel debugPrev, oc::Channel debugNext) {
+        mDebug = true;
+        mDebugPartyIdx = partyIdx;
+        mDebugPrev = std::move(debugPrev);
+        mDebugNext = std::move(debugNext);
+    }
+    // number of instance-gates that failed the last check (0 after a clean run)
+    u64 mDebugMismatches = 0;
+    void validateMemory();
 
     u64 shareCount() const { return mWidth; }
     u64 rowBytes() const { return mRowBytes; }

@@ -641,6 +641,49 @@ int sh3h_bin_eval(sh3h* h, const uint32_t* gates, uint32_t gate_count, uint32_t 
     });
 }
 
+// Evaluate a circuit and then run the device-side shadow check (Sh3BinaryEvaluator::enableDebug / validateMemory) over
+// separate debug channels.  tamper_wire >= 0: before the check, party `tamper_party` flips instance 0 of that wire in its
+// own share plane (a fault the check must find).  *mismatches = instance-gates that disagree (summed over the parties'
+// identical views / 3).  Returns 0 also when the check fails: the count is the result.
+int sh3h_bin_eval_check(sh3h* h, const uint32_t* gates, uint32_t gate_count, uint32_t wire_count,
+                        const uint32_t* level_gates, uint32_t level_count,
+                        const uint32_t* input_first, const uint32_t* input_bits, uint32_t num_inputs,
+                        const uint32_t* output_off, const uint32_t* output_bits, const uint32_t* output_wires,
+                        const uint8_t* output_invert, uint32_t num_outputs,
+                        const int* input_ids, int64_t tamper_wire, int tamper_party, uint64_t* mismatches) {
+    // debug channels: a second, independent set of pipes between the same contexts
+    auto d01 = oc::Channel::makePair(h->p[0].ctx.get(), h->p[1].ctx.get());
+    auto d02 = oc::Channel::makePair(h->p[0].ctx.get(), h->p[2].ctx.get());
+    auto d12 = oc::Channel::makePair(h->p[1].ctx.get(), h->p[2].ctx.get());
+    oc::Channel dprev[3] = {d02.first, d01.second, d12.second}, dnext[3] = {d01.first, d12.first, d02.second};
+    std::atomic<uint64_t> total{0};
+    int rc = h->run([&](int i) {
+        Party& P = h->p[i];
+        oc::BetaCircuit cir;
+        cir.loadFlat(gates, gate_count, wire_count, level_gates, level_count, input_first, input_bits, num_inputs,
+                     output_off, output_bits, output_wires, output_invert, num_outputs);
+        Sh3BinaryEvaluator ev;
+        const u64 width = P.bins.at(input_ids[0])->rows();
+        ev.setCir(&cir, width, P.eval.mShareGen);
+        for (uint32_t k = 0; k < num_inputs; ++k) ev.setInput(k, *P.bins.at(input_ids[k]));
+        ev.asyncEvaluate(P.rt).get();
+        if (tamper_wire >= 0 && i == tamper_party) {
+            u64 word = 0;
+            u8* at = (u8*)ev.planeDevice(0) + (u64)tamper_wire * ev.rowBytes();
+            gpu::check(aby3cu_d2h(P.ctx->h(), &word, at, 8));
+            P.ctx->sync();
+            word ^= 1;
+            gpu::check(aby3cu_h2d(P.ctx->h(), at, &word, 8));
+            P.ctx->sync();
+        }
+        ev.enableDebug(i, dprev[i], dnext[i]);
+        try { ev.validateMemory(); } catch (const std::runtime_error&) {}
+        total += ev.mDebugMismatches;
+    });
+    *mismatches = total.load();
+    return rc;
+}
+
 // Same evaluation, but inputs and outputs travel through the engine as sPackedBin (bit-sliced):
 // sbMatrix -> sPackedBin by a first engine pass, setInput(sPackedBin), getOutput(sPackedBin),
 // and the packed output is transposed back to an sbMatrix for comparison.

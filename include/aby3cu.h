@@ -251,6 +251,13 @@ int aby3cu_bin_pack_rows(aby3cu_ctx* ctx, const void* d_mem, uint64_t row_bytes,
 /* receive scatter (:555-573): first nbytes of row locs[j] of mem = in[j*nbytes ..) */
 int aby3cu_bin_scatter_rows(aby3cu_ctx* ctx, void* d_mem, uint64_t row_bytes, const uint32_t* d_locs,
                             uint32_t n_locs, uint64_t nbytes, const void* d_in);
+/* Shadow evaluation (the reference's BINARY_ENGINE_DEBUG checker, Sh3BinaryEvaluator.cpp:1469-1601): given ALL THREE share
+ * planes of the wire memory, re-evaluates the n_gates gates ([n][4] = in0, in1, out, type) on the reconstructed wires and
+ * counts the instances whose output wire disagrees (skip[g] != 0 exempts a gate).  *d_bad_count = mismatching instance-gates,
+ * *d_first_bad_gate = lowest failing gate index (0xFFFFFFFF: none). */
+int aby3cu_bin_check_gates(aby3cu_ctx* ctx, const uint32_t* d_gates, const uint8_t* d_skip, uint32_t n_gates, const void* d_plane_a,
+                           const void* d_plane_b, const void* d_plane_c, uint64_t row_bytes, uint64_t width,
+                           uint64_t* d_bad_count, uint32_t* d_first_bad_gate);
 
 #ifdef __cplusplus
 }

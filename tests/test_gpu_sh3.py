@@ -578,3 +578,28 @@ def test_random_shapes_products_match_oracle(pair):
             continue                                         # 1 x 1 is a (1 x 1) matrix product on both sides
         assert np.array_equal(s.get_shares(s.mul(A, B)), r.mul(Ao, Bo, mode=1))
         assert np.array_equal(s.get_shares(s.mul(A, B, shift=16)), r.mul_trunc(Ao, Bo, 16, mode=1))
+
+
+def test_shadow_evaluator_finds_injected_faults(pair):
+    """The device-side counterpart of the reference's BINARY_ENGINE_DEBUG checker: a clean evaluation has no disagreeing
+    gate; a single flipped bit in one party's share of an internal wire is reported (by the gate that wrote the wire and
+    by every gate that reads it), whichever party holds the fault."""
+    import circuits_random as cr
+    s, _ = pair
+    for name in ("lt", "add_depth"):
+        cir = harness.library_circuit(name, 64)
+        x, y = rnd(80, (777, 1)), rnd(81, (777, 1))
+        X, Y = s.share_bin(0, x, 64), s.share_bin(1, y, 64)
+        assert s.bin_eval_check(cir, [X, Y]) == 0
+        g = cir["gates"].reshape(-1, 4)
+        and_out = int(g[g[:, 3] == 8][5, 2])                       # output wire of some AND gate
+        readers = int(np.sum((g[:, 0] == and_out) | ((g[:, 1] == and_out) & (g[:, 3] != 10))))
+        for party in range(3):
+            bad = s.bin_eval_check(cir, [X, Y], tamper_wire=and_out, tamper_party=party)
+            # the faulty share is seen by its holder and by the previous party (who fetches it as its third plane); the
+            # next party reads its own stale copy.  The writing gate always disagrees, a reader only if the fault propagates.
+            assert 2 <= bad <= 2 * (1 + readers), (name, party, bad, readers)
+    rc = cr.random_circuit(3, n_gates=200)
+    ins = [np.random.default_rng(5).integers(0, 2 ** int(b), 500, dtype=np.uint64) for b in rc["input_bits"]]
+    S = [s.share_bin(k % 3, v.view(np.int64).reshape(500, 1), int(rc["input_bits"][k])) for k, v in enumerate(ins)]
+    assert s.bin_eval_check(rc, S) == 0
