@@ -227,9 +227,29 @@ int aby3cu_d2h(aby3cu_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
     ABY3CU_CHECK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
 }
+// Direct GPU-to-GPU access over NVLink has to be switched on once per ordered device pair; without it a peer copy is
+// staged through host memory (an order of magnitude slower).
+static void enable_peer(int from, int to) {
+    static std::mutex mtx;
+    static bool done[64][64];
+    if (from == to || from < 0 || to < 0 || from >= 64 || to >= 64) return;
+    std::lock_guard<std::mutex> l(mtx);
+    if (done[from][to]) return;
+    done[from][to] = true;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, from, to) != cudaSuccess || !can) { (void)cudaGetLastError(); return; }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(from);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+    if (e != cudaSuccess) (void)cudaGetLastError();             // already enabled (e.g. by NCCL) is fine
+    if (prev >= 0) cudaSetDevice(prev);
+}
+
 int aby3cu_d2d(aby3cu_ctx* ctx, void* d_dst, int dst_device, const void* d_src, int src_device, size_t bytes) {
     ABY3CU_REQUIRE(ctx && ((d_dst && d_src) || !bytes), "d2d: null argument");
     if (!bytes) return 0;
+    if (dst_device != src_device) { enable_peer(dst_device, src_device); enable_peer(src_device, dst_device); }
     DeviceGuard g(ctx->device);
     if (dst_device == src_device)
         ABY3CU_CHECK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));

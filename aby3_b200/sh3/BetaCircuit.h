@@ -210,11 +210,9 @@ public:
     // the most significant bit of a + b (int_comp_helper / fetch_msb)
     BetaCircuit* int_int_add_msb(u64 bits) {
         return cached("addmsb" + std::to_string(bits), [&](BetaCircuit& cd) {
-            BetaBundle a(bits), b(bits), c(1), t(bits);
+            BetaBundle a(bits), b(bits), c(1);
             cd.addInputBundle(a); cd.addInputBundle(b); cd.addOutputBundle(c);
-            cd.addTempWireBundle(t);
-            prefixAdd(cd, a, b, t, false);
-            cd.addCopy(t[bits - 1], c[0]);
+            msbOfSum(cd, a, b, c[0]);
         });
     }
     // c = (a < b) for signed two's-complement inputs of equal width
@@ -280,10 +278,8 @@ public:
             for (auto& c : cc) cd.addOutputBundle(c);
             std::vector<BetaWire> th(numThresholds);
             for (u64 t = 0; t < numThresholds; ++t) {
-                BetaBundle sum(size);
-                cd.addTempWireBundle(sum);
-                prefixAdd(cd, aa[t], b, sum, false);
-                th[t] = sum[size - 1];                        // sign bit of a_t + b
+                th[t] = cd.addTempWire();
+                msbOfSum(cd, aa[t], b, th[t]);                // sign bit of a_t + b
             }
             cd.addCopy(th[0], cc[0][0]);
             for (u64 t = 1; t < numThresholds; ++t) cd.addGate(th[t - 1], th[t], GateType::na_And, cc[t][0]);
@@ -361,8 +357,52 @@ private:
         }
         return g;
     }
+    // Carry out of the whole (g, p) vector only: a reduction TREE instead of the full Kogge-Stone scan -- the same
+    // ceil(log2 n) AND levels, but ~2n instead of ~2n log2 n AND gates.  Comparisons and MSB-of-sum tests (lt,
+    // int_comp_helper, the piecewise region tests) need nothing but this one carry.
+    // Segment (G, P) of bits [lo, hi): G = carry out given carry-in 0, P = all bits propagate.  Combining a low and a
+    // high segment: G = G_hi ^ (P_hi & G_lo)  (never both 1), P = P_hi & P_lo.  A segment that starts at bit 0 is only
+    // ever the low operand, so its P is never built.
     static BetaWire prefixCarry(BetaCircuit& cd, const std::vector<BetaWire>& g, const std::vector<BetaWire>& p) {
-        return prefixAll(cd, g, p).back();
+        struct Seg { BetaWire G, P; bool first; };
+        std::vector<Seg> cur(g.size());
+        for (u64 i = 0; i < g.size(); ++i) cur[i] = Seg{g[i], p[i], i == 0};
+        while (cur.size() > 1) {
+            std::vector<Seg> nx;
+            for (u64 i = 0; i + 1 < cur.size(); i += 2) {
+                const Seg& lo = cur[i];
+                const Seg& hi = cur[i + 1];
+                Seg c{cd.addTempWire(), (BetaWire)-1, lo.first};
+                BetaWire t = cd.addTempWire();
+                cd.addGate(hi.P, lo.G, GateType::And, t);
+                cd.addGate(hi.G, t, GateType::Xor, c.G);
+                if (!lo.first) {
+                    c.P = cd.addTempWire();
+                    cd.addGate(hi.P, lo.P, GateType::And, c.P);
+                }
+                nx.push_back(c);
+            }
+            if (cur.size() & 1) nx.push_back(cur.back());
+            cur.swap(nx);
+        }
+        return cur[0].G;
+    }
+    // out = most significant bit of a + b (same width): p_msb ^ carry into the top bit, the carry by the reduction tree
+    static void msbOfSum(BetaCircuit& cd, const BetaBundle& a, const BetaBundle& b, BetaWire out) {
+        const u64 n = a.size();
+        if (b.size() != n || n == 0) throw RTE_LOC;
+        BetaWire pTop = cd.addTempWire();
+        cd.addGate(a[n - 1], b[n - 1], GateType::Xor, pTop);
+        if (n == 1) { cd.addCopy(pTop, out); return; }
+        std::vector<BetaWire> g(n - 1), p(n - 1);
+        for (u64 i = 0; i + 1 < n; ++i) {
+            g[i] = cd.addTempWire();
+            cd.addGate(a[i], b[i], GateType::And, g[i]);
+            if (i) { p[i] = cd.addTempWire(); cd.addGate(a[i], b[i], GateType::Xor, p[i]); }      // p_0 is never used
+            else p[i] = (BetaWire)-1;
+        }
+        BetaWire carry = prefixCarry(cd, g, p);
+        cd.addGate(pTop, carry, GateType::Xor, out);
     }
     // depth-optimised adder: log2(bits)+1 AND levels
     static void prefixAdd(BetaCircuit& cd, const BetaBundle& a, const BetaBundle& b, const BetaBundle& c, bool) {

@@ -441,7 +441,7 @@ public:
     // after the call (asyncSendCopy at Sh3Evaluator.cpp:109, :681-684).
     void asyncSendDevice(const void* d_src, size_t bytes) {
         require();
-        mBytesSent += bytes;
+        *mBytesSent += bytes;
         mT->sendDevice(d_src, bytes);
     }
     // Receive into device memory: blocks the HOST at most until the peer has posted
@@ -461,7 +461,7 @@ public:
     // other transports copy as above.
     void asyncSendDeviceShared(const std::shared_ptr<aby3::gpu::SharedBuffer>& buf, size_t bytes) {
         require();
-        mBytesSent += bytes;
+        *mBytesSent += bytes;
         mT->sendDeviceShared(buf, bytes);
     }
     std::future<void> asyncRecvDeviceBorrow(size_t bytes, Borrowed* out) {
@@ -470,11 +470,13 @@ public:
     }
 
     // ------------------------------------------------------------------ stats -
-    u64 getTotalDataSent() const { return mBytesSent; }
-    void resetStats() { mBytesSent = 0; }
+    // copies of a Channel are handles to the same endpoint: they share the counter
+    u64 getTotalDataSent() const { return mBytesSent ? mBytesSent->load() : 0; }
+    void resetStats() { if (mBytesSent) mBytesSent->store(0); }
 
 private:
-    explicit Channel(std::shared_ptr<detail::Transport> t) : mT(std::move(t)), mRecvQ(std::make_shared<detail::RecvQueue>()) {}
+    explicit Channel(std::shared_ptr<detail::Transport> t)
+        : mT(std::move(t)), mRecvQ(std::make_shared<detail::RecvQueue>()), mBytesSent(std::make_shared<std::atomic<u64>>(0)) {}
     void require() const {
         if (!mT) throw std::runtime_error("Channel: not connected " LOCATION);
     }
@@ -486,7 +488,7 @@ private:
     }
     void sendBytes(const u8* p, size_t n) {
         require();
-        mBytesSent += n;
+        *mBytesSent += n;
         mT->sendHost(p, n);
     }
     void recvBytes(u8* p, size_t n) {
@@ -498,7 +500,7 @@ private:
 
     std::shared_ptr<detail::Transport> mT;
     std::shared_ptr<detail::RecvQueue> mRecvQ;
-    u64 mBytesSent = 0;
+    std::shared_ptr<std::atomic<u64>> mBytesSent;
 };
 
 }  // namespace oc
