@@ -267,3 +267,83 @@ def test_gemm_skinny_shapes(ctx):
             dc.free()
         for x in d:
             x.free()
+
+
+def test_graph_capture_and_iteration_relative_entry_points(ctx):
+    """aby3cu_capture_begin/end + graph_launch with the *_at entry points: a captured (truncation pair, gather, counter
+    increment) replayed k times produces what the plain entry points give at offsets base + it * stride."""
+    n, stride, d, rows, cols, nb = 37, 50, 16, 40, 6, 8
+    idx = np.random.default_rng(90).integers(0, rows, 5 * nb).astype(np.uint64)
+    src = rnd(91, rows * cols).reshape(rows, cols)
+    d_idx, d_src = ctx.upload(idx), ctx.upload(src)
+    d_iter = ctx.upload(np.zeros(2, dtype=np.uint64))
+    negr, rt0, rt1, out = ctx.alloc(8 * n), ctx.alloc(8 * n), ctx.alloc(8 * n), ctx.alloc(8 * nb * cols)
+    in_p, out_p, cols_a = (C.c_void_p * 1)(d_src.p), (C.c_void_p * 1)(out.p), (C.c_uint64 * 1)(cols)
+
+    def issue():
+        abi.check(lib.aby3cu_trunc_tuple_at(ctx.h, KEY_A, 4, KEY_B, 9, d_iter.p, stride, d, None, negr.p, rt0.p, rt1.p, n))
+        abi.check(lib.aby3cu_gather_rows_multi_at(ctx.h, 1, in_p, cols_a, out_p, d_idx.p, nb, d_iter.p))
+        abi.check(lib.aby3cu_counter_add(ctx.h, d_iter.p, 1))
+
+    def expect(it):
+        e_negr, e0, e1 = ctx.alloc(8 * n), ctx.alloc(8 * n), ctx.alloc(8 * n)
+        abi.check(lib.aby3cu_trunc_tuple(ctx.h, KEY_A, 4 + it * stride, KEY_B, 9 + it * stride, d, None, e_negr.p, e0.p, e1.p, n))
+        return [ctx.download(b, n) for b in (e_negr, e0, e1)], src[idx[it * nb:(it + 1) * nb].astype(np.int64)]
+
+    issue()                                      # iteration 0, eagerly
+    (a, b, c), g = expect(0)
+    assert np.array_equal(ctx.download(negr, n), a) and np.array_equal(ctx.download(rt0, n), b) and np.array_equal(ctx.download(rt1, n), c)
+    assert np.array_equal(ctx.download(out, (nb, cols)), g)
+    abi.check(lib.aby3cu_capture_begin(ctx.h))
+    issue()                                      # recorded, not executed
+    exec_ = C.c_void_p()
+    abi.check(lib.aby3cu_capture_end(ctx.h, C.byref(exec_)))
+    assert int(ctx.download(d_iter, 2, U64)[0]) == 1          # the captured increment did not run
+    l0 = ctx.launches
+    for it in (1, 2, 3, 4):
+        abi.check(lib.aby3cu_graph_launch(ctx.h, exec_, 3))
+        (a, b, c), g = expect(it)
+        assert np.array_equal(ctx.download(negr, n), a) and np.array_equal(ctx.download(rt0, n), b) and np.array_equal(ctx.download(rt1, n), c), it
+        assert np.array_equal(ctx.download(out, (nb, cols)), g), it
+    assert int(ctx.download(d_iter, 2, U64)[0]) == 5
+    assert ctx.launches - l0 >= 12               # 4 replays x 3 kernels are counted
+    abi.check(lib.aby3cu_graph_destroy(exec_))
+
+
+def test_converter_and_checker_kernels(ctx):
+    """bits_expand / bitinj_msgs (Sh3Converter::bitInjection) and bin_check_gates (shadow evaluation) at the ABI level"""
+    rows, words, bits = 50, 2, 91
+    m0, m1 = rnd(92, rows * words).reshape(rows, words), rnd(93, rows * words).reshape(rows, words)
+    d0, d1 = ctx.upload(m0), ctx.upload(m1)
+    ex = ctx.alloc(8 * rows * bits)
+    abi.check(lib.aby3cu_bits_expand(ctx.h, d0.p, rows, words, bits, ex.p))
+    want = np.stack([(m0[:, j // 64] >> (j % 64)) & 1 for j in range(bits)], axis=1)
+    assert np.array_equal(ctx.download(ex, (rows, bits)), want)
+    n = rows * bits
+    o0, o1, msgs = ctx.alloc(8 * n), ctx.alloc(8 * n), ctx.alloc(16 * n)
+    abi.check(lib.aby3cu_bitinj_msgs(ctx.h, d0.p, d1.p, rows, words, bits, KEY_A, 3, KEY_B, 8, o0.p, o1.p, msgs.p))
+    x0, x1 = o.stream_u64(KEY_A, 3, n), o.stream_u64(KEY_B, 8, n)
+    assert np.array_equal(ctx.download(o0, n, U64), x0) and np.array_equal(ctx.download(o1, n, U64), x1)
+    b = np.stack([((m0 ^ m1)[:, j // 64] >> (j % 64)) & 1 for j in range(bits)], axis=1).reshape(-1).astype(U64)
+    base = (U64(0) - x0 - x1)
+    mm = ctx.download(msgs, (n, 2), U64)
+    assert np.array_equal(mm[:, 0], base + b) and np.array_equal(mm[:, 1], base + (U64(1) - b))
+    # shadow check: planes of a tiny wire memory whose XOR satisfies out = a & b, then one flipped bit
+    width = 200
+    rb = lib.aby3cu_bin_row_bytes(width)
+    rw = rb // 8
+    rng = np.random.default_rng(94)
+    planes = rng.integers(0, 2**63, (3, 3, rw), dtype=np.int64)           # [plane][wire 0..2][word]
+    a = planes[0, 0] ^ planes[1, 0] ^ planes[2, 0]
+    bb = planes[0, 1] ^ planes[1, 1] ^ planes[2, 1]
+    planes[2, 2] = (a & bb) ^ planes[0, 2] ^ planes[1, 2]
+    gates = ctx.upload(np.array([[0, 1, 2, 8]], dtype=np.uint32))
+    res = ctx.alloc(16)
+    dp = [ctx.upload(planes[k]) for k in range(3)]
+    abi.check(lib.aby3cu_bin_check_gates(ctx.h, gates.p, None, 1, dp[0].p, dp[1].p, dp[2].p, rb, width, res.p, res.at(8)))
+    assert int(ctx.download(res, 1, U64)[0]) == 0
+    planes[1, 2, 0] ^= 1 << 5
+    dp[1] = ctx.upload(planes[1])
+    abi.check(lib.aby3cu_bin_check_gates(ctx.h, gates.p, None, 1, dp[0].p, dp[1].p, dp[2].p, rb, width, res.p, res.at(8)))
+    assert int(ctx.download(res, 1, U64)[0]) == 1
+    assert int(ctx.download(res, 4, np.uint32)[2]) == 0                     # first failing gate index
