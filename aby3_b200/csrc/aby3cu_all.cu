@@ -7,3 +7,4 @@
 #include "gemm_tc.cu"
 #include "binary.cu"
 #include "sharedot.cu"
+#include "batched.cu"

@@ -1,8 +1,9 @@
 // SgdGraph.h -- SGD_Linear (aby3-ML/Regression.h:112-184) for three parties that share ONE GPU, replayed as a
 // CUDA graph.  An iteration of the reference loop is ~28 small kernels spread over three party threads; issued
-// one by one it is bound by driver calls, not by the device.  Here ONE thread issues the three parties' kernels of
-// an iteration on their three streams (the reshare between co-located parties is a pointer: the opened xy - r is
-// read in place, ordered by events), captures that once, and replays it with a single launch per iteration.
+// one by one it is bound by driver calls, not by the device.  Here ONE thread issues an iteration of all three parties
+// -- every protocol step as one launch over the three parties' pointers (aby3cu_*_batch; the reshare between co-located
+// parties is a pointer: the opened xy - r is read in place) -- captures that once, and replays it with a single launch
+// per iteration: 10 kernels instead of 28.
 // Everything that changes from one iteration to the next -- the mini-batch rows and the offsets into the
 // common-PRNG keystreams -- is read from a device-resident iteration counter (aby3cu_*_at entry points).
 //
@@ -76,7 +77,7 @@ public:
             W[p].kp = g.mPrevCommon.getSeed();
             W[p].evV1 = c->newEvent(); W[p].evV2 = c->newEvent(); W[p].evDone = c->newEvent();
             W[p].evT1 = c->newEvent(); W[p].evT2 = c->newEvent(); W[p].evG = c->newEvent();
-            W[p].side.reset(new gpu::Context(c->device()));
+            if (p == 0) W[p].side.reset(new gpu::Context(c->device()));
         }
         void* evFork = c0->newEvent();
         const u64* it = (const u64*)dIter.ptr();
@@ -84,89 +85,96 @@ public:
 
         // one iteration of all three parties; dependencies between parties are events, so the same code runs
         // eagerly (first iteration) and under stream capture (the graph)
+        // One iteration of all three parties.  Every protocol step is ONE launch over the three parties' pointers
+        // (aby3cu_*_batch): the same kernel would otherwise be launched once per party (and per share plane).
+        // Main stream: the critical chain  gather -> XX*w -> open/truncate -> XX^T*error -> open/truncate -> w -= update.
+        // Side stream: what does not sit on it -- both truncation pairs of all parties (they depend only on the iteration
+        // counter), error -= YY (applied to RTrunc BEFORE the opened value is added: addition commutes mod 2^64) and the
+        // transposes of the batch.  The same code runs eagerly (first iteration) and under stream capture (the graph).
+        aby3cu_ctx* hm = c0->h();
+        aby3cu_ctx* hs = W[0].side->h();
         auto issue = [&] {
             kernels = 0;
-            gpu::check(aby3cu_event_record(c0->h(), evFork));
-            for (int p = 1; p < 3; ++p) gpu::check(aby3cu_event_wait(P[p].ctx->h(), evFork));
-            // Main stream of a party: the critical chain  gather -> XX*w -> open/truncate -> XX^T*error -> open/truncate -> w -= update.
-            // Side stream: both truncation pairs (they depend only on the iteration counter) and error -= YY (applied to
-            // RTrunc BEFORE the opened value is added: addition commutes mod 2^64).  The transpose of the batch fills the
-            // main stream's wait for the first truncation pair.
-            for (int p = 0; p < 3; ++p) {
-                aby3cu_ctx* h = P[p].ctx->h();
-                auto& X = *P[p].X; auto& Y = *P[p].Y;
-                const int64_t* in[4] = {X[0].dev(), X[1].dev(), Y[0].dev(), Y[1].dev()};
-                int64_t* out[4] = {(i64*)W[p].XX[0].ptr(), (i64*)W[p].XX[1].ptr(), (i64*)W[p].YY[0].ptr(), (i64*)W[p].YY[1].ptr()};
-                const uint64_t cols[4] = {F, F, 1, 1};
-                gpu::check(aby3cu_gather_rows_multi_at(h, 4, in, cols, out, (const u64*)dIdx.ptr(), B, it));            // extractBatch
-                gpu::check(aby3cu_event_record(h, W[p].evG));
-                gpu::check(aby3cu_transpose_i64_2(h, (const i64*)W[p].XX[0].ptr(), (const i64*)W[p].XX[1].ptr(), B, F,
-                                                  (i64*)W[p].XT[0].ptr(), (i64*)W[p].XT[1].ptr()));                                             // XX^T
-                kernels += 2;
+            gpu::check(aby3cu_event_record(hm, evFork));
+            gpu::check(aby3cu_event_wait(hs, evFork));
+            {   // extractBatch for every party: rows of X and Y, both planes
+                const int64_t* in[12]; int64_t* out[12]; uint64_t cols[12];
+                for (int p = 0; p < 3; ++p) {
+                    auto& X = *P[p].X; auto& Y = *P[p].Y;
+                    in[4 * p] = X[0].dev(); in[4 * p + 1] = X[1].dev(); in[4 * p + 2] = Y[0].dev(); in[4 * p + 3] = Y[1].dev();
+                    out[4 * p] = (i64*)W[p].XX[0].ptr(); out[4 * p + 1] = (i64*)W[p].XX[1].ptr();
+                    out[4 * p + 2] = (i64*)W[p].YY[0].ptr(); out[4 * p + 3] = (i64*)W[p].YY[1].ptr();
+                    cols[4 * p] = cols[4 * p + 1] = F; cols[4 * p + 2] = cols[4 * p + 3] = 1;
+                }
+                gpu::check(aby3cu_gather_rows_multi_at(hm, 12, in, cols, out, (const u64*)dIdx.ptr(), B, it));
+                gpu::check(aby3cu_event_record(hm, W[0].evG));
+                ++kernels;
             }
-            for (int p = 0; p < 3; ++p) {
-                aby3cu_ctx* hs = W[p].side->h();
-                i64* e0 = (i64*)W[p].E[0].ptr();
-                i64* e1 = (i64*)W[p].E[1].ptr();
-                gpu::check(aby3cu_event_wait(hs, evFork));
-                gpu::check(aby3cu_trunc_tuple_at(hs, W[p].kn.data(), W[p].en, W[p].kp.data(), W[p].ep, it, S, D, nullptr,
-                                                 (i64*)W[p].V1.ptr(), e0, e1, B));                                       // V1 = -r, E = RTrunc
-                gpu::check(aby3cu_event_record(hs, W[p].evT1));
-                gpu::check(aby3cu_trunc_tuple_at(hs, W[p].kn.data(), W[p].en + B, W[p].kp.data(), W[p].ep + B, it, S, D + aB, nullptr,
-                                                 (i64*)W[p].V2.ptr(), (i64*)W[p].U[0].ptr(), (i64*)W[p].U[1].ptr(), F));
-                gpu::check(aby3cu_event_wait(hs, W[p].evG));
-                gpu::check(aby3cu_share_op2(hs, ABY3CU_OP_SUB, e0, (const i64*)W[p].YY[0].ptr(), e0, e1, (const i64*)W[p].YY[1].ptr(), e1, B));  // error -= YY
-                gpu::check(aby3cu_event_record(hs, W[p].evT2));
+            {   // side: V1 = -r, E = RTrunc (shift D, n = B) and V2 = -r', U = RTrunc' (shift D + aB, n = F) for every party
+                const uint8_t* kn[6]; const uint8_t* kp[6]; uint64_t en[6], ep[6], sh[6], cnt[6]; int64_t* negr[6]; int64_t* r0[6]; int64_t* r1[6];
+                for (int p = 0; p < 3; ++p) {
+                    kn[p] = kn[3 + p] = W[p].kn.data(); kp[p] = kp[3 + p] = W[p].kp.data();
+                    en[p] = W[p].en; ep[p] = W[p].ep; sh[p] = D; cnt[p] = B;
+                    negr[p] = (i64*)W[p].V1.ptr(); r0[p] = (i64*)W[p].E[0].ptr(); r1[p] = (i64*)W[p].E[1].ptr();
+                    en[3 + p] = W[p].en + B; ep[3 + p] = W[p].ep + B; sh[3 + p] = D + aB; cnt[3 + p] = F;
+                    negr[3 + p] = (i64*)W[p].V2.ptr(); r0[3 + p] = (i64*)W[p].U[0].ptr(); r1[3 + p] = (i64*)W[p].U[1].ptr();
+                }
+                gpu::check(aby3cu_trunc_tuple_batch_at(hs, 6, kn, en, kp, ep, sh, cnt, negr, r0, r1, it, S));
+                gpu::check(aby3cu_event_record(hs, W[0].evT1));
+                gpu::check(aby3cu_event_wait(hs, W[0].evG));
+                const int64_t* x[6]; const int64_t* y[6]; int64_t* o[6]; const int64_t* tin[6]; int64_t* tout[6];
+                for (int p = 0; p < 3; ++p)
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                        x[2 * p + s2] = (const i64*)W[p].E[s2].ptr(); y[2 * p + s2] = (const i64*)W[p].YY[s2].ptr(); o[2 * p + s2] = (i64*)W[p].E[s2].ptr();
+                        tin[2 * p + s2] = (const i64*)W[p].XX[s2].ptr(); tout[2 * p + s2] = (i64*)W[p].XT[s2].ptr();
+                    }
+                gpu::check(aby3cu_share_op_batch(hs, ABY3CU_OP_SUB, 6, x, y, o, B));                       // error -= YY
+                gpu::check(aby3cu_transpose_i64_batch(hs, 6, tin, B, F, tout));                            // XX^T
+                gpu::check(aby3cu_event_record(hs, W[0].evT2));
                 kernels += 3;
             }
-            for (int p = 0; p < 3; ++p) {
-                // error = mul(XX, w): V1 += XX*w   (Sh3Evaluator.cpp:651-700)
-                aby3cu_ctx* h = P[p].ctx->h();
-                auto& w = *P[p].w;
-                gpu::check(aby3cu_event_wait(h, W[p].evT1));
-                gpu::check(aby3cu_gemm_cross(h, ABY3CU_GEMM_AUTO, (const i64*)W[p].XX[0].ptr(), (const i64*)W[p].XX[1].ptr(),
-                                             w[0].dev(), w[1].dev(), B, F, 1, (i64*)W[p].V1.ptr(), 1));
-                gpu::check(aby3cu_event_record(h, W[p].evV1));
-                ++kernels;
-            }
-            for (int p = 0; p < 3; ++p) {
-                aby3cu_ctx* h = P[p].ctx->h();
-                gpu::check(aby3cu_event_wait(h, W[p].evT2));       // side stream done: E -= YY, XX^T, V2 = -r, U = RTrunc
-                if (p < 2) {                                       // parties 0 and 1 open xy - r and truncate (:703-724)
-                    const int nx = (p + 1) % 3, pv = (p + 2) % 3;
-                    gpu::check(aby3cu_event_wait(h, W[nx].evV1));
-                    gpu::check(aby3cu_event_wait(h, W[pv].evV1));
-                    gpu::check(aby3cu_trunc_finish(h, (const i64*)W[nx].V1.ptr(), (const i64*)W[pv].V1.ptr(), (const i64*)W[p].V1.ptr(),
-                                                   (i64*)W[p].E[p].ptr(), B, D));
-                    ++kernels;
+            const int64_t* a0[3]; const int64_t* a1[3]; const int64_t* b0[3]; const int64_t* b1[3]; int64_t* cc[3];
+            const int64_t* f0[2]; const int64_t* f1[2]; const int64_t* f2[2]; int64_t* fc[2];
+            {   // error = mul(XX, w): V1 += XX*w   (Sh3Evaluator.cpp:651-700), then parties 0 and 1 open and truncate (:703-724)
+                for (int p = 0; p < 3; ++p) {
+                    auto& w = *P[p].w;
+                    a0[p] = (const i64*)W[p].XX[0].ptr(); a1[p] = (const i64*)W[p].XX[1].ptr(); b0[p] = w[0].dev(); b1[p] = w[1].dev();
+                    cc[p] = (i64*)W[p].V1.ptr();
                 }
-                // update = mulTruncate(XX^T, error, aB)
-                gpu::check(aby3cu_gemm_cross(h, ABY3CU_GEMM_AUTO, (const i64*)W[p].XT[0].ptr(), (const i64*)W[p].XT[1].ptr(),
-                                             (const i64*)W[p].E[0].ptr(), (const i64*)W[p].E[1].ptr(), F, B, 1, (i64*)W[p].V2.ptr(), 1));
-                gpu::check(aby3cu_event_record(h, W[p].evV2));
-                ++kernels;
-            }
-            for (int p = 0; p < 3; ++p) {
-                aby3cu_ctx* h = P[p].ctx->h();
-                if (p < 2) {
-                    const int nx = (p + 1) % 3, pv = (p + 2) % 3;
-                    gpu::check(aby3cu_event_wait(h, W[nx].evV2));
-                    gpu::check(aby3cu_event_wait(h, W[pv].evV2));
-                    gpu::check(aby3cu_trunc_finish(h, (const i64*)W[nx].V2.ptr(), (const i64*)W[pv].V2.ptr(), (const i64*)W[p].V2.ptr(),
-                                                   (i64*)W[p].U[p].ptr(), F, D + aB));
-                    ++kernels;
+                gpu::check(aby3cu_event_wait(hm, W[0].evT1));
+                gpu::check(aby3cu_gemv_cross_batch(hm, 3, a0, a1, b0, b1, B, F, cc, 1));
+                for (int p = 0; p < 2; ++p) {
+                    f0[p] = (const i64*)W[(p + 1) % 3].V1.ptr(); f1[p] = (const i64*)W[(p + 2) % 3].V1.ptr(); f2[p] = (const i64*)W[p].V1.ptr();
+                    fc[p] = (i64*)W[p].E[p].ptr();
                 }
-                // w -= update, in place: the graph must find w where it left it
-                auto& w = *P[p].w;
-                i64* w0 = w[0].devMut();
-                i64* w1 = w[1].devMut();
-                gpu::check(aby3cu_share_op2(h, ABY3CU_OP_SUB, w0, (const i64*)W[p].U[0].ptr(), w0, w1, (const i64*)W[p].U[1].ptr(), w1, F));
-                gpu::check(aby3cu_event_record(h, W[p].evDone));
-                ++kernels;
+                gpu::check(aby3cu_event_wait(hm, W[0].evT2));          // side stream done: E -= YY, XX^T, V2, U
+                gpu::check(aby3cu_trunc_finish_batch(hm, 2, f0, f1, f2, fc, B, D));
+                kernels += 2;
             }
-            for (int p = 1; p < 3; ++p) gpu::check(aby3cu_event_wait(c0->h(), W[p].evDone));
-            gpu::check(aby3cu_counter_add(c0->h(), (u64*)dIter.ptr(), 1));
-            ++kernels;
+            {   // update = mulTruncate(XX^T, error, aB)
+                for (int p = 0; p < 3; ++p) {
+                    a0[p] = (const i64*)W[p].XT[0].ptr(); a1[p] = (const i64*)W[p].XT[1].ptr();
+                    b0[p] = (const i64*)W[p].E[0].ptr(); b1[p] = (const i64*)W[p].E[1].ptr(); cc[p] = (i64*)W[p].V2.ptr();
+                }
+                gpu::check(aby3cu_gemv_cross_batch(hm, 3, a0, a1, b0, b1, F, B, cc, 1));
+                for (int p = 0; p < 2; ++p) {
+                    f0[p] = (const i64*)W[(p + 1) % 3].V2.ptr(); f1[p] = (const i64*)W[(p + 2) % 3].V2.ptr(); f2[p] = (const i64*)W[p].V2.ptr();
+                    fc[p] = (i64*)W[p].U[p].ptr();
+                }
+                gpu::check(aby3cu_trunc_finish_batch(hm, 2, f0, f1, f2, fc, F, D + aB));
+                kernels += 2;
+            }
+            {   // w -= update, in place: the graph must find w where it left it
+                const int64_t* x[6]; const int64_t* y[6]; int64_t* o[6];
+                for (int p = 0; p < 3; ++p)
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                        i64* wp = (*P[p].w)[s2].devMut();
+                        x[2 * p + s2] = wp; y[2 * p + s2] = (const i64*)W[p].U[s2].ptr(); o[2 * p + s2] = wp;
+                    }
+                gpu::check(aby3cu_share_op_batch(hm, ABY3CU_OP_SUB, 6, x, y, o, F));
+                gpu::check(aby3cu_counter_add(hm, (u64*)dIter.ptr(), 1));
+                kernels += 2;
+            }
         };
 
         // every party stream must be idle-ordered behind what it did before: the fork event covers party 0's stream,
@@ -186,7 +194,7 @@ public:
         for (int p = 0; p < 3; ++p) {
             P[p].ctx->recycleEvent(W[p].evV1); P[p].ctx->recycleEvent(W[p].evV2); P[p].ctx->recycleEvent(W[p].evDone);
             P[p].ctx->recycleEvent(W[p].evT1); P[p].ctx->recycleEvent(W[p].evT2); P[p].ctx->recycleEvent(W[p].evG);
-            W[p].side->sync();
+            if (W[p].side) W[p].side->sync();
             auto& g = P[p].eval->mShareGen;
             g.mNextCommon.skip(8 * S * iters);               // what the kernels consumed
             g.mPrevCommon.skip(8 * S * iters);

@@ -193,7 +193,7 @@ int aby3cu_transpose_i64_2(aby3cu_ctx* ctx, const int64_t* d_in0, const int64_t*
                            int64_t* d_out0, int64_t* d_out1);
 /* up to ABY3CU_MAX_GATHER_JOBS row gathers sharing one index vector in one launch: job j copies rows
  * idx[0..nrows) of in[j] (cols[j] wide) to out[j]  (extractBatch takes the same rows of X and Y, both planes) */
-#define ABY3CU_MAX_GATHER_JOBS 4
+#define ABY3CU_MAX_GATHER_JOBS 12
 int aby3cu_gather_rows_multi(aby3cu_ctx* ctx, int njobs, const int64_t* const* d_in, const uint64_t* cols,
                              int64_t* const* d_out, const uint64_t* d_idx, uint64_t nrows);
 /* the same, replayable inside a CUDA graph: the batch is idx[*d_iter * nrows ...) (d_iter: device counter, may be NULL) */
@@ -201,6 +201,32 @@ int aby3cu_gather_rows_multi_at(aby3cu_ctx* ctx, int njobs, const int64_t* const
                                 int64_t* const* d_out, const uint64_t* d_idx, uint64_t nrows, const uint64_t* d_iter);
 /* *d_counter += inc on the context's stream (the iteration counter of a replayed graph) */
 int aby3cu_counter_add(aby3cu_ctx* ctx, uint64_t* d_counter, uint64_t inc);
+/* ---- the small kernels of a protocol step, batched over independent problems (blockIdx.y) -------------------------
+ * Parties that share a GPU run the SAME kernel on three sets of pointers at every step of a latency-bound loop (SGD,
+ * aby3-ML/Regression.h:142-171); one launch for all of them shortens the replayed CUDA graph (aby3_b200/ml/SgdGraph.h).
+ * Arithmetic and keystream offsets are those of the single-problem entry points; at most ABY3CU_MAX_BATCH problems. */
+#define ABY3CU_MAX_BATCH 6
+/* getTruncationTuple (Sh3Evaluator.cpp:503-566) for njobs (key pair, offsets, shift, count) tuples: negr = -(t0>>2),
+ * rt0 = t0 >> (shift+2), rt1 = t1 >> (shift+2); stream offsets elem + *d_iter * iter_stride (d_iter may be NULL) */
+int aby3cu_trunc_tuple_batch_at(aby3cu_ctx* ctx, int njobs, const uint8_t* const* keys_next, const uint64_t* elem_next,
+                                const uint8_t* const* keys_prev, const uint64_t* elem_prev, const uint64_t* shifts,
+                                const uint64_t* counts, int64_t* const* d_negr, int64_t* const* d_rt0, int64_t* const* d_rt1,
+                                const uint64_t* d_iter, uint64_t iter_stride);
+/* out[p] = x[p] op y[p] for nplanes share planes of n elements (Sh3Types.h:805-820) */
+int aby3cu_share_op_batch(aby3cu_ctx* ctx, int op, int nplanes, const int64_t* const* d_x, const int64_t* const* d_y,
+                          int64_t* const* d_out, size_t n);
+/* out[p] = in[p]^T for nplanes row-major rows x cols planes (Sh3Types.h:822-838) */
+int aby3cu_transpose_i64_batch(aby3cu_ctx* ctx, int nplanes, const int64_t* const* d_in, uint64_t rows, uint64_t cols,
+                               int64_t* const* d_out);
+/* C[j] += (s0[j] + s1[j] + s2[j]) >> shift  (Sh3Evaluator.cpp:712-718) for njobs parties */
+int aby3cu_trunc_finish_batch(aby3cu_ctx* ctx, int njobs, const int64_t* const* d_s0, const int64_t* const* d_s1,
+                              const int64_t* const* d_s2, int64_t* const* d_C, size_t n, uint64_t shift);
+/* the cross term with a one-column right operand, C[j] (+)= A0[j] (B0[j] + B1[j]) + A1[j] B0[j], A M x K
+ * (Sh3Evaluator.cpp:662-665 at the shapes of aby3-ML/Regression.h:157,166) */
+int aby3cu_gemv_cross_batch(aby3cu_ctx* ctx, int njobs, const int64_t* const* d_A0, const int64_t* const* d_A1,
+                            const int64_t* const* d_B0, const int64_t* const* d_B1, uint64_t M, uint64_t K,
+                            int64_t* const* d_C, int accumulate);
+
 /* gather rows: out[r,:] = in[idx[r],:]  (extractBatch, aby3-ML/Regression.h:43-58) */
 int aby3cu_gather_rows(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t cols, const uint64_t* d_idx,
                        uint64_t nrows, int64_t* d_out);

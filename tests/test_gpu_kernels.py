@@ -347,3 +347,62 @@ def test_converter_and_checker_kernels(ctx):
     abi.check(lib.aby3cu_bin_check_gates(ctx.h, gates.p, None, 1, dp[0].p, dp[1].p, dp[2].p, rb, width, res.p, res.at(8)))
     assert int(ctx.download(res, 1, U64)[0]) == 1
     assert int(ctx.download(res, 4, np.uint32)[2]) == 0                     # first failing gate index
+
+
+def test_batched_entry_points_equal_the_single_problem_ones(ctx):
+    """aby3cu_*_batch: one launch over several problems gives exactly what the single-problem entry points give"""
+    def ptrs(bufs):
+        return (C.c_void_p * len(bufs))(*[b.p for b in bufs])
+    # truncation pairs: 3 jobs with different keys / offsets / shifts / counts
+    keys = [bytes(range(k, k + 16)) for k in (1, 20, 40, 60, 80, 100)]
+    jobs = [(keys[0], 5, keys[1], 11, 16, 37), (keys[2], 0, keys[3], 3, 23, 128), (keys[4], 1000, keys[5], 7, 16, 1)]
+    outs = [[ctx.alloc(8 * j[5]) for _ in range(3)] for j in jobs]
+    kn = (C.c_char_p * 3)(*[j[0] for j in jobs]); kp = (C.c_char_p * 3)(*[j[2] for j in jobs])
+    en = (C.c_uint64 * 3)(*[j[1] for j in jobs]); ep = (C.c_uint64 * 3)(*[j[3] for j in jobs])
+    sh = (C.c_uint64 * 3)(*[j[4] for j in jobs]); cnt = (C.c_uint64 * 3)(*[j[5] for j in jobs])
+    abi.check(lib.aby3cu_trunc_tuple_batch_at(ctx.h, 3, kn, en, kp, ep, sh, cnt, ptrs([o_[0] for o_ in outs]), ptrs([o_[1] for o_ in outs]),
+                                              ptrs([o_[2] for o_ in outs]), None, 0))
+    for j, o_ in zip(jobs, outs):
+        e = [ctx.alloc(8 * j[5]) for _ in range(3)]
+        abi.check(lib.aby3cu_trunc_tuple(ctx.h, j[0], j[1], j[2], j[3], j[4], None, e[0].p, e[1].p, e[2].p, j[5]))
+        for got, want in zip(o_, e):
+            assert np.array_equal(ctx.download(got, j[5]), ctx.download(want, j[5]))
+    # share ops, transposes, open-and-truncate, GEMV cross term
+    n = 1001
+    xs, ys = [rnd(200 + k, n) for k in range(6)], [rnd(210 + k, n) for k in range(6)]
+    dx, dy, do = [ctx.upload(a) for a in xs], [ctx.upload(a) for a in ys], [ctx.alloc(8 * n) for _ in range(6)]
+    for op, f in ((0, lambda a, b: a.view(U64) + b.view(U64)), (1, lambda a, b: a.view(U64) - b.view(U64)), (2, lambda a, b: a.view(U64) ^ b.view(U64))):
+        abi.check(lib.aby3cu_share_op_batch(ctx.h, op, 6, ptrs(dx), ptrs(dy), ptrs(do), n))
+        for k in range(6):
+            assert np.array_equal(ctx.download(do[k], n, U64), f(xs[k], ys[k]))
+    r, c = 70, 33
+    ms = [rnd(220 + k, r * c).reshape(r, c) for k in range(4)]
+    dm, dt = [ctx.upload(m) for m in ms], [ctx.alloc(8 * r * c) for _ in range(4)]
+    abi.check(lib.aby3cu_transpose_i64_batch(ctx.h, 4, ptrs(dm), r, c, ptrs(dt)))
+    for k in range(4):
+        assert np.array_equal(ctx.download(dt[k], (c, r)), ms[k].T)
+    s = [[rnd(230 + 4 * k + q, n) for q in range(4)] for k in range(2)]
+    ds = [[ctx.upload(a) for a in row] for row in s]
+    abi.check(lib.aby3cu_trunc_finish_batch(ctx.h, 2, ptrs([d_[0] for d_ in ds]), ptrs([d_[1] for d_ in ds]), ptrs([d_[2] for d_ in ds]),
+                                            ptrs([d_[3] for d_ in ds]), n, 13))
+    for k in range(2):
+        want = s[k][3].view(U64) + ((s[k][0].view(U64) + s[k][1].view(U64) + s[k][2].view(U64)).view(np.int64) >> 13).view(U64)
+        assert np.array_equal(ctx.download(ds[k][3], n, U64), want)
+    for (M, K) in ((128, 1024), (1024, 128), (37, 5000), (1, 1)):
+        A0 = [rnd(240 + k, M * K).reshape(M, K) for k in range(3)]; A1 = [rnd(250 + k, M * K).reshape(M, K) for k in range(3)]
+        B0 = [rnd(260 + k, K).reshape(K, 1) for k in range(3)]; B1 = [rnd(270 + k, K).reshape(K, 1) for k in range(3)]
+        C0 = [rnd(280 + k, M).reshape(M, 1) for k in range(3)]
+        d = [[ctx.upload(a) for a in grp] for grp in (A0, A1, B0, B1, C0)]
+        abi.check(lib.aby3cu_gemv_cross_batch(ctx.h, 3, ptrs(d[0]), ptrs(d[1]), ptrs(d[2]), ptrs(d[3]), M, K, ptrs(d[4]), 1))
+        for k in range(3):
+            want = o.cross_term(A0[k], A1[k], B0[k], B1[k]).view(U64) + C0[k].view(U64)
+            assert np.array_equal(ctx.download(d[4][k], (M, 1), U64), want), (M, K, k)
+    # twelve gathers in one launch
+    rows, nb = 300, 64
+    idx = np.random.default_rng(5).integers(0, rows, nb).astype(np.uint64)
+    srcs = [rnd(300 + k, rows * (k % 3 + 1)).reshape(rows, k % 3 + 1) for k in range(12)]
+    dsrc, dout = [ctx.upload(a) for a in srcs], [ctx.alloc(8 * nb * (k % 3 + 1)) for k in range(12)]
+    cols = (C.c_uint64 * 12)(*[k % 3 + 1 for k in range(12)])
+    abi.check(lib.aby3cu_gather_rows_multi(ctx.h, 12, ptrs(dsrc), cols, ptrs(dout), ctx.upload(idx).p, nb))
+    for k in range(12):
+        assert np.array_equal(ctx.download(dout[k], (nb, k % 3 + 1)), srcs[k][idx.astype(np.int64)])
