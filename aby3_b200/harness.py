@@ -33,6 +33,9 @@ def _load():
     l.sh3h_cursors.argtypes = [p, i32, p]
     l.sh3h_plain_create.argtypes = [p, i32, u64, u64, C.POINTER(p)]
     l.sh3h_plain_touch.argtypes = [p, i32, i32]
+    l.sh3h_plain_prefetch.argtypes = [p, i32, i32]
+    l.sh3h_reveal_plain_async.argtypes = [p, i32, i32, i32]
+    l.sh3h_plain_wait.argtypes = [p, i32, i32]
     l.sh3h_share.argtypes = [p, i32, i32, u64, u64, i32, u64]
     l.sh3h_set_shares.argtypes = [p, p, u64, u64, i32, u64]
     l.sh3h_get_shares.argtypes = [p, i32, i32, p]
@@ -142,6 +145,19 @@ class Session:
 
     def plain_touch(self, owner, hid):
         self._chk(lib.sh3h_plain_touch(self.h, owner, hid))
+
+    def plain_prefetch(self, owner, hid):
+        """Start uploading a plaintext matrix on the owner's copy stream (overlaps queued kernels); the next device
+        use of the matrix waits for it.  Do not write the numpy view until the data has been shared."""
+        self._chk(lib.sh3h_plain_prefetch(self.h, owner, hid))
+
+    def reveal_plain_async(self, hid, party, plain_id):
+        """revealAll; `party`'s result is downloaded into its plaintext matrix on the copy stream without blocking.
+        Call plain_wait before reading the numpy view."""
+        self._chk(lib.sh3h_reveal_plain_async(self.h, hid, party, plain_id))
+
+    def plain_wait(self, party, plain_id):
+        self._chk(lib.sh3h_plain_wait(self.h, party, plain_id))
 
     def share_int(self, owner, values):
         values = np.ascontiguousarray(values, dtype=np.int64)

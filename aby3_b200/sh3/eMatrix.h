@@ -78,6 +78,7 @@ public:
     T* devMut() { touchDev(); mHostValid = false; return static_cast<T*>(mDev.ptr()); }
     // write-only device pointer: no upload, previous contents are dropped
     T* devOut() {
+        orderBehindPrefetch();
         ensureDevBuffer();
         mDevValid = true; mHostValid = false;
         return static_cast<T*>(mDev.ptr());
@@ -88,6 +89,42 @@ public:
         mDevValid = true; mHostValid = false;
     }
     gpu::Context* ctx() const { return mDev.ctx() ? mDev.ctx() : gpu::current(); }
+
+    // ---------------------------------------------- overlapped transfers -----
+    // Upload the host copy on ANOTHER context's stream (a copy stream), so that it overlaps the kernels queued on the
+    // party's own stream; the first device use waits for it.  The caller guarantees that no kernel still reads the
+    // previous device contents and must not write the host copy until the upload has run.
+    void prefetchDevice(gpu::Context* copy) {
+        if (!mHostValid || !size()) return;
+        ensureDevBuffer();
+        gpu::check(aby3cu_h2d(copy->h(), mDev.ptr(), mHost.data(), size() * sizeof(T)));
+        dropEvent(mDevReady, mDevReadyDevice);
+        mDevReady = copy->recordEvent();
+        mDevReadyDevice = copy->device();
+        mDevValid = true;
+        mUploadInFlight = true;
+    }
+    // Download the device copy on a copy stream once the calling party's stream has produced it; waitHost() (or any
+    // host access) completes it.  The host vector keeps its address when the shape is unchanged.
+    void fetchHostAsync(gpu::Context* copy) {
+        if (!mDevValid || !size()) return;
+        touchDev();
+        mHost.resize(size());
+        void* produced = gpu::current()->recordEvent();
+        gpu::check(aby3cu_event_wait(copy->h(), produced));
+        gpu::current()->recycleEvent(produced);
+        gpu::check(aby3cu_d2h(copy->h(), mHost.data(), mDev.ptr(), size() * sizeof(T)));
+        dropEvent(mHostReady, mHostReadyDevice);
+        mHostReady = copy->recordEvent();
+        mHostReadyDevice = copy->device();
+        mHostValid = true;
+    }
+    void waitHost() const {
+        if (!mHostReady) return;
+        gpu::check(aby3cu_event_sync(mHostReady));
+        gpu::EventPool::put(mHostReadyDevice, mHostReady);
+        mHostReady = nullptr;
+    }
 
     // -------------------------------------------------------- fills ----------
     void setZero() {
@@ -234,7 +271,18 @@ private:
         const size_t bytes = std::max<size_t>(size() * sizeof(T), 16);
         if (!mDev || mDev.bytes() < bytes) mDev.reset(gpu::current(), bytes);
     }
+    static void dropEvent(void*& e, int device) {
+        if (e) { aby3cu_event_sync(e); gpu::EventPool::put(device, e); e = nullptr; }
+    }
+    // a prefetch on a copy stream: order the calling party's stream behind it
+    void orderBehindPrefetch() const {
+        if (!mDevReady) return;
+        gpu::check(aby3cu_event_wait(gpu::current()->h(), mDevReady));
+        gpu::EventPool::put(mDevReadyDevice, mDevReady);
+        mDevReady = nullptr;
+    }
     void touchDev() const {
+        orderBehindPrefetch();
         if (mDevValid) return;
         auto* self = const_cast<eMatrix*>(this);
         self->ensureDevBuffer();
@@ -250,6 +298,7 @@ private:
     }
     void touchHost(bool willWrite) const {
         auto* self = const_cast<eMatrix*>(this);
+        waitHost();
         if (!mHostValid) {
             if (mDevValid) self->mHost.resize(size());        // no fill: the d2h below overwrites it
             else self->mHost.assign(size(), T{});
@@ -260,6 +309,7 @@ private:
             self->mHostValid = true;
         }
         if (willWrite) {
+            dropEvent(self->mDevReady, mDevReadyDevice);          // a prefetch still reads the host copy
             if (mUploadInFlight && mDev.ctx()) mDev.ctx()->sync();
             self->mUploadInFlight = false;
             self->mDevValid = false;
@@ -268,6 +318,8 @@ private:
     // page-locked host blocks are recycled (gpu::PinnedPool): an asynchronous upload
     // reading this matrix's host copy must have run before that copy is released
     void settleUpload() {
+        dropEvent(mDevReady, mDevReadyDevice);
+        dropEvent(mHostReady, mHostReadyDevice);
         if (mUploadInFlight && mDev.ctx()) {
             try { mDev.ctx()->sync(); } catch (...) {}
         }
@@ -284,6 +336,7 @@ private:
                                       o.mDev.ctx()->device(), size() * sizeof(T)));
             mDevValid = true;
         } else {
+            o.waitHost();
             mHost = o.mHost; mHostValid = o.mHostValid; mDevValid = false;
             mDev.free();
         }
@@ -294,6 +347,8 @@ private:
         mHost = std::move(o.mHost); mHostValid = o.mHostValid;
         mDev = std::move(o.mDev); mDevValid = o.mDevValid;
         mUploadInFlight = o.mUploadInFlight; o.mUploadInFlight = false;
+        mDevReady = o.mDevReady; mDevReadyDevice = o.mDevReadyDevice; o.mDevReady = nullptr;
+        mHostReady = o.mHostReady; mHostReadyDevice = o.mHostReadyDevice; o.mHostReady = nullptr;
         o.mRows = o.mCols = 0; o.mHostValid = false; o.mDevValid = false; o.mHost.clear();
     }
     eMatrix binary(const eMatrix& b, int op) const {
@@ -339,6 +394,9 @@ private:
     mutable gpu::Buffer mDev;
     mutable bool mDevValid = false;
     mutable bool mUploadInFlight = false;
+    mutable void* mDevReady = nullptr;      // prefetch in flight on a copy stream
+    mutable void* mHostReady = nullptr;     // download in flight on a copy stream
+    mutable int mDevReadyDevice = 0, mHostReadyDevice = 0;
 };
 
 template <typename T>

@@ -69,6 +69,7 @@ struct Worker {
 
 struct Party {
     std::unique_ptr<gpu::Context> ctx;
+    std::unique_ptr<gpu::Context> copy;      // second stream of the party: overlapped h2d / d2h of plaintext matrices
     CommPkg comm;
     Sh3Runtime rt;
     Sh3Encryptor enc;
@@ -184,6 +185,7 @@ void sh3h_destroy(sh3h* h) {
     h->run([&](int i) {
         Party& P = h->p[i];
         P.ints.clear(); P.bins.clear(); P.plains.clear(); P.packs.clear();
+        if (P.copy) P.copy->sync();
         P.ctx->sync();
     });
     for (int i = 0; i < 3; ++i) {
@@ -231,6 +233,34 @@ int sh3h_plain_create(sh3h* h, int owner, uint64_t rows, uint64_t cols, int64_t*
 // after the caller has (re)written the host values
 int sh3h_plain_touch(sh3h* h, int owner, int id) {
     return h->run([&](int i) { if (i == owner) (void)h->p[i].plains.at(id)->data(); });
+}
+
+// ---- overlapped transfers (eMatrix::prefetchDevice / fetchHostAsync) -------------------------------------------
+static gpu::Context* copyCtx(Party& P) {
+    if (!P.copy) P.copy.reset(new gpu::Context(P.ctx->device()));
+    return P.copy.get();
+}
+// start the upload of a plaintext matrix on the owner's copy stream; a later sh3h_share waits for it on the device
+int sh3h_plain_prefetch(sh3h* h, int owner, int id) {
+    return h->run([&](int i) { if (i == owner) h->p[i].plains.at(id)->prefetchDevice(copyCtx(h->p[i])); });
+}
+// enc.revealAll on every party; party `who` reveals into its plaintext matrix `plain_id` and starts the download on its
+// copy stream WITHOUT waiting for it (sh3h_plain_wait completes it)
+int sh3h_reveal_plain_async(sh3h* h, int id, int who, int plain_id) {
+    return h->run([&](int i) {
+        Party& P = h->p[i];
+        if (i == who) {
+            i64Matrix& dest = *P.plains.at(plain_id);
+            P.enc.revealAll(P.comm, *P.ints.at(id), dest);
+            dest.fetchHostAsync(copyCtx(P));
+        } else {
+            i64Matrix dest;
+            P.enc.revealAll(P.comm, *P.ints.at(id), dest);
+        }
+    });
+}
+int sh3h_plain_wait(sh3h* h, int who, int plain_id) {
+    return h->run([&](int i) { if (i == who) h->p[i].plains.at(plain_id)->waitHost(); });
 }
 
 // Sh3Encryptor::localIntMatrix at `owner`, remoteIntMatrix elsewhere (binary: *BinMatrix).
