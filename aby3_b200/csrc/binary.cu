@@ -2,6 +2,8 @@
 // the row-major sbMatrix layout and the bit-sliced wire memory, the per-level
 // gate interpreter with in-register AES-CTR zero shares, and the send-buffer
 // pack / receive scatter.  All HBM-bound bitwise work on 128-bit words.
+#include <stdlib.h>
+
 #include "aes.cuh"
 
 namespace aby3cu {
@@ -89,6 +91,59 @@ __device__ __forceinline__ u64 block_of(const u64 r[8]) {
     const u32 lo = gather_byte<B>((u32)(r[0] >> (32 * W)), (u32)(r[1] >> (32 * W)), (u32)(r[2] >> (32 * W)), (u32)(r[3] >> (32 * W)));
     const u32 hi = gather_byte<B>((u32)(r[4] >> (32 * W)), (u32)(r[5] >> (32 * W)), (u32)(r[6] >> (32 * W)), (u32)(r[7] >> (32 * W)));
     return ((u64)hi << 32) | lo;
+}
+
+// 32 x 32 bit-matrix transpose in registers, LSB-first: out[b] bit i = in[i] bit b.  Five masked exchange stages,
+// 16 register pairs each (SHF + LOP3 + LOP3 + SHF + LOP3): 400 ops per 128 bytes.
+__device__ __forceinline__ void transpose32(u32 A[32]) {
+    constexpr u32 M[5] = {0x0000FFFFu, 0x00FF00FFu, 0x0F0F0F0Fu, 0x33333333u, 0x55555555u};
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int j = 16 >> s;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            if (k & j) continue;
+            const u32 t = ((A[k] >> j) ^ A[k | j]) & M[s];
+            A[k] ^= t << j;
+            A[k | j] ^= t;
+        }
+    }
+}
+
+// Fast path, 32 instances per thread: the thread's 32 x 64 bit block is two 32 x 32 register transposes, and every
+// bit-row leaves as one 32-bit word -- a warp writes 128 contiguous bytes of a row, no shared-memory staging.
+// in: `rows` instances x W words (in_stride = 8 W); out row (64 w + b) = bit b of word w of every instance.
+__global__ void __launch_bounds__(128) k_bits_to_sliced32(const u64* __restrict__ in, u64 rows, u64 cols, u64 W,
+                                                          u8* __restrict__ out, u64 out_stride, int vec) {
+    const u64 groups = (rows + 31) / 32;
+    for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < groups * W; g += (u64)gridDim.x * blockDim.x) {
+        const u64 w = g / groups, t = g - w * groups, i0 = 32 * t;
+        u32 lo[32], hi[32];
+        if (vec && i0 + 32 <= rows) {                   // W == 1, 16-byte aligned: 16 x LDG.128 of 256 contiguous bytes
+            const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + i0);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const ulonglong2 v = p[i];
+                lo[2 * i] = (u32)v.x; hi[2 * i] = (u32)(v.x >> 32);
+                lo[2 * i + 1] = (u32)v.y; hi[2 * i + 1] = (u32)(v.y >> 32);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const u64 v = (i0 + i < rows) ? in[(i0 + i) * W + w] : 0;
+                lo[i] = (u32)v; hi[i] = (u32)(v >> 32);
+            }
+        }
+        transpose32(lo);
+        transpose32(hi);
+        u8* base = out + 4 * t;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const u64 r0 = 64 * w + b, r1 = r0 + 32;
+            if (r0 < cols) *reinterpret_cast<u32*>(base + r0 * out_stride) = lo[b];
+            if (r1 < cols) *reinterpret_cast<u32*>(base + r1 * out_stride) = hi[b];
+        }
+    }
 }
 
 constexpr int kFastInst = 2048;      // instances per CTA tile (256 threads x 8)
@@ -304,7 +359,14 @@ int launch_transpose(aby3cu_ctx* ctx, const void* in, const u32* row_index, u64 
     // fast path 1: instances x 64-bit words -> bit-sliced rows (setInput)
     if (!row_index && !invert && in_stride % 8 == 0 && in_stride <= 128 && rows > cols && cols <= in_stride * 8 &&
         out_stride % 16 == 0 && out_stride >= ((((rows + 7) / 8) + 15) & ~15ull) && al(in, 8) && al(out, 16)) {
-        const u64 W = in_stride / 8, tiles = ((rows + kFastInst - 1) / kFastInst) * W;
+        const u64 W = in_stride / 8;
+        if (!getenv("ABY3CU_TRANSPOSE8")) {
+            const u64 threads = ((rows + 31) / 32) * W, blocks = (threads + 127) / 128, capb = (u64)ctx->sm_count * 8;
+            k_bits_to_sliced32<<<(unsigned)(blocks < capb ? blocks : capb), 128, 0, ctx->stream>>>((const u64*)in, rows, cols, W, (u8*)out, out_stride,
+                                                                                                    W == 1 && al(in, 16));
+            return post_launch(ctx, "k_bits_to_sliced32");
+        }
+        const u64 tiles = ((rows + kFastInst - 1) / kFastInst) * W;
         const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
         k_bits_to_sliced<<<grid, 256, 0, ctx->stream>>>((const u64*)in, rows, cols, W, (u8*)out, out_stride);
         return post_launch(ctx, "k_bits_to_sliced");
@@ -312,7 +374,10 @@ int launch_transpose(aby3cu_ctx* ctx, const void* in, const u32* row_index, u64 
     // fast path 2: bit-sliced rows -> instances x 64-bit words (getOutput)
     if (out_stride % 8 == 0 && out_stride <= 128 && cols > rows && rows <= out_stride * 8 && in_stride % 16 == 0 &&
         in_stride >= ((((cols + 7) / 8) + 15) & ~15ull) && al(in, 16) && al(out, 8)) {
-        const u64 W = out_stride / 8, tiles = ((cols + kFastInst - 1) / kFastInst) * W;
+        // (the 32-instance register transpose does not pay off in this direction: 64 four-byte row reads per thread ran
+        // at half the rate of the shared-memory staged 8 x 8 kernel)
+        const u64 W = out_stride / 8;
+        const u64 tiles = ((cols + kFastInst - 1) / kFastInst) * W;
         const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
         k_sliced_to_bits<<<grid, 256, 0, ctx->stream>>>((const u8*)in, row_index, rows, cols, in_stride, (u64*)out, W, invert);
         return post_launch(ctx, "k_sliced_to_bits");
