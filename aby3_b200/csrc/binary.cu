@@ -213,12 +213,30 @@ __global__ void __launch_bounds__(256) k_sliced_to_bits(const u8* __restrict__ i
             for (int j = 0; j < 8; ++j) x |= (u64)sIn[8 * k + j][threadIdx.x] << (8 * j);
             blk[k] = transpose8x8(x);        // byte i = bits 8k..8k+7 of instance i
         }
+        u64 v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            u64 v = 0;
+            v[i] = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v |= ((blk[k] >> (8 * i)) & 0xFFull) << (8 * k);
-            if (i0 + i < width) out[(i0 + i) * W + w] = v;
+            for (int k = 0; k < 8; ++k) v[i] |= ((blk[k] >> (8 * i)) & 0xFFull) << (8 * k);
+        }
+        if (W == 1) {
+            // the tile's 2048 output words are contiguous: stage them through the (now free) shared tile so that a warp
+            // stores 256 contiguous bytes per instruction instead of 32 eight-byte pieces 64 bytes apart
+            __syncthreads();
+            u64* so = reinterpret_cast<u64*>(&sIn[0][0]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const u32 n = 8 * threadIdx.x + i; so[n + (n >> 5)] = v[i]; }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const u32 n = j * 256 + threadIdx.x;
+                if (c0 + n < width) out[c0 + n] = so[n + (n >> 5)];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i0 + i < width) out[(i0 + i) * W + w] = v[i];
         }
         __syncthreads();
     }
