@@ -551,6 +551,20 @@ int aby3cu_gather_rows_multi(aby3cu_ctx* ctx, int njobs, const i64* const* in, c
 
 __global__ void k_counter_add(u64* c, u64 inc) { *c += inc; }
 
+// x[r, cols-1] &= mask for every row (sbMatrix::trim, Sh3Types.h:128-160; Sh3Converter.cpp:97-106)
+__global__ void __launch_bounds__(256) k_mask_last_word(i64* __restrict__ x, u64 rows, u64 cols, u64 mask) {
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (u64)gridDim.x * blockDim.x)
+        x[r * cols + cols - 1] = (i64)((u64)x[r * cols + cols - 1] & mask);
+}
+
+int aby3cu_mask_last_word(aby3cu_ctx* ctx, i64* d_x, u64 rows, u64 cols, u64 mask) {
+    ABY3CU_REQUIRE(ctx && (d_x || !(rows * cols)), "mask_last_word: null argument");
+    if (!(rows * cols)) return 0;
+    DeviceGuard g(ctx->device);
+    k_mask_last_word<<<ew_grid(ctx, rows, 256, 8), 256, 0, ctx->stream>>>(d_x, rows, cols, mask);
+    return post_launch(ctx, "k_mask_last_word");
+}
+
 int aby3cu_counter_add(aby3cu_ctx* ctx, u64* d_counter, u64 inc) {
     ABY3CU_REQUIRE(ctx && d_counter, "counter_add: null argument");
     DeviceGuard g(ctx->device);

@@ -51,7 +51,7 @@ def _load():
     l.sh3h_share_packed.argtypes = [p, i32, i32, u64, u64, i32, p]
     l.sh3h_reveal_packed.argtypes = [p, i32, i32, p]
     l.sh3h_conv_init.argtypes = [p]
-    l.sh3h_conv_a2b.argtypes = [p, i32]
+    l.sh3h_conv_a2b.argtypes = [p, i32, u64]
     l.sh3h_conv_bit_injection.argtypes = [p, i32, i32]
     l.sh3h_conv_packed_roundtrip.argtypes = [p, i32, p, C.POINTER(u64)]
     l.sh3h_reveal.argtypes = [p, i32, i32, i32, p]
@@ -246,9 +246,10 @@ class Session:
         """Sh3Converter::init(rt, eval.mShareGen) on every party"""
         self._chk(lib.sh3h_conv_init(self.h))
 
-    def conv_a2b(self, x):
-        """Sh3Converter::toBinaryMatrix(si64Matrix): arithmetic sharing -> binary sharing (64 bits per word)"""
-        return self._id(lib.sh3h_conv_a2b(self.h, x))
+    def conv_a2b(self, x, bits=0):
+        """Sh3Converter::toBinaryMatrix(si64Matrix): arithmetic sharing -> binary sharing (64 bits per word, or a
+        pre-sized destination of `bits` bits per row)"""
+        return self._id(lib.sh3h_conv_a2b(self.h, x, int(bits)))
 
     def conv_bit_injection(self, b, two_rounds=False):
         """Sh3Converter::bitInjection: binary sharing (rows x bits) -> arithmetic sharing, one element per bit"""

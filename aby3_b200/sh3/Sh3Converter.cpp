@@ -30,12 +30,10 @@ void Sh3Converter::toBinaryMatrix(const sPackedBin& in, sbMatrix& dest) {
 }
 
 namespace {
-// keep the low bitCount % 64 bits of the last word of every row (Sh3Converter.cpp:97-106).  Only ragged bit
-// counts take this path; it goes through the host view (conversions are not on the hot path).
-void maskLastWord(gpu::Context*, eMatrix<i64>& m, u64 bitCount) {
+// keep the low bitCount % 64 bits of the last word of every row (Sh3Converter.cpp:97-106)
+void maskLastWord(gpu::Context* ctx, eMatrix<i64>& m, u64 bitCount) {
     if (bitCount % 64 == 0 || !m.size()) return;
-    const i64 mask = (i64)((1ull << (bitCount % 64)) - 1);
-    for (u64 r = 0; r < m.rows(); ++r) m(r, m.cols() - 1) &= mask;
+    gpu::check(aby3cu_mask_last_word(ctx->h(), m.devMut(), m.rows(), m.cols(), (1ull << (bitCount % 64)) - 1));
 }
 }  // namespace
 

@@ -162,9 +162,14 @@ struct sbMatrix {
     void trim() {
         const u64 rem = mBitCount % 64;
         if (!rem || !i64Cols()) return;
-        const i64 mask = (i64)((1ull << rem) - 1);
-        for (auto& s : mShares)
-            for (u64 r = 0; r < s.rows(); ++r) s(r, s.cols() - 1) &= mask;
+        const u64 mask = (1ull << rem) - 1;
+        for (auto& s : mShares) {
+            if (s.onDevice()) {
+                gpu::check(aby3cu_mask_last_word(s.ctx()->h(), s.devMut(), s.rows(), s.cols(), mask));
+            } else {
+                for (u64 r = 0; r < s.rows(); ++r) s(r, s.cols() - 1) &= (i64)mask;
+            }
+        }
     }
     bool operator==(const sbMatrix& b) const {
         if (rows() != b.rows() || bitCount() != b.bitCount()) return false;

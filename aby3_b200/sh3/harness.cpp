@@ -429,11 +429,12 @@ int sh3h_conv_init(sh3h* h) {
     return h->run([&](int i) { (void)converter(h->p[i]); });
 }
 // conv.toBinaryMatrix(rt, si64Matrix in, sbMatrix dest).get(): arithmetic -> binary, 64 bits per word
-int sh3h_conv_a2b(sh3h* h, int in_id) {
+int sh3h_conv_a2b(sh3h* h, int in_id, uint64_t bits) {
     const int id = h->next_handle++;
     int rc = h->run([&](int i) {
         Party& P = h->p[i];
         auto m = std::make_unique<sbMatrix>();
+        if (bits) m->resize(P.ints.at(in_id)->rows(), bits);        // a pre-sized destination fixes the bit count (ragged last word)
         converter(P).toBinaryMatrix(P.rt.noDependencies(), *P.ints.at(in_id), *m).get();
         // the closure completes with the last circuit round; getOutput and the state-keeping continuation hang
         // off the inner closure (Sh3BinaryEvaluator.cpp:467-473, Sh3Converter.cpp:112) and run with the queue,

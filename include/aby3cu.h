@@ -199,6 +199,9 @@ int aby3cu_gather_rows_multi(aby3cu_ctx* ctx, int njobs, const int64_t* const* d
 /* the same, replayable inside a CUDA graph: the batch is idx[*d_iter * nrows ...) (d_iter: device counter, may be NULL) */
 int aby3cu_gather_rows_multi_at(aby3cu_ctx* ctx, int njobs, const int64_t* const* d_in, const uint64_t* cols,
                                 int64_t* const* d_out, const uint64_t* d_idx, uint64_t nrows, const uint64_t* d_iter);
+/* x[r, cols-1] &= mask for every row of a rows x cols word matrix: keeps the low bitCount % 64 bits of binary shares
+ * (sbMatrix::trim, Sh3Types.h:128-160, 383-386; Sh3Converter.cpp:97-106) */
+int aby3cu_mask_last_word(aby3cu_ctx* ctx, int64_t* d_x, uint64_t rows, uint64_t cols, uint64_t mask);
 /* *d_counter += inc on the context's stream (the iteration counter of a replayed graph) */
 int aby3cu_counter_add(aby3cu_ctx* ctx, uint64_t* d_counter, uint64_t inc);
 /* ---- the small kernels of a protocol step, batched over independent problems (blockIdx.y) -------------------------

@@ -641,3 +641,17 @@ def test_overlapped_transfers_give_the_same_product(pair):
             ref = (a[i * rb:(i + 1) * rb] @ b) >> D
             assert np.max(np.abs(pc[i][1] - ref)) <= 4
     assert_cursors(s, r)
+
+
+def test_converter_ragged_bit_count_and_trim(pair):
+    """toBinaryMatrix into a destination of 91 bits per row (Sh3_convert_arithToBinaryMatrix_test: n = 43, m = 91): the
+    last word is masked on the device (aby3cu_mask_last_word); the revealed low 91 bits are the input's."""
+    s, _ = pair
+    rows, bits = 43, 91
+    x = rnd(95, (rows, 2))
+    x[:, 1] &= (1 << (bits - 64)) - 1                      # aby3::details::trim(x, m)
+    X = s.share_int(0, x)
+    Y = s.conv_a2b(X, bits=bits)
+    got = s.reveal(Y, 1, binary=True)
+    got[:, 1] &= (1 << (bits - 64)) - 1
+    assert np.array_equal(got, x)
