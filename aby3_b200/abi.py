@@ -63,6 +63,7 @@ PROTOTYPES = {
     "aby3cu_event_destroy": (_int, [_p]),
     "aby3cu_event_record": (_int, [_p, _p]),
     "aby3cu_event_wait": (_int, [_p, _p]),
+    "aby3cu_ctx_set_corun": (_int, [_p, _int]),
     "aby3cu_event_sync": (_int, [_p]),
     "aby3cu_event_elapsed_ms": (_int, [_p, _p, C.POINTER(C.c_float)]),
     "aby3cu_host_keystream": (_int, [_key, _u64, _sz, _p]),
@@ -74,6 +75,7 @@ PROTOTYPES = {
     "aby3cu_trunc_tuple_at": (_int, [_p, _key, _u64, _key, _u64, _p, _u64, _u64, _p, _p, _p, _p, _sz]),
     "aby3cu_trunc_finish": (_int, [_p, _p, _p, _p, _p, _sz, _u64]),
     "aby3cu_gemm_cross": (_int, [_p, _int, _p, _p, _p, _p, _u64, _u64, _u64, _p, _int]),
+    "aby3cu_gemm_cross_after": (_int, [_p, _int, _p, _p, _p, _p, _u64, _u64, _u64, _p, _int, _p]),
     "aby3cu_gemm_last_algo": (_int, [_p]),
     "aby3cu_gemm_last_main_kernel_ms": (_int, [_p, C.POINTER(C.c_float)]),
     "aby3cu_ot_send": (_int, [_p, _key, _u64, _p, _p, _sz]),

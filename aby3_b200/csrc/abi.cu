@@ -165,6 +165,11 @@ int aby3cu_ctx_destroy(aby3cu_ctx* ctx) {
     delete ctx;
     return 0;
 }
+int aby3cu_ctx_set_corun(aby3cu_ctx* ctx, int on) {
+    ABY3CU_REQUIRE(ctx, "ctx_set_corun: null context");
+    ctx->corun = on ? 1 : 0;
+    return 0;
+}
 int aby3cu_ctx_device(const aby3cu_ctx* ctx) { return ctx ? ctx->device : -1; }
 void* aby3cu_ctx_stream(const aby3cu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t aby3cu_launch_count(const aby3cu_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -366,7 +371,22 @@ int aby3cu_gemm_cross(aby3cu_ctx* ctx, int algo, const i64* A0, const i64* A1, c
     if (algo == ABY3CU_GEMM_AUTO) algo = gemm_tc_profitable(M, K, N) ? ABY3CU_GEMM_TCGEN05 : ABY3CU_GEMM_IMAD;
     ctx->last_gemm_algo = algo;
     if (algo == ABY3CU_GEMM_TCGEN05) return gemm_cross_tc(ctx, A0, A1, B0, B1, M, K, N, C, accumulate);
+    if (ctx->c_ready) { ABY3CU_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->c_ready, 0)); ctx->c_ready = nullptr; }
     return gemm_cross_imad(ctx, A0, A1, B0, B1, M, K, N, C, accumulate);
+}
+
+int aby3cu_gemm_cross_after(aby3cu_ctx* ctx, int algo, const i64* A0, const i64* A1, const i64* B0, const i64* B1,
+                            u64 M, u64 K, u64 N, i64* C, int accumulate, void* c_ready) {
+    ABY3CU_REQUIRE(ctx, "gemm_cross_after: null context");
+    ctx->c_ready = (cudaEvent_t)c_ready;
+    if (c_ready && (M == 0 || N == 0 || K == 0)) {
+        DeviceGuard g(ctx->device);
+        ABY3CU_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->c_ready, 0));
+        ctx->c_ready = nullptr;
+    }
+    const int rc = aby3cu_gemm_cross(ctx, algo, A0, A1, B0, B1, M, K, N, C, accumulate);
+    ctx->c_ready = nullptr;
+    return rc;
 }
 
 int aby3cu_gemm_last_algo(const aby3cu_ctx* ctx) { return ctx ? ctx->last_gemm_algo : 0; }

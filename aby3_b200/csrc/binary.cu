@@ -445,6 +445,7 @@ int aby3cu_bin_level(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void* d_m
     if (key_prev) {
         AesKey kp, kn; host_expand_key(key_prev, &kp); host_expand_key(key_next, &kn);
         ABY3CU_CHECK(cudaFuncSetAttribute(k_bin_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
+        if (prefer_max_smem(k_bin_level<true>)) return 1;
         const unsigned grid = ew_grid(ctx, chunks, 256, 3);
         k_bin_level<true><<<grid, 256, kAesTableBytes, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0, (u64*)d_mem1, rw, kp, kn, and_index0);
     } else {
@@ -463,6 +464,7 @@ int aby3cu_bin_and_layer(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void*
     DeviceGuard g(ctx->device);
     AesKey kp, kn; host_expand_key(key_prev, &kp); host_expand_key(key_next, &kn);
     ABY3CU_CHECK(cudaFuncSetAttribute(k_bin_and_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
+    if (prefer_max_smem(k_bin_and_layer)) return 1;
     const u64 chunks = row_bytes / 16;
     const u64 gx = (chunks + 255) / 256 < 32 ? (chunks + 255) / 256 : 32;
     u64 gy = ((u64)ctx->sm_count * 3 + gx - 1) / gx;

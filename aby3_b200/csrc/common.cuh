@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 #include <string>
@@ -32,6 +33,8 @@ struct aby3cu_ctx {
     int sm_count = 148;
     u64 launches = 0;
     int last_gemm_algo = 0;
+    int corun = 0;                       // aby3cu_ctx_set_corun: AES kernels of this context are shaped to fit next to a running GEMM
+    cudaEvent_t c_ready = nullptr;       // aby3cu_gemm_cross_after: waited for before the first kernel that touches C
     aby3cu::GemmWorkspace gemm_ws;   // limb planes for the tcgen05 GEMM
     cudaEvent_t ev_gemm0 = nullptr, ev_gemm1 = nullptr;   // bracket the main GEMM kernel
 };
@@ -77,6 +80,18 @@ inline int post_launch(aby3cu_ctx* ctx, const char* name) {
         return 1;
     }
     ctx->launches++;
+    return 0;
+}
+
+// Kernels that are meant to share an SM with another party's kernel (the 64 KiB T-table AES kernels next to the
+// 145 KiB tcgen05 GEMM) ask for the largest shared-memory carve-out: with the default preference the driver sizes the
+// carve-out for the kernel that got there first and the second one has to wait for the SM to drain.
+// ABY3CU_NO_CARVEOUT=1 keeps the driver's default (for A/B measurements).
+template <class K>
+inline int prefer_max_smem(K kernel) {
+    static const bool off = [] { const char* e = getenv("ABY3CU_NO_CARVEOUT"); return e && e[0] == '1'; }();
+    if (off) return 0;
+    ABY3CU_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     return 0;
 }
 

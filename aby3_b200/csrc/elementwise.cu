@@ -351,6 +351,7 @@ int upload_aes_constants() {
 template <class K>
 static int enable_big_smem(K kernel) {
     ABY3CU_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
+    if (prefer_max_smem(kernel)) return 1;
     return 0;
 }
 
@@ -427,12 +428,16 @@ static int launch_trunc(aby3cu_ctx* ctx, bool crossterm, const i64* A0, const i6
     AesKey kn = kZeroKey, kp = kZeroKey;
     if (rnd) { host_expand_key(key_next, &kn); host_expand_key(key_prev, &kp); }
     const unsigned d2 = (unsigned)d + 2;
-    const unsigned grid = ew_grid(ctx, (n + 1) / 2, kThreads, rnd ? kCtasPerSm : 8);
+    // A context marked "corun" issues work that should run UNDER another party's tcgen05 GEMM (148 CTAs x 6 warps x 224
+    // registers: two of the four register files of an SM are left with 2048 free registers, one 64-register warp).  A
+    // 256-thread CTA needs two warps per register file and is never admitted next to the GEMM; a 128-thread CTA is.
+    const unsigned threads = (rnd && ctx->corun) ? 128 : kThreads;
+    const unsigned grid = ew_grid(ctx, (n + 1) / 2, threads, rnd ? kCtasPerSm : 8);
     const size_t smem = rnd ? kAesTableBytes : 0;
 #define ABY3CU_LAUNCH_TRUNC(C, Rn)                                                                              \
     do {                                                                                                        \
         if (Rn && enable_big_smem(k_trunc<C, Rn>)) return 1;                                                    \
-        k_trunc<C, Rn><<<grid, kThreads, smem, ctx->stream>>>(A0, A1, B0, B1, kn, en, kp, ep, d2, V, R, NEGR,   \
+        k_trunc<C, Rn><<<grid, threads, smem, ctx->stream>>>(A0, A1, B0, B1, kn, en, kp, ep, d2, V, R, NEGR,    \
                                                               RT0, RT1, n, vec, iter, iter_stride);             \
     } while (0)
     if (crossterm) { if (rnd) ABY3CU_LAUNCH_TRUNC(true, true); else ABY3CU_LAUNCH_TRUNC(true, false); }

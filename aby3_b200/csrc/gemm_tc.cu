@@ -370,6 +370,7 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
     using namespace tc;
     ABY3CU_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm_cross(tcgen05): C must be 16-byte aligned");
     ABY3CU_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    if (prefer_max_smem(k_gemm_tc)) return 1;
     const u64 ntiles = (N + TN - 1) / TN;
     // bound the limb-plane workspace: B panel for one K chunk + A panel for one row block
     // (ABY3CU_WS_LIMIT_MB shrinks it so that tests can exercise the row-block loop)
@@ -402,6 +403,7 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
             p.mtiles = (u32)mtiles; p.ntiles = (u32)ntiles; p.kblocks = (u32)kblocks; p.accumulate = acc_this;
             const u64 tiles = mtiles * ntiles;
             const unsigned grid = (unsigned)(tiles < (u64)ctx->sm_count ? tiles : (u64)ctx->sm_count);
+            if (ctx->c_ready) { ABY3CU_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->c_ready, 0)); ctx->c_ready = nullptr; }   // after the limb pre-pass
             if (k0 == 0 && r0 == 0) ABY3CU_CHECK(cudaEventRecord(ctx->ev_gemm0, ctx->stream));
             k_gemm_tc<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(p);
             if (post_launch(ctx, "k_gemm_tc")) return 1;

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(kOtThreads) k_bitinj_msgs(const u64* __restric
 template <class K>
 int big_smem(K kernel) {
     ABY3CU_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
+    if (prefer_max_smem(kernel)) return 1;
     return 0;
 }
 inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

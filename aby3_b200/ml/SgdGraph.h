@@ -184,7 +184,12 @@ public:
         void* exec = nullptr;
         if (iters > 1) {
             gpu::check(aby3cu_capture_begin(c0->h()));
-            try { issue(); } catch (...) { void* dead = nullptr; aby3cu_capture_end(c0->h(), &dead); aby3cu_graph_destroy(dead); throw; }
+            for (int p = 0; p < 3; ++p) P[p].ctx->setCapturing(true);        // pool releases record no events meanwhile
+            try { issue(); } catch (...) {
+                for (int p = 0; p < 3; ++p) P[p].ctx->setCapturing(false);
+                void* dead = nullptr; aby3cu_capture_end(c0->h(), &dead); aby3cu_graph_destroy(dead); throw;
+            }
+            for (int p = 0; p < 3; ++p) P[p].ctx->setCapturing(false);
             gpu::check(aby3cu_capture_end(c0->h(), &exec));
             for (u64 i = 1; i < iters; ++i) gpu::check(aby3cu_graph_launch(c0->h(), exec, kernels));
         }

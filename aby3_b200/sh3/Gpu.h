@@ -3,6 +3,7 @@
 // host implementation behind it; without libaby3cu.so + a B200 every call throws.
 #pragma once
 #include <map>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -65,10 +66,13 @@ public:
     Context& operator=(const Context&) = delete;
     ~Context() {
         if (!mCtx) return;
+        if (mAux) aby3cu_sync(mAux->h());
         aby3cu_sync(mCtx);
+        mAux.reset();
         for (auto& kv : mFree)
             for (auto& e : kv.second) {
                 if (e.event) EventPool::put(e.eventDevice, e.event);
+                if (e.pos) EventPool::put(mDevice, e.pos);
                 aby3cu_free(mCtx, e.ptr);
             }
         aby3cu_ctx_destroy(mCtx);
@@ -76,12 +80,38 @@ public:
 
     aby3cu_ctx* h() const { return mCtx; }
     int device() const { return mDevice; }
-    void sync() { check(aby3cu_sync(mCtx)); }
+    void sync() {
+        if (mAux) check(aby3cu_sync(mAux->h()));
+        check(aby3cu_sync(mCtx));
+    }
+
+    // ---- the party's second compute stream ------------------------------------------------------------------
+    // Input-independent work of a protocol step (the truncation pair of a fixed-point product: keystream only)
+    // is issued here so that it runs under the PREVIOUS step's kernels instead of behind them.  Buffers it writes
+    // come from allocEarly(); joinAux() orders the party's own stream behind everything issued on this one.
+    Context* aux() {
+        if (!mAux) {
+            mAux.reset(new Context(mDevice));
+            check(aby3cu_ctx_set_corun(mAux->h(), 1));
+        }
+        return mAux.get();
+    }
+    bool hasAux() const { return (bool)mAux; }
+    void joinAux() {
+        if (!mAux) return;
+        void* e = mAux->recordEvent();
+        check(aby3cu_event_wait(mCtx, e));
+        mAux->recycleEvent(e);
+    }
+    // kernels launched on this context's stream and on its second stream
+    u64 launchCount() const { return aby3cu_launch_count(mCtx) + (mAux ? aby3cu_launch_count(mAux->h()) : 0); }
+    // no ordering events are recorded at release while the stream is being captured into a graph
+    void setCapturing(bool on) { mCapturing = on; }
 
     void* alloc(size_t bytes) {
         if (bytes == 0) return nullptr;
         bytes = roundSize(bytes);
-        Entry e{nullptr, nullptr, -1};
+        Entry e{nullptr, nullptr, -1, nullptr};
         {
             std::lock_guard<std::mutex> g(mMtx);
             auto it = mFree.find(bytes);
@@ -96,16 +126,45 @@ public:
                 check(aby3cu_event_wait(mCtx, e.event));
                 EventPool::put(e.eventDevice, e.event);
             }
+            if (e.pos) EventPool::put(mDevice, e.pos);       // this stream is behind its own earlier position anyway
             return e.ptr;
         }
-        void* p = nullptr;
-        if (aby3cu_malloc(mCtx, &p, bytes) != 0) {
-            // HBM is exhausted by blocks this pool keeps for reuse: hand them back and try once more
-            trim();
-            check(aby3cu_malloc(mCtx, &p, bytes));
+        return fresh(bytes);
+    }
+    // A block whose first writer runs on the aux stream.  Blocks of kEarlyMin bytes and more are parked together
+    // with the position of the party's stream at their release; the aux stream waits for that position (and for a
+    // foreign reader, if any) instead of for everything the party has enqueued since.  The OLDEST parked block is
+    // taken and the newest one is always left in place -- its last reader typically ends the step that is still
+    // executing -- so the pool settles one block above what in-order recycling would need.
+    void* allocEarly(size_t bytes) {
+        if (bytes == 0) return nullptr;
+        bytes = roundSize(bytes);
+        Entry e{nullptr, nullptr, -1, nullptr};
+        {
+            std::lock_guard<std::mutex> g(mMtx);
+            auto it = mFree.find(bytes);
+            if (it != mFree.end() && it->second.size() >= 2) {
+                e = it->second.front();
+                it->second.erase(it->second.begin());
+                mCached -= bytes;
+            }
         }
-        ++mMallocs; mMallocBytes += bytes;
-        return p;
+        if (!e.ptr) return fresh(bytes);
+        Context* a = aux();
+        if (e.event) {
+            check(aby3cu_event_wait(a->h(), e.event));
+            EventPool::put(e.eventDevice, e.event);
+        }
+        if (e.pos) {
+            check(aby3cu_event_wait(a->h(), e.pos));
+            EventPool::put(mDevice, e.pos);
+        } else {
+            // parked without a position (released under capture): order behind the whole stream
+            void* now = recordEvent();
+            check(aby3cu_event_wait(a->h(), now));
+            EventPool::put(mDevice, now);
+        }
+        return e.ptr;
     }
     // give every cached block back to the driver (between workloads with different buffer sizes)
     void trim() {
@@ -115,10 +174,12 @@ public:
             drop.swap(mFree);
             mCached = 0;
         }
+        if (mAux) aby3cu_sync(mAux->h());
         aby3cu_sync(mCtx);
         for (auto& kv : drop)
             for (auto& e : kv.second) {
                 if (e.event) { aby3cu_event_sync(e.event); EventPool::put(e.eventDevice, e.event); }
+                if (e.pos) EventPool::put(mDevice, e.pos);
                 aby3cu_free(mCtx, e.ptr);
                 ++mFrees;
             }
@@ -133,10 +194,12 @@ public:
         if (!p) return;
         bytes = roundSize(bytes);
         if (after && afterDevice < 0) afterDevice = mDevice;
+        // where this party's stream stands now: everything the party itself enqueued on the block precedes it
+        void* pos = (bytes >= kEarlyMin && !mCapturing) ? recordEvent() : nullptr;
         {
             std::lock_guard<std::mutex> g(mMtx);
             if (mCached + bytes <= kCacheCap) {
-                mFree[bytes].push_back(Entry{p, after, afterDevice});
+                mFree[bytes].push_back(Entry{p, after, afterDevice, pos});
                 mCached += bytes;
                 return;
             }
@@ -144,6 +207,7 @@ public:
         // the cache is full: give the block back to the driver (workloads whose buffer sizes keep
         // changing -- e.g. the shrinking stages of a merge network -- must not hoard HBM)
         if (after) { aby3cu_event_sync(after); EventPool::put(afterDevice, after); }
+        if (pos) EventPool::put(mDevice, pos);
         aby3cu_free(mCtx, p);
         ++mFrees;
     }
@@ -162,10 +226,24 @@ public:
         return (b + step - 1) / step * step;
     }
 
+    static constexpr size_t kEarlyMin = size_t(4) << 20;
+
 private:
-    struct Entry { void* ptr; void* event; int eventDevice; };
+    struct Entry { void* ptr; void* event; int eventDevice; void* pos; };
+    void* fresh(size_t bytes) {
+        void* p = nullptr;
+        if (aby3cu_malloc(mCtx, &p, bytes) != 0) {
+            // HBM is exhausted by blocks this pool keeps for reuse: hand them back and try once more
+            trim();
+            check(aby3cu_malloc(mCtx, &p, bytes));
+        }
+        ++mMallocs; mMallocBytes += bytes;
+        return p;
+    }
     aby3cu_ctx* mCtx = nullptr;
     int mDevice = 0;
+    std::unique_ptr<Context> mAux;
+    bool mCapturing = false;
     std::mutex mMtx;
     std::map<size_t, std::vector<Entry>> mFree;
     size_t mCached = 0;
@@ -184,11 +262,15 @@ inline Context* current() {
 }
 inline void setCurrent(Context* c) { currentSlot() = c; }
 
+struct Early {};
+
 // RAII device allocation drawn from a context's pool
 class Buffer {
 public:
     Buffer() = default;
     Buffer(Context* c, size_t bytes) { reset(c, bytes); }
+    // first written on c's aux stream (Context::allocEarly)
+    Buffer(Context* c, size_t bytes, Early) : mCtx(c), mPtr(c->allocEarly(bytes)), mBytes(bytes) {}
     Buffer(const Buffer&) = delete;
     Buffer& operator=(const Buffer&) = delete;
     Buffer(Buffer&& o) noexcept { *this = std::move(o); }
@@ -228,6 +310,7 @@ private:
 class SharedBuffer {
 public:
     SharedBuffer(Context* c, size_t bytes) : mBuf(c, bytes) {}
+    SharedBuffer(Context* c, size_t bytes, Early e) : mBuf(c, bytes, e) {}
     SharedBuffer(const SharedBuffer&) = delete;
     SharedBuffer& operator=(const SharedBuffer&) = delete;
     ~SharedBuffer() {

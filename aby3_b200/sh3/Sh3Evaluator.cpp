@@ -138,20 +138,34 @@ Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64Matrix& A, const si
         struct Scratch { std::shared_ptr<gpu::SharedBuffer> v; oc::Borrowed s0, s1; };
         auto sc = std::make_shared<Scratch>();
         const size_t bytes = std::max<size_t>(n * sizeof(i64), 16);
-        sc->v = std::make_shared<gpu::SharedBuffer>(ctx, bytes);
+        // The truncation pair depends on the common keystreams only, not on A or B.  For a matrix product big enough to
+        // matter it is produced on the party's second stream into blocks that are free EARLY (gpu::Context::allocEarly),
+        // so it runs under whatever this party and its neighbours still have in flight -- typically the contraction of
+        // the previous product -- and the party's own stream meets it just before the contraction (joinAux).
+        const bool early = mode == MulMode::Matmul && bytes >= gpu::Context::kEarlyMin && mEarlyTruncation;
+        sc->v = early ? std::make_shared<gpu::SharedBuffer>(ctx, bytes, gpu::Early{})
+                      : std::make_shared<gpu::SharedBuffer>(ctx, bytes);
         i64* V = (i64*)sc->v->ptr();
 
         // RTrunc is produced into fresh matrices and moved into C only after the
         // cross term has been enqueued, so C may alias A or B (as in the reference,
         // where C.mShares = move(RTrunc.mShares) follows the product, :673)
         eMatrix<i64> rt0(M, N), rt1(M, N);
+        if (early) {
+            rt0.adoptDevice(gpu::Buffer(ctx, bytes, gpu::Early{}));
+            rt1.adoptDevice(gpu::Buffer(ctx, bytes, gpu::Early{}));
+        }
         i64* RT0 = rt0.devOut();
         i64* RT1 = rt1.devOut();
         if (mode == MulMode::Matmul) {
             // V = -r (pre-load), then V += A0*B0 + A0*B1 + A1*B0   (:662-665, :672)
-            gpu::check(aby3cu_trunc_tuple(ctx->h(), kn, en, kp, ep, shift, nullptr, V, RT0, RT1, n));
-            gpu::check(aby3cu_gemm_cross(ctx->h(), mGemmAlgo, A.mShares[0].dev(), A.mShares[1].dev(),
-                                         B.mShares[0].dev(), B.mShares[1].dev(), M, A.cols(), N, V, 1));
+            gpu::check(aby3cu_trunc_tuple(early ? ctx->aux()->h() : ctx->h(), kn, en, kp, ep, shift, nullptr, V, RT0, RT1, n));
+            // the limb pre-pass of the operands does not wait for the pair, the contraction (which accumulates onto -r) does
+            const i64 *a0 = A.mShares[0].dev(), *a1 = A.mShares[1].dev(), *b0 = B.mShares[0].dev(), *b1 = B.mShares[1].dev();
+            void* pairDone = early ? ctx->aux()->recordEvent() : nullptr;
+            const int rc = aby3cu_gemm_cross_after(ctx->h(), mGemmAlgo, a0, a1, b0, b1, M, A.cols(), N, V, 1, pairDone);
+            if (pairDone) ctx->aux()->recycleEvent(pairDone);
+            gpu::check(rc);
         } else {
             gpu::check(aby3cu_mul_hadamard_trunc(ctx->h(), A.mShares[0].dev(), A.mShares[1].dev(), B.mShares[0].dev(),
                                                  B.mShares[1].dev(), kn, en, kp, ep, shift, V, RT0, RT1, n));

@@ -10,6 +10,7 @@
 // (this fork's loop at Sh3Evaluator.cpp:101-105 / :667-668, what aby3-Basic's
 // n x 1 vectors expect); anything else throws.
 #pragma once
+#include <cstdlib>
 #include "Sh3FixedPoint.h"
 #include "Sh3Runtime.h"
 #include "Sh3ShareGen.h"
@@ -77,6 +78,13 @@ public:
     bool DEBUG_disable_randomization = false;
     // force a GEMM algorithm (ABY3CU_GEMM_*); AUTO picks tcgen05 for dense shapes
     int mGemmAlgo = ABY3CU_GEMM_AUTO;
+    // truncation pairs of large matrix products are produced ahead on the party's second stream (Sh3Evaluator.cpp,
+    // truncating asyncMul); ABY3_EARLY_TRUNCATION=0 in the environment keeps them on the party's own stream
+    bool mEarlyTruncation = earlyTruncationDefault();
+    static bool earlyTruncationDefault() {
+        const char* e = std::getenv("ABY3_EARLY_TRUNCATION");
+        return !(e && e[0] == '0');
+    }
 
     Sh3Task asyncMul(Sh3Task dependency, const si64& A, const si64& B, si64& C);
     Sh3Task asyncMul(Sh3Task dependency, const si64Matrix& A, const si64Matrix& B, si64Matrix& C);

@@ -771,6 +771,8 @@ int sh3h_timer_begin(sh3h* h) {
     try {
         gpu::check(aby3cu_event_record(h->p[0].ctx->h(), h->p[0].ev_start));
         for (int i = 1; i < 3; ++i) gpu::check(aby3cu_event_wait(h->p[i].ctx->h(), h->p[0].ev_start));
+        // work a party issues ahead on its second stream belongs to the timed region too
+        for (int i = 0; i < 3; ++i) gpu::check(aby3cu_event_wait(h->p[i].ctx->aux()->h(), h->p[0].ev_start));
     } catch (const std::exception& e) { g_err = e.what(); return 1; }
     return 0;
 }
@@ -787,7 +789,7 @@ int sh3h_timer_end(sh3h* h, float* ms) {
 int sh3h_sync(sh3h* h) { return h->run([&](int i) { h->p[i].ctx->sync(); }); }
 uint64_t sh3h_launch_count(sh3h* h) {
     uint64_t n = 0;
-    for (int i = 0; i < 3; ++i) n += aby3cu_launch_count(h->p[i].ctx->h());
+    for (int i = 0; i < 3; ++i) n += h->p[i].ctx->launchCount();
     return n;
 }
 // return every cached device block of the parties' pools to the driver

@@ -43,6 +43,10 @@ int aby3cu_ctx_create(int device, aby3cu_ctx** out);
 /* Same, but work is enqueued on a caller-owned cudaStream_t (e.g. a torch stream). */
 int aby3cu_ctx_create_on_stream(int device, void* cuda_stream, aby3cu_ctx** out);
 int aby3cu_ctx_destroy(aby3cu_ctx* ctx);
+/* Mark a context whose work is meant to run UNDER another context's tensor-core GEMM on the same GPU (a party's
+ * second stream: the truncation pairs of the next product, Sh3Evaluator.cpp:503-566 -- input independent): its
+ * keystream kernels use CTAs small enough to be co-resident with the GEMM's. */
+int aby3cu_ctx_set_corun(aby3cu_ctx* ctx, int on);
 int aby3cu_ctx_device(const aby3cu_ctx* ctx);
 void* aby3cu_ctx_stream(const aby3cu_ctx* ctx);
 int aby3cu_sync(aby3cu_ctx* ctx);
@@ -133,6 +137,13 @@ int aby3cu_gemm_cross(aby3cu_ctx* ctx, int algo,
                       const int64_t* d_A0, const int64_t* d_A1,
                       const int64_t* d_B0, const int64_t* d_B1,
                       uint64_t M, uint64_t K, uint64_t N, int64_t* d_C, int accumulate);
+/* The same; the first kernel that touches C waits for `c_ready` (an aby3cu event, may be NULL): C was pre-loaded on
+ * another stream (-r of the truncation pair, produced ahead of the product: Sh3Evaluator.cpp:670-672), the limb
+ * pre-pass of the operands does not wait. */
+int aby3cu_gemm_cross_after(aby3cu_ctx* ctx, int algo,
+                            const int64_t* d_A0, const int64_t* d_A1,
+                            const int64_t* d_B0, const int64_t* d_B1,
+                            uint64_t M, uint64_t K, uint64_t N, int64_t* d_C, int accumulate, void* c_ready);
 /* algo actually used by the last aby3cu_gemm_cross on this context */
 int aby3cu_gemm_last_algo(const aby3cu_ctx* ctx);
 /* device time (CUDA events on the context's stream) of the main GEMM kernel of the
