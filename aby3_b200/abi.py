@@ -95,6 +95,8 @@ PROTOTYPES = {
     "aby3cu_gather_rows_multi": (_int, [_p, _int, _p, _p, _p, _p, _u64]),
     "aby3cu_gather_rows_multi_at": (_int, [_p, _int, _p, _p, _p, _p, _u64, _p]),
     "aby3cu_counter_add": (_int, [_p, _p, _u64]),
+    "aby3cu_sgd_linear_colocated_work_bytes": (_sz, [_u64]),
+    "aby3cu_sgd_linear_colocated": (_int, [_p, _p, _p, _p, _p, _u64, _u64, _u64, _u64, _u64, _p, _p, _p, _p, _p]),
     "aby3cu_mask_last_word": (_int, [_p, _p, _u64, _u64, _u64]),
     "aby3cu_trunc_tuple_batch_at": (_int, [_p, _int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _u64]),
     "aby3cu_share_op_batch": (_int, [_p, _int, _int, _p, _p, _p, _sz]),

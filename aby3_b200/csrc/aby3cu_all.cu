@@ -8,3 +8,4 @@
 #include "binary.cu"
 #include "sharedot.cu"
 #include "batched.cu"
+#include "sgd_fused.cu"

@@ -62,6 +62,7 @@ def _load():
     l.sh3h_linreg.argtypes = [p, i32, i32, i32, p, u64, u64, C.c_double]
     l.sh3h_logreg.argtypes = l.sh3h_linreg.argtypes
     l.sh3h_linreg_graph.argtypes = l.sh3h_linreg.argtypes
+    l.sh3h_linreg_fused.argtypes = l.sh3h_linreg.argtypes
     l.sh3h_bin_eval_packed.argtypes = l.sh3h_bin_eval.argtypes
     l.sh3h_timer_begin.argtypes = [p]
     l.sh3h_timer_end.argtypes = [p, C.POINTER(C.c_float)]
@@ -342,6 +343,12 @@ class Session:
         batch_idx = np.ascontiguousarray(batch_idx, dtype=np.uint64)
         assert batch_idx.size == iters * batch
         self._chk(lib.sh3h_linreg_graph(self.h, X, Y, w, _ptr(batch_idx), iters, batch, float(lr)))
+
+    def linreg_fused(self, X, Y, w, batch_idx, iters, batch, lr):
+        """SGD_Linear for co-located parties, the whole run as one persistent kernel (csrc/sgd_fused.cu); same result as linreg."""
+        batch_idx = np.ascontiguousarray(batch_idx, dtype=np.uint64)
+        assert batch_idx.size == iters * batch
+        self._chk(lib.sh3h_linreg_fused(self.h, X, Y, w, _ptr(batch_idx), iters, batch, float(lr)))
 
     def logreg(self, X, Y, w, batch_idx, iters, batch, lr):
         """aby3-ML SGD_Logistic (ml/Regression.h) on sf64<D16> shares; w is updated in place."""

@@ -207,6 +207,57 @@ public:
         c0->recycleEvent(evFork);
         return kernels;
     }
+
+    // whether runFused() takes this problem (else run() -- the graph replay -- does)
+    static bool fusedSupports(u64 B, u64 F) { return F >= 2 && F % 2 == 0 && B >= 1 && B <= 2048; }
+
+    // The same training run as ONE persistent kernel (csrc/sgd_fused.cu): the grid walks the iterations itself, two grid
+    // barriers per iteration, batch rows read straight from X.  Same arithmetic and keystream offsets as run().
+    static void runFused(std::array<PartyRef, 3> P, const RegressionParam& params, const std::vector<u64>& batchIndices) {
+        const u64 B = params.mBatchSize, iters = params.mIterations;
+        const u64 F = P[0].X->cols(), rows = P[0].X->rows();
+        if (!iters) return;
+        if (batchIndices.size() != iters * B) throw std::runtime_error(LOCATION);
+        if (!fusedSupports(B, F)) throw std::runtime_error("ColocatedSgdLinear::runFused: unsupported shape " LOCATION);
+        for (auto& p : P) {
+            if (p.ctx->device() != P[0].ctx->device()) throw std::runtime_error("ColocatedSgdLinear: the parties must share one GPU " LOCATION);
+            if (p.X->rows() != rows || p.X->cols() != F || p.Y->rows() != rows || p.Y->cols() != 1 || p.w->rows() != F || p.w->cols() != 1)
+                throw std::runtime_error(LOCATION);
+            if (p.eval->DEBUG_disable_randomization) throw std::runtime_error("ColocatedSgdLinear: randomisation must be on " LOCATION);
+        }
+        for (u64 i : batchIndices) if (i >= rows) throw std::runtime_error("ColocatedSgdLinear: batch index out of range " LOCATION);
+        const u64 aB = (u64)std::log2(1 / (params.mLearningRate / B));      // Regression.h:139
+        const u64 S = B + F;
+
+        gpu::Context* c0 = P[0].ctx;
+        gpu::Buffer dIdx(c0, std::max<size_t>(batchIndices.size() * 8, 16)), work(c0, aby3cu_sgd_linear_colocated_work_bytes(B));
+        gpu::check(aby3cu_h2d(c0->h(), dIdx.ptr(), batchIndices.data(), batchIndices.size() * 8));
+        const int64_t* X[6]; const int64_t* Y[6]; int64_t* w[6];
+        const uint8_t* kn[3]; const uint8_t* kp[3]; uint64_t en[3], ep[3];
+        block seedN[3], seedP[3];
+        for (int p = 0; p < 3; ++p) {
+            for (int s = 0; s < 2; ++s) {
+                X[2 * p + s] = (*P[p].X)[s].dev(); Y[2 * p + s] = (*P[p].Y)[s].dev(); w[2 * p + s] = (*P[p].w)[s].devMut();
+            }
+            auto& g = P[p].eval->mShareGen;
+            seedN[p] = g.mNextCommon.getSeed(); seedP[p] = g.mPrevCommon.getSeed();
+            kn[p] = seedN[p].data(); kp[p] = seedP[p].data();
+            en[p] = Sh3Evaluator::streamElem(g.mNextCommon); ep[p] = Sh3Evaluator::streamElem(g.mPrevCommon);
+        }
+        // the other parties' streams may still be producing X, Y or w: party 0's stream runs the kernel behind them
+        for (int p = 1; p < 3; ++p) {
+            void* e = P[p].ctx->recordEvent();
+            gpu::check(aby3cu_event_wait(c0->h(), e));
+            P[p].ctx->recycleEvent(e);
+        }
+        gpu::check(aby3cu_sgd_linear_colocated(c0->h(), X, Y, w, (const u64*)dIdx.ptr(), F, B, iters, D, D + aB, kn, en, kp, ep, work.ptr()));
+        c0->sync();                                                         // batchIndices may be pageable; w is final
+        for (int p = 0; p < 3; ++p) {
+            auto& g = P[p].eval->mShareGen;
+            g.mNextCommon.skip(8 * S * iters);               // what the kernel consumed
+            g.mPrevCommon.skip(8 * S * iters);
+        }
+    }
 };
 
 }  // namespace aby3

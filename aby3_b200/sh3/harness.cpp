@@ -630,6 +630,23 @@ int sh3h_linreg_graph(sh3h* h, int x_id, int y_id, int w_id, const uint64_t* bat
     } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }
 
+// The same as ONE persistent kernel for the whole run (csrc/sgd_fused.cu); shapes it does not take go to the graph.
+int sh3h_linreg_fused(sh3h* h, int x_id, int y_id, int w_id, const uint64_t* batch_idx, uint64_t iters, uint64_t batch, double lr) {
+    try {
+        std::array<ColocatedSgdLinear<D16>::PartyRef, 3> P;
+        for (int i = 0; i < 3; ++i) {
+            Party& p = h->p[i];
+            P[i] = {p.ctx.get(), &p.eval, &reinterpret_cast<sf64Matrix<D16>&>(*p.ints.at(x_id)),
+                    &reinterpret_cast<sf64Matrix<D16>&>(*p.ints.at(y_id)), &reinterpret_cast<sf64Matrix<D16>&>(*p.ints.at(w_id))};
+        }
+        RegressionParam params{iters, batch, lr};
+        std::vector<u64> idx(batch_idx, batch_idx + iters * batch);
+        if (ColocatedSgdLinear<D16>::fusedSupports(batch, P[0].X->cols())) ColocatedSgdLinear<D16>::runFused(P, params, idx);
+        else ColocatedSgdLinear<D16>::run(P, params, idx);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
 int sh3h_logreg(sh3h* h, int x_id, int y_id, int w_id, const uint64_t* batch_idx, uint64_t iters, uint64_t batch, double lr) {
     return h->run([&](int i) {
         Party& P = h->p[i];

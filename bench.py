@@ -334,9 +334,23 @@ def linreg_bench(sess, samples, features=1024, batch=128, iters=300, lr=2.0 ** -
     sess.linreg_graph(X, Y, W, gidx, giters, batch, lr)
     sess.sync()
     dt = time.perf_counter() - t0
-    out = {"iters_per_s": giters / dt, "iters": giters, "batch": batch, "features": features, "samples": samples,
-           "decimal": "D16", "lr": lr, "kernels_per_iter": (sess.launches - l0) / giters,
-           "path": "SGD_Linear, three co-located parties, one CUDA-graph launch per iteration (graph capture included in the time)",
+    graph_kernels = (sess.launches - l0) / giters
+    # (3) the whole run as ONE persistent kernel (csrc/sgd_fused.cu): the grid walks the iterations, two grid barriers per
+    # iteration; identical results (tests/test_gpu_sh3.py::test_fused_sgd_matches_facade_and_oracle)
+    fiters = 4 * giters
+    fidx = rng.integers(0, samples, fiters * batch).astype(np.uint64)
+    sess.linreg_fused(X, Y, W, fidx[:20 * batch], 20, batch, lr)   # warm-up
+    sess.sync()
+    l0 = sess.launches
+    t0 = time.perf_counter()
+    sess.linreg_fused(X, Y, W, fidx, fiters, batch, lr)
+    sess.sync()
+    dtf = time.perf_counter() - t0
+    out = {"iters_per_s": fiters / dtf, "iters": fiters, "batch": batch, "features": features, "samples": samples,
+           "decimal": "D16", "lr": lr, "kernel_launches": sess.launches - l0,
+           "path": "SGD_Linear, three co-located parties, the whole run as one persistent cooperative kernel "
+                   "(upload of the batch indices and the final sync included in the time)",
+           "graph_replay_iters_per_s": giters / dt, "graph_replay_kernels_per_iter": graph_kernels,
            "facade_loop_iters_per_s": iters / dt_loop, "facade_loop_kernel_launches_per_iter": launches_loop,
            "timing": "host wall clock around the training call, device drained at the end"}
     for h in (X, Y, W):

@@ -213,6 +213,18 @@ int aby3cu_gather_rows_multi_at(aby3cu_ctx* ctx, int njobs, const int64_t* const
 /* x[r, cols-1] &= mask for every row of a rows x cols word matrix: keeps the low bitCount % 64 bits of binary shares
  * (sbMatrix::trim, Sh3Types.h:128-160, 383-386; Sh3Converter.cpp:97-106) */
 int aby3cu_mask_last_word(aby3cu_ctx* ctx, int64_t* d_x, uint64_t rows, uint64_t cols, uint64_t mask);
+/* ---- SGD_Linear (aby3-ML/Regression.h:112-184) for three parties on ONE GPU as ONE persistent kernel --------------
+ * `iters` iterations of: XX = X[batch rows], error = mul(XX, w) - YY (shift1 = D), update = mul(XX^T, error) (shift2 =
+ * D + log2(B / lr)), w -= update -- the truncating products as in Sh3Evaluator.cpp:651-724 with the truncation pairs drawn
+ * from the common keystreams (key_next[p] / key_prev[p], first elements elem_next[p] / elem_prev[p]; an iteration consumes
+ * B + F elements of each stream: B for the first product, then F).  d_X, d_Y, d_w: [2 * party + share plane], X rows x F,
+ * Y rows x 1, w F x 1 (updated in place); d_batch_idx: iters x B row indices.  F must be even.  d_work: scratch of
+ * aby3cu_sgd_linear_colocated_work_bytes(B) bytes.  The grid is launched cooperatively (two grid barriers per iteration). */
+size_t aby3cu_sgd_linear_colocated_work_bytes(uint64_t B);
+int aby3cu_sgd_linear_colocated(aby3cu_ctx* ctx, const int64_t* const* d_X, const int64_t* const* d_Y, int64_t* const* d_w,
+                                const uint64_t* d_batch_idx, uint64_t F, uint64_t B, uint64_t iters, uint64_t shift1,
+                                uint64_t shift2, const uint8_t* const* key_next, const uint64_t* elem_next,
+                                const uint8_t* const* key_prev, const uint64_t* elem_prev, void* d_work);
 /* *d_counter += inc on the context's stream (the iteration counter of a replayed graph) */
 int aby3cu_counter_add(aby3cu_ctx* ctx, uint64_t* d_counter, uint64_t inc);
 /* ---- the small kernels of a protocol step, batched over independent problems (blockIdx.y) -------------------------

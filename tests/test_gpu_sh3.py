@@ -532,6 +532,33 @@ def test_graph_sgd_matches_facade_and_oracle(pair):
     assert_cursors(s, r)
 
 
+@pytest.mark.parametrize("N,F,B,iters", [(700, 40, 16, 37), (3000, 1024, 128, 9), (500, 6, 200, 5), (64, 258, 3, 4)])
+def test_fused_sgd_matches_facade_and_oracle(pair, N, F, B, iters):
+    """csrc/sgd_fused.cu: SGD_Linear as ONE persistent kernel (two grid barriers per iteration) gives the same w shares
+    and PRNG cursors as the oracle; further stretches through the graph replay and the facade loop continue from there."""
+    s, r = pair
+    lr, D = 2.0 ** -6, 16
+    rng = np.random.default_rng(52 + F)
+    x = rng.normal(1, 1, (N, F))
+    y = x[:, :3] @ np.array([[2.0], [-1.0], [0.5]])
+    fx, fy, fw = fixed(x, D), fixed(y, D), fixed(rng.normal(0, 1, (F, 1)), D)
+    idx = rng.integers(0, N, (iters + 5) * B).astype(np.uint64)
+    X, Y, W = s.share_int(0, fx), s.share_int(1, fy), s.share_int(2, fw)
+    Xo, Yo, Wo = r.share_int(0, fx), r.share_int(1, fy), r.share_int(2, fw)
+    launches = s.launches
+    s.linreg_fused(X, Y, W, idx[:iters * B], iters, B, lr)
+    assert s.launches - launches == 1                                  # the whole run is one kernel
+    Wo = oracle_linreg(r, Xo, Yo, Wo, idx[:iters * B], iters, B, lr, D)
+    assert np.array_equal(s.get_shares(W), Wo)
+    assert_cursors(s, r)
+    s.linreg_graph(X, Y, W, idx[iters * B:(iters + 2) * B], 2, B, lr)
+    s.linreg_fused(X, Y, W, idx[(iters + 2) * B:(iters + 4) * B], 2, B, lr)
+    s.linreg(X, Y, W, idx[(iters + 4) * B:], 1, B, lr)
+    Wo = oracle_linreg(r, Xo, Yo, Wo, idx[iters * B:], 5, B, lr, D)
+    assert np.array_equal(s.get_shares(W), Wo)
+    assert_cursors(s, r)
+
+
 @pytest.mark.parametrize("seed,width", [(0, 1), (1, 64), (2, 65), (3, 300), (4, 2049), (5, 77), (6, 100000), (7, 31)])
 def test_random_circuits_match_oracle(pair, seed, width):
     """Random circuits over every supported gate type with inverted outputs, ragged widths: device == oracle share for
