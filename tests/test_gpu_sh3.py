@@ -532,10 +532,11 @@ def test_graph_sgd_matches_facade_and_oracle(pair):
     assert_cursors(s, r)
 
 
-@pytest.mark.parametrize("N,F,B,iters", [(700, 40, 16, 37), (3000, 1024, 128, 9), (500, 6, 200, 5), (64, 258, 3, 4)])
+@pytest.mark.parametrize("N,F,B,iters", [(700, 40, 16, 37), (3000, 1024, 128, 9), (500, 6, 200, 5), (64, 258, 3, 4), (2000, 1024, 130, 3), (900, 1184, 77, 6)])
 def test_fused_sgd_matches_facade_and_oracle(pair, N, F, B, iters):
-    """csrc/sgd_fused.cu: SGD_Linear as ONE persistent kernel (two grid barriers per iteration) gives the same w shares
-    and PRNG cursors as the oracle; further stretches through the graph replay and the facade loop continue from there."""
+    """csrc/sgd_fused.cu: SGD_Linear as ONE persistent kernel gives the same w shares and PRNG cursors as the oracle; further
+    stretches through the graph replay and the facade loop continue from there.  B <= 128 and F <= 8 * SMs run the
+    feature-resident kernel (one grid barrier per iteration), the other shapes the row / slab kernel (two barriers)."""
     s, r = pair
     lr, D = 2.0 ** -6, 16
     rng = np.random.default_rng(52 + F)
