@@ -548,12 +548,16 @@ def main():
             sess.free(h)
 
     e2e_once()
+    e2e_once()          # the second pass settles the buffer pools (the first one grows them)
+    sess.sync()
     barrier()
+    pool0 = sess.pool_stats
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_once()
     sess.sync()
     e2e_single = (time.perf_counter() - t0) / e2e_steps
+    pool1 = sess.pool_stats
 
     # The same end-to-end step with the transfers overlapped: B is uploaded first, A travels as NB row blocks on the
     # owner's copy stream while the previous block is being multiplied, and each block of the result is downloaded on
@@ -649,6 +653,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": world * step_macs / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * (M * K + K * N), "d2h_bytes_per_step": 8 * M * N,
                     "ms_per_step": e2e_t * 1e3, "steps": e2e_steps, "single_call_ms_per_step": e2e_single * 1e3, "variant": e2e_path,
+                    "driver_allocations_during_single_call_steps": int(pool1[0] - pool0[0]),
                     "path": "enc.localIntMatrix(page-locked host a,b) -> eval.asyncMul(..., shift) -> enc.revealAll -> page-locked host c; "
                             "streamed variant: b first, a as %d row blocks prefetched on a copy stream, result blocks downloaded on the copy stream" % NB},
             "gpu_launches": launches,
