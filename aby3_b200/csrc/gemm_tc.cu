@@ -44,6 +44,10 @@ constexpr u32 B_CHUNK = 8 * TN * TK;      // 16384 B
 constexpr u32 STAGE_BYTES = A_CHUNK + B_CHUNK;
 constexpr u32 SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // + barriers, tmem slot, alignment slack
 constexpr int THREADS = 192;
+#ifndef ABY3CU_GEMM_BALANCED
+#define ABY3CU_GEMM_BALANCED 1
+#endif
+constexpr bool kBalancedSplit = ABY3CU_GEMM_BALANCED;
 constexpr u64 K_MAX = 8192;        // per launch, see the exactness bound above
 constexpr u32 RASTER_M = 8;        // tile rows per rasterisation group
 
@@ -259,8 +263,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
                         const int n = TN * (8 - i);
                         const u32 acc = (i == 0) ? first : 1u;
                         if (n > 256) {
-                            mma_i8(tmem + 64 * i, ad, bd0, make_idesc(256), acc);
-                            mma_i8(tmem + 64 * i + 256, ad, bd1, make_idesc(n - 256), acc);
+                            // two equal halves (256, 224, 192, 160 wide) instead of 256 + a narrow remainder
+                            const int h = (kBalancedSplit ? n / 2 : 256);
+                            mma_i8(tmem + 64 * i, ad, bd0, make_idesc(h), acc);
+                            mma_i8(tmem + 64 * i + h, ad, kBalancedSplit ? smem_desc(sb + h * 16, 8192, 128) : bd1, make_idesc(n - h), acc);
                         } else {
                             mma_i8(tmem + 64 * i, ad, bd0, make_idesc(n), acc);
                         }
