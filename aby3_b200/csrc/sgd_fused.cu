@@ -376,13 +376,6 @@ __device__ __forceinline__ void red_add(unsigned long long* p, u64 v) {
 }
 
 struct alignas(32) U64x4 { u64 v[4]; };
-// 256-bit load (sm_100: LDG.E.256): the SM tracks outstanding load INSTRUCTIONS (about 64 per SM before the issue of the
-// next one blocks), so the 48 KiB of batch pieces a CTA needs per iteration travel as 48 warp-wide loads, not 96
-__device__ __forceinline__ U64x4 ld_cg4(const u64* p) {
-    U64x4 r;
-    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3]) : "l"(p));
-    return r;
-}
 
 __global__ void __launch_bounds__(kSgdThreads, 1) k_sgd_linear_slab(const __grid_constant__ SlabParams P, const __grid_constant__ SgdKeys K) {
     u64* sm = reinterpret_cast<u64*>(aby3_smem + kAesTableWords);
@@ -390,6 +383,7 @@ __global__ void __launch_bounds__(kSgdThreads, 1) k_sgd_linear_slab(const __grid
     u64* sRed = sW + 48;                 // [8 warps][24]
     u64* sKs = sRed + 8 * 24;            // [2][24]  second truncation pair of the slab
     u64* sE = sKs + 48;                  // [6][128] e0 + e1 and e0 of the opened error, per party
+    u64* sX = sE + 6 * 128;              // [2][6][128][8] the slab's pieces of the batch: this iteration's and the next one's (cp.async)
     aes_table_init();
 
     // thread = (batch row, half of the slab): four features of one row, three parties, both planes, in registers
@@ -409,20 +403,26 @@ __global__ void __launch_bounds__(kSgdThreads, 1) k_sgd_linear_slab(const __grid
 
     auto rowIdx = [&](u64 it) -> u64 { return __ldg(P.idx + it * B + bRow); };       // multiplied by F where it is used
     u64 r1 = 0, r2 = 0;                                  // this thread's row one and two iterations ahead
-    U64x4 xa[3], xb[3], na[3], nb[3];                    // planes 0 / 1 of the current and of the next iteration
+    // The batch pieces travel global -> shared by cp.async (LDGSTS): no registers are held while they are in flight and the
+    // issuing thread does not queue behind them, so they are issued a whole barrier ahead.  A thread only ever reads the
+    // 6 x 32 bytes it copied itself: cp.async.wait_group is all the synchronisation they need.
+    auto pieces = [&](u64 rowIndex, u32 buf) {
+        const u64 off = rowIndex * F + fq;
 #pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-        for (int h = 0; h < 4; ++h) xa[p].v[h] = xb[p].v[h] = na[p].v[h] = nb[p].v[h] = 0;
-    if (rOk && P.iters) {
-        if (live) {
-            const u64 off = rowIdx(0) * F + fq;
-#pragma unroll
-            for (int p = 0; p < 3; ++p) { xa[p] = ld_cg4(P.X[p][0] + off); xb[p] = ld_cg4(P.X[p][1] + off); }
+        for (int pl = 0; pl < 6; ++pl) {
+            const u64* src = P.X[pl >> 1][pl & 1] + off;
+            const u32 dst = (u32)__cvta_generic_to_shared(sX + ((buf * 6 + pl) * 128 + bRow) * 8 + 4 * q);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 2) : "memory");
         }
+    };
+    U64x4 xa[3], xb[3];                                  // planes 0 / 1 of the current iteration
+    if (rOk && P.iters) {
+        if (live) pieces(rowIdx(0), 0);
         if (P.iters > 1) r1 = rowIdx(1);
         if (P.iters > 2) r2 = rowIdx(2);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // first truncation pair word and label of the owned row (first pass), one iteration ahead
     u64 ks = 0, yy = 0;
     auto pair1 = [&](u64 it, u64 b, u64& ks_, u64& yy_) {
@@ -438,6 +438,17 @@ __global__ void __launch_bounds__(kSgdThreads, 1) k_sgd_linear_slab(const __grid
         unsigned long long* Sit = P.S + (it % 3) * B;
         u64* Eit = P.E + (it & 1) * 6 * B;
         SLAB_STAMP(0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            if (live) {
+                xa[p] = *reinterpret_cast<const U64x4*>(sX + (((it & 1) * 6 + 2 * p) * 128 + bRow) * 8 + 4 * q);
+                xb[p] = *reinterpret_cast<const U64x4*>(sX + (((it & 1) * 6 + 2 * p + 1) * 128 + bRow) * 8 + 4 * q);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) xa[p].v[h] = xb[p].v[h] = 0;
+            }
+        }
         // ---- first product: partial over the slab, summed over the parties, one RED per row
         {
             u64 v = 0;
@@ -466,13 +477,13 @@ __global__ void __launch_bounds__(kSgdThreads, 1) k_sgd_linear_slab(const __grid
         // ---- between arrive and wait: keystream words (second pair of this slab, first pair of the owned row, next iteration)
         c_pairs(P, K, it, f0, tid, sKs);
         if (ownerT && oRow0 < B && it + 1 < P.iters) pair1(it + 1, oRow0, ks, yy);
+        if (it + 1 < P.iters && live) pieces(r1, (u32)((it + 1) & 1));          // the next iteration's batch pieces
+        asm volatile("cp.async.commit_group;" ::: "memory");
         SLAB_STAMP(4);
         grid_wait(P.bar, passed);
         SLAB_STAMP(5);
 
         // ---- open the first product: thread b < B reads row b's S and E once (coalesced, L2), the CTA shares them.
-        // These loads go out first; the loads of the next iteration's batch pieces queue up BEHIND them in the SM's load
-        // pipe and complete under the second product.
         u64 sv = 0, ev[3][2] = {{0, 0}, {0, 0}, {0, 0}};
         if (tid < B) {
             sv = __ldcg(Sit + tid);
@@ -480,12 +491,7 @@ __global__ void __launch_bounds__(kSgdThreads, 1) k_sgd_linear_slab(const __grid
             for (int p = 0; p < 3; ++p) { ev[p][0] = __ldcg(Eit + (2 * p) * B + tid); ev[p][1] = __ldcg(Eit + (2 * p + 1) * B + tid); }
         }
         SLAB_STAMP(8);
-        // ---- the next iteration's batch pieces (L2), the row index three ahead, whole rows two ahead into L2
-        if (it + 1 < P.iters && live) {
-            const u64 off = r1 * F + fq;
-#pragma unroll
-            for (int p = 0; p < 3; ++p) { na[p] = ld_cg4(P.X[p][0] + off); nb[p] = ld_cg4(P.X[p][1] + off); }
-        }
+        // ---- the row index three ahead, whole rows two ahead into L2
         if ((P.flags & 1) && it + 8 < P.iters && tid * 16 < B) prefetch_l2(P.idx + (it + 8) * B + tid * 16);     // the index lines themselves
         u64 r3 = 0;
         if (it + 3 < P.iters && rOk) r3 = rowIdx(it + 3);
@@ -544,8 +550,6 @@ __global__ void __launch_bounds__(kSgdThreads, 1) k_sgd_linear_slab(const __grid
         }
         // S of iteration it + 2 starts from zero (its last readers were released by this iteration's barrier)
         if (tid < 128) for (u64 b = (u64)blockIdx.x + (u64)tid * gridDim.x; b < B; b += 128ull * gridDim.x) P.S[((it + 2) % 3) * B + b] = 0;
-#pragma unroll
-        for (int p = 0; p < 3; ++p) { xa[p] = na[p]; xb[p] = nb[p]; }
         r1 = r2; r2 = r3;
         __syncthreads();
         SLAB_STAMP(7);
@@ -578,7 +582,7 @@ int aby3cu_sgd_linear_colocated(aby3cu_ctx* ctx, const int64_t* const* d_X, cons
     static const bool force_rows = [] { const char* e = getenv("ABY3CU_SGD_VARIANT"); return e && e[0] == 'r'; }();
     bool slab = !force_rows && B <= kSgdThreads / 2 && F % 4 == 0 && slabs <= (u64)ctx->sm_count;
     for (int i = 0; i < 6; ++i) slab = slab && (reinterpret_cast<uintptr_t>(d_X[i]) & 31) == 0;          // 256-bit loads
-    const size_t smem = slab ? (size_t)kAesTableBytes + (48 + 8 * 24 + 48 + 6 * 128) * 8 : (size_t)kAesTableBytes + (7 * B + 8 * 24 + 48) * 8;
+    const size_t smem = slab ? (size_t)kAesTableBytes + (48 + 8 * 24 + 48 + 6 * 128 + 2 * 6 * 128 * 8) * 8 : (size_t)kAesTableBytes + (7 * B + 8 * 24 + 48) * 8;
     ABY3CU_REQUIRE(smem <= 200 * 1024, "sgd_linear_colocated: batch too large for the shared-memory staging");
     SgdParams P;
     SlabParams Q;
