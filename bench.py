@@ -342,12 +342,16 @@ def linreg_bench(sess, samples, features=1024, batch=128, iters=300, lr=2.0 ** -
     sess.linreg_fused(X, Y, W, fidx[:20 * batch], 20, batch, lr)   # warm-up
     sess.sync()
     l0 = sess.launches
+    fsampler = ClockSampler(0)
+    fsampler.start()
+    fsampler.mark()
     t0 = time.perf_counter()
     sess.linreg_fused(X, Y, W, fidx, fiters, batch, lr)
     sess.sync()
     dtf = time.perf_counter() - t0
+    fclocks = fsampler.stop()
     out = {"iters_per_s": fiters / dtf, "iters": fiters, "batch": batch, "features": features, "samples": samples,
-           "decimal": "D16", "lr": lr, "kernel_launches": sess.launches - l0,
+           "decimal": "D16", "lr": lr, "kernel_launches": sess.launches - l0, "ms_total": dtf * 1e3, "clocks": fclocks,
            "path": "SGD_Linear, three co-located parties, the whole run as one persistent cooperative kernel "
                    "(upload of the batch indices and the final sync included in the time)",
            "graph_replay_iters_per_s": giters / dt, "graph_replay_kernels_per_iter": graph_kernels,

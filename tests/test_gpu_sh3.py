@@ -683,3 +683,35 @@ def test_converter_ragged_bit_count_and_trim(pair):
     got = s.reveal(Y, 1, binary=True)
     got[:, 1] &= (1 << (bits - 64)) - 1
     assert np.array_equal(got, x)
+
+
+def test_early_truncation_pair_stream_matches_oracle(pair):
+    """Products of 4 MiB and more draw their truncation pair AHEAD on the party's second stream, into pool blocks that
+    are free early (sh3/Gpu.h allocEarly, aby3cu_gemm_cross_after).  A chain of such products with the output reused,
+    freed and aliased -- the pool rotates through every case -- gives the oracle's shares, reveals and PRNG cursors."""
+    s, r = pair
+    rng = np.random.default_rng(71)
+    M, K, N, D = 768, 48, 768, 16                           # M * N * 8 = 4.5 MiB >= Context::kEarlyMin
+    a, b = fixed(rng.normal(0, 20, (M, K)), D), fixed(rng.normal(0, 20, (K, N)), D)
+    q = fixed(rng.normal(0, 1, (N, N)), D)
+    A, B, Q = s.share_int(0, a), s.share_int(1, b), s.share_int(2, q)
+    Ao, Bo, Qo = r.share_int(0, a), r.share_int(1, b), r.share_int(2, q)
+    C = s.mul(A, B, shift=D)
+    Co = r.mul_trunc(Ao, Bo, D)
+    assert np.array_equal(s.get_shares(C), Co)
+    for rep in range(4):                                    # same output handle: its old planes go back to the pool
+        s.mul(A, B, shift=D, out=C)
+        Co = r.mul_trunc(Ao, Bo, D)
+        assert np.array_equal(s.get_shares(C), Co), rep
+    E = s.mul(C, Q, shift=D)                                # a product of a product (M x N) * (N x N)
+    Eo = r.mul_trunc(Co, Qo, D)
+    assert np.array_equal(s.get_shares(E), Eo)
+    s.mul(E, Q, shift=D, out=E)                             # output aliases an operand
+    Eo = r.mul_trunc(Eo, Qo, D)
+    assert np.array_equal(s.get_shares(E), Eo)
+    s.free(C)
+    F = s.mul(A, B, shift=D)                                # after a free: blocks parked with their release position
+    assert np.array_equal(s.get_shares(F), r.mul_trunc(Ao, Bo, D))
+    ref = (a @ b) >> D
+    assert np.max(np.abs(s.reveal(F, 0) - ref)) <= 4
+    assert_cursors(s, r)
