@@ -122,17 +122,25 @@ __device__ __forceinline__ u32 limb4(const u64* v, int limb) {
 // A chunk (mt, kb): [limb 8][kc 2][row-group 16][row 8][16 B]; one thread = one
 // row x 16 k: reads 128 contiguous bytes, writes 8 x 16 bytes.
 __global__ void __launch_bounds__(256) k_pack_a(const u64* __restrict__ A0, const u64* __restrict__ A1,
-                                                u64 row0, u64 rows, u64 M, u64 K, u64 k0, u64 kblocks_half, u8* __restrict__ out) {
+                                                u64 row0, u64 rows, u64 M, u64 K, u64 k0, u64 kblocks_half, u8* __restrict__ out, int vec) {
     const u64 kb = blockIdx.x, mt = blockIdx.y;          // kb over both halves
     const int r = threadIdx.x & 127, kc = threadIdx.x >> 7;
     const u64* A = (kb < kblocks_half) ? A0 : A1;
     const u64 kbase = k0 + (kb % kblocks_half) * TK + kc * 16;
     const u64 m = row0 + mt * TM + r;
     u64 v[16];
+    if (vec && m < row0 + rows && m < M && kbase + 16 <= K) {
+        // the thread's 128 bytes as four 256-bit loads (a warp touches 32 rows: 128 line wavefronts instead of 512)
+        const u64* src = A + m * K + kbase;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const u64 k = kbase + j;
-        v[j] = (m < row0 + rows && m < M && k < K) ? A[m * K + k] : 0;
+        for (int j = 0; j < 16; j += 4)
+            asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v[j]), "=l"(v[j + 1]), "=l"(v[j + 2]), "=l"(v[j + 3]) : "l"(src + j));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const u64 k = kbase + j;
+            v[j] = (m < row0 + rows && m < M && k < K) ? A[m * K + k] : 0;
+        }
     }
     u8* chunk = out + (mt * (2 * kblocks_half) + kb) * A_CHUNK + kc * 2048 + (r >> 3) * 128 + (r & 7) * 16;
 #pragma unroll
@@ -385,6 +393,8 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
         const long mb = atol(e);
         if (mb > 0) WS_A_LIMIT = (size_t)mb << 20;
     }
+    // 256-bit loads of A need 32-byte aligned rows
+    const int vec_a = ((reinterpret_cast<uintptr_t>(A0) | reinterpret_cast<uintptr_t>(A1)) & 31) == 0 && K % 4 == 0;
     for (u64 k0 = 0; k0 < K; k0 += K_MAX) {
         const u64 kc = (K - k0 < K_MAX) ? (K - k0) : K_MAX;
         const u64 kbh = (kc + TK - 1) / TK, kblocks = 2 * kbh;
@@ -402,7 +412,7 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
         for (u64 r0 = 0; r0 < M; r0 += rows_per_block) {
             const u64 rows = (M - r0 < rows_per_block) ? (M - r0) : rows_per_block;
             const u64 mtiles = (rows + TM - 1) / TM;
-            k_pack_a<<<dim3((unsigned)kblocks, (unsigned)mtiles), 256, 0, ctx->stream>>>((const u64*)A0, (const u64*)A1, r0, rows, M, K, k0, kbh, pa);
+            k_pack_a<<<dim3((unsigned)kblocks, (unsigned)mtiles), 256, 0, ctx->stream>>>((const u64*)A0, (const u64*)A1, r0, rows, M, K, k0, kbh, pa, vec_a);
             if (post_launch(ctx, "k_pack_a")) return 1;
             Params p;
             p.pa = pa; p.pb = pb; p.C = (u64*)C; p.row0 = r0; p.rows_end = r0 + rows; p.N = N;
