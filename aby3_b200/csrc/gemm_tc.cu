@@ -120,35 +120,40 @@ __device__ __forceinline__ u32 limb4(const u64* v, int limb) {
     return __byte_perm(t01, t23, 0x5410);
 }
 // A chunk (mt, kb): [limb 8][kc 2][row-group 16][row 8][16 B]; one thread = one
-// row x 16 k: reads 128 contiguous bytes, writes 8 x 16 bytes.
-__global__ void __launch_bounds__(256) k_pack_a(const u64* __restrict__ A0, const u64* __restrict__ A1,
+// row x 2 x 16 k: reads 2 x 128 contiguous bytes, writes 2 x 8 x 16 bytes.
+__global__ void __launch_bounds__(128) k_pack_a(const u64* __restrict__ A0, const u64* __restrict__ A1,
                                                 u64 row0, u64 rows, u64 M, u64 K, u64 k0, u64 kblocks_half, u8* __restrict__ out, int vec) {
+    // 128-thread CTAs (one warp per register file, 48 registers): admitted next to a running GEMM CTA of another party,
+    // where this HBM-bound pass costs the tensor pipe nothing
     const u64 kb = blockIdx.x, mt = blockIdx.y;          // kb over both halves
-    const int r = threadIdx.x & 127, kc = threadIdx.x >> 7;
+    const int r = threadIdx.x;
     const u64* A = (kb < kblocks_half) ? A0 : A1;
-    const u64 kbase = k0 + (kb % kblocks_half) * TK + kc * 16;
     const u64 m = row0 + mt * TM + r;
-    u64 v[16];
-    if (vec && m < row0 + rows && m < M && kbase + 16 <= K) {
-        // the thread's 128 bytes as four 256-bit loads (a warp touches 32 rows: 128 line wavefronts instead of 512)
-        const u64* src = A + m * K + kbase;
+#pragma unroll 1
+    for (int kc = 0; kc < 2; ++kc) {
+        const u64 kbase = k0 + (kb % kblocks_half) * TK + kc * 16;
+        u64 v[16];
+        if (vec && m < row0 + rows && m < M && kbase + 16 <= K) {
+            // the thread's 128 bytes as four 256-bit loads (a warp touches 32 rows: 128 line wavefronts instead of 512)
+            const u64* src = A + m * K + kbase;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-            asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v[j]), "=l"(v[j + 1]), "=l"(v[j + 2]), "=l"(v[j + 3]) : "l"(src + j));
-    } else {
+            for (int j = 0; j < 16; j += 4)
+                asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v[j]), "=l"(v[j + 1]), "=l"(v[j + 2]), "=l"(v[j + 3]) : "l"(src + j));
+        } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const u64 k = kbase + j;
-            v[j] = (m < row0 + rows && m < M && k < K) ? A[m * K + k] : 0;
+            for (int j = 0; j < 16; ++j) {
+                const u64 k = kbase + j;
+                v[j] = (m < row0 + rows && m < M && k < K) ? A[m * K + k] : 0;
+            }
         }
-    }
-    u8* chunk = out + (mt * (2 * kblocks_half) + kb) * A_CHUNK + kc * 2048 + (r >> 3) * 128 + (r & 7) * 16;
+        u8* chunk = out + (mt * (2 * kblocks_half) + kb) * A_CHUNK + kc * 2048 + (r >> 3) * 128 + (r & 7) * 16;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        u32 w[4];
+        for (int i = 0; i < 8; ++i) {
+            u32 w[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) w[q] = limb4(v + 4 * q, i);
-        *reinterpret_cast<uint4*>(chunk + i * 4096) = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int q = 0; q < 4; ++q) w[q] = limb4(v + 4 * q, i);
+            *reinterpret_cast<uint4*>(chunk + i * 4096) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
 }
 
@@ -385,6 +390,8 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
     ABY3CU_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm_cross(tcgen05): C must be 16-byte aligned");
     ABY3CU_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     if (prefer_max_smem(k_gemm_tc)) return 1;
+    // the limb pre-pass of ANOTHER party is meant to run beside a GEMM CTA: same carve-out, or the SM has to drain first
+    if (prefer_max_smem(k_pack_a) || prefer_max_smem(k_pack_b)) return 1;
     const u64 ntiles = (N + TN - 1) / TN;
     // bound the limb-plane workspace: B panel for one K chunk + A panel for one row block
     // (ABY3CU_WS_LIMIT_MB shrinks it so that tests can exercise the row-block loop)
@@ -412,7 +419,7 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
         for (u64 r0 = 0; r0 < M; r0 += rows_per_block) {
             const u64 rows = (M - r0 < rows_per_block) ? (M - r0) : rows_per_block;
             const u64 mtiles = (rows + TM - 1) / TM;
-            k_pack_a<<<dim3((unsigned)kblocks, (unsigned)mtiles), 256, 0, ctx->stream>>>((const u64*)A0, (const u64*)A1, r0, rows, M, K, k0, kbh, pa, vec_a);
+            k_pack_a<<<dim3((unsigned)kblocks, (unsigned)mtiles), 128, 0, ctx->stream>>>((const u64*)A0, (const u64*)A1, r0, rows, M, K, k0, kbh, pa, vec_a);
             if (post_launch(ctx, "k_pack_a")) return 1;
             Params p;
             p.pa = pa; p.pb = pb; p.C = (u64*)C; p.row0 = r0; p.rows_end = r0 + rows; p.N = N;
