@@ -2,6 +2,8 @@
 // C ABI (include/aby3cu.h) with a small stream-ordered buffer pool.  There is no
 // host implementation behind it; without libaby3cu.so + a B200 every call throws.
 #pragma once
+#include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -195,7 +197,7 @@ public:
         bytes = roundSize(bytes);
         if (after && afterDevice < 0) afterDevice = mDevice;
         // where this party's stream stands now: everything the party itself enqueued on the block precedes it
-        void* pos = (bytes >= kEarlyMin && !mCapturing) ? recordEvent() : nullptr;
+        void* pos = (bytes >= kEarlyMin && !mCapturing && earlyEnabled()) ? recordEvent() : nullptr;
         {
             std::lock_guard<std::mutex> g(mMtx);
             if (mCached + bytes <= kCacheCap) {
@@ -227,6 +229,11 @@ public:
     }
 
     static constexpr size_t kEarlyMin = size_t(4) << 20;
+    // ABY3_EARLY_TRUNCATION=0: nothing is issued ahead on the second stream, so releases record no positions either
+    static bool earlyEnabled() {
+        static const bool on = [] { const char* e = std::getenv("ABY3_EARLY_TRUNCATION"); return !(e && e[0] == '0'); }();
+        return on;
+    }
 
 private:
     struct Entry { void* ptr; void* event; int eventDevice; void* pos; };
