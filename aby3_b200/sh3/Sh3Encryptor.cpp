@@ -47,8 +47,16 @@ Sh3Task Sh3Encryptor::remoteBinary(Sh3Task dep, sb64& dest) { return localBinary
 std::future<void> Sh3Encryptor::shareMatrix(CommPkg& comm, const i64Matrix* m, eMatrix<i64>& x0, eMatrix<i64>& x1, bool binary) {
     gpu::Context* ctx = gpu::current();
     const u64 n = x0.size();
-    const i64* addend = m ? m->dev() : nullptr;
-    mShareGen.getShares(ctx, addend, x0.devOut(), n, binary);        // Sh3Encryptor.cpp:222-223 / 258-259 / 303-304
+    if (m && m->prefetchPending() && n * sizeof(i64) >= (size_t(1) << 20)) {
+        // the plaintext is still on its way (eMatrix::prefetchDevice on a copy stream): the zero share -- keystream only --
+        // is drawn first and the plaintext added once it has arrived, instead of the fused kernel waiting for the upload
+        mShareGen.getShares(ctx, nullptr, x0.devOut(), n, binary);
+        const i64* addend = m->dev();                                 // orders this party's stream behind the upload
+        gpu::check(aby3cu_share_op(ctx->h(), binary ? ABY3CU_OP_XOR : ABY3CU_OP_ADD, x0.dev(), addend, x0.devMut(), n));
+    } else {
+        const i64* addend = m ? m->dev() : nullptr;
+        mShareGen.getShares(ctx, addend, x0.devOut(), n, binary);    // Sh3Encryptor.cpp:222-223 / 258-259 / 303-304
+    }
     comm.mNext.asyncSendDevice(x0.dev(), n * sizeof(i64));
     x1.resizeLike(x0);
     return comm.mPrev.asyncRecvDevice(x1.devOut(), n * sizeof(i64));

@@ -89,6 +89,8 @@ public:
         mDevValid = true; mHostValid = false;
     }
     gpu::Context* ctx() const { return mDev.ctx() ? mDev.ctx() : gpu::current(); }
+    // an upload started by prefetchDevice() that no stream has been ordered behind yet
+    bool prefetchPending() const { return mDevReady != nullptr; }
 
     // ---------------------------------------------- overlapped transfers -----
     // Upload the host copy on ANOTHER context's stream (a copy stream), so that it overlaps the kernels queued on the

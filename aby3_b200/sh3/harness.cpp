@@ -69,7 +69,8 @@ struct Worker {
 
 struct Party {
     std::unique_ptr<gpu::Context> ctx;
-    std::unique_ptr<gpu::Context> copy;      // second stream of the party: overlapped h2d / d2h of plaintext matrices
+    std::unique_ptr<gpu::Context> copy;      // upload stream of the party: overlapped h2d of plaintext matrices
+    std::unique_ptr<gpu::Context> copyOut;   // download stream: PCIe is full duplex, results must not queue behind the next inputs
     CommPkg comm;
     Sh3Runtime rt;
     Sh3Encryptor enc;
@@ -186,6 +187,7 @@ void sh3h_destroy(sh3h* h) {
         Party& P = h->p[i];
         P.ints.clear(); P.bins.clear(); P.plains.clear(); P.packs.clear();
         if (P.copy) P.copy->sync();
+        if (P.copyOut) P.copyOut->sync();
         P.ctx->sync();
     });
     for (int i = 0; i < 3; ++i) {
@@ -240,6 +242,10 @@ static gpu::Context* copyCtx(Party& P) {
     if (!P.copy) P.copy.reset(new gpu::Context(P.ctx->device()));
     return P.copy.get();
 }
+static gpu::Context* copyOutCtx(Party& P) {
+    if (!P.copyOut) P.copyOut.reset(new gpu::Context(P.ctx->device()));
+    return P.copyOut.get();
+}
 // start the upload of a plaintext matrix on the owner's copy stream; a later sh3h_share waits for it on the device
 int sh3h_plain_prefetch(sh3h* h, int owner, int id) {
     return h->run([&](int i) { if (i == owner) h->p[i].plains.at(id)->prefetchDevice(copyCtx(h->p[i])); });
@@ -252,7 +258,7 @@ int sh3h_reveal_plain_async(sh3h* h, int id, int who, int plain_id) {
         if (i == who) {
             i64Matrix& dest = *P.plains.at(plain_id);
             P.enc.revealAll(P.comm, *P.ints.at(id), dest);
-            dest.fetchHostAsync(copyCtx(P));
+            dest.fetchHostAsync(copyOutCtx(P));
         } else {
             i64Matrix dest;
             P.enc.revealAll(P.comm, *P.ints.at(id), dest);
