@@ -577,7 +577,7 @@ def main():
     # owner's copy stream while the previous block is being multiplied, and each block of the result is downloaded on
     # the copy stream while the next block computes.  Same public calls (localIntMatrix / asyncMul / revealAll), same
     # bytes over PCIe every step.
-    NB = int(os.environ.get("ABY3_BENCH_ROW_BLOCKS", "4"))
+    NB = int(os.environ.get("ABY3_BENCH_ROW_BLOCKS", "2"))      # 2048-row blocks: 1024 tiles = 6.9 waves of 148 (4 blocks: 3.5 waves, 86% full)
     if NB < 1 or M % NB:
         NB = 1
     rb = M // NB
