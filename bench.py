@@ -287,9 +287,9 @@ def gemm_roofline(device):
     # (kind::i8 issues at twice the bf16 rate); the nominal dense int8 figure is 4500 TOP/s
     peak = max(int8 or 0.0, twice_bf16)
     return {"bound": "tensor", "kernel": "k_gemm_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": 2.69e9, "traffic_source": "profiles/r1_gemm_tc_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full", "ms_per_launch": ms,
+            "traffic": 2.65e9, "traffic_source": "profiles/r1_gemm_tc_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full", "ms_per_launch": ms,
             "peak_cublaslt_int8_8192": int8, "peak_twice_measured_bf16": twice_bf16, "frac_of_nominal_4500": achieved / 4500.0,
-            "tensor_pipe_active_pct_ncu": 88.1,
+            "tensor_pipe_active_pct_ncu": 91.5,
             "note": "int8 TOP/s (144*M*N*K ops per launch); frac is of %s: peak = max(cuBLASLt int8 GEMM measured live on this GPU, 2 x the %s dense "
                     "bf16 rate of MEASURED_PEAKS.json -- kind::i8 issues at twice the bf16 rate); a library GEMM as denominator lets a good kernel read a little above 1"
                     % (("measured", "measured") if bf16 else ("fallback", "fallback"))}
@@ -659,7 +659,7 @@ def main():
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
             "config": {"workload": "sf64<D16> 3PC matmul+truncation %dx%dx%d per GPU (BASELINE configs[1]); three parties co-located on each GPU" % (M, K, N),
-                       "global_rows": M * world, "gemm": "tcgen05 u8-limb (kind::i8), 128x64 tiles, 12 MMA per 32-deep k-step",
+                       "global_rows": M * world, "gemm": "tcgen05 u8-limb (kind::i8), 128x64 tiles, 12 MMA per 32-deep k-step (wide limbs split in equal halves)",
                        "l2": "inputs larger than L2 (per party 4 x %d MiB share planes + %d MiB limb planes)" % (8 * M * K >> 20, 2 * 16 * M * K >> 20),
                        "timing": "CUDA events across the three party streams (fork/join on one start and one end event), max over ranks",
                        "executed_u64_mac_per_s": 6.0 * value, "max_abs_err_ulp_vs_plain": max_err, "cpu_affinity": numa},
