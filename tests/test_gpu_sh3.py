@@ -532,7 +532,8 @@ def test_graph_sgd_matches_facade_and_oracle(pair):
     assert_cursors(s, r)
 
 
-@pytest.mark.parametrize("N,F,B,iters", [(700, 40, 16, 37), (3000, 1024, 128, 9), (500, 6, 200, 5), (64, 258, 3, 4), (2000, 1024, 130, 3), (900, 1184, 77, 6)])
+@pytest.mark.parametrize("N,F,B,iters", [(700, 40, 16, 37), (3000, 1024, 128, 9), (500, 6, 200, 5), (64, 258, 3, 4), (2000, 1024, 130, 3), (900, 1184, 77, 6),
+                                           (50, 8, 1, 3), (300, 1188, 128, 2), (4096, 4, 128, 1)])
 def test_fused_sgd_matches_facade_and_oracle(pair, N, F, B, iters):
     """csrc/sgd_fused.cu: SGD_Linear as ONE persistent kernel gives the same w shares and PRNG cursors as the oracle; further
     stretches through the graph replay and the facade loop continue from there.  B <= 128 and F <= 8 * SMs run the
