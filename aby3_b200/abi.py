@@ -64,6 +64,9 @@ PROTOTYPES = {
     "aby3cu_event_record": (_int, [_p, _p]),
     "aby3cu_event_wait": (_int, [_p, _p]),
     "aby3cu_ctx_set_corun": (_int, [_p, _int]),
+    "aby3cu_trace_begin": (_int, [_p]),
+    "aby3cu_trace_mark": (_int, [_p, C.c_char_p]),
+    "aby3cu_trace_dump": (_int, [C.c_char_p]),
     "aby3cu_event_sync": (_int, [_p]),
     "aby3cu_event_elapsed_ms": (_int, [_p, _p, C.POINTER(C.c_float)]),
     "aby3cu_host_keystream": (_int, [_key, _u64, _sz, _p]),

@@ -98,6 +98,9 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
 bool gemm_tc_profitable(u64 M, u64 K, u64 N);
 
 static int init_ctx(int device, cudaStream_t stream, bool owns, aby3cu_ctx** out) {
+    // more hardware work queues than the default 8: a party keeps four streams busy and three parties may share a GPU
+    // (read by the driver when the CUDA context is created; no effect if the host application created it already)
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -168,6 +171,42 @@ int aby3cu_ctx_destroy(aby3cu_ctx* ctx) {
 int aby3cu_ctx_set_corun(aby3cu_ctx* ctx, int on) {
     ABY3CU_REQUIRE(ctx, "ctx_set_corun: null context");
     ctx->corun = on ? 1 : 0;
+    return 0;
+}
+int aby3cu_trace_begin(aby3cu_ctx* ctx) {
+    ABY3CU_REQUIRE(ctx, "trace_begin: null context");
+    TraceState& t = trace_state();
+    if (!t.on) return 0;
+    DeviceGuard g(ctx->device);
+    std::lock_guard<std::mutex> l(t.mtx);
+    for (auto& r : t.recs) cudaEventDestroy(r.end);
+    t.recs.clear();
+    if (!t.base) ABY3CU_CHECK(cudaEventCreate(&t.base));
+    ABY3CU_CHECK(cudaEventRecord(t.base, ctx->stream));
+    return 0;
+}
+int aby3cu_trace_mark(aby3cu_ctx* ctx, const char* static_name) {
+    ABY3CU_REQUIRE(ctx && static_name, "trace_mark: null argument");
+    DeviceGuard g(ctx->device);
+    trace_mark(ctx, static_name);
+    return 0;
+}
+int aby3cu_trace_dump(const char* path) {
+    ABY3CU_REQUIRE(path, "trace_dump: null path");
+    TraceState& t = trace_state();
+    if (!t.on || !t.base) return 0;
+    ABY3CU_CHECK(cudaDeviceSynchronize());
+    FILE* f = fopen(path, "w");
+    ABY3CU_REQUIRE(f, "trace_dump: cannot open the output file");
+    std::lock_guard<std::mutex> l(t.mtx);
+    fprintf(f, "stream,kernel,end_ms\n");
+    for (auto& r : t.recs) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.base, r.end) == cudaSuccess) fprintf(f, "%p,%s,%.4f\n", (void*)r.stream, r.name, ms);
+        cudaEventDestroy(r.end);
+    }
+    t.recs.clear();
+    fclose(f);
     return 0;
 }
 int aby3cu_ctx_device(const aby3cu_ctx* ctx) { return ctx ? ctx->device : -1; }

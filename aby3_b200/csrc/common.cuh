@@ -6,7 +6,9 @@
 #include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/aby3cu.h"
 
@@ -73,6 +75,33 @@ struct DeviceGuard {
     int want = -1;
 };
 
+// ABY3CU_TRACE=1: every launch leaves an event behind it on its stream; aby3cu_trace_dump() writes "stream, kernel, ms since
+// aby3cu_trace_begin" -- the END time of every kernel on every stream of the device, enough to reconstruct how the streams of
+// the three parties interleave (there is no nsys in this image).  Off: one predictable branch per launch.
+struct TraceRec { cudaStream_t stream; const char* name; cudaEvent_t end; };
+struct TraceState {
+    bool on = false;
+    std::mutex mtx;
+    cudaEvent_t base = nullptr;
+    std::vector<TraceRec> recs;
+};
+inline TraceState& trace_state() {
+    static TraceState* t = [] { auto* s = new TraceState; const char* e = getenv("ABY3CU_TRACE"); s->on = e && e[0] == '1'; return s; }();
+    return *t;
+}
+
+// a mark on the stream BEFORE a launch: its time is when the stream became ready for the kernel (all waits satisfied)
+inline void trace_mark(aby3cu_ctx* ctx, const char* name) {
+    TraceState& t = trace_state();
+    if (t.on && t.base) {
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) == cudaSuccess && cudaEventRecord(ev, ctx->stream) == cudaSuccess) {
+            std::lock_guard<std::mutex> g(t.mtx);
+            t.recs.push_back(TraceRec{ctx->stream, name, ev});
+        }
+    }
+}
+
 inline int post_launch(aby3cu_ctx* ctx, const char* name) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -80,6 +109,14 @@ inline int post_launch(aby3cu_ctx* ctx, const char* name) {
         return 1;
     }
     ctx->launches++;
+    TraceState& t = trace_state();
+    if (t.on && t.base) {
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) == cudaSuccess && cudaEventRecord(ev, ctx->stream) == cudaSuccess) {
+            std::lock_guard<std::mutex> g(t.mtx);
+            t.recs.push_back(TraceRec{ctx->stream, name, ev});
+        }
+    }
     return 0;
 }
 

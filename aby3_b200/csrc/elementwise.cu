@@ -434,6 +434,7 @@ static int launch_trunc(aby3cu_ctx* ctx, bool crossterm, const i64* A0, const i6
     const unsigned threads = (rnd && ctx->corun) ? 128 : kThreads;
     const unsigned grid = ew_grid(ctx, (n + 1) / 2, threads, rnd ? kCtasPerSm : 8);
     const size_t smem = rnd ? kAesTableBytes : 0;
+    trace_mark(ctx, "(k_trunc ready)");
 #define ABY3CU_LAUNCH_TRUNC(C, Rn)                                                                              \
     do {                                                                                                        \
         if (Rn && enable_big_smem(k_trunc<C, Rn>)) return 1;                                                    \

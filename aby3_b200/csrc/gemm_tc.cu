@@ -428,6 +428,7 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
             const unsigned grid = (unsigned)(tiles < (u64)ctx->sm_count ? tiles : (u64)ctx->sm_count);
             if (ctx->c_ready) { ABY3CU_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->c_ready, 0)); ctx->c_ready = nullptr; }   // after the limb pre-pass
             if (k0 == 0 && r0 == 0) ABY3CU_CHECK(cudaEventRecord(ctx->ev_gemm0, ctx->stream));
+            trace_mark(ctx, "(k_gemm_tc ready)");
             k_gemm_tc<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(p);
             if (post_launch(ctx, "k_gemm_tc")) return 1;
             ABY3CU_CHECK(cudaEventRecord(ctx->ev_gemm1, ctx->stream));

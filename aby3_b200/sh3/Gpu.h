@@ -3,6 +3,7 @@
 // host implementation behind it; without libaby3cu.so + a B200 every call throws.
 #pragma once
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <memory>
@@ -73,7 +74,7 @@ public:
         mAux.reset();
         for (auto& kv : mFree)
             for (auto& e : kv.second) {
-                if (e.event) EventPool::put(e.eventDevice, e.event);
+                for (auto& ev : e.events) EventPool::put(ev.first, ev.second);
                 if (e.pos) EventPool::put(mDevice, e.pos);
                 aby3cu_free(mCtx, e.ptr);
             }
@@ -113,20 +114,20 @@ public:
     void* alloc(size_t bytes) {
         if (bytes == 0) return nullptr;
         bytes = roundSize(bytes);
-        Entry e{nullptr, nullptr, -1, nullptr};
+        Entry e{nullptr, {}, nullptr};
         {
             std::lock_guard<std::mutex> g(mMtx);
             auto it = mFree.find(bytes);
             if (it != mFree.end() && !it->second.empty()) {
-                e = it->second.back();
+                e = std::move(it->second.back());
                 it->second.pop_back();
                 mCached -= bytes;
             }
         }
         if (e.ptr) {
-            if (e.event) {
-                check(aby3cu_event_wait(mCtx, e.event));
-                EventPool::put(e.eventDevice, e.event);
+            for (auto& ev : e.events) {                      // readers on other streams: waited for only now, at reuse
+                check(aby3cu_event_wait(mCtx, ev.second));
+                EventPool::put(ev.first, ev.second);
             }
             if (e.pos) EventPool::put(mDevice, e.pos);       // this stream is behind its own earlier position anyway
             return e.ptr;
@@ -136,26 +137,29 @@ public:
     // A block whose first writer runs on the aux stream.  Blocks of kEarlyMin bytes and more are parked together
     // with the position of the party's stream at their release; the aux stream waits for that position (and for a
     // foreign reader, if any) instead of for everything the party has enqueued since.  The OLDEST parked block is
-    // taken and the newest one is always left in place -- its last reader typically ends the step that is still
-    // executing -- so the pool settles one block above what in-order recycling would need.
+    // taken and the kEarlySpare newest ones are always left in place (the newest block's last reader typically ends the
+    // step that is still executing), so the pool settles kEarlySpare blocks per size class in use above what in-order
+    // recycling would need.  (Measured with tools/step_trace.py: the pairs become ready when the step before them ends --
+    // they leave the gap between two products but do not yet run under the previous product's GEMMs; a deeper rotation,
+    // kEarlySpare = 3, did not change that.)
     void* allocEarly(size_t bytes) {
         if (bytes == 0) return nullptr;
         bytes = roundSize(bytes);
-        Entry e{nullptr, nullptr, -1, nullptr};
+        Entry e{nullptr, {}, nullptr};
         {
             std::lock_guard<std::mutex> g(mMtx);
             auto it = mFree.find(bytes);
-            if (it != mFree.end() && it->second.size() >= 2) {
-                e = it->second.front();
+            if (it != mFree.end() && it->second.size() > kEarlySpare) {
+                e = std::move(it->second.front());
                 it->second.erase(it->second.begin());
                 mCached -= bytes;
             }
         }
         if (!e.ptr) return fresh(bytes);
         Context* a = aux();
-        if (e.event) {
-            check(aby3cu_event_wait(a->h(), e.event));
-            EventPool::put(e.eventDevice, e.event);
+        for (auto& ev : e.events) {
+            check(aby3cu_event_wait(a->h(), ev.second));
+            EventPool::put(ev.first, ev.second);
         }
         if (e.pos) {
             check(aby3cu_event_wait(a->h(), e.pos));
@@ -180,7 +184,7 @@ public:
         aby3cu_sync(mCtx);
         for (auto& kv : drop)
             for (auto& e : kv.second) {
-                if (e.event) { aby3cu_event_sync(e.event); EventPool::put(e.eventDevice, e.event); }
+                for (auto& ev : e.events) { aby3cu_event_sync(ev.second); EventPool::put(ev.first, ev.second); }
                 if (e.pos) EventPool::put(mDevice, e.pos);
                 aby3cu_free(mCtx, e.ptr);
                 ++mFrees;
@@ -193,22 +197,28 @@ public:
     // `after` (may be null): a pooled event recorded on ANOTHER stream (of device `afterDevice`) that still
     // reads the buffer
     void release(void* p, size_t bytes, void* after = nullptr, int afterDevice = -1) {
-        if (!p) return;
+        std::vector<std::pair<int, void*>> readers;
+        if (after) readers.emplace_back(afterDevice < 0 ? mDevice : afterDevice, after);
+        releaseShared(p, bytes, std::move(readers));
+    }
+    // the same for a block several other streams read (SharedBuffer): their events travel with the block and are waited
+    // for when it is handed out again, not now -- the party's stream must not stall behind its neighbours' readers
+    void releaseShared(void* p, size_t bytes, std::vector<std::pair<int, void*>>&& readers) {
+        if (!p) { for (auto& ev : readers) EventPool::put(ev.first, ev.second); return; }
         bytes = roundSize(bytes);
-        if (after && afterDevice < 0) afterDevice = mDevice;
         // where this party's stream stands now: everything the party itself enqueued on the block precedes it
         void* pos = (bytes >= kEarlyMin && !mCapturing && earlyEnabled()) ? recordEvent() : nullptr;
         {
             std::lock_guard<std::mutex> g(mMtx);
             if (mCached + bytes <= kCacheCap) {
-                mFree[bytes].push_back(Entry{p, after, afterDevice, pos});
+                mFree[bytes].push_back(Entry{p, std::move(readers), pos});
                 mCached += bytes;
                 return;
             }
         }
         // the cache is full: give the block back to the driver (workloads whose buffer sizes keep
         // changing -- e.g. the shrinking stages of a merge network -- must not hoard HBM)
-        if (after) { aby3cu_event_sync(after); EventPool::put(afterDevice, after); }
+        for (auto& ev : readers) { aby3cu_event_sync(ev.second); EventPool::put(ev.first, ev.second); }
         if (pos) EventPool::put(mDevice, pos);
         aby3cu_free(mCtx, p);
         ++mFrees;
@@ -229,6 +239,7 @@ public:
     }
 
     static constexpr size_t kEarlyMin = size_t(4) << 20;
+    static constexpr size_t kEarlySpare = 1;
     // ABY3_EARLY_TRUNCATION=0: nothing is issued ahead on the second stream, so releases record no positions either
     static bool earlyEnabled() {
         static const bool on = [] { const char* e = std::getenv("ABY3_EARLY_TRUNCATION"); return !(e && e[0] == '0'); }();
@@ -236,7 +247,8 @@ public:
     }
 
 private:
-    struct Entry { void* ptr; void* event; int eventDevice; void* pos; };
+    // events: pooled events (device, event) of OTHER streams that still read the block; pos: this party's stream at release
+    struct Entry { void* ptr; std::vector<std::pair<int, void*>> events; void* pos; };
     void* fresh(size_t bytes) {
         void* p = nullptr;
         if (aby3cu_malloc(mCtx, &p, bytes) != 0) {
@@ -301,6 +313,12 @@ public:
         else if (after) aby3cu_event_destroy(after);        // no owner to hand it to
         mPtr = nullptr; mBytes = 0; mCtx = nullptr;
     }
+    // readers: (device, pooled event) pairs marking the last reads by other streams
+    void freeShared(std::vector<std::pair<int, void*>>&& readers) {
+        if (mPtr && mCtx) mCtx->releaseShared(mPtr, mBytes, std::move(readers));
+        else for (auto& ev : readers) EventPool::put(ev.first, ev.second);
+        mPtr = nullptr; mBytes = 0; mCtx = nullptr;
+    }
     void* ptr() const { return mPtr; }
     size_t bytes() const { return mBytes; }
     Context* ctx() const { return mCtx; }
@@ -312,8 +330,8 @@ private:
 };
 
 // A device buffer several parties read: the producer sends it WITHOUT a staging copy, every reader
-// reports the event after its last read, and the block returns to the producer's pool once the
-// producer's stream has been ordered behind all of them.  Contents are immutable once shared.
+// reports the event after its last read, and the block returns to the producer's pool together with
+// those events: whoever takes it next waits for them.  Contents are immutable once shared.
 class SharedBuffer {
 public:
     SharedBuffer(Context* c, size_t bytes) : mBuf(c, bytes) {}
@@ -321,12 +339,8 @@ public:
     SharedBuffer(const SharedBuffer&) = delete;
     SharedBuffer& operator=(const SharedBuffer&) = delete;
     ~SharedBuffer() {
-        Context* c = mBuf.ctx();
         std::lock_guard<std::mutex> g(mMtx);
-        for (auto& r : mReaders) {
-            if (c) aby3cu_event_wait(c->h(), r.second);
-            EventPool::put(r.first, r.second);
-        }
+        mBuf.freeShared(std::move(mReaders));        // the readers' events go to the pool with the block
     }
     void* ptr() const { return mBuf.ptr(); }
     size_t bytes() const { return mBuf.bytes(); }

@@ -26,6 +26,9 @@ import time
 
 import numpy as np
 
+# before anything creates the CUDA context (torch included): see aby3_b200/__init__.py
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 

@@ -47,6 +47,13 @@ int aby3cu_ctx_destroy(aby3cu_ctx* ctx);
  * second stream: the truncation pairs of the next product, Sh3Evaluator.cpp:503-566 -- input independent): its
  * keystream kernels use CTAs small enough to be co-resident with the GEMM's. */
 int aby3cu_ctx_set_corun(aby3cu_ctx* ctx, int on);
+/* Kernel timeline without a profiler (ABY3CU_TRACE=1 in the environment, else both are no-ops): after trace_begin every
+ * launch of the library records an event behind itself; trace_dump synchronises the device and writes
+ * "stream,kernel,end_ms" (milliseconds since trace_begin) for all of them. */
+int aby3cu_trace_begin(aby3cu_ctx* ctx);
+/* a named mark on the context's stream (the string must outlive the dump): its time is when the stream got there */
+int aby3cu_trace_mark(aby3cu_ctx* ctx, const char* static_name);
+int aby3cu_trace_dump(const char* path);
 int aby3cu_ctx_device(const aby3cu_ctx* ctx);
 void* aby3cu_ctx_stream(const aby3cu_ctx* ctx);
 int aby3cu_sync(aby3cu_ctx* ctx);
