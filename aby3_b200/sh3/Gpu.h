@@ -95,7 +95,8 @@ public:
     Context* aux() {
         if (!mAux) {
             mAux.reset(new Context(mDevice));
-            check(aby3cu_ctx_set_corun(mAux->h(), 1));
+            static const bool corun = [] { const char* e = std::getenv("ABY3_AUX_CORUN"); return !(e && e[0] == '0'); }();
+            check(aby3cu_ctx_set_corun(mAux->h(), corun ? 1 : 0));
         }
         return mAux.get();
     }
