@@ -71,6 +71,7 @@ def _load():
     l.sh3h_launch_count.argtypes = [p]
     l.sh3h_trim.argtypes = [p]
     l.sh3h_pool_stats.argtypes = [p, p]
+    l.sh3h_guard_selftest.argtypes = [p, u64, u64]
     l.sh3h_bytes_sent.restype = u64
     l.sh3h_bytes_sent.argtypes = [p]
     return l
@@ -382,6 +383,10 @@ class Session:
         a = np.zeros(3, dtype=np.uint64)
         lib.sh3h_pool_stats(self.h, _ptr(a))
         return tuple(int(x) for x in a)
+
+    def guard_selftest(self, nbytes, overrun):
+        """ABY3_POOL_GUARD=1 only: write `overrun` bytes past a pool block; 1 = the guard caught it, 0 = clean, -1 = guard off"""
+        return int(lib.sh3h_guard_selftest(self.h, int(nbytes), int(overrun)))
 
     @property
     def bytes_sent(self):

@@ -76,8 +76,11 @@ public:
             for (auto& e : kv.second) {
                 for (auto& ev : e.events) EventPool::put(ev.first, ev.second);
                 if (e.pos) EventPool::put(mDevice, e.pos);
-                aby3cu_free(mCtx, e.ptr);
+                driverFree(e.ptr, kv.first, /*noexcept*/ true);
             }
+        if (guardEnabled())
+            std::fprintf(stderr, "[pool guard] device %d: %llu block checks, %llu damaged\n", mDevice,
+                         (unsigned long long)mGuardChecks, (unsigned long long)mGuardBad);
         aby3cu_ctx_destroy(mCtx);
     }
 
@@ -131,6 +134,7 @@ public:
                 EventPool::put(ev.first, ev.second);
             }
             if (e.pos) EventPool::put(mDevice, e.pos);       // this stream is behind its own earlier position anyway
+            if (guardEnabled()) guardReuse(this, e.ptr, bytes);
             return e.ptr;
         }
         return fresh(bytes);
@@ -171,6 +175,7 @@ public:
             check(aby3cu_event_wait(a->h(), now));
             EventPool::put(mDevice, now);
         }
+        if (guardEnabled()) guardReuse(a, e.ptr, bytes);
         return e.ptr;
     }
     // give every cached block back to the driver (between workloads with different buffer sizes)
@@ -187,7 +192,7 @@ public:
             for (auto& e : kv.second) {
                 for (auto& ev : e.events) { aby3cu_event_sync(ev.second); EventPool::put(ev.first, ev.second); }
                 if (e.pos) EventPool::put(mDevice, e.pos);
-                aby3cu_free(mCtx, e.ptr);
+                driverFree(e.ptr, kv.first);
                 ++mFrees;
             }
     }
@@ -221,7 +226,8 @@ public:
         // changing -- e.g. the shrinking stages of a merge network -- must not hoard HBM)
         for (auto& ev : readers) { aby3cu_event_sync(ev.second); EventPool::put(ev.first, ev.second); }
         if (pos) EventPool::put(mDevice, pos);
-        aby3cu_free(mCtx, p);
+        if (guardEnabled()) { if (mAux) aby3cu_sync(mAux->h()); aby3cu_sync(mCtx); }
+        driverFree(p, bytes);
         ++mFrees;
     }
     // a recycled ordering event for this context's device / recorded on this context's stream
@@ -242,6 +248,10 @@ public:
     static constexpr size_t kEarlyMin = size_t(4) << 20;
     static constexpr size_t kEarlySpare = 1;
     // ABY3_EARLY_TRUNCATION=0: nothing is issued ahead on the second stream, so releases record no positions either
+    static bool guardEnabled() {
+        static const bool on = [] { const char* e = std::getenv("ABY3_POOL_GUARD"); return e && e[0] == '1'; }();
+        return on;
+    }
     static bool earlyEnabled() {
         static const bool on = [] { const char* e = std::getenv("ABY3_EARLY_TRUNCATION"); return !(e && e[0] == '0'); }();
         return on;
@@ -252,14 +262,62 @@ private:
     struct Entry { void* ptr; std::vector<std::pair<int, void*>> events; void* pos; };
     void* fresh(size_t bytes) {
         void* p = nullptr;
-        if (aby3cu_malloc(mCtx, &p, bytes) != 0) {
+        const size_t total = bytes + (guardEnabled() ? 2 * kGuard : 0);
+        if (aby3cu_malloc(mCtx, &p, total) != 0) {
             // HBM is exhausted by blocks this pool keeps for reuse: hand them back and try once more
             trim();
-            check(aby3cu_malloc(mCtx, &p, bytes));
+            check(aby3cu_malloc(mCtx, &p, total));
         }
         ++mMallocs; mMallocBytes += bytes;
+        if (guardEnabled()) {
+            check(aby3cu_memset(mCtx, p, kCanary, kGuard));
+            check(aby3cu_memset(mCtx, (char*)p + kGuard + bytes, kCanary, kGuard));
+            check(aby3cu_memset(mCtx, (char*)p + kGuard, kPoison, bytes));
+            p = (char*)p + kGuard;
+        }
         return p;
     }
+    // ---- ABY3_POOL_GUARD=1 (debug): what compute-sanitizer's memcheck / initcheck would look for, done by the pool ------
+    // (the reference's own equivalent is the poison value mCheckBlock of Sh3BinaryEvaluator.cpp:578-621).
+    // Every block carries kGuard canary bytes on both sides, verified whenever the block changes hands or goes back to
+    // the driver: a kernel writing outside its buffer trips it.  A block handed out again is first filled with a poison
+    // pattern on the stream that will write it -- AFTER the waits on every recorded reader -- so a reader the pool failed
+    // to order (the early-free path hands blocks to the second stream while other parties may still read them) sees
+    // poison instead of its data and the share-level parity tests fail.
+    void checkGuards(void* p, size_t bytes, bool quiet = false) {
+        unsigned char h[2 * kGuard];
+        if (aby3cu_d2h(mCtx, h, (char*)p - kGuard, kGuard) || aby3cu_d2h(mCtx, h + kGuard, (char*)p + bytes, kGuard) || aby3cu_sync(mCtx)) {
+            if (quiet) return;
+            check(1);
+        }
+        ++mGuardChecks;
+        for (size_t i = 0; i < 2 * kGuard; ++i)
+            if (h[i] != kCanary) {
+                ++mGuardBad;
+                char msg[160];
+                std::snprintf(msg, sizeof msg, "pool guard: %zu-byte block %p was written %s its bounds (offset %zd)", bytes, p,
+                              i < kGuard ? "BEFORE" : "PAST", i < kGuard ? (ptrdiff_t)i - (ptrdiff_t)kGuard : (ptrdiff_t)(i - kGuard));
+                std::fprintf(stderr, "%s\n", msg);
+                if (!quiet) throw std::runtime_error(msg);
+                return;
+            }
+    }
+    // `on`: the context whose stream has just been ordered behind every recorded reader of the block
+    void guardReuse(Context* on, void* p, size_t bytes) {
+        check(aby3cu_sync(on->h()));
+        checkGuards(p, bytes);
+        check(aby3cu_memset(on->h(), p, kPoison, bytes));
+    }
+    void driverFree(void* p, size_t bytes, bool quiet = false) {
+        if (guardEnabled()) {
+            checkGuards(p, bytes, quiet);
+            p = (char*)p - kGuard;
+        }
+        aby3cu_free(mCtx, p);
+    }
+    static constexpr size_t kGuard = 512;
+    static constexpr int kCanary = 0xA5, kPoison = 0xCD;
+    u64 mGuardChecks = 0, mGuardBad = 0;
     aby3cu_ctx* mCtx = nullptr;
     int mDevice = 0;
     std::unique_ptr<Context> mAux;

@@ -150,6 +150,7 @@ public:
     eMatrix& operator-=(const eMatrix& b) { return inplace(b, ABY3CU_OP_SUB); }
     eMatrix operator-() const {
         eMatrix z(mRows, mCols);
+        z.setZero();                       // explicit: a fresh matrix has no defined contents on either side
         return z - *this;
     }
     // plaintext matrix product (wrapping), used by callers for expected values
@@ -295,6 +296,10 @@ private:
             // large host copies are page-locked (gpu::HostAllocator): the upload is truly
             // asynchronous and the host copy must not be written before it has run
             self->mUploadInFlight = size() * sizeof(T) >= gpu::HostAllocator<T>::kPinThreshold;
+        } else if (size()) {
+            // never written on either side: the host path reads such a matrix as zeros (touchHost zero-fills), so the
+            // device path must too -- a recycled pool block holds someone else's old data
+            gpu::check(aby3cu_memset(mDev.ctx()->h(), mDev.ptr(), 0, size() * sizeof(T)));
         }
         self->mDevValid = true;
     }

@@ -817,6 +817,25 @@ uint64_t sh3h_launch_count(sh3h* h) {
 }
 // return every cached device block of the parties' pools to the driver
 int sh3h_trim(sh3h* h) { return h->run([&](int i) { h->p[i].ctx->trim(); }); }
+
+// ABY3_POOL_GUARD=1 self-test: party 0 takes a block from its pool, writes `overrun` bytes past its end (0 = a clean
+// block) and gives it back to the driver.  Returns 1 when the pool's guard check threw, 0 when it passed, -1 when the
+// guard mode is off.
+int sh3h_guard_selftest(sh3h* h, uint64_t bytes, uint64_t overrun) {
+    if (!gpu::Context::guardEnabled()) return -1;
+    int caught = 0;
+    h->run([&](int i) {
+        if (i != 0) return;
+        gpu::Context* c = h->p[0].ctx.get();
+        c->trim();
+        void* p = c->alloc(bytes);
+        const size_t cls = gpu::Context::roundSize(bytes);
+        gpu::check(aby3cu_memset(c->h(), p, 0x11, cls + overrun));
+        c->release(p, bytes);
+        try { c->trim(); } catch (const std::exception&) { caught = 1; }
+    });
+    return caught;
+}
 // driver allocations / frees behind the parties' buffer pools: [0] mallocs, [1] bytes, [2] frees
 void sh3h_pool_stats(sh3h* h, uint64_t out[3]) {
     out[0] = out[1] = out[2] = 0;

@@ -66,6 +66,77 @@ def test_sf64_matmul_trunc_4096_cubed_properties():
         s.close()
 
 
+def test_config1_1024_cubed_every_share_plane_bit_exact():
+    """BASELINE configs[0]: si64Matrix 1024^3 with the seeds of aby3_tests/Sh3EvaluatorTests.cpp:41-47 (the session
+    defaults) and operands drawn like its PRNG(ZeroBlock) fill (:57-63).  ALL six share planes of the product -- the
+    tcgen05 path over 128 output tiles and 2^20 zero-share elements -- against the oracle, then the truncating form."""
+    n = 1024
+    s, r = harness.Session(), o.Session()
+    try:
+        s.set_gemm_algo(abi.GEMM_TCGEN05)
+        ks = o.keystream(bytes(16), 0, 2 * n * n * 8).view(np.int64)
+        a, b = ks[:n * n].reshape(n, n).copy(), ks[n * n:].reshape(n, n).copy()
+        A, B = s.share_int(0, a), s.share_int(1, b)
+        Ao, Bo = r.share_int(0, a), r.share_int(1, b)
+        assert np.array_equal(s.get_shares(A), Ao) and np.array_equal(s.get_shares(B), Bo)
+        C = s.mul(A, B)
+        Co = r.mul(Ao, Bo, nthreads=6)
+        assert np.array_equal(s.get_shares(C), Co)
+        assert np.array_equal(s.reveal(C, 0), o.plain_mul(a, b, nthreads=4))
+        T = s.mul(A, B, shift=16)
+        assert np.array_equal(s.get_shares(T), r.mul_trunc(Ao, Bo, 16, nthreads=6))
+        for p in range(3):
+            assert list(s.cursors(p)) == list(r.cursors(p))
+    finally:
+        s.close()
+        r.close()
+
+
+@pytest.mark.parametrize("algo", [abi.GEMM_AUTO])
+def test_4096_cubed_all_six_share_planes_on_sampled_rows(algo):
+    """BASELINE configs[1] size: the input sharings in full and, on rows sampled from every 128-row tile band plus
+    the matrix edges, all six share planes of BOTH products (zero-share form and truncating form) against the oracle
+    evaluated lazily (tests/sampled_rows.py: row i needs A's row i, B, and the keystreams at element offset i * N).
+    A tile-rasterisation or keystream-offset bug anywhere in the 2048 output tiles shows up here as a share mismatch;
+    Freivalds above only sees the reconstructed value."""
+    import sampled_rows as sr
+    n, d = 4096, 16
+    s, r = harness.Session(), o.Session()
+    try:
+        s.set_gemm_algo(algo)
+        rng = np.random.default_rng(21)
+        a, b = rnd(22, (n, n)), rnd(23, (n, n))
+        A, B = s.share_int(0, a), s.share_int(2, b)
+        Ao, Bo = r.share_int(0, a), r.share_int(2, b)
+        assert np.array_equal(s.get_shares(A), Ao)
+        assert np.array_equal(s.get_shares(B), Bo)
+        rows = np.unique(np.concatenate([[0, 1, 127, 128, n - 129, n - 128, n - 1],
+                                         np.arange(32) * 128 + rng.integers(0, 128, 32)]))
+        cur = [s.cursors(p) for p in range(3)]
+        assert all(list(cur[p]) == list(r.cursors(p)) for p in range(3))
+        C = s.mul(A, B)
+        got = s.get_shares(C)
+        exp = sr.mul_rows(r, cur, Ao, Bo, rows)
+        assert np.array_equal(got[:, :, rows], exp)
+        for p in range(3):                                        # the other rows: replicated-share consistency
+            assert np.array_equal(got[(p + 1) % 3, 1], got[p, 0])
+        s.free(C)
+        # the truncating form twice: the second call starts from advanced common-keystream cursors and, with the
+        # early truncation pair, from recycled pool blocks
+        for it in range(2):
+            cur = [s.cursors(p) for p in range(3)]
+            T = s.mul(A, B, shift=d)
+            got = s.get_shares(T)
+            exp = sr.mul_trunc_rows(r, cur, Ao, Bo, d, rows)
+            assert np.array_equal(got[:, :, rows], exp), it
+            for p in range(3):
+                assert np.array_equal(got[(p + 1) % 3, 1], got[p, 0])
+            s.free(T)
+    finally:
+        s.close()
+        r.close()
+
+
 def test_binary_and_layer_2_pow_22_instances():
     """config 5 scale (bitwiseAnd(64) over millions of instances): reveal == a & b, consistency."""
     width = 1 << 22

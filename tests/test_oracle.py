@@ -274,3 +274,24 @@ def test_sh3_asyncPubArithBinMul_test():
         for p in range(3):
             assert np.array_equal(o.reveal(Cs, p).reshape(n), a * b)
             assert np.array_equal(Cs[(p + 1) % 3, 1], Cs[p, 0])
+
+
+def test_sampled_rows_helper_is_the_oracle_evaluated_lazily():
+    """tests/sampled_rows.py (used by the GPU tests at 4096^3) against the C oracle's full result at small sizes,
+    across two products each so that non-zero keystream cursors are covered."""
+    import sampled_rows as sr
+    r = o.Session()
+    rng = np.random.default_rng(0)
+    for (M, K, N) in ((37, 20, 11), (5, 3, 700)):
+        a = rng.integers(-2**63, 2**63, (M, K), dtype=np.int64)
+        b = rng.integers(-2**63, 2**63, (K, N), dtype=np.int64)
+        A, B = r.share_int(0, a), r.share_int(1, b)
+        rows = np.array([0, M - 1, M // 2, 0])
+        for _ in range(2):
+            cur = [r.cursors(p) for p in range(3)]
+            C = r.mul(A, B)
+            assert np.array_equal(sr.mul_rows(r, cur, A, B, rows), C[:, :, rows])
+            cur = [r.cursors(p) for p in range(3)]
+            C = r.mul_trunc(A, B, 16)
+            assert np.array_equal(sr.mul_trunc_rows(r, cur, A, B, 16, rows), C[:, :, rows])
+    r.close()
