@@ -41,7 +41,9 @@ def test_targets_under_pool_guard(target):
     """tools/sanitize_targets.py (every target checks its own result) with canaries + poison-on-reuse on"""
     out = _guarded([os.path.join(ROOT, "tools", "sanitize_targets.py"), target])
     assert out.returncode == 0, out.stdout[-3000:]
-    assert "[pool guard]" in out.stdout and "pool guard:" not in out.stdout, out.stdout[-3000:]
+    assert "pool guard:" not in out.stdout, out.stdout[-3000:]
+    # (the "gemm" target drives the C ABI directly: no facade pool, no summary line)
+    assert target == "gemm" or "[pool guard]" in out.stdout, out.stdout[-3000:]
     for line in out.stdout.splitlines():
         if line.startswith("[pool guard]"):
             assert line.rstrip().endswith(" 0 damaged"), line
