@@ -20,8 +20,19 @@
 #include <aby3/sh3/Sh3Piecewise.h>
 #include <aby3/sh3/Sh3Runtime.h>
 
+#include <aby3-ML/aby3ML.h>
+#include <aby3-ML/LinearModelGen.h>
+#include <aby3-ML/Regression.h>
+#include <aby3-Basic/Basics.h>
+#include <aby3-Basic/BuildingBlocks.h>
+#include <aby3-Basic/Sort.h>
+#include <cryptoTools/Common/CLP.h>
+
+#include <atomic>
 #include <chrono>
 #include <thread>
+
+int linear_main_3pc_sh(oc::CLP& cmd);        // aby3-ML/main-linear.cpp:173 (compiled unmodified)
 
 using namespace aby3;
 
@@ -405,6 +416,147 @@ double ref_time_mul_trunc(ref_session* s, uint64_t M, uint64_t K, uint64_t N, ui
         if (rc) return -1.0;
     }
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+}
+
+
+// ---- the reference's APPLICATIONS on top of its own sh3 layer (CPU baselines of BASELINE configs 3 and 5, and the
+// ---- expected values of tests/test_compat.py, where the same unmodified sources run on the B200 facade) --------------
+
+// aby3-ML/main-linear.cpp's own entry point, argv-style ("-N 1000 -D 100 -B 32 -I 50 -testN 100"): three party
+// threads, loopback sessions, LinearModelGen data, SGD_Linear; it prints its own iters/s line (main-linear.cpp:147-149).
+int ref_main_linear(int argc, const char* const* argv) {
+    try {
+        oc::CLP cmd;
+        cmd.parse(argc, argv);
+        return linear_main_3pc_sh(cmd);
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// aby3-ML linear regression exactly as main-linear.cpp:31-133 sets it up (aby3ML engine seeded toBlock(pIdx), D16,
+// lr = 2^-10, party 0 inputs everything), with the data passed in instead of LinearModelGen's, timing SGD_Linear
+// (Regression.h:112-184) alone.  x: N x F doubles, y: N doubles.  w_shares: [3][2][F] (may be null).
+// Returns seconds for `iters` iterations, < 0 on error.
+double ref_sgd_linear(const double* x, const double* y, uint64_t N, uint64_t F, uint64_t B, uint64_t iters, double lr, int64_t* w_shares) {
+    static std::atomic<int> instance{0};
+    const std::string tag = "sgd" + std::to_string(instance++);
+    oc::IOService ios;
+    std::string errs[3];
+    double secs[3] = {0, 0, 0};
+    std::thread th[3];
+    for (int i = 0; i < 3; ++i)
+        th[i] = std::thread([&, i] {
+            try {
+                const u64 next = (i + 1) % 3, prev = (i + 2) % 3;
+                auto name = [&](u64 a, u64 b) { return tag + std::to_string(std::min(a, b)) + std::to_string(std::max(a, b)); };
+                oc::Session epNext(ios, "127.0.0.1", 1212 + std::min<u64>(i, next), (u64)i < next ? oc::SessionMode::Server : oc::SessionMode::Client, name(i, next));
+                oc::Session epPrev(ios, "127.0.0.1", 1212 + std::min<u64>(i, prev), (u64)i < prev ? oc::SessionMode::Server : oc::SessionMode::Client, name(i, prev));
+                const Decimal D = D16;
+                aby3ML p;
+                p.mPrint = false;
+                p.init(i, epPrev, epNext, oc::toBlock(i));
+                sf64Matrix<D> X, Y, W;
+                if (i == 0) {
+                    eMatrix<double> vx(N, F), vy(N, 1), vw(F, 1);
+                    memcpy(vx.data(), x, N * F * sizeof(double));
+                    memcpy(vy.data(), y, N * sizeof(double));
+                    vw.setZero();
+                    X = p.localInput<D>(vx); Y = p.localInput<D>(vy); W = p.localInput<D>(vw);
+                } else {
+                    X = p.remoteInput<D>(0); Y = p.remoteInput<D>(0); W = p.remoteInput<D>(0);
+                }
+                RegressionParam params;
+                params.mBatchSize = B; params.mIterations = iters; params.mLearningRate = lr;
+                auto t0 = std::chrono::steady_clock::now();
+                SGD_Linear(params, p, X, Y, W);
+                secs[i] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                if (w_shares) storeInt(W.i64Cast(), w_shares, i);
+            } catch (const std::exception& e) { errs[i] = e.what(); } catch (...) { errs[i] = "unknown exception"; }
+        });
+    for (auto& t : th) t.join();
+    for (int i = 0; i < 3; ++i)
+        if (!errs[i].empty()) { g_err = "party " + std::to_string(i) + ": " + errs[i]; return -1.0; }
+    return std::max(secs[0], std::max(secs[1], secs[2]));
+}
+
+// aby3-Basic on binary sharings of 64-bit values (n rows): op 0 = bool_cipher_lt (BoolBasic.cpp:20-40), 1 = bool_cipher_eq,
+// 2 = bool_cipher_and, 3 = bool_cipher_or, 4 = bool_cipher_add, 5 = bool_cipher_max, 6 = bool_cipher_min.
+// A, B, out: [3][2][n] (lt / eq: out holds one bit per row in bit 0).  seconds (wall, slowest party) in *secs.
+int ref_basic_bool(ref_session* s, int op, const int64_t* A, const int64_t* B, uint64_t n, int64_t* out, double* secs) {
+    double t[3] = {0, 0, 0};
+    int rc = s->run([&](int i) {
+        RefParty& P = s->p[i];
+        sbMatrix a, b, r;
+        loadBin(a, A, i, n, 64);
+        loadBin(b, B, i, n, 64);
+        auto t0 = std::chrono::steady_clock::now();
+        switch (op) {
+        case 0: bool_cipher_lt(i, a, b, r, P.enc, P.eval, P.rt); break;
+        case 1: bool_cipher_eq(i, a, b, r, P.enc, P.eval, P.rt); break;
+        case 2: bool_cipher_and(i, a, b, r, P.enc, P.eval, P.rt); break;
+        case 3: bool_cipher_or(i, a, b, r, P.enc, P.eval, P.rt); break;
+        case 4: bool_cipher_add(i, a, b, r, P.enc, P.eval, P.rt); break;
+        case 5: bool_cipher_max(i, a, b, r, P.enc, P.eval, P.rt); break;
+        case 6: bool_cipher_min(i, a, b, r, P.enc, P.eval, P.rt); break;
+        default: throw std::runtime_error("ref_basic_bool: unknown op");
+        }
+        t[i] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (r.rows() != n) throw std::runtime_error("ref_basic_bool: unexpected result shape");
+        storeBin(r, out, i);
+    });
+    if (secs) *secs = std::max(t[0], std::max(t[1], t[2]));
+    return rc;
+}
+// cipher_gt on arithmetic sharings (BuildingBlocks.cpp:525-532: MSB of b - a); out: [3][2][n], bit 0
+int ref_basic_cipher_gt(ref_session* s, const int64_t* A, const int64_t* B, uint64_t n, int64_t* out, double* secs) {
+    double t[3] = {0, 0, 0};
+    int rc = s->run([&](int i) {
+        RefParty& P = s->p[i];
+        si64Matrix a, b;
+        sbMatrix r;
+        loadInt(a, A, i, n, 1);
+        loadInt(b, B, i, n, 1);
+        auto t0 = std::chrono::steady_clock::now();
+        cipher_gt(i, a, b, r, P.eval, P.rt);
+        t[i] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (r.rows() != n) throw std::runtime_error("ref_basic_cipher_gt: unexpected result shape");
+        storeBin(r, out, i);
+    });
+    if (secs) *secs = std::max(t[0], std::max(t[1], t[2]));
+    return rc;
+}
+// bool_cipher_max_min_split (BoolBasic.cpp:275-312); mx, mn: [3][2][n]
+int ref_basic_max_min_split(ref_session* s, const int64_t* A, const int64_t* B, uint64_t n, int64_t* mx, int64_t* mn, double* secs) {
+    double t[3] = {0, 0, 0};
+    int rc = s->run([&](int i) {
+        RefParty& P = s->p[i];
+        sbMatrix a, b, hi, lo;
+        loadBin(a, A, i, n, 64);
+        loadBin(b, B, i, n, 64);
+        auto t0 = std::chrono::steady_clock::now();
+        bool_cipher_max_min_split(i, a, b, hi, lo, P.enc, P.eval, P.rt);
+        t[i] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        storeBin(hi, mx, i);
+        storeBin(lo, mn, i);
+    });
+    if (secs) *secs = std::max(t[0], std::max(t[1], t[2]));
+    return rc;
+}
+// odd_even_merge of two sorted binary sharings (Sort.cpp:327-406); out: [3][2][n1 + n2]
+int ref_basic_odd_even_merge(ref_session* s, const int64_t* A, uint64_t n1, const int64_t* B, uint64_t n2, int64_t* out, double* secs) {
+    double t[3] = {0, 0, 0};
+    int rc = s->run([&](int i) {
+        RefParty& P = s->p[i];
+        sbMatrix a, b, r;
+        loadBin(a, A, i, n1, 64);
+        loadBin(b, B, i, n2, 64);
+        auto t0 = std::chrono::steady_clock::now();
+        odd_even_merge(a, b, r, i, P.enc, P.eval, P.rt);
+        t[i] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (r.rows() != n1 + n2) throw std::runtime_error("ref_basic_odd_even_merge: unexpected result shape");
+        storeBin(r, out, i);
+    });
+    if (secs) *secs = std::max(t[0], std::max(t[1], t[2]));
+    return rc;
 }
 
 }  // extern "C"

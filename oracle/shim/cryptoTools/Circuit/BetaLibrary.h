@@ -71,11 +71,38 @@ public:
             add_build(cd, a, b, c, t, IntType::TwosComplement, op);
         });
     }
+    // c = a - b = a + ~b + 1: the same prefix network with generate = a & ~b, propagate = a ^ ~b and the carry-in folded
+    // into bit 0 (aby3-Basic/BoolBasic.cpp:174)
+    BetaCircuit* int_int_subtract(u64 aBits, u64 bBits, u64 cBits, Optimized = Optimized::Size) {
+        return named("sub" + std::to_string(aBits) + "_" + std::to_string(bBits) + "_" + std::to_string(cBits), [&](BetaCircuit& cd) {
+            BetaBundle a(aBits), b(bBits), c(cBits);
+            cd.addInputBundle(a); cd.addInputBundle(b); cd.addOutputBundle(c);
+            const u64 n = cBits;
+            std::vector<BetaWire> g(n), p(n);
+            for (u64 i = 0; i < n; ++i) {
+                const BetaWire x = ext(cd, a, i, IntType::TwosComplement), y = ext(cd, b, i, IntType::TwosComplement);
+                cd.addTempWire(g[i]); cd.addTempWire(p[i]);
+                cd.addGate(y, x, GateType::na_And, g[i]);          // x & ~y
+                cd.addGate(x, y, GateType::Nxor, p[i]);            // x ^ ~y
+            }
+            // carry-in 1: carry out of bit 0 = g0 | p0 = g0 ^ p0 (g0 & p0 = 0); sum bit 0 = p0 ^ 1
+            std::vector<BetaWire> gg = g;
+            BetaWire g0; cd.addTempWire(g0);
+            cd.addGate(g[0], p[0], GateType::Xor, g0);
+            gg[0] = g0;
+            std::vector<BetaWire> G = prefixAll(cd, gg, p);
+            cd.addInvert(p[0], c[0]);
+            for (u64 i = 1; i < n; ++i) cd.addGate(p[i], G[i - 1], GateType::Xor, c[i]);
+        });
+    }
+    // Operand order: the only thing in the reference tree that pins it is aby3-Basic's caller, which feeds the circuit
+    // (input 0 = B, input 1 = A) for "A < B" (BoolBasic.cpp:31-32) and whose test expects bool_cipher_lt(Y, X) to reveal
+    // x > y (aby3_tests/BoolTest.cpp:68,122,283) -- i.e. the circuit answers "input 1 < input 0".
     BetaCircuit* int_int_lt(u64 aBits, u64 bBits) {
         return named("lt" + std::to_string(aBits) + "_" + std::to_string(bBits), [&](BetaCircuit& cd) {
             BetaBundle a(aBits), b(bBits), c(1);
             cd.addInputBundle(a); cd.addInputBundle(b); cd.addOutputBundle(c);
-            lessThan_build(cd, a, b, c, IntType::TwosComplement, Optimized::Depth);
+            lessThan_build(cd, b, a, c, IntType::TwosComplement, Optimized::Depth);
         });
     }
     BetaCircuit* int_eq(u64 bits) {

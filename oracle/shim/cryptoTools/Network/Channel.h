@@ -97,6 +97,14 @@ public:
     template <typename C>
     typename std::enable_if<is_container<C>::value>::type asyncSend(std::unique_ptr<C> c) { sendBytes(c->data(), c->size() * sizeof(*c->data())); }
 
+    // sends copy, so the future is ready on return (aby3-Basic/Basic.cpp:17)
+    template <typename T>
+    typename std::enable_if<std::is_pod<T>::value, std::future<void>>::type asyncSendFuture(const T* p, u64 n) {
+        sendBytes(p, n * sizeof(T));
+        std::promise<void> pr; pr.set_value();
+        return pr.get_future();
+    }
+
     // ---- receives ---------------------------------------------------------------------------
     template <typename T>
     typename std::enable_if<std::is_pod<T>::value, std::future<void>>::type asyncRecv(T* p, u64 n) {

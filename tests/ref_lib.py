@@ -58,6 +58,13 @@ def lib():
         l.ref_share_reveal_packed.argtypes = [_p, _int, _p, _u64, _u64, _p, _p]
         l.ref_time_mul_trunc.restype = C.c_double
         l.ref_time_mul_trunc.argtypes = [_p, _u64, _u64, _u64, _u64, _int]
+        l.ref_main_linear.argtypes = [_int, _p]
+        l.ref_sgd_linear.restype = C.c_double
+        l.ref_sgd_linear.argtypes = [_p, _p, _u64, _u64, _u64, _u64, C.c_double, _p]
+        l.ref_basic_bool.argtypes = [_p, _int, _p, _p, _u64, _p, _p]
+        l.ref_basic_cipher_gt.argtypes = [_p, _p, _p, _u64, _p, _p]
+        l.ref_basic_max_min_split.argtypes = [_p, _p, _p, _u64, _p, _p, _p]
+        l.ref_basic_odd_even_merge.argtypes = [_p, _p, _u64, _p, _u64, _p, _p]
         _lib = l
     return _lib
 
@@ -213,6 +220,72 @@ class Session:
         if t < 0:
             raise RuntimeError("reference: " + lib().ref_last_error().decode())
         return t
+
+
+BOOL_OPS = {"lt": 0, "eq": 1, "and": 2, "or": 3, "add": 4, "max": 5, "min": 6}
+
+
+def _basic(self, fn, *args):
+    secs = C.c_double(0)
+    _chk(fn(self.h, *args, C.byref(secs)))
+    return secs.value
+
+
+def _session_basic_methods():
+    def basic_bool(self, op, A, B):
+        """aby3-Basic bool_cipher_<op> (BoolBasic.cpp) on binary sharings [3][2][n][1] -> (out, seconds)"""
+        A, B = np.ascontiguousarray(A, dtype=np.int64), np.ascontiguousarray(B, dtype=np.int64)
+        n = A.shape[2]
+        out = np.zeros((3, 2, n, 1), dtype=np.int64)
+        t = _basic(self, lib().ref_basic_bool, BOOL_OPS[op], ptr(A), ptr(B), n, ptr(out))
+        return out, t
+
+    def cipher_gt(self, A, B):
+        A, B = np.ascontiguousarray(A, dtype=np.int64), np.ascontiguousarray(B, dtype=np.int64)
+        n = A.shape[2]
+        out = np.zeros((3, 2, n, 1), dtype=np.int64)
+        t = _basic(self, lib().ref_basic_cipher_gt, ptr(A), ptr(B), n, ptr(out))
+        return out, t
+
+    def max_min_split(self, A, B):
+        A, B = np.ascontiguousarray(A, dtype=np.int64), np.ascontiguousarray(B, dtype=np.int64)
+        n = A.shape[2]
+        mx, mn = np.zeros((3, 2, n, 1), dtype=np.int64), np.zeros((3, 2, n, 1), dtype=np.int64)
+        t = _basic(self, lib().ref_basic_max_min_split, ptr(A), ptr(B), n, ptr(mx), ptr(mn))
+        return mx, mn, t
+
+    def odd_even_merge(self, A, B):
+        A, B = np.ascontiguousarray(A, dtype=np.int64), np.ascontiguousarray(B, dtype=np.int64)
+        n1, n2 = A.shape[2], B.shape[2]
+        out = np.zeros((3, 2, n1 + n2, 1), dtype=np.int64)
+        t = _basic(self, lib().ref_basic_odd_even_merge, ptr(A), n1, ptr(B), n2, ptr(out))
+        return out, t
+
+    for f in (basic_bool, cipher_gt, max_min_split, odd_even_merge):
+        setattr(Session, f.__name__, f)
+
+
+_session_basic_methods()
+
+
+def sgd_linear(x, y, batch, iters, lr=2.0 ** -10, want_shares=True):
+    """The reference's aby3-ML linear regression (aby3ML engine + Regression.h SGD_Linear, D16) on x (N x F doubles),
+    y (N) -> (seconds for `iters` iterations, w shares [3][2][F][1] or None)"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+    N, F = x.shape
+    w = np.zeros((3, 2, F, 1), dtype=np.int64) if want_shares else None
+    t = lib().ref_sgd_linear(ptr(x), ptr(y), N, F, batch, iters, float(lr), ptr(w) if want_shares else None)
+    if t < 0:
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+    return t, w
+
+
+def main_linear(*args):
+    """aby3-ML/main-linear.cpp's linear_main_3pc_sh(CLP&) with argv-style arguments, e.g. main_linear("-N", 1000, "-D", 100)"""
+    argv = [b"main-linear"] + [str(a).encode() for a in args]
+    arr = (C.c_char_p * len(argv))(*argv)
+    _chk(lib().ref_main_linear(len(argv), arr))
 
 
 def piecewise_plain(x, thresholds, coefficients, D):

@@ -348,3 +348,54 @@ def test_scheduler_orders_hold_for_the_reference_runtime(tmp_path):
     out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
     assert out.returncode == 0, out.stdout
     assert "ALL OK" in out.stdout
+
+
+# ---- the reference's APPLICATIONS (aby3-Basic, aby3-ML) compiled unmodified into oracle/_ref --------------------------
+# These are the expected values of tests/test_compat.py (the same sources on the B200 facade) and bench.py's CPU figures
+# for BASELINE configs 3 and 5.
+
+def test_reference_aby3_basic_on_cpu():
+    """aby3-Basic/BoolBasic.cpp, BuildingBlocks.cpp, Sort.cpp as the reference's own tests use them
+    (aby3_tests/BoolTest.cpp:60-283, SortTest.cpp:354-486): reveals equal the plaintext functions."""
+    e, v = o.default_seeds()
+    s = r.Session(e, v)
+    rng = np.random.default_rng(0)
+    n = 700
+    a = rng.integers(-2**62, 2**62, (n, 1), dtype=np.int64)
+    b = rng.integers(-2**62, 2**62, (n, 1), dtype=np.int64)
+    b[:20] = a[:20]
+    A, B = s.share_bin(0, a), s.share_bin(1, b)
+    plain = {"lt": (a < b).astype(np.int64), "eq": (a == b).astype(np.int64), "and": a & b, "or": a | b, "add": a + b,
+             "max": np.maximum(a, b), "min": np.minimum(a, b)}
+    for op, exp in plain.items():
+        out, _ = s.basic_bool(op, A, B)
+        rev = s.reveal_all(out, binary=True)
+        for p in range(3):
+            got = rev[p] & 1 if op in ("lt", "eq") else rev[p]
+            assert np.array_equal(got, exp), (op, p)
+    out, _ = s.cipher_gt(s.share_int(0, a), s.share_int(2, b))
+    assert np.array_equal(s.reveal_all(out, binary=True)[1] & 1, (a > b).astype(np.int64))
+    mx, mn, _ = s.max_min_split(A, B)
+    assert np.array_equal(s.reveal_all(mx, binary=True)[0], np.maximum(a, b))
+    assert np.array_equal(s.reveal_all(mn, binary=True)[2], np.minimum(a, b))
+    d1 = np.sort(rng.integers(-2**40, 2**40, 50)).reshape(-1, 1)           # SortTest.cpp:363: 50 + 98 elements
+    d2 = np.sort(rng.integers(-2**40, 2**40, 98)).reshape(-1, 1)
+    out, _ = s.odd_even_merge(s.share_bin(0, d1), s.share_bin(0, d2))
+    assert np.array_equal(s.reveal_all(out, binary=True)[0].reshape(-1), np.sort(np.concatenate([d1[:, 0], d2[:, 0]])))
+    s.close()
+
+
+def test_reference_aby3_ml_linear_on_cpu(capfd):
+    """aby3-ML/main-linear.cpp's own entry point (three party threads over loopback sessions, LinearModelGen data,
+    SGD_Linear) runs to completion on the stand-in headers and prints its iters/s line (main-linear.cpp:147-149);
+    ref_lib.sgd_linear (the same engine + Regression.h on caller-supplied data) returns replicated w shares."""
+    r.main_linear("-N", 600, "-D", 48, "-B", 16, "-I", 40, "-testN", 50)
+    out = capfd.readouterr().out
+    assert "iters/s" in out and "N: 600 D:48 B:16 IT:40" in out
+    rng = np.random.default_rng(1)
+    x = rng.normal(1, 1, (300, 40))
+    y = x[:, :3] @ np.array([2.0, -1.0, 0.5])
+    t, w = r.sgd_linear(x, y, 16, 25, lr=2.0 ** -6)
+    assert t > 0
+    for p in range(3):
+        assert np.array_equal(w[(p + 1) % 3, 1], w[p, 0])
