@@ -36,7 +36,7 @@ inline oc::BetaLibrary& library() { static thread_local oc::BetaLibrary lib; ret
 // res = (A < B) as a one-bit sharing, signed comparison (BoolBasic.cpp:20-40; pinned by
 // aby3_tests/BoolTest.cpp:122, 573: bool_cipher_lt(Y, X) reveals x > y)
 inline void bool_cipher_lt(int, sbMatrix& A, sbMatrix& B, sbMatrix& res, Sh3Encryptor&, Sh3Evaluator& eval, Sh3Runtime& rt) {
-    detail::runCircuit(detail::library().int_int_lt(A.bitCount(), B.bitCount()), A, B, res, 1, eval, rt);
+    detail::runCircuit(detail::library().int_int_lt_ab(A.bitCount(), B.bitCount()), A, B, res, 1, eval, rt);
 }
 inline void bool_cipher_eq(int, sbMatrix& A, sbMatrix& B, sbMatrix& res, Sh3Encryptor&, Sh3Evaluator& eval, Sh3Runtime& rt) {
     detail::runCircuit(detail::library().int_eq(A.bitCount()), A, B, res, 1, eval, rt);

@@ -207,6 +207,14 @@ public:
             else rippleAdd(cd, a, b, c);
         });
     }
+    // c = a - b = a + ~b + 1 (aby3-Basic/BoolBasic.cpp:174): the prefix adder on (a, ~b) with the carry-in folded into bit 0
+    BetaCircuit* int_int_subtract(u64 aBits, u64 bBits, u64 cBits, Optimized = Optimized::Size) {
+        return cached("sub" + std::to_string(aBits) + "_" + std::to_string(bBits) + "_" + std::to_string(cBits), [&](BetaCircuit& cd) {
+            BetaBundle a(aBits), b(bBits), c(cBits);
+            cd.addInputBundle(a); cd.addInputBundle(b); cd.addOutputBundle(c);
+            prefixAdd(cd, a, b, c, true);
+        });
+    }
     // the most significant bit of a + b (int_comp_helper / fetch_msb)
     BetaCircuit* int_int_add_msb(u64 bits) {
         return cached("addmsb" + std::to_string(bits), [&](BetaCircuit& cd) {
@@ -215,13 +223,21 @@ public:
             msbOfSum(cd, a, b, c[0]);
         });
     }
-    // c = (a < b) for signed two's-complement inputs of equal width
-    BetaCircuit* int_int_lt(u64 aBits, u64 bBits) {
+    // cryptoTools' BetaLibrary::int_int_lt as this fork's callers rely on it: aby3-Basic feeds (input 0 = B, input 1 = A)
+    // for "A < B" (BoolBasic.cpp:29-32) and its test expects bool_cipher_lt(Y, X) to reveal x > y
+    // (aby3_tests/BoolTest.cpp:68,122,283) -- the circuit answers "input 1 < input 0".
+    BetaCircuit* int_int_lt(u64 aBits, u64 bBits) { return lessThan(aBits, bBits, true); }
+    // c = (input 0 < input 1), the order the facade's own callers and tests use
+    BetaCircuit* int_int_lt_ab(u64 aBits, u64 bBits) { return lessThan(aBits, bBits, false); }
+    // c = (a < b) for signed two's-complement inputs of equal width; swapped: a = input 1, b = input 0
+    BetaCircuit* lessThan(u64 aBits, u64 bBits, bool swapped) {
         if (aBits != bBits) throw RTE_LOC;
-        return cached("lt" + std::to_string(aBits), [&](BetaCircuit& cd) {
+        return cached((swapped ? "ltswap" : "lt") + std::to_string(aBits), [&](BetaCircuit& cd) {
             const u64 n = aBits;
-            BetaBundle a(n), b(n), c(1);
-            cd.addInputBundle(a); cd.addInputBundle(b); cd.addOutputBundle(c);
+            BetaBundle in0(n), in1(n), c(1);
+            cd.addInputBundle(in0); cd.addInputBundle(in1); cd.addOutputBundle(c);
+            const BetaBundle& a = swapped ? in1 : in0;
+            const BetaBundle& b = swapped ? in0 : in1;
             // a < b  <=>  sign of (a - b) computed on n+1 bits (sign-extended operands):
             // a - b = a + ~b + 1.  Borrow-chain formulation: lt = MSB(diff_ext).
             // diff_ext bit n = a_s ^ ~b_s ^ carry_n, with carry from a + ~b + 1.
@@ -405,16 +421,26 @@ private:
         cd.addGate(pTop, carry, GateType::Xor, out);
     }
     // depth-optimised adder: log2(bits)+1 AND levels
-    static void prefixAdd(BetaCircuit& cd, const BetaBundle& a, const BetaBundle& b, const BetaBundle& c, bool) {
+    // c = a + b, or with subtract: c = a + ~b + 1 (generate a & ~b, propagate a ^ ~b, carry-in folded into bit 0:
+    // carry out of bit 0 = g0 | p0 = g0 ^ p0 since g0 & p0 = 0; sum bit 0 = p0 ^ 1)
+    static void prefixAdd(BetaCircuit& cd, const BetaBundle& a, const BetaBundle& b, const BetaBundle& c, bool subtract) {
         const u64 n = c.size();
         std::vector<BetaWire> g(n), p(n);
         for (u64 i = 0; i < n; ++i) {
             g[i] = cd.addTempWire(); p[i] = cd.addTempWire();
-            cd.addGate(at(a, i), at(b, i), GateType::And, g[i]);
-            cd.addGate(at(a, i), at(b, i), GateType::Xor, p[i]);
+            if (subtract) {
+                cd.addGate(at(b, i), at(a, i), GateType::na_And, g[i]);
+                cd.addGate(at(a, i), at(b, i), GateType::Nxor, p[i]);
+            } else {
+                cd.addGate(at(a, i), at(b, i), GateType::And, g[i]);
+                cd.addGate(at(a, i), at(b, i), GateType::Xor, p[i]);
+            }
         }
-        std::vector<BetaWire> G = prefixAll(cd, g, p);
-        cd.addCopy(p[0], c[0]);
+        std::vector<BetaWire> gg = g;
+        if (subtract) { gg[0] = cd.addTempWire(); cd.addGate(g[0], p[0], GateType::Xor, gg[0]); }
+        std::vector<BetaWire> G = prefixAll(cd, gg, p);
+        if (subtract) cd.addInvert(p[0], c[0]);
+        else cd.addCopy(p[0], c[0]);
         for (u64 i = 1; i < n; ++i) cd.addGate(p[i], G[i - 1], GateType::Xor, c[i]);
     }
 };

@@ -147,6 +147,9 @@ struct Transport {
     }
     virtual void flush() {}
     virtual aby3::gpu::Context* context() const = 0;
+    // late binding of the endpoint's device context (a Session hands out channels before it knows which party
+    // thread -- and so which device -- will hold each end)
+    virtual void bind(aby3::gpu::Context*) { throw std::runtime_error("Channel: this transport has a fixed context " LOCATION); }
 };
 
 struct LocalTransport : Transport {
@@ -154,6 +157,7 @@ struct LocalTransport : Transport {
     aby3::gpu::Context* ctx = nullptr;
     void* peerStream = nullptr;           // the stream of the context at the other end
     aby3::gpu::Context* context() const override { return ctx; }
+    void bind(aby3::gpu::Context* c) override { ctx = c; }
     void requireCtx() const {
         if (!ctx) throw std::runtime_error("Channel: device transfer on a channel without a device context " LOCATION);
     }
@@ -381,6 +385,10 @@ public:
     }
 
     bool isConnected() const { return (bool)mT; }
+    void waitForConnection() {}
+    void close() {}
+    void cancel() {}
+    void bindContext(aby3::gpu::Context* c) { require(); mT->bind(c); }
     aby3::gpu::Context* context() const { return mT ? mT->context() : nullptr; }
     // issue everything this party has queued on an NCCL transport (no-op for local channels)
     void flush() { if (mT) mT->flush(); }
@@ -395,6 +403,12 @@ public:
     void asyncSendCopy(const span<T>& s) { sendBytes(reinterpret_cast<const u8*>(s.data()), s.size() * sizeof(T)); }
     template <typename T>
     void asyncSendCopy(const std::vector<T>& v) { sendBytes(reinterpret_cast<const u8*>(v.data()), v.size() * sizeof(T)); }
+    // any other contiguous container with data() / size() -- a share plane, for one (aby3-Basic/BoolBasic.cpp:872)
+    template <typename C>
+    auto asyncSendCopy(const C& c) -> typename std::enable_if<!std::is_trivially_copyable<C>::value,
+                                                              decltype((void)c.data(), (void)c.size(), void())>::type {
+        sendBytes(reinterpret_cast<const u8*>(c.data()), c.size() * sizeof(*c.data()));
+    }
     // both transports copy eagerly, so the no-copy forms are aliases
     template <typename T>
     void asyncSend(const T* p, u64 n) { asyncSendCopy(p, n); }
@@ -403,6 +417,14 @@ public:
     template <typename T>
     typename std::enable_if<std::is_trivially_copyable<T>::value && !std::is_pointer<T>::value>::type
     asyncSend(const T& v) { asyncSendCopy(v); }
+    // sends copy eagerly, so the completion future is ready on return (aby3-Basic/Basic.cpp:17)
+    template <typename T>
+    std::future<void> asyncSendFuture(const T* p, u64 n) {
+        asyncSendCopy(p, n);
+        std::promise<void> pr;
+        pr.set_value();
+        return pr.get_future();
+    }
     template <typename T>
     void send(const T* p, u64 n) { asyncSendCopy(p, n); }
     template <typename T>

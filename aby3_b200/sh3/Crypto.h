@@ -7,6 +7,7 @@
 // never runs the hot loop.
 #pragma once
 #include "Gpu.h"
+#include "BitVector.h"
 
 namespace oc {
 
@@ -31,6 +32,13 @@ public:
     void get(T* dst, u64 n) { getBytes(reinterpret_cast<u8*>(dst), n * sizeof(T)); }
     template <typename T>
     void get(span<T> s) { getBytes(reinterpret_cast<u8*>(s.data()), s.size() * sizeof(T)); }
+
+    // usable as a standard random source and as std::random_shuffle's functor (aby3-ML/Regression.h:36)
+    typedef u32 result_type;
+    static constexpr result_type min() { return 0; }
+    static constexpr result_type max() { return (result_type)-1; }
+    result_type operator()() { return get<result_type>(); }
+    u64 operator()(u64 mod) { return get<u64>() % mod; }
 
     // bulk draw straight into device memory (offset and size multiples of 8)
     void getDevice(aby3::gpu::Context* ctx, void* d_dst, u64 bytes) {
@@ -83,5 +91,8 @@ public:
 private:
     block mKey;
 };
+
+// a fresh non-deterministic seed (cryptoTools sysRandomSeed(); aby3-Basic/BuildingBlocks.cpp:64)
+block sysRandomSeed();
 
 }  // namespace oc

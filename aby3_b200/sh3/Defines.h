@@ -10,6 +10,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #define ABY3_STRINGIZE_DETAIL(x) #x
@@ -65,7 +66,9 @@ template <typename T>
 class span {
 public:
     span() = default;
-    span(T* p, u64 n) : mPtr(p), mSize(n) {}
+    // any integer length (gsl::span's index type is signed: callers write {ptr, i64(n)})
+    template <typename I, typename = typename std::enable_if<std::is_integral<I>::value>::type>
+    span(T* p, I n) : mPtr(p), mSize((u64)n) {}
     template <typename C>
     span(C& c) : mPtr(c.data()), mSize(c.size()) {}
     T* data() const { return mPtr; }

@@ -59,6 +59,9 @@ public:
     // number of instance-gates that failed the last check (0 after a clean run)
     u64 mDebugMismatches = 0;
     void validateMemory();
+    // the reference's debug-input exchange (Sh3BinaryEvaluator.cpp:381-425); the device-side checker exchanges whole share
+    // planes after the last round instead, so there is nothing to do up front (callers: aby3-Basic/BuildingBlocks.cpp:656)
+    void distributeInputs() {}
 
     u64 shareCount() const { return mWidth; }
     u64 rowBytes() const { return mRowBytes; }

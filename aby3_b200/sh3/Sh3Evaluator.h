@@ -28,8 +28,11 @@ struct TruncationPair {
 class SharedOT {
 public:
     void setSeed(const block& seed, u64 seedIdx = 0) { mKey = seed; mIdx = seedIdx; }
+    // an OT whose key was never set would pad every message with a default key: a silent loss of privacy (SharedOT.cpp:10-11)
+    void requireSeed() const { if (mIdx == ~0ull) throw RTE_LOC; }
     // masks n message pairs (d_msgs: n x 2 int64) and sends them to `recver`
     void send(oc::Channel& recver, const i64* d_msgs, u64 n) {
+        requireSeed();
         gpu::Context* ctx = gpu::current();
         gpu::Buffer masked(ctx, std::max<size_t>(16 * n, 16));
         gpu::check(aby3cu_ot_send(ctx->h(), mKey.data(), mIdx, d_msgs, (i64*)masked.ptr(), n));
@@ -38,6 +41,7 @@ public:
     }
     // sends pad_i[choice_i] for the receiver's choice bits (bit 0 of each word of d_choice)
     void help(oc::Channel& recver, const i64* d_choice, u64 n) {
+        requireSeed();
         gpu::Context* ctx = gpu::current();
         gpu::Buffer mc(ctx, std::max<size_t>(8 * n, 16));
         gpu::check(aby3cu_ot_help(ctx->h(), mKey.data(), mIdx, d_choice, (i64*)mc.ptr(), n));
@@ -66,8 +70,60 @@ public:
         r.fHelp = helper.asyncRecvDevice(r.help->ptr(), 8 * n).share();
         return r;
     }
+    // ---- the reference's HOST signatures (aby3/OT/SharedOT.h:13-46; callers: aby3-Basic/BuildingBlocks.cpp:335-380) ----
+    // Host vectors in, host spans out; the pads are still drawn by the device kernels above.
+    void send(oc::Channel& recver, span<std::array<i64, 2>> msgs) {
+        gpu::Context* ctx = gpu::current();
+        const u64 n = msgs.size();
+        gpu::Buffer d(ctx, std::max<size_t>(16 * n, 16));
+        if (n) gpu::check(aby3cu_h2d(ctx->h(), d.ptr(), msgs.data(), 16 * n));
+        send(recver, (const i64*)d.ptr(), n);
+    }
+    void help(oc::Channel& recver, const oc::BitVector& choices) {
+        gpu::Buffer d = uploadChoices(choices);
+        help(recver, (const i64*)d.ptr(), choices.size());
+    }
+    struct HostAsyncRecv {
+        AsyncRecv dev;
+        std::shared_ptr<gpu::Buffer> choice;
+        span<i64> out;
+        void get() const {
+            gpu::Context* ctx = gpu::current();
+            gpu::Buffer o(ctx, std::max<size_t>(8 * dev.n, 16));
+            dev.finish((const i64*)choice->ptr(), (i64*)o.ptr(), false);
+            if (dev.n) gpu::check(aby3cu_d2h(ctx->h(), out.data(), o.ptr(), 8 * dev.n));
+            ctx->sync();
+        }
+    };
+    static HostAsyncRecv asyncRecv(oc::Channel& sender, oc::Channel& helper, oc::BitVector&& choices, span<i64> recvMsgs) {
+        if (recvMsgs.size() != choices.size()) throw RTE_LOC;
+        HostAsyncRecv r;
+        r.choice = std::make_shared<gpu::Buffer>(uploadChoices(choices));
+        r.out = recvMsgs;
+        r.dev = asyncRecv(sender, helper, choices.size());
+        return r;
+    }
+    static void recv(oc::Channel& sender, oc::Channel& helper, const oc::BitVector& choices, span<i64> recvMsgs) {
+        oc::BitVector c = choices;
+        asyncRecv(sender, helper, std::move(c), recvMsgs).get();
+    }
     block mKey;
     u64 mIdx = (u64)-1;
+
+private:
+    // one int64 word per choice bit (the layout aby3cu_ot_help / _recv read)
+    static gpu::Buffer uploadChoices(const oc::BitVector& choices) {
+        gpu::Context* ctx = gpu::current();
+        const u64 n = choices.size();
+        std::vector<i64> w(n);
+        for (u64 i = 0; i < n; ++i) w[i] = choices[i];
+        gpu::Buffer d(ctx, std::max<size_t>(8 * n, 16));
+        if (n) {
+            gpu::check(aby3cu_h2d(ctx->h(), d.ptr(), w.data(), 8 * n));
+            ctx->sync();                    // w dies with this scope
+        }
+        return d;
+    }
 };
 
 class Sh3Evaluator {

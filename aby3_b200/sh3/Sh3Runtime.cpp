@@ -8,6 +8,19 @@ gpu::Context*& gpu::currentSlot() {
     return c;
 }
 
+}  // namespace aby3
+
+#include <random>
+namespace oc {
+block sysRandomSeed() {
+    std::random_device rd;
+    const u64 a = ((u64)rd() << 32) | rd(), b = ((u64)rd() << 32) | rd();
+    return toBlock(a, b);
+}
+}  // namespace oc
+
+namespace aby3 {
+
 Sh3Task Sh3Task::then(RoundFunc task) { return getRuntime().addTask({this, 1}, std::move(task), {}); }
 Sh3Task Sh3Task::then(ContinuationFunc task) { return getRuntime().addTask({this, 1}, std::move(task), {}); }
 Sh3Task Sh3Task::then(RoundFunc task, std::string name) { return getRuntime().addTask({this, 1}, std::move(task), std::move(name)); }

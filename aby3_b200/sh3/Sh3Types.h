@@ -36,10 +36,10 @@ struct Share {
     Share(const std::array<value_type, 2>& d) : mData(d) {}
     Share(const Ref<Share>& s) { mData[0] = *s.mData[0]; mData[1] = *s.mData[1]; }
     Share operator+(const Share& r) const {
-        return Share({{(i64)((u64)mData[0] + (u64)r.mData[0]), (i64)((u64)mData[1] + (u64)r.mData[1])}});
+        return Share(std::array<value_type, 2>{{(i64)((u64)mData[0] + (u64)r.mData[0]), (i64)((u64)mData[1] + (u64)r.mData[1])}});
     }
     Share operator-(const Share& r) const {
-        return Share({{(i64)((u64)mData[0] - (u64)r.mData[0]), (i64)((u64)mData[1] - (u64)r.mData[1])}});
+        return Share(std::array<value_type, 2>{{(i64)((u64)mData[0] - (u64)r.mData[0]), (i64)((u64)mData[1] - (u64)r.mData[1])}});
     }
     value_type& operator[](u64 i) { return mData[i]; }
     const value_type& operator[](u64 i) const { return mData[i]; }

@@ -69,6 +69,11 @@ public:
     T& operator()(u64 r, u64 c) { touchHost(true); return mHost[r * mCols + c]; }
     const T& operator()(u64 r, u64 c) const { touchHost(false); return mHost[r * mCols + c]; }
     const T* hostData() const { touchHost(false); return mHost.data(); }
+    // element iterators over the host view (aby3-Basic/BoolBasic.cpp:804-809 std::copy's share planes)
+    T* begin() { return data(); }
+    T* end() { return data() + size(); }
+    const T* begin() const { return hostData(); }
+    const T* end() const { return hostData() + size(); }
 
     // ---------------------------------------------------- device access ------
     bool onDevice() const { return mDevValid; }
@@ -251,15 +256,24 @@ public:
     struct RowRef {
         eMatrix& m; u64 i;
         RowRef& operator=(const RowRef& o) { for (u64 j = 0; j < m.cols(); ++j) m(i, j) = o.m(o.i, j); return *this; }
+        template <typename R, typename = decltype(std::declval<const R&>().m)>
+        RowRef& operator=(const R& o) { for (u64 j = 0; j < m.cols(); ++j) m(i, j) = o.m(o.i, j); return *this; }
         T& operator()(u64 j) { return m(i, j); }
     };
     struct ColRef {
         eMatrix& m; u64 j;
         ColRef& operator=(const ColRef& o) { for (u64 i = 0; i < m.rows(); ++i) m(i, j) = o.m(i, o.j); return *this; }
+        template <typename R, typename = decltype(std::declval<const R&>().m)>
+        ColRef& operator=(const R& o) { for (u64 i = 0; i < m.rows(); ++i) m(i, j) = o.m(i, o.j); return *this; }
         T& operator()(u64 i) { return m(i, j); }
     };
     RowRef row(u64 i) { return RowRef{*this, i}; }
     ColRef col(u64 j) { return ColRef{*this, j}; }
+    // read-only rows / columns of a const matrix (XX.row(i) = X.row(k), aby3-ML/Regression.h:55-56)
+    struct ConstRowRef { const eMatrix& m; u64 i; const T& operator()(u64 j) const { return m(i, j); } };
+    struct ConstColRef { const eMatrix& m; u64 j; const T& operator()(u64 i) const { return m(i, j); } };
+    ConstRowRef row(u64 i) const { return ConstRowRef{*this, i}; }
+    ConstColRef col(u64 j) const { return ConstColRef{*this, j}; }
     eMatrix block(u64 r, u64 c, u64 h, u64 w) const {
         eMatrix b(h, w);
         const T* A = hostData();

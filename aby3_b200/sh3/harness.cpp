@@ -870,7 +870,9 @@ sh3h_circuit* sh3h_circuit_build(const char* name, uint32_t bits) {
         else if (n == "add") c->cir = c->lib.int_int_add(bits, bits, bits, oc::BetaLibrary::Optimized::Size);
         else if (n == "add_depth") c->cir = c->lib.int_int_add(bits, bits, bits, oc::BetaLibrary::Optimized::Depth);
         else if (n == "add_msb") c->cir = c->lib.int_int_add_msb(bits);
-        else if (n == "lt") c->cir = c->lib.int_int_lt(bits, bits);
+        else if (n == "lt") c->cir = c->lib.int_int_lt_ab(bits, bits);
+        else if (n == "lt_swapped") c->cir = c->lib.int_int_lt(bits, bits);
+        else if (n == "sub") c->cir = c->lib.int_int_subtract(bits, bits, bits);
         else if (n == "eq") c->cir = c->lib.int_eq(bits);
         else if (n.rfind("piecewise", 0) == 0) c->cir = c->lib.int_Sh3Piecewise_helper(bits, std::stoul(n.substr(9)));
         else if (n == "a2b") {            // Sh3Converter::getArithToBinCircuit(64, bits), levelised as setCir does

@@ -1,0 +1,4 @@
+#pragma once
+// compat: cryptoTools/Common/MatrixView.h
+#include "aby3_b200/sh3/Defines.h"
+#include "compat_surface.h"

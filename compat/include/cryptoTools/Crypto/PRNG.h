@@ -1,0 +1,4 @@
+#pragma once
+// compat: cryptoTools/Crypto/PRNG.h -> aby3_b200/sh3/Crypto.h
+#include "aby3_b200/sh3/Crypto.h"
+#include "compat_surface.h"

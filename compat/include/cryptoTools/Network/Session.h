@@ -1,0 +1,3 @@
+#pragma once
+// compat: cryptoTools/Network/Session.h -> the facade's channel + the in-process session shim
+#include "compat_net.h"
