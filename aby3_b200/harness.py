@@ -72,6 +72,10 @@ def _load():
     l.sh3h_trim.argtypes = [p]
     l.sh3h_pool_stats.argtypes = [p, p]
     l.sh3h_guard_selftest.argtypes = [p, u64, u64]
+    l.sh3h_device_ptrs.argtypes = [p, i32, p]
+    l.sh3h_alloc_shares.argtypes = [p, u64, u64]
+    l.sh3h_party_stream.restype = p
+    l.sh3h_party_stream.argtypes = [p, i32]
     l.sh3h_bytes_sent.restype = u64
     l.sh3h_bytes_sent.argtypes = [p]
     return l
@@ -383,6 +387,20 @@ class Session:
         a = np.zeros(3, dtype=np.uint64)
         lib.sh3h_pool_stats(self.h, _ptr(a))
         return tuple(int(x) for x in a)
+
+    def device_ptrs(self, hid):
+        """device addresses [party][plane] of an arithmetic sharing (interop: e.g. wrap them as torch tensors)"""
+        arr = (C.c_void_p * 6)()
+        self._chk(lib.sh3h_device_ptrs(self.h, hid, arr))
+        return [[int(arr[2 * i] or 0), int(arr[2 * i + 1] or 0)] for i in range(3)]
+
+    def alloc_shares(self, rows, cols):
+        """an arithmetic sharing with device planes allocated but not written (filled through device_ptrs)"""
+        return self._id(lib.sh3h_alloc_shares(self.h, rows, cols))
+
+    def party_stream(self, party):
+        """the party's cudaStream_t as an integer"""
+        return int(lib.sh3h_party_stream(self.h, party) or 0)
 
     def guard_selftest(self, nbytes, overrun):
         """ABY3_POOL_GUARD=1 only: write `overrun` bytes past a pool block; 1 = the guard caught it, 0 = clean, -1 = guard off"""

@@ -810,6 +810,30 @@ int sh3h_timer_end(sh3h* h, float* ms) {
     return 0;
 }
 int sh3h_sync(sh3h* h) { return h->run([&](int i) { h->p[i].ctx->sync(); }); }
+
+// ---- interop with another CUDA user of the same process (bench.py: torch.distributed / NCCL collectives) -------------
+// the six device pointers [party][plane] of an arithmetic sharing (valid in stream order on the owning party's stream)
+int sh3h_device_ptrs(sh3h* h, int id, void* out[6]) {
+    return h->run([&](int i) {
+        auto& m = *h->p[i].ints.at(id);
+        out[2 * i + 0] = (void*)m.mShares[0].devMut();
+        out[2 * i + 1] = (void*)m.mShares[1].devMut();
+    });
+}
+// an arithmetic sharing whose planes are allocated on the device but not written (the caller fills them through
+// sh3h_device_ptrs, e.g. as the destination of a broadcast)
+int sh3h_alloc_shares(sh3h* h, uint64_t rows, uint64_t cols) {
+    const int id = h->next_handle++;
+    int rc = h->run([&](int i) {
+        auto m = std::make_unique<si64Matrix>(rows, cols);
+        (void)m->mShares[0].devOut();
+        (void)m->mShares[1].devOut();
+        h->p[i].ints[id] = std::move(m);
+    });
+    return rc ? -1 : id;
+}
+// cudaStream_t of a party (wrap it, do not destroy it)
+void* sh3h_party_stream(sh3h* h, int party) { return h->p[party].ctx->stream(); }
 uint64_t sh3h_launch_count(sh3h* h) {
     uint64_t n = 0;
     for (int i = 0; i < 3; ++i) n += h->p[i].ctx->launchCount();

@@ -398,7 +398,10 @@ int ref_share_reveal_packed(ref_session* s, int owner, const int64_t* plain, uin
 // of Sh3Evaluator.cpp:662-665 (here: the shim's blocked loop), the fork's element-wise overwrite (:667-668,
 // needs K >= max(M, N)), truncation pair, the open to parties 0/1 and the final pass.  Seconds per call.
 double ref_time_mul_trunc(ref_session* s, uint64_t M, uint64_t K, uint64_t N, uint64_t shift, int reps) {
-    if (K < M || K < N) { g_err = "ref_time_mul_trunc needs K >= max(M, N)"; return -1.0; }
+    // the fork's element-wise overwrite (:667-668) indexes A0 and B0 with the RESULT's linear index: that stays inside A
+    // when N <= K and inside B (plus the 8192 zero elements of slack the Eigen stand-in keeps behind every matrix) when
+    // M * N <= K * N + 8192
+    if (N > K || M * N > K * N + 8192) { g_err = "ref_time_mul_trunc: the fork's element-wise pass would read outside the operands for this shape"; return -1.0; }
     std::vector<si64Matrix> a(3), b(3), c(3);
     for (int i = 0; i < 3; ++i) {
         a[i].resize(M, K); b[i].resize(K, N);
@@ -557,6 +560,40 @@ int ref_basic_odd_even_merge(ref_session* s, const int64_t* A, uint64_t n1, cons
     });
     if (secs) *secs = std::max(t[0], std::max(t[1], t[2]));
     return rc;
+}
+
+
+// Time aby3-ML's logistic inference step y = logisticFunc(X * W) (aby3-ML/aby3ML.h:102-139) on the reference's own code:
+// asyncMul(X (rows x F), W (F x 1), shift) then Sh3Piecewise::eval with thresholds +-0.5.  Seconds per pass.
+double ref_time_logistic(ref_session* s, uint64_t rows, uint64_t F, uint64_t D, int reps) {
+    if (rows > F + 8192) { g_err = "ref_time_logistic: rows must stay <= F + 8192 (see ref_time_mul_trunc)"; return -1.0; }
+    std::vector<si64Matrix> x(3), w(3), z(3), y(3);
+    for (int i = 0; i < 3; ++i) {
+        x[i].resize(rows, F); w[i].resize(F, 1);
+        for (int p = 0; p < 2; ++p) {
+            for (u64 j = 0; j < rows * F; ++j) x[i].mShares[p](j) = i64((j * 0x9E3779B97F4A7C15ull + i + p) >> 44);
+            for (u64 j = 0; j < F; ++j) w[i].mShares[p](j) = i64((j * 0xC2B2AE3D27D4EB4Full + i + p) >> 50);
+        }
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; ++r) {
+        int rc = s->run([&](int i) {
+            RefParty& P = s->p[i];
+            P.eval.asyncMul(P.rt.noDependencies(), x[i], w[i], z[i], D).get();
+            Sh3Piecewise pw;
+            pw.mThresholds.resize(2);
+            pw.mThresholds[0] = -0.5; pw.mThresholds[1] = 0.5;
+            pw.mCoefficients.resize(3);
+            pw.mCoefficients[1].resize(2);
+            pw.mCoefficients[1][0] = 0.5; pw.mCoefficients[1][1] = 1;
+            pw.mCoefficients[2].resize(1);
+            pw.mCoefficients[2][0] = 1;
+            y[i].resize(rows, 1);
+            pw.eval(P.rt.noDependencies(), z[i], y[i], D, P.eval).get();
+        });
+        if (rc) return -1.0;
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
 }
 
 }  // extern "C"

@@ -58,6 +58,8 @@ def lib():
         l.ref_share_reveal_packed.argtypes = [_p, _int, _p, _u64, _u64, _p, _p]
         l.ref_time_mul_trunc.restype = C.c_double
         l.ref_time_mul_trunc.argtypes = [_p, _u64, _u64, _u64, _u64, _int]
+        l.ref_time_logistic.restype = C.c_double
+        l.ref_time_logistic.argtypes = [_p, _u64, _u64, _u64, _int]
         l.ref_main_linear.argtypes = [_int, _p]
         l.ref_sgd_linear.restype = C.c_double
         l.ref_sgd_linear.argtypes = [_p, _p, _u64, _u64, _u64, _u64, C.c_double, _p]
@@ -286,6 +288,17 @@ def main_linear(*args):
     argv = [b"main-linear"] + [str(a).encode() for a in args]
     arr = (C.c_char_p * len(argv))(*argv)
     _chk(lib().ref_main_linear(len(argv), arr))
+
+
+def _time_logistic(self, rows, features, D=16, reps=1):
+    """seconds per pass of y = logisticFunc(X * W) on the reference's own code (X rows x features)"""
+    t = lib().ref_time_logistic(self.h, rows, features, D, reps)
+    if t < 0:
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+    return t
+
+
+Session.time_logistic = _time_logistic
 
 
 def piecewise_plain(x, thresholds, coefficients, D):
