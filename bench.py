@@ -425,7 +425,7 @@ def gemm_roofline(device, ms_per_step=None):
            "note": "int8 TOP/s (144*M*N*K ops per launch); frac is of %s: peak = max(cuBLASLt int8 GEMM measured live on this GPU, 2 x the %s dense "
                    "bf16 rate of MEASURED_PEAKS.json -- kind::i8 issues at twice the bf16 rate), i.e. %.2f of 2x-bf16-measured and %.2f of the 4500 TOP/s "
                    "nominal; a library GEMM as denominator lets a good kernel read a little above 1"
-                   % (("measured", "measured") if bf16 else ("fallback", "fallback"), achieved / twice_bf16, achieved / 4500.0)}
+                   % (("measured", "measured", achieved / twice_bf16, achieved / 4500.0) if bf16 else ("fallback", "fallback", achieved / twice_bf16, achieved / 4500.0))}
     if ms_per_step:
         # what the tensor pipe does over the WHOLE step: three parties' launches over the device-timed step
         out["step_frac"] = 3.0 * ops / (ms_per_step * 1e-3) / 1e12 / peak
