@@ -23,8 +23,8 @@ inline void runCircuit(oc::BetaCircuit* cir, const sbMatrix& in0, const sbMatrix
     Sh3BinaryEvaluator binEng;
     const u64 n = in0.rows();
     binEng.setCir(cir, n, eval.mShareGen);
-    binEng.setInput(0, in0);
-    binEng.setInput(1, in1);
+    binEng.setInputRef(0, in0);          // in0 / in1 outlive the .get() below
+    binEng.setInputRef(1, in1);
     binEng.asyncEvaluate(runtime).then([&](Sh3Task) {
         res.resize(n, outBits);
         binEng.getOutput(0, res);

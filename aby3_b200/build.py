@@ -66,8 +66,21 @@ def build_sh3(force=False):
     return so
 
 
+def build_compat():
+    """compat/_build/libcompat_apps.so: the reference's application sources against the facade headers (compat/Makefile).
+    Rebuilt whenever the facade changes -- it embeds the facade's class layouts.  Needs the reference tree; elsewhere the
+    prebuilt library is used as it is."""
+    ref = os.environ.get("ABY3_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "aby3-ML")) or not os.path.isdir(os.path.join(ROOT, "compat")):
+        return None
+    _run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "compat"), "REF=" + ref])
+    return os.path.join(ROOT, "compat", "_build", "libcompat_apps.so")
+
+
 def build_all(force=False):
-    return [build_cuda(force), build_sh3(force)]
+    out = [build_cuda(force), build_sh3(force)]
+    c = build_compat()
+    return out + ([c] if c else [])
 
 
 if __name__ == "__main__":

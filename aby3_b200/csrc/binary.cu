@@ -332,6 +332,78 @@ __global__ void __launch_bounds__(256) k_bin_and_layer(const uint4* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------
+// One-level BITWISE circuit (int_int_bitwiseAnd / bitwiseOr: gate g = bit g of every instance) evaluated on the
+// ROW-MAJOR share words, without moving the operands into the bit-sliced wire memory and back (SURVEY section 7,
+// "Transposes around shallow circuits").  The zero share of the reference is defined per (gate, instance column)
+// -- gate g draws the keystream blocks [(and0 + g) * chunks, +chunks), bit j of that range masks instance j
+// (Sh3BinaryEvaluator.cpp:1406-1442) -- so only z is produced bit-sliced and transposed, in registers:
+// a warp owns a tile of 128 instances; lane l encrypts block `tile` of gates l and l + 32 under both keys (4 AES
+// blocks: 2 x 128 bits of z), eight 32 x 32 bit transposes across the warp turn them into the 64-bit z word of
+// instances 32q + l (q = 0..3), and the AND / OR formula runs on the row-major words.  Same shares, bit for bit,
+// as k_bin_and_layer on the transposed operands.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ u32 warp_transpose32(u32 x, u32 lane) {
+    // lane l holds row l; on return lane l holds column l (bit r = row r's bit l), LSB first
+    u32 m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const u32 y = __shfl_xor_sync(0xFFFFFFFFu, x, j);
+        const bool lower = (lane & j) == 0;
+        const u32 sh = lower ? (y << j) : (y >> j);
+        const u32 mm = lower ? m : ~m;
+        x = (x & mm) | (sh & ~mm);
+        m ^= m << (j >> 1);
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(256) k_bitwise_rowmajor(const u64* __restrict__ a0, const u64* __restrict__ a1,
+                                                          const u64* __restrict__ b0, const u64* __restrict__ b1,
+                                                          u64* __restrict__ out0, u64* __restrict__ out_copy, u64 n, u32 bits, u64 chunks,
+                                                          const __grid_constant__ AesKey kp, const __grid_constant__ AesKey kn,
+                                                          u64 and0, u32 type) {
+    aes_table_init();
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31, Tl = lane * 4;
+    const u64 tiles = (n + 127) / 128;
+    const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const u64 keep = bits >= 64 ? ~0ull : ((1ull << bits) - 1);
+    for (u64 t = (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5); t < tiles; t += warps) {
+        u32 zl[4] = {0, 0, 0, 0}, zh[4] = {0, 0, 0, 0};
+        if (lane < bits) {
+            u32 p[4], q[4];
+            const u64 ctr = (and0 + lane) * chunks + t;
+            aes_encrypt_ctr(Tl, kp, ctr, p);
+            aes_encrypt_ctr(Tl, kn, ctr, q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) zl[i] = p[i] ^ q[i];
+        }
+        if (lane + 32 < bits) {
+            u32 p[4], q[4];
+            const u64 ctr = (and0 + lane + 32) * chunks + t;
+            aes_encrypt_ctr(Tl, kp, ctr, p);
+            aes_encrypt_ctr(Tl, kn, ctr, q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) zh[i] = p[i] ^ q[i];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u32 lo = warp_transpose32(zl[q], lane);
+            const u32 hi = bits > 32 ? warp_transpose32(zh[q], lane) : 0u;
+            const u64 j = t * 128 + 32 * q + lane;
+            if (j < n) {
+                const u64 x0 = a0[j], x1 = a1[j], y0 = b0[j], y1 = b1[j];
+                u64 o = (x0 & y0) ^ (x0 & y1) ^ (x1 & y0);
+                if (type == 14) o ^= x0 ^ y0;                                   // Or (:912-981)
+                o = (o ^ (((u64)hi << 32) | lo)) & keep;
+                out0[j] = o;
+                if (out_copy) out_copy[j] = o;
+            }
+        }
+    }
+}
+
 // rows <-> contiguous message; VEC = bytes moved per thread step (16, 8 or 1).  PACK may
 // complement the rows flagged in `invert` (inverted output wires, getOutput :1252-1258).
 template <int VEC, bool PACK>
@@ -472,6 +544,25 @@ int aby3cu_bin_and_layer(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void*
     k_bin_and_layer<<<dim3((unsigned)gx, (unsigned)gy), 256, kAesTableBytes, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0,
                                                                                             (const u64*)d_mem1, row_bytes / 8, kp, kn, and_index0);
     return post_launch(ctx, "k_bin_and_layer");
+}
+
+int aby3cu_bin_bitwise_rowmajor(aby3cu_ctx* ctx, uint32_t gate_type, const int64_t* d_a0, const int64_t* d_a1, const int64_t* d_b0,
+                                const int64_t* d_b1, int64_t* d_out0, int64_t* d_out_copy, uint64_t n, uint32_t bits, uint64_t row_bytes,
+                                const u8 key_prev[16], const u8 key_next[16], uint64_t and_index0) {
+    ABY3CU_REQUIRE(ctx && key_prev && key_next && ((d_a0 && d_a1 && d_b0 && d_b1 && d_out0) || !n), "bin_bitwise_rowmajor: null argument");
+    ABY3CU_REQUIRE(gate_type == 8 || gate_type == 14, "bin_bitwise_rowmajor: gate type must be And (8) or Or (14)");
+    ABY3CU_REQUIRE(bits >= 1 && bits <= 64, "bin_bitwise_rowmajor: 1..64 bits per instance");
+    ABY3CU_REQUIRE(row_bytes % 16 == 0 && row_bytes * 8 >= n, "bin_bitwise_rowmajor: row_bytes must be the wire-row size of the circuit (a multiple of 16 covering n bits)");
+    if (!n) return 0;
+    DeviceGuard g(ctx->device);
+    AesKey kp, kn; host_expand_key(key_prev, &kp); host_expand_key(key_next, &kn);
+    ABY3CU_CHECK(cudaFuncSetAttribute(k_bitwise_rowmajor, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
+    if (prefer_max_smem(k_bitwise_rowmajor)) return 1;
+    const u64 tiles = (n + 127) / 128;
+    const unsigned grid = ew_grid(ctx, tiles * 32, 256, 3);
+    k_bitwise_rowmajor<<<grid, 256, kAesTableBytes, ctx->stream>>>((const u64*)d_a0, (const u64*)d_a1, (const u64*)d_b0, (const u64*)d_b1,
+                                                                   (u64*)d_out0, (u64*)d_out_copy, n, bits, row_bytes / 16, kp, kn, and_index0, gate_type);
+    return post_launch(ctx, "k_bitwise_rowmajor");
 }
 
 // The shadow evaluator of the reference's BINARY_ENGINE_DEBUG build (Sh3BinaryEvaluator.cpp:1469-1601), on the device:

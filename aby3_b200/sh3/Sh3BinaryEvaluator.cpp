@@ -5,6 +5,32 @@ namespace aby3 {
 
 using oc::GateType;
 
+// gate g: (input 0 bit g, input 1 bit g) -> output bit g, all gates the same nonlinear type, one level
+bool Sh3BinaryEvaluator::fastEligible(const oc::BetaCircuit& cir, u32& type, u32& bits) {
+    static const bool on = [] { const char* e = std::getenv("ABY3_BIN_ROWMAJOR"); return !(e && e[0] == '0'); }();
+    if (!on || cir.mLevelCounts.size() != 1 || cir.mInputs.size() != 2 || cir.mOutputs.size() != 1) return false;
+    const u64 n = cir.mInputs[0].size();
+    if (!n || n > 64 || cir.mInputs[1].size() != n || cir.mOutputs[0].size() != n || cir.mGates.size() != n) return false;
+    const GateType t = cir.mGates[0].mType;
+    if (t != GateType::And && t != GateType::Or) return false;
+    for (u64 g = 0; g < n; ++g) {
+        const auto& G = cir.mGates[g];
+        if (G.mType != t || G.mInput[0] != cir.mInputs[0][g] || G.mInput[1] != cir.mInputs[1][g] || G.mOutput != cir.mOutputs[0][g]) return false;
+        if (cir.isInvert(G.mOutput)) return false;
+    }
+    type = (u32)t;
+    bits = (u32)n;
+    return true;
+}
+
+void Sh3BinaryEvaluator::allocWireMemory() {
+    const u64 planeBytes = std::max<u64>((u64)mCir->mWireCount * mRowBytes, 16);
+    for (int s = 0; s < 2; ++s) {
+        mMem[s].reset(mCtx, planeBytes);
+        gpu::check(aby3cu_memset(mCtx->h(), mMem[s].ptr(), 0, planeBytes));
+    }
+}
+
 void Sh3BinaryEvaluator::setCir(oc::BetaCircuit* cir, u64 width, block prevSeed, block nextSeed) {
     if (cir->mLevelCounts.size() == 0) cir->levelByAndDepth();        // .cpp:69-78
     mCir = cir;
@@ -16,11 +42,13 @@ void Sh3BinaryEvaluator::setCir(oc::BetaCircuit* cir, u64 width, block prevSeed,
     mShareAES[0].setKey(prevSeed);                                     // :87-88
     mShareAES[1].setKey(nextSeed);
 
-    const u64 planeBytes = std::max<u64>((u64)cir->mWireCount * mRowBytes, 16);
-    for (int s = 0; s < 2; ++s) {
-        mMem[s].reset(mCtx, planeBytes);
-        gpu::check(aby3cu_memset(mCtx->h(), mMem[s].ptr(), 0, planeBytes));
-    }
+    mFast = !mDebug && width && fastEligible(*cir, mFastType, mFastBits);
+    mFastTaken = false;
+    mFastPtr = {};
+    for (auto& in : mFastIn) for (auto& b : in) b.free();
+    for (auto& b : mFastOut) b.free();
+    if (mFast) { mMem[0].free(); mMem[1].free(); }
+    else allocWireMemory();
     // gate list and the per-level AND output wires, uploaded once
     std::vector<u32> flat(4 * cir->mGates.size()), locs;
     for (u64 g = 0; g < cir->mGates.size(); ++g) {
@@ -63,9 +91,73 @@ void Sh3BinaryEvaluator::setInput(u64 i, const sbMatrix& in) {
 }
 
 // transpose both share planes of `in` into the wire rows of the bundle (.cpp:200-253)
-void Sh3BinaryEvaluator::setInput(const oc::BetaBundle& inWires, const sbMatrix& in) {
+void Sh3BinaryEvaluator::setInputRef(u64 i, const sbMatrix& in) {
+    if (!mCir || i >= mCir->mInputs.size()) throw std::runtime_error(LOCATION);
+    if (mFast) fastSetInput(mCir->mInputs[i], in, false);
+    else setInput(mCir->mInputs[i], in);
+}
+
+void Sh3BinaryEvaluator::fastSetInput(const oc::BetaBundle& inWires, const sbMatrix& in, bool copy) {
     mLevel = 0;
+    if (in.bitCount() != inWires.size()) throw std::invalid_argument("input data wrong size");
+    if (in.rows() != mWidth) throw std::invalid_argument("incorrect number of rows");
+    const int k = inWires.front() == mCir->mInputs[0].mWires.front() ? 0 : 1;
+    for (int s = 0; s < 2; ++s) {
+        if (copy) {
+            mFastIn[k][s].reset(mCtx, mWidth * 8);
+            gpu::check(aby3cu_d2d(mCtx->h(), mFastIn[k][s].ptr(), mCtx->device(), in.mShares[s].dev(), mCtx->device(), mWidth * 8));
+            mFastPtr[k][s] = (const i64*)mFastIn[k][s].ptr();
+        } else {
+            mFastPtr[k][s] = in.mShares[s].dev();
+        }
+    }
+}
+
+// leave the row-major path (a call it does not cover arrived): wire memory as the general engine expects it
+void Sh3BinaryEvaluator::materialize() {
+    if (!mFast) return;
+    mFast = false;
+    allocWireMemory();
+    for (int k = 0; k < 2; ++k) {
+        if (!mFastPtr[k][0]) continue;
+        for (int s = 0; s < 2; ++s) {
+            u8* dst = (u8*)mMem[s].ptr() + (u64)mCir->mInputs[k].mWires.front() * mRowBytes;
+            gpu::check(aby3cu_bit_transpose(mCtx->h(), mFastPtr[k][s], mWidth, mFastBits, 8, dst, mRowBytes, nullptr));
+        }
+    }
+    if (mLevel > 0 && mFastOut[0]) {           // already evaluated: the output wires too
+        if (mFastRecv.valid()) mFastRecv.get();
+        for (int s = 0; s < 2; ++s) {
+            u8* dst = (u8*)mMem[s].ptr() + (u64)mCir->mOutputs[0].mWires.front() * mRowBytes;
+            gpu::check(aby3cu_bit_transpose(mCtx->h(), mFastOut[s].ptr(), mWidth, mFastBits, 8, dst, mRowBytes, nullptr));
+        }
+        mLevel = mCir->mLevelCounts.size() + 1;
+    }
+}
+
+// level 0 of the row-major path: the whole circuit + the reshare (:1161-1171; the message is the row-major plane)
+void Sh3BinaryEvaluator::fastRound(CommPkg& comm) {
+    if (!mFastPtr[0][0] || !mFastPtr[1][0]) throw std::runtime_error("binary engine: inputs missing " LOCATION);
+    if (mShareIdx != 0) throw RTE_LOC;
+    const u64 bytes = mWidth * 8;
+    for (auto& b : mFastOut) b.reset(mCtx, bytes);
+    gpu::check(aby3cu_bin_bitwise_rowmajor(mCtx->h(), mFastType, mFastPtr[0][0], mFastPtr[0][1], mFastPtr[1][0], mFastPtr[1][1],
+                                           (i64*)mFastOut[0].ptr(), nullptr, mWidth, mFastBits, mRowBytes,
+                                           mShareAES[0].key().data(), mShareAES[1].key().data(), mShareIdx));
+    mShareIdx += mFastBits;
+    comm.mNext.asyncSendDevice(mFastOut[0].ptr(), bytes);
+    mFastRecv = comm.mPrev.asyncRecvDevice(mFastOut[1].ptr(), bytes);
+    for (auto& in : mFastIn) for (auto& b : in) b.free();       // stream-ordered: the kernel above has been enqueued
+}
+
+void Sh3BinaryEvaluator::setInput(const oc::BetaBundle& inWires, const sbMatrix& in) {
     if (!mCir) throw std::runtime_error(LOCATION);
+    if (mFast) {
+        const bool whole = (inWires.mWires == mCir->mInputs[0].mWires) || (inWires.mWires == mCir->mInputs[1].mWires);
+        if (whole) { fastSetInput(inWires, in, true); return; }
+        materialize();
+    }
+    mLevel = 0;
     if (in.bitCount() != inWires.size()) throw std::invalid_argument("input data wrong size");
     if (in.rows() != mWidth) throw std::invalid_argument("incorrect number of rows");
     for (u64 k = 0; k + 1 < inWires.size(); ++k)
@@ -82,6 +174,7 @@ void Sh3BinaryEvaluator::setInput(u64 idx, const sPackedBin& in) {
     if (!mCir) throw std::runtime_error(LOCATION);
     if (idx >= mCir->mInputs.size()) throw std::invalid_argument("input index out of bounds");
     if (in.shareCount() != mWidth) throw std::runtime_error(LOCATION);
+    materialize();
     const auto& wires = mCir->mInputs[idx].mWires;
     if (in.bitCount() != wires.size()) throw std::runtime_error(LOCATION);
     mLevel = 0;
@@ -120,6 +213,17 @@ Sh3Task Sh3BinaryEvaluator::asyncEvaluate(Sh3Task dependency, oc::BetaCircuit* c
 void Sh3BinaryEvaluator::roundCallback(CommPkg& comm, Sh3Task task) {
     const u64 levels = mCir->mLevelCounts.size();
     if (mLevel > levels) throw std::runtime_error("evaluateRound() was called but no rounds remain... " LOCATION);
+    if (mFast && mDebug) materialize();
+    if (mFast) {
+        if (mLevel == 0) fastRound(comm);
+        else if (mFastRecv.valid()) mFastRecv.get();
+        mLevel++;
+        if (hasMoreRounds()) {
+            auto t = task.then([this](CommPkg& comm, Sh3Task& task) { roundCallback(comm, task); });
+            t.name() = "callback";
+        }
+        return;
+    }
     // each AND output row travels as ceil(width/8) bytes (.cpp:795-796), padded to 16 so that the
     // pack / scatter kernels move whole 128-bit words (the pad carries bits beyond `width` only)
     const u64 sendBytes = (((mWidth + 7) / 8) + 15) & ~15ull;
@@ -177,6 +281,7 @@ void Sh3BinaryEvaluator::roundCallback(CommPkg& comm, Sh3Task task) {
 // reconstruct every wire and re-evaluate every gate on the device.
 void Sh3BinaryEvaluator::validateMemory() {
     if (!mDebug) return;
+    materialize();
     if (!mDebugPrev.isConnected() || !mDebugNext.isConnected()) throw std::runtime_error("enableDebug needs both debug channels " LOCATION);
     const u64 planeBytes = (u64)mCir->mWireCount * mRowBytes;
     gpu::Buffer third(mCtx, std::max<u64>(planeBytes, 16)), res(mCtx, 16);
@@ -224,6 +329,18 @@ void Sh3BinaryEvaluator::getOutput(u64 i, sbMatrix& out, bool allowUninitialized
 // gather the output wires (complementing inverted ones) and transpose back (.cpp:1285-1404)
 void Sh3BinaryEvaluator::getOutput(const std::vector<oc::BetaWire>& outWires, sbMatrix& out, bool) {
     if (outWires.size() != out.bitCount()) throw std::runtime_error(LOCATION);
+    if (mFast) {
+        if (outWires == mCir->mOutputs[0].mWires && !mFastTaken && mLevel > mCir->mLevelCounts.size() && mFastOut[0]) {
+            // the result planes become the output matrix: no copy
+            if (mFastRecv.valid()) mFastRecv.get();
+            out.resize(mWidth, out.bitCount());
+            for (int s = 0; s < 2; ++s) out.mShares[s].adoptDevice(std::move(mFastOut[s]));
+            mFastTaken = true;
+            return;
+        }
+        if (mFastTaken) throw std::runtime_error("binary engine: the output of this evaluation has already been taken " LOCATION);
+        materialize();
+    }
     if (out.rows() != mWidth) out.resize(mWidth, out.bitCount());
     const u64 bits = outWires.size();
     std::vector<u32> idx(outWires.begin(), outWires.end());
@@ -251,6 +368,8 @@ void Sh3BinaryEvaluator::getOutput(u64 i, sPackedBin& out, bool allowUninitializ
 
 // bit-sliced output: gather the wire rows, complementing inverted wires (.cpp:1213-1283)
 void Sh3BinaryEvaluator::getOutput(const std::vector<oc::BetaWire>& outWires, sPackedBin& out, bool) {
+    if (mFast && mFastTaken) throw std::runtime_error("binary engine: the output of this evaluation has already been taken " LOCATION);
+    materialize();
     out.reset(mWidth, outWires.size());
     const u64 n = outWires.size();
     std::vector<u32> idx(outWires.begin(), outWires.end());

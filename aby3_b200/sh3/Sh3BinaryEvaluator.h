@@ -28,6 +28,9 @@ public:
 
     void setInput(u64 i, const sbMatrix& in);
     void setInput(const oc::BetaBundle& wires, const sbMatrix& in);
+    // as setInput(i, in), but `in` is only READ when the evaluation is enqueued: the caller keeps it alive and unmodified
+    // until asyncEvaluate(...).get() / roundCallback has run (saves the copy on the row-major path below)
+    void setInputRef(u64 i, const sbMatrix& in);
     void setInput(u64 i, const sPackedBin& in);
     void setReplicatedInput(u64 i, const sbMatrix& in) { setInput(i, in); }
 
@@ -71,7 +74,24 @@ public:
     std::array<oc::AES, 2> mShareAES;   // [0] prev key, [1] next key
     u64 mShareIdx = 0;                  // nonlinear gates evaluated so far (z counter = mShareIdx * rowBytes/16)
 
+    // One-level bitwise circuits (int_int_bitwiseAnd / bitwiseOr) are evaluated on the row-major share words
+    // (aby3cu_bin_bitwise_rowmajor): no wire memory, no transposes; identical shares.  ABY3_BIN_ROWMAJOR=0 turns it off.
+    bool rowMajorPath() const { return mFast; }
+
 private:
+    // ---- the row-major path ------------------------------------------------------------------------------------
+    bool mFast = false, mFastTaken = false;
+    u32 mFastType = 0, mFastBits = 0;
+    std::array<std::array<gpu::Buffer, 2>, 2> mFastIn;          // [input][plane] copies (setInput)
+    std::array<std::array<const i64*, 2>, 2> mFastPtr{};        // [input][plane] what the kernel reads
+    std::array<gpu::Buffer, 2> mFastOut;                        // result planes, handed to the output matrix
+    std::future<void> mFastRecv;
+    static bool fastEligible(const oc::BetaCircuit& cir, u32& type, u32& bits);
+    void fastSetInput(const oc::BetaBundle& wires, const sbMatrix& in, bool copy);
+    void fastRound(CommPkg& comm);
+    void materialize();                                          // leave the row-major path: build the wire memory
+    void allocWireMemory();
+
     gpu::Context* mCtx = nullptr;
     u64 mWidth = 0, mRowBytes = 0;
     std::array<gpu::Buffer, 2> mMem;

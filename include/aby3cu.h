@@ -302,6 +302,15 @@ int aby3cu_bin_level(aby3cu_ctx* ctx, const uint32_t* d_gates, uint32_t n_gates,
  * block range of nonlinear gate and_index0 + g, exactly as aby3cu_bin_level would. */
 int aby3cu_bin_and_layer(aby3cu_ctx* ctx, const uint32_t* d_gates, uint32_t n_gates, void* d_mem0, const void* d_mem1,
                          uint64_t row_bytes, const uint8_t key_prev[16], const uint8_t key_next[16], uint64_t and_index0);
+/* A ONE-LEVEL bitwise circuit (oc::BetaLibrary::int_int_bitwiseAnd / bitwiseOr as aby3-Basic/BoolBasic.cpp:100-123,
+ * 193-209 evaluate them: gate g combines bit g of every instance) on ROW-MAJOR share words: setInput's transposes
+ * (:252), the gate loop (:729-798 / :912-981), getShares (:1406-1442) and getOutput's transpose (:1365) in one pass.
+ * out0[j] = f(a, b)[j] ^ z[j], bit g of z[j] = bit j of the zero-share blocks of nonlinear gate and_index0 + g
+ * (row_bytes = aby3cu_bin_row_bytes(n): the wire-row size that fixes the block ranges).  Same values as
+ * bit_transpose + bin_and_layer + bit_transpose_gather.  d_out_copy (may be NULL) receives a second copy (the message). */
+int aby3cu_bin_bitwise_rowmajor(aby3cu_ctx* ctx, uint32_t gate_type /* 8 = And, 14 = Or */, const int64_t* d_a0, const int64_t* d_a1,
+                                const int64_t* d_b0, const int64_t* d_b1, int64_t* d_out0, int64_t* d_out_copy, uint64_t n, uint32_t bits,
+                                uint64_t row_bytes, const uint8_t key_prev[16], const uint8_t key_next[16], uint64_t and_index0);
 /* sendBuff packing (:795-796) and getOutput(sPackedBin) (:1213-1283):
  * out[j*nbytes .. ) = first nbytes of row locs[j] of mem, complemented where d_invert[j] != 0
  * (d_invert may be NULL). */

@@ -406,3 +406,30 @@ def test_batched_entry_points_equal_the_single_problem_ones(ctx):
     abi.check(lib.aby3cu_gather_rows_multi(ctx.h, 12, ptrs(dsrc), cols, ptrs(dout), ctx.upload(idx).p, nb))
     for k in range(12):
         assert np.array_equal(ctx.download(dout[k], (nb, k % 3 + 1)), srcs[k][idx.astype(np.int64)])
+
+
+@pytest.mark.parametrize("gate", [8, 14])
+def test_bitwise_rowmajor_equals_the_sliced_definition(ctx, gate):
+    """aby3cu_bin_bitwise_rowmajor (one-level bitwise circuit on row-major words, z transposed in registers) against the
+    definition: out[j] bit g = f(a, b)[j] bit g ^ (bit j of the zero-share blocks of nonlinear gate and0 + g), keystreams
+    from the oracle.  Ragged instance counts, every bit width class, a non-zero first gate index."""
+    rng = np.random.default_rng(gate)
+    kp, kn = bytes(range(16)), bytes(range(100, 116))
+    for n, bits, and0 in ((1, 64, 0), (127, 64, 0), (128, 1, 3), (129, 13, 0), (3000, 32, 1), (2049, 33, 0), (70000, 64, 5), (4096, 63, 0)):
+        rb = int(lib.aby3cu_bin_row_bytes(n))
+        a0, a1, b0, b1 = (rng.integers(-2**63, 2**63, n, dtype=np.int64) for _ in range(4))
+        d = [ctx.upload(x) for x in (a0, a1, b0, b1)]
+        out, cp = ctx.alloc(8 * n), ctx.alloc(8 * n)
+        abi.check(lib.aby3cu_bin_bitwise_rowmajor(ctx.h, gate, d[0].p, d[1].p, d[2].p, d[3].p, out.p, cp.p, n, bits, rb, kp, kn, and0))
+        got = ctx.download(out, n)
+        assert np.array_equal(ctx.download(cp, n), got)
+        z = np.zeros((64, rb), dtype=np.uint8)
+        for g in range(bits):
+            z[g] = o.keystream(kp, (and0 + g) * rb, rb) ^ o.keystream(kn, (and0 + g) * rb, rb)
+        # z is 64 rows (gates) x n columns (instances), LSB first: transpose to n words of 64 bits
+        zt = o.bit_transpose(z.reshape(-1), 64, n, rb, 8).view(np.int64)[:n]
+        f = (a0 & b0) ^ (a0 & b1) ^ (a1 & b0)
+        if gate == 14:
+            f ^= a0 ^ b0
+        keep = np.int64(-1) if bits == 64 else np.int64((1 << bits) - 1)
+        assert np.array_equal(got, (f ^ zt) & keep), (n, bits, and0)

@@ -36,6 +36,7 @@ def main():
         print(name, "gates", len(cir["gates"]) // 4, "nonlinear", cir["nonlinear"], "levels", len(cir["level_gates"]), "wires", cir["wire_count"])
         timed(s, "bin_eval %s n=%d" % (name, n), lambda: [s.free(h) for h in s.bin_eval(cir, [A, B])])
     timed(s, "max_min_split n=%d" % n, lambda: [s.free(h) for h in s.max_min_split(A, B)])
+    timed(s, "max_min_split n=%d (10 reps)" % n, lambda: [s.free(h) for h in s.max_min_split(A, B)], reps=10)
     # one merge of two sorted halves of n elements each: where do the stages spend their time?
     d1 = np.sort(a[:, 0]).reshape(-1, 1)
     d2 = np.sort(b[:, 0]).reshape(-1, 1)
