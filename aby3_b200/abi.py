@@ -79,6 +79,7 @@ PROTOTYPES = {
     "aby3cu_trunc_finish": (_int, [_p, _p, _p, _p, _p, _sz, _u64]),
     "aby3cu_gemm_cross": (_int, [_p, _int, _p, _p, _p, _p, _u64, _u64, _u64, _p, _int]),
     "aby3cu_gemm_cross_after": (_int, [_p, _int, _p, _p, _p, _p, _u64, _u64, _u64, _p, _int, _p]),
+    "aby3cu_gemm_cross_blocks": (_int, [_p, _int, _p, _p, _p, _p, _u64, _u64, _u64, _p, _int, _p, _u64, _p, C.c_uint32]),
     "aby3cu_gemm_last_algo": (_int, [_p]),
     "aby3cu_gemm_last_main_kernel_ms": (_int, [_p, C.POINTER(C.c_float)]),
     "aby3cu_ot_send": (_int, [_p, _key, _u64, _p, _p, _sz]),

@@ -424,7 +424,32 @@ int aby3cu_gemm_cross_after(aby3cu_ctx* ctx, int algo, const i64* A0, const i64*
         ctx->c_ready = nullptr;
     }
     const int rc = aby3cu_gemm_cross(ctx, algo, A0, A1, B0, B1, M, K, N, C, accumulate);
-    ctx->c_ready = nullptr;
+    // an early exit (bad alignment, workspace allocation failure ...) must not leave the stream un-ordered behind the
+    // producer of C: buffers written there are about to be recycled by the caller's error path
+    if (ctx->c_ready) {
+        DeviceGuard g(ctx->device);
+        cudaStreamWaitEvent(ctx->stream, ctx->c_ready, 0);
+        ctx->c_ready = nullptr;
+    }
+    return rc;
+}
+
+int aby3cu_gemm_cross_blocks(aby3cu_ctx* ctx, int algo, const i64* A0, const i64* A1, const i64* B0, const i64* B1,
+                             u64 M, u64 K, u64 N, i64* C, int accumulate, void* c_ready, u64 block_rows, void** block_events, u32 n_blocks) {
+    ABY3CU_REQUIRE(ctx, "gemm_cross_blocks: null context");
+    ABY3CU_REQUIRE(block_rows && block_rows % 128 == 0 && block_events && (u64)n_blocks * block_rows >= M && (u64)(n_blocks - 1) * block_rows < M,
+                   "gemm_cross_blocks: block_rows must be a multiple of 128 and n_blocks = ceil(M / block_rows)");
+    ctx->blk_rows = block_rows;
+    ctx->blk_events = (cudaEvent_t*)block_events;
+    ctx->blk_n = n_blocks;
+    ctx->blk_done = 0;
+    const int rc = aby3cu_gemm_cross_after(ctx, algo, A0, A1, B0, B1, M, K, N, C, accumulate, c_ready);
+    // whatever ran (another algorithm, an early exit): every block event is recorded, so that nobody waits forever
+    {
+        DeviceGuard g(ctx->device);
+        for (; ctx->blk_done < ctx->blk_n; ++ctx->blk_done) cudaEventRecord(ctx->blk_events[ctx->blk_done], ctx->stream);
+    }
+    ctx->blk_rows = 0; ctx->blk_events = nullptr; ctx->blk_n = 0; ctx->blk_done = 0;
     return rc;
 }
 

@@ -37,6 +37,10 @@ struct aby3cu_ctx {
     int last_gemm_algo = 0;
     int corun = 0;                       // aby3cu_ctx_set_corun: AES kernels of this context are shaped to fit next to a running GEMM
     cudaEvent_t c_ready = nullptr;       // aby3cu_gemm_cross_after: waited for before the first kernel that touches C
+    // aby3cu_gemm_cross_blocks: rows per output block and the events recorded when each block of C is final
+    u64 blk_rows = 0;
+    cudaEvent_t* blk_events = nullptr;
+    u32 blk_n = 0, blk_done = 0;
     aby3cu::GemmWorkspace gemm_ws;   // limb planes for the tcgen05 GEMM
     cudaEvent_t ev_gemm0 = nullptr, ev_gemm1 = nullptr;   // bracket the main GEMM kernel
 };

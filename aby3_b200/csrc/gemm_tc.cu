@@ -407,6 +407,11 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
         const u64 kbh = (kc + TK - 1) / TK, kblocks = 2 * kbh;
         const size_t b_bytes = (size_t)ntiles * kblocks * B_CHUNK;
         u64 rows_per_block = (WS_A_LIMIT / ((size_t)kblocks * A_CHUNK)) * TM;
+        // aby3cu_gemm_cross_blocks: the caller wants C in row blocks of blk_rows (a multiple of the tile height) with an
+        // event after each; the workspace bound may only make the launches smaller, as long as they divide a block
+        const bool blocks = ctx->blk_rows && ctx->blk_events && ctx->blk_rows % TM == 0;
+        if (blocks && rows_per_block > ctx->blk_rows) rows_per_block = ctx->blk_rows;
+        if (blocks && ctx->blk_rows % rows_per_block) rows_per_block = TM;
         if (rows_per_block < TM) rows_per_block = TM;
         if (rows_per_block > M) rows_per_block = ((M + TM - 1) / TM) * TM;
         const size_t a_bytes = (size_t)(rows_per_block / TM) * kblocks * A_CHUNK;
@@ -432,6 +437,14 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
             k_gemm_tc<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(p);
             if (post_launch(ctx, "k_gemm_tc")) return 1;
             ABY3CU_CHECK(cudaEventRecord(ctx->ev_gemm1, ctx->stream));
+            // the last K chunk makes the rows final: signal every block that is complete now
+            if (blocks && k0 + K_MAX >= K) {
+                const u64 done_rows = r0 + rows;
+                while (ctx->blk_done < ctx->blk_n && ((u64)(ctx->blk_done + 1) * ctx->blk_rows <= done_rows || done_rows >= M)) {
+                    ABY3CU_CHECK(cudaEventRecord(ctx->blk_events[ctx->blk_done], ctx->stream));
+                    ++ctx->blk_done;
+                }
+            }
         }
     }
     return 0;

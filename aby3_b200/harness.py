@@ -30,6 +30,7 @@ def _load():
     l.sh3h_destroy.argtypes = [p]
     l.sh3h_set_disable_randomization.argtypes = [p, i32]
     l.sh3h_set_gemm_algo.argtypes = [p, i32]
+    l.sh3h_set_open_blocks.argtypes = [p, u64]
     l.sh3h_cursors.argtypes = [p, i32, p]
     l.sh3h_plain_create.argtypes = [p, i32, u64, u64, C.POINTER(p)]
     l.sh3h_plain_touch.argtypes = [p, i32, i32]
@@ -132,6 +133,10 @@ class Session:
 
     def disable_randomization(self, on=True):
         lib.sh3h_set_disable_randomization(self.h, int(on))
+
+    def set_open_blocks(self, blocks):
+        """row blocks in which the opened xy - r of a truncating matrix product travels (1 = one message)"""
+        lib.sh3h_set_open_blocks(self.h, int(blocks))
 
     def set_gemm_algo(self, algo):
         lib.sh3h_set_gemm_algo(self.h, int(algo))

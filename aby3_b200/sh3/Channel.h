@@ -38,6 +38,7 @@ struct Message {
     std::vector<u8> host;                 // host payload (when dev / shared are empty)
     aby3::gpu::Buffer dev;                // device payload (staging buffer owned by the sender's pool)
     std::shared_ptr<aby3::gpu::SharedBuffer> shared;   // device payload sent without a copy
+    size_t offset = 0;                    // payload starts this many bytes into `shared`
     void* ready = nullptr;                // event: payload complete on the sender's stream (null: same stream)
     int readyDevice = 0;
     size_t bytes = 0;
@@ -145,6 +146,11 @@ struct Transport {
         out->bytes = n;
         return postRecvDevice(out->own.ptr(), n);
     }
+    // The same on ANOTHER stream of the party (`on`, e.g. gpu::Context::comm()): a slice of a buffer the protocol never
+    // writes again leaves while the party's own stream keeps computing (the opened xy - r, block by block).
+    virtual void sendDeviceSharedOn(aby3::gpu::Context* on, const std::shared_ptr<aby3::gpu::SharedBuffer>& b, size_t off, size_t n) = 0;
+    virtual std::function<void()> postRecvDeviceOn(aby3::gpu::Context* on, void* d, size_t n) = 0;
+    virtual void flushOn(aby3::gpu::Context*) {}
     virtual void flush() {}
     virtual aby3::gpu::Context* context() const = 0;
     // late binding of the endpoint's device context (a Session hands out channels before it knows which party
@@ -176,7 +182,7 @@ struct LocalTransport : Transport {
             // device message consumed on the host (e.g. reveal into an i64Matrix)
             requireCtx();
             waitReady(m);
-            if (n) aby3::gpu::check(aby3cu_d2h(ctx->h(), p, m.dev ? m.dev.ptr() : m.shared->ptr(), n));
+            if (n) aby3::gpu::check(aby3cu_d2h(ctx->h(), p, m.dev ? m.dev.ptr() : (const u8*)m.shared->ptr() + m.offset, n));
             ctx->sync();
             m.dev.free();
             m.shared.reset();
@@ -202,6 +208,25 @@ struct LocalTransport : Transport {
         markReady(m);
         out->push(std::move(m));
     }
+    void sendDeviceSharedOn(aby3::gpu::Context* on, const std::shared_ptr<aby3::gpu::SharedBuffer>& b, size_t off, size_t n) override {
+        requireCtx();
+        if (b->ctx() != ctx) throw std::runtime_error("Channel: a shared buffer must come from the sender's own context " LOCATION);
+        Message m;
+        m.bytes = n;
+        m.shared = b;
+        m.offset = off;
+        m.ready = on->recordEvent();              // everything `on` was ordered behind (the block's GEMM) precedes it
+        m.readyDevice = on->device();
+        out->push(std::move(m));
+    }
+    std::function<void()> postRecvDeviceOn(aby3::gpu::Context* on, void* d, size_t n) override {
+        return [this, on, d, n] {
+            requireCtx();
+            Message m = in->pop();
+            if (m.bytes != n) throw std::runtime_error("Channel: message size mismatch " LOCATION);
+            deliver(m, d, n, on);
+        };
+    }
     // Parties whose contexts share ONE stream are ordered by enqueue order alone: the receiver's host thread
     // only learns of a message after the sender has enqueued its producer, so no event is needed.
     bool sameStream() const { return peerStream && peerStream == ctx->stream(); }
@@ -225,7 +250,7 @@ struct LocalTransport : Transport {
             aby3::gpu::Context* owner = m.shared ? m.shared->ctx() : (m.dev ? m.dev.ctx() : nullptr);
             if (owner && owner->device() == ctx->device()) {
                 waitReady(m);
-                if (m.shared) { b->shared = std::move(m.shared); b->ptr = b->shared->ptr(); }
+                if (m.shared) { b->shared = std::move(m.shared); b->ptr = (const u8*)b->shared->ptr() + m.offset; }
                 else { b->own = std::move(m.dev); b->ownedByPeer = true; b->ptr = b->own.ptr(); }
                 return;
             }
@@ -241,22 +266,28 @@ struct LocalTransport : Transport {
         if (m.bytes != n) throw std::runtime_error("Channel: message size mismatch " LOCATION);
         deliver(m, d, n);
     }
-    void deliver(Message& m, void* d, size_t n) {
+    // `on`: the stream (context) of this party that performs the copy; defaults to the party's own
+    void deliver(Message& m, void* d, size_t n, aby3::gpu::Context* on = nullptr) {
+        aby3::gpu::Context* c = on ? on : ctx;
         if (m.dev || m.shared) {
             aby3::gpu::Context* owner = m.dev ? m.dev.ctx() : m.shared->ctx();
-            const void* src = m.dev ? m.dev.ptr() : m.shared->ptr();
+            const void* src = m.dev ? m.dev.ptr() : (const void*)((const u8*)m.shared->ptr() + m.offset);
             const bool same = !m.ready;
-            waitReady(m);
-            if (n) aby3::gpu::check(aby3cu_d2d(ctx->h(), d, ctx->device(), src, owner->device(), n));
+            if (m.ready) {
+                aby3::gpu::check(aby3cu_event_wait(c->h(), m.ready));
+                aby3::gpu::EventPool::put(m.readyDevice, m.ready);
+                m.ready = nullptr;
+            }
+            if (n) aby3::gpu::check(aby3cu_d2d(c->h(), d, c->device(), src, owner->device(), n));
             // the payload returns to the sender's pool once OUR copy has run
-            if (m.dev) m.dev.free(same ? nullptr : ctx->recordEvent(), ctx->device());
+            if (m.dev) m.dev.free(same ? nullptr : c->recordEvent(), c->device());
             else {
-                if (!same) m.shared->addReader(ctx->device(), ctx->recordEvent());
+                if (!same) m.shared->addReader(c->device(), c->recordEvent());
                 m.shared.reset();
             }
         } else if (n) {
-            aby3::gpu::check(aby3cu_h2d(ctx->h(), d, m.host.data(), n));
-            ctx->sync();   // m.host dies with this scope
+            aby3::gpu::check(aby3cu_h2d(c->h(), d, m.host.data(), n));
+            c->sync();   // m.host dies with this scope
         }
     }
 };
@@ -301,21 +332,26 @@ private:
 struct NcclEndpoint {
     NcclApi::comm_t comm = nullptr;
     aby3::gpu::Context* ctx = nullptr;
-    struct Op { bool send; int peer; void* ptr; size_t bytes; };
+    struct Op { bool send; int peer; void* ptr; size_t bytes; std::shared_ptr<aby3::gpu::SharedBuffer> keep; };
     std::vector<Op> pending;
     std::vector<aby3::gpu::Buffer> staging;       // send copies, released after the flush
-    void flush() {
+    void flush() { flushOn(ctx); }
+    // issue everything queued as ONE group on `on`'s stream (the party's own, or its communication stream)
+    void flushOn(aby3::gpu::Context* on) {
         if (pending.empty()) return;
         auto& api = NcclApi::get();
-        void* stream = aby3cu_ctx_stream(ctx->h());
+        void* stream = aby3cu_ctx_stream(on->h());
         api.check(api.GroupStart(), "GroupStart");
         for (auto& op : pending) {
             if (op.send) api.check(api.Send(op.ptr, op.bytes, /*ncclUint8*/ 1, op.peer, comm, stream), "Send");
             else api.check(api.Recv(op.ptr, op.bytes, /*ncclUint8*/ 1, op.peer, comm, stream), "Recv");
         }
         api.check(api.GroupEnd(), "GroupEnd");
+        // buffers sent without a staging copy stay alive until the send has run on `on`
+        for (auto& op : pending)
+            if (op.keep) op.keep->addReader(on->device(), on->recordEvent());
         pending.clear();
-        staging.clear();                           // stream-ordered reuse: the sends above run first
+        if (on == ctx) staging.clear();            // stream-ordered reuse: the sends above run first (staging is drawn on ctx's stream)
     }
 };
 
@@ -327,11 +363,21 @@ struct NcclTransport : Transport {
         if (!n) return;
         aby3::gpu::Buffer b(ep->ctx, n);
         aby3::gpu::check(aby3cu_d2d(ep->ctx->h(), b.ptr(), ep->ctx->device(), d, ep->ctx->device(), n));
-        ep->pending.push_back({true, peer, b.ptr(), n});
+        ep->pending.push_back({true, peer, b.ptr(), n, nullptr});
         ep->staging.push_back(std::move(b));
     }
+    void sendDeviceSharedOn(aby3::gpu::Context*, const std::shared_ptr<aby3::gpu::SharedBuffer>& b, size_t off, size_t n) override {
+        if (!n) return;
+        ep->pending.push_back({true, peer, (u8*)b->ptr() + off, n, b});
+    }
+    std::function<void()> postRecvDeviceOn(aby3::gpu::Context* on, void* d, size_t n) override {
+        if (n) ep->pending.push_back({false, peer, d, n, nullptr});
+        auto e = ep;
+        return [e, on] { e->flushOn(on); };
+    }
+    void flushOn(aby3::gpu::Context* on) override { ep->flushOn(on); }
     std::function<void()> postRecvDevice(void* d, size_t n) override {
-        if (n) ep->pending.push_back({false, peer, d, n});
+        if (n) ep->pending.push_back({false, peer, d, n, nullptr});
         auto e = ep;
         return [e] { e->flush(); };
     }
@@ -340,12 +386,12 @@ struct NcclTransport : Transport {
         aby3::gpu::Buffer b(ep->ctx, n);
         aby3::gpu::check(aby3cu_h2d(ep->ctx->h(), b.ptr(), p, n));
         ep->ctx->sync();                           // p may be a temporary
-        ep->pending.push_back({true, peer, b.ptr(), n});
+        ep->pending.push_back({true, peer, b.ptr(), n, nullptr});
         ep->staging.push_back(std::move(b));
     }
     std::function<void()> postRecvHost(u8* p, size_t n) override {
         auto b = std::make_shared<aby3::gpu::Buffer>(ep->ctx, std::max<size_t>(n, 16));
-        if (n) ep->pending.push_back({false, peer, b->ptr(), n});
+        if (n) ep->pending.push_back({false, peer, b->ptr(), n, nullptr});
         auto e = ep;
         return [e, b, p, n] {
             e->flush();
@@ -490,6 +536,17 @@ public:
         require();
         return post(mT->postRecvDeviceBorrow(bytes, out));
     }
+    // Slices of such a buffer, moved by ANOTHER stream of the party (`on`): see Transport::sendDeviceSharedOn
+    void asyncSendDeviceSharedOn(aby3::gpu::Context* on, const std::shared_ptr<aby3::gpu::SharedBuffer>& buf, size_t off, size_t bytes) {
+        require();
+        *mBytesSent += bytes;
+        mT->sendDeviceSharedOn(on, buf, off, bytes);
+    }
+    std::future<void> asyncRecvDeviceOn(aby3::gpu::Context* on, void* d_dst, size_t bytes) {
+        require();
+        return post(mT->postRecvDeviceOn(on, d_dst, bytes));
+    }
+    void flushOn(aby3::gpu::Context* on) { if (mT) mT->flushOn(on); }
 
     // ------------------------------------------------------------------ stats -
     // copies of a Channel are handles to the same endpoint: they share the counter

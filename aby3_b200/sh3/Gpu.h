@@ -70,8 +70,10 @@ public:
     ~Context() {
         if (!mCtx) return;
         if (mAux) aby3cu_sync(mAux->h());
+        if (mComm) aby3cu_sync(mComm->h());
         aby3cu_sync(mCtx);
         mAux.reset();
+        mComm.reset();
         for (auto& kv : mFree)
             for (auto& e : kv.second) {
                 for (auto& ev : e.events) EventPool::put(ev.first, ev.second);
@@ -88,6 +90,7 @@ public:
     int device() const { return mDevice; }
     void sync() {
         if (mAux) check(aby3cu_sync(mAux->h()));
+        if (mComm) check(aby3cu_sync(mComm->h()));
         check(aby3cu_sync(mCtx));
     }
 
@@ -104,6 +107,17 @@ public:
         return mAux.get();
     }
     bool hasAux() const { return (bool)mAux; }
+    // ---- the party's communication stream: transfers that overlap the party's own kernels (block-wise opens) --------
+    Context* comm() {
+        if (!mComm) mComm.reset(new Context(mDevice));
+        return mComm.get();
+    }
+    void joinComm() {
+        if (!mComm) return;
+        void* e = mComm->recordEvent();
+        check(aby3cu_event_wait(mCtx, e));
+        mComm->recycleEvent(e);
+    }
     void joinAux() {
         if (!mAux) return;
         void* e = mAux->recordEvent();
@@ -320,7 +334,7 @@ private:
     u64 mGuardChecks = 0, mGuardBad = 0;
     aby3cu_ctx* mCtx = nullptr;
     int mDevice = 0;
-    std::unique_ptr<Context> mAux;
+    std::unique_ptr<Context> mAux, mComm;
     bool mCapturing = false;
     std::mutex mMtx;
     std::map<size_t, std::vector<Entry>> mFree;

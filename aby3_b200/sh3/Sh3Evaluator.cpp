@@ -157,14 +157,29 @@ Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64Matrix& A, const si
         }
         i64* RT0 = rt0.devOut();
         i64* RT1 = rt1.devOut();
+        // block-wise open (parties on different GPUs): same for every party, a function of the shape only
+        u64 blockRows = 0, nBlocks = 1;
+        if (mode == MulMode::Matmul && mOpenBlocks > 1 && M >= 256) {
+            blockRows = ((M + mOpenBlocks - 1) / mOpenBlocks + 127) / 128 * 128;
+            nBlocks = (M + blockRows - 1) / blockRows;
+        }
+        std::vector<void*> blockDone;
         if (mode == MulMode::Matmul) {
             // V = -r (pre-load), then V += A0*B0 + A0*B1 + A1*B0   (:662-665, :672)
             gpu::check(aby3cu_trunc_tuple(early ? ctx->aux()->h() : ctx->h(), kn, en, kp, ep, shift, nullptr, V, RT0, RT1, n));
             // the limb pre-pass of the operands does not wait for the pair, the contraction (which accumulates onto -r) does
             const i64 *a0 = A.mShares[0].dev(), *a1 = A.mShares[1].dev(), *b0 = B.mShares[0].dev(), *b1 = B.mShares[1].dev();
             void* pairDone = early ? ctx->aux()->recordEvent() : nullptr;
-            const int rc = aby3cu_gemm_cross_after(ctx->h(), mGemmAlgo, a0, a1, b0, b1, M, A.cols(), N, V, 1, pairDone);
+            int rc;
+            if (nBlocks > 1) {
+                for (u64 b = 0; b < nBlocks; ++b) blockDone.push_back(ctx->newEvent());
+                rc = aby3cu_gemm_cross_blocks(ctx->h(), mGemmAlgo, a0, a1, b0, b1, M, A.cols(), N, V, 1, pairDone, blockRows,
+                                              blockDone.data(), (u32)nBlocks);
+            } else {
+                rc = aby3cu_gemm_cross_after(ctx->h(), mGemmAlgo, a0, a1, b0, b1, M, A.cols(), N, V, 1, pairDone);
+            }
             if (pairDone) ctx->aux()->recycleEvent(pairDone);
+            if (rc) for (void* e : blockDone) ctx->recycleEvent(e);
             gpu::check(rc);
         } else {
             gpu::check(aby3cu_mul_hadamard_trunc(ctx->h(), A.mShares[0].dev(), A.mShares[1].dev(), B.mShares[0].dev(),
@@ -177,6 +192,41 @@ Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64Matrix& A, const si
         // open xy - r to parties 0 and 1 (:676-684)
         auto& rt = self.getRuntime();
         const u64 next = (rt.mPartyIdx + 1) % 3, prev = (rt.mPartyIdx + 2) % 3;
+        if (nBlocks > 1) {
+            // block b travels on the communication stream once its rows are final; later blocks are still multiplying
+            gpu::Context* cm = ctx->comm();
+            struct Recv { gpu::Buffer s0, s1; std::vector<std::shared_future<void>> fu; };
+            auto rc = std::make_shared<Recv>();
+            if (rt.mPartyIdx < 2) { rc->s0.reset(ctx, bytes); rc->s1.reset(ctx, bytes); }
+            {   // the receive buffers come from the party's pool: the communication stream starts behind their last use
+                void* e = ctx->recordEvent();
+                gpu::check(aby3cu_event_wait(cm->h(), e));
+                ctx->recycleEvent(e);
+            }
+            for (u64 b = 0; b < nBlocks; ++b) {
+                const u64 r0 = b * blockRows, rows = std::min(blockRows, M - r0);
+                const size_t off = r0 * N * sizeof(i64), len = rows * N * sizeof(i64);
+                gpu::check(aby3cu_event_wait(cm->h(), blockDone[b]));
+                ctx->recycleEvent(blockDone[b]);
+                if (next < 2) comm.mNext.asyncSendDeviceSharedOn(cm, sc->v, off, len);
+                if (prev < 2) comm.mPrev.asyncSendDeviceSharedOn(cm, sc->v, off, len);
+                if (rt.mPartyIdx < 2) {
+                    rc->fu.push_back(comm.mNext.asyncRecvDeviceOn(cm, (u8*)rc->s0.ptr() + off, len).share());
+                    rc->fu.push_back(comm.mPrev.asyncRecvDeviceOn(cm, (u8*)rc->s1.ptr() + off, len).share());
+                }
+                comm.mNext.flushOn(cm);          // NCCL: the block's sends and receives are ONE group (both channels share the endpoint)
+                comm.mPrev.flushOn(cm);
+            }
+            if (rt.mPartyIdx < 2) {
+                self.then([rc, sc, &C, shift, n, ctx, this](CommPkg&, Sh3Task&) mutable {
+                    for (auto& f : rc->fu) f.get();
+                    ctx->joinComm();
+                    gpu::check(aby3cu_trunc_finish(ctx->h(), (const i64*)rc->s0.ptr(), (const i64*)rc->s1.ptr(),
+                                                   (const i64*)sc->v->ptr(), C.mShares[mPartyIdx].devMut(), n, shift));
+                });
+            }
+            return;
+        }
         if (next < 2) comm.mNext.asyncSendDeviceShared(sc->v, n * sizeof(i64));
         if (prev < 2) comm.mPrev.asyncSendDeviceShared(sc->v, n * sizeof(i64));
         if (rt.mPartyIdx < 2) {

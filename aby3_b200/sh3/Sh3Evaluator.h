@@ -142,6 +142,11 @@ public:
         return !(e && e[0] == '0');
     }
 
+    // Parties on DIFFERENT GPUs: the opened xy - r of a truncating matrix product (Sh3Evaluator.cpp:681-684) leaves in
+    // mOpenBlocks row blocks, each on the party's communication stream as soon as its rows are final, while the later
+    // blocks still multiply.  A protocol parameter: every party must use the same value (1 = one message, the default).
+    u64 mOpenBlocks = 1;
+
     Sh3Task asyncMul(Sh3Task dependency, const si64& A, const si64& B, si64& C);
     Sh3Task asyncMul(Sh3Task dependency, const si64Matrix& A, const si64Matrix& B, si64Matrix& C);
     Sh3Task asyncMul(Sh3Task dependency, const si64Matrix& A, const si64Matrix& B, si64Matrix& C, u64 shift);

@@ -169,6 +169,11 @@ static sh3h* create_impl(int dev0, int dev1, int dev2, const uint8_t* enc_seeds,
             P.rt.init(i, P.comm);
             P.enc.init(i, blk(enc_seeds + (2 * i) * 16), blk(enc_seeds + (2 * i + 1) * 16));
             P.eval.init(i, blk(eval_seeds + (2 * i) * 16), blk(eval_seeds + (2 * i + 1) * 16));
+            // parties on different GPUs: the opened xy - r leaves in row blocks while the product is still running
+            if (dev[0] != dev[1] || dev[1] != dev[2]) {
+                const char* e = std::getenv("ABY3_OPEN_BLOCKS");
+                P.eval.mOpenBlocks = e ? std::max(1, atoi(e)) : 4;
+            }
             gpu::check(aby3cu_event_create(P.ctx->h(), &P.ev_start));
             gpu::check(aby3cu_event_create(P.ctx->h(), &P.ev_stop));
         });
@@ -204,6 +209,10 @@ void sh3h_destroy(sh3h* h) {
 
 int sh3h_set_disable_randomization(sh3h* h, int on) {
     for (int i = 0; i < 3; ++i) h->p[i].eval.DEBUG_disable_randomization = on != 0;
+    return 0;
+}
+int sh3h_set_open_blocks(sh3h* h, uint64_t blocks) {
+    for (int i = 0; i < 3; ++i) h->p[i].eval.mOpenBlocks = blocks ? blocks : 1;
     return 0;
 }
 int sh3h_set_gemm_algo(sh3h* h, int algo) {

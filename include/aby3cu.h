@@ -151,6 +151,13 @@ int aby3cu_gemm_cross_after(aby3cu_ctx* ctx, int algo,
                             const int64_t* d_A0, const int64_t* d_A1,
                             const int64_t* d_B0, const int64_t* d_B1,
                             uint64_t M, uint64_t K, uint64_t N, int64_t* d_C, int accumulate, void* c_ready);
+/* The same product delivered in ROW BLOCKS: block b = rows [b * block_rows, (b + 1) * block_rows) of C is final when
+ * block_events[b] (caller-created events, n_blocks = ceil(M / block_rows), block_rows a multiple of 128) has been
+ * reached on the context's stream -- the reshare of xy - r (Sh3Evaluator.cpp:681-684) of block b can then travel on
+ * another stream while block b + 1 is still being multiplied.  Every event is recorded even on failure. */
+int aby3cu_gemm_cross_blocks(aby3cu_ctx* ctx, int algo, const int64_t* d_A0, const int64_t* d_A1, const int64_t* d_B0,
+                             const int64_t* d_B1, uint64_t M, uint64_t K, uint64_t N, int64_t* d_C, int accumulate,
+                             void* c_ready_event, uint64_t block_rows, void** block_events, uint32_t n_blocks);
 /* algo actually used by the last aby3cu_gemm_cross on this context */
 int aby3cu_gemm_last_algo(const aby3cu_ctx* ctx);
 /* device time (CUDA events on the context's stream) of the main GEMM kernel of the

@@ -716,3 +716,24 @@ def test_early_truncation_pair_stream_matches_oracle(pair):
     ref = (a @ b) >> D
     assert np.max(np.abs(s.reveal(F, 0) - ref)) <= 4
     assert_cursors(s, r)
+
+
+@pytest.mark.parametrize("blocks,dims", [(4, (1024, 96, 200)), (3, (700, 64, 130)), (8, (256, 64, 64)), (4, (130, 64, 64))])
+def test_block_wise_open_of_the_truncating_product_matches_oracle(pair, blocks, dims):
+    """Sh3Evaluator::mOpenBlocks > 1 (the distributed placement's overlap of reshare and contraction): the opened xy - r
+    travels in row blocks on the parties' communication streams, each as soon as aby3cu_gemm_cross_blocks has made its
+    rows final.  Same shares and cursors as the one-message form, ragged last block and tiny shapes (no blocking) included."""
+    s, r = pair
+    s.set_gemm_algo(abi.GEMM_TCGEN05)
+    s.set_open_blocks(blocks)
+    M, K, N = dims
+    rng = np.random.default_rng(M)
+    a = (rng.uniform(-8, 8, (M, K)) * 65536).astype(np.int64)
+    b = (rng.uniform(-8, 8, (K, N)) * 65536).astype(np.int64)
+    A, B = s.share_int(0, a), s.share_int(2, b)
+    Ao, Bo = r.share_int(0, a), r.share_int(2, b)
+    for _ in range(3):
+        C = s.mul(A, B, shift=16)
+        assert np.array_equal(s.get_shares(C), r.mul_trunc(Ao, Bo, 16))
+        s.free(C)
+    assert_cursors(s, r)
