@@ -162,6 +162,9 @@ int aby3cu_ctx_destroy(aby3cu_ctx* ctx) {
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->gemm_ws.ptr) cudaFree(ctx->gemm_ws.ptr);
+    if (ctx->progress_stream) { cudaStreamSynchronize(ctx->progress_stream); cudaStreamDestroy(ctx->progress_stream); }
+    if (ctx->progress_reset) cudaEventDestroy(ctx->progress_reset);
+    if (ctx->progress) cudaFree(ctx->progress);
     if (ctx->ev_gemm0) cudaEventDestroy(ctx->ev_gemm0);
     if (ctx->ev_gemm1) cudaEventDestroy(ctx->ev_gemm1);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);

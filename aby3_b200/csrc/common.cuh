@@ -41,6 +41,11 @@ struct aby3cu_ctx {
     u64 blk_rows = 0;
     cudaEvent_t* blk_events = nullptr;
     u32 blk_n = 0, blk_done = 0;
+    // one launch, many blocks: the GEMM counts finished tiles per raster group in `progress` (device memory) and a helper
+    // stream turns "group complete" into the caller's block events (cuStreamWaitValue32)
+    u32* progress = nullptr;
+    cudaStream_t progress_stream = nullptr;
+    cudaEvent_t progress_reset = nullptr;
     aby3cu::GemmWorkspace gemm_ws;   // limb planes for the tcgen05 GEMM
     cudaEvent_t ev_gemm0 = nullptr, ev_gemm1 = nullptr;   // bracket the main GEMM kernel
 };

@@ -197,6 +197,7 @@ struct Params {
     u64 N;
     u32 mtiles, ntiles, kblocks;
     int accumulate;
+    u32* progress;      // may be NULL: progress[g] += 1 per epilogue warp per finished tile of raster group g
 };
 
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ Params p) {
@@ -353,6 +354,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
             }
             tc_fence_before();
             mbar_arrive(tmem_empty);
+            if (p.progress) {
+                // this warp's 32 rows of the tile are in memory: count them towards the tile's raster group
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(p.progress + t / (RASTER_M * p.ntiles), 1u);
+            }
         }
     }
 
@@ -371,6 +378,20 @@ bool gemm_tc_profitable(u64 M, u64 K, u64 N) {
     // amortise the limb-split pre-pass; skinny shapes go to the CUDA-core kernels
     return N >= 32 && M >= 64 && K >= 64 && M * N * K >= (1ull << 21);
 }
+
+// cuStreamWaitValue32 through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long /*CUdeviceptr*/, unsigned int, unsigned int);
+static StreamWaitValue32Fn stream_wait_value32() {
+    static StreamWaitValue32Fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        (void)cudaGetLastError();
+        return (StreamWaitValue32Fn)p;
+    }();
+    return fn;
+}
+constexpr u32 kProgressSlots = 1024;
 
 static int ensure_ws(aby3cu_ctx* ctx, size_t bytes) {
     if (ctx->gemm_ws.bytes >= bytes) return 0;
@@ -410,9 +431,42 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
         // aby3cu_gemm_cross_blocks: the caller wants C in row blocks of blk_rows (a multiple of the tile height) with an
         // event after each; the workspace bound may only make the launches smaller, as long as they divide a block
         const bool blocks = ctx->blk_rows && ctx->blk_events && ctx->blk_rows % TM == 0;
-        if (blocks && rows_per_block > ctx->blk_rows) rows_per_block = ctx->blk_rows;
-        if (blocks && ctx->blk_rows % rows_per_block) rows_per_block = TM;
+        // ONE launch when the whole product fits the workspace and the blocks are whole raster groups: the kernel counts
+        // finished tiles per group and a helper stream fires the block events (no wave quantisation per block);
+        // otherwise one launch per block
+        const u64 group_rows = (u64)RASTER_M * TM;
+        const bool progress = blocks && K <= K_MAX && rows_per_block >= M && ctx->blk_rows % group_rows == 0 &&
+                              (M + group_rows - 1) / group_rows <= kProgressSlots && stream_wait_value32() != nullptr &&
+                              !getenv("ABY3CU_NO_PROGRESS");
+        if (blocks && !progress && rows_per_block > ctx->blk_rows) rows_per_block = ctx->blk_rows;
+        if (blocks && !progress && ctx->blk_rows % rows_per_block) rows_per_block = TM;
         if (rows_per_block < TM) rows_per_block = TM;
+        if (progress) {
+            if (!ctx->progress) {
+                ABY3CU_CHECK(cudaMalloc(&ctx->progress, kProgressSlots * sizeof(u32)));
+                ABY3CU_CHECK(cudaStreamCreateWithFlags(&ctx->progress_stream, cudaStreamNonBlocking));
+                ABY3CU_CHECK(cudaEventCreateWithFlags(&ctx->progress_reset, cudaEventDisableTiming));
+            }
+            // the helper stream must have fired the previous product's events before the counters are cleared
+            ABY3CU_CHECK(cudaEventRecord(ctx->progress_reset, ctx->progress_stream));
+            ABY3CU_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->progress_reset, 0));
+            ABY3CU_CHECK(cudaMemsetAsync(ctx->progress, 0, kProgressSlots * sizeof(u32), ctx->stream));
+            ABY3CU_CHECK(cudaEventRecord(ctx->progress_reset, ctx->stream));
+            ABY3CU_CHECK(cudaStreamWaitEvent(ctx->progress_stream, ctx->progress_reset, 0));
+            const u64 mt_all = (M + TM - 1) / TM, gpb = ctx->blk_rows / group_rows, ngroups = (mt_all + RASTER_M - 1) / RASTER_M;
+            for (u32 b = 0; b < ctx->blk_n; ++b) {
+                for (u64 g = b * gpb; g < (b + 1) * gpb && g < ngroups; ++g) {
+                    const u64 gm = (mt_all - g * RASTER_M < RASTER_M) ? (mt_all - g * RASTER_M) : RASTER_M;
+                    const u32 target = (u32)(gm * ntiles * 4);            // four epilogue warps per tile
+                    if (stream_wait_value32()(ctx->progress_stream, (unsigned long long)(uintptr_t)(ctx->progress + g), target, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) {
+                        set_error("cuStreamWaitValue32 failed");
+                        return 1;
+                    }
+                }
+                ABY3CU_CHECK(cudaEventRecord(ctx->blk_events[b], ctx->progress_stream));
+            }
+            ctx->blk_done = ctx->blk_n;          // all events are armed
+        }
         if (rows_per_block > M) rows_per_block = ((M + TM - 1) / TM) * TM;
         const size_t a_bytes = (size_t)(rows_per_block / TM) * kblocks * A_CHUNK;
         if (ensure_ws(ctx, a_bytes + b_bytes)) return 1;
@@ -429,6 +483,7 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
             Params p;
             p.pa = pa; p.pb = pb; p.C = (u64*)C; p.row0 = r0; p.rows_end = r0 + rows; p.N = N;
             p.mtiles = (u32)mtiles; p.ntiles = (u32)ntiles; p.kblocks = (u32)kblocks; p.accumulate = acc_this;
+            p.progress = progress ? ctx->progress : nullptr;
             const u64 tiles = mtiles * ntiles;
             const unsigned grid = (unsigned)(tiles < (u64)ctx->sm_count ? tiles : (u64)ctx->sm_count);
             if (ctx->c_ready) { ABY3CU_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->c_ready, 0)); ctx->c_ready = nullptr; }   // after the limb pre-pass
@@ -438,7 +493,7 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
             if (post_launch(ctx, "k_gemm_tc")) return 1;
             ABY3CU_CHECK(cudaEventRecord(ctx->ev_gemm1, ctx->stream));
             // the last K chunk makes the rows final: signal every block that is complete now
-            if (blocks && k0 + K_MAX >= K) {
+            if (blocks && !progress && k0 + K_MAX >= K) {
                 const u64 done_rows = r0 + rows;
                 while (ctx->blk_done < ctx->blk_n && ((u64)(ctx->blk_done + 1) * ctx->blk_rows <= done_rows || done_rows >= M)) {
                     ABY3CU_CHECK(cudaEventRecord(ctx->blk_events[ctx->blk_done], ctx->stream));

@@ -140,7 +140,10 @@ struct Transport {
     virtual std::function<void()> postRecvDevice(void* d, size_t n) = 0;
     // zero-copy forms; the defaults fall back to the copying ones
     virtual void sendDeviceShared(const std::shared_ptr<aby3::gpu::SharedBuffer>& b, size_t n) { sendDevice(b->ptr(), n); }
-    virtual std::function<void()> postRecvDeviceBorrow(size_t n, Borrowed* out) {
+    // `on` (may be null = the party's own stream): the stream that performs a cross-device copy, so that two incoming
+    // messages from two different GPUs travel side by side instead of one after the other
+    virtual std::function<void()> postRecvDeviceBorrow(size_t n, Borrowed* out, aby3::gpu::Context* on = nullptr) {
+        (void)on;
         out->own.reset(context(), std::max<size_t>(n, 16));
         out->ptr = out->own.ptr();
         out->bytes = n;
@@ -241,8 +244,8 @@ struct LocalTransport : Transport {
         aby3::gpu::EventPool::put(m.readyDevice, m.ready);
         m.ready = nullptr;
     }
-    std::function<void()> postRecvDeviceBorrow(size_t n, Borrowed* b) override {
-        return [this, n, b] {
+    std::function<void()> postRecvDeviceBorrow(size_t n, Borrowed* b, aby3::gpu::Context* on = nullptr) override {
+        return [this, n, b, on] {
             requireCtx();
             Message m = in->pop();
             if (m.bytes != n) throw std::runtime_error("Channel: message size mismatch " LOCATION);
@@ -257,7 +260,12 @@ struct LocalTransport : Transport {
             // another GPU (NVLink peer copy) or a host payload: land it in a buffer of our own
             b->own.reset(ctx, std::max<size_t>(n, 16));
             b->ptr = b->own.ptr();
-            deliver(m, b->own.ptr(), n);
+            if (on) {       // the buffer comes from the party's pool (own-stream order): `on` starts behind its last use
+                void* e = ctx->recordEvent();
+                aby3::gpu::check(aby3cu_event_wait(on->h(), e));
+                ctx->recycleEvent(e);
+            }
+            deliver(m, b->own.ptr(), n, on);
         };
     }
     void recvDevice(void* d, size_t n) {
@@ -532,9 +540,9 @@ public:
         *mBytesSent += bytes;
         mT->sendDeviceShared(buf, bytes);
     }
-    std::future<void> asyncRecvDeviceBorrow(size_t bytes, Borrowed* out) {
+    std::future<void> asyncRecvDeviceBorrow(size_t bytes, Borrowed* out, aby3::gpu::Context* on = nullptr) {
         require();
-        return post(mT->postRecvDeviceBorrow(bytes, out));
+        return post(mT->postRecvDeviceBorrow(bytes, out, on));
     }
     // Slices of such a buffer, moved by ANOTHER stream of the party (`on`): see Transport::sendDeviceSharedOn
     void asyncSendDeviceSharedOn(aby3::gpu::Context* on, const std::shared_ptr<aby3::gpu::SharedBuffer>& buf, size_t off, size_t bytes) {

@@ -230,10 +230,14 @@ Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64Matrix& A, const si
         if (next < 2) comm.mNext.asyncSendDeviceShared(sc->v, n * sizeof(i64));
         if (prev < 2) comm.mPrev.asyncSendDeviceShared(sc->v, n * sizeof(i64));
         if (rt.mPartyIdx < 2) {
+            // two senders, possibly on two other GPUs: the second message lands through the communication stream so that
+            // the two NVLink copies run side by side
+            const bool big = bytes >= (size_t(8) << 20);
             auto fu0 = comm.mNext.asyncRecvDeviceBorrow(n * sizeof(i64), &sc->s0).share();
-            auto fu1 = comm.mPrev.asyncRecvDeviceBorrow(n * sizeof(i64), &sc->s1).share();
-            self.then([fu0, fu1, sc, &C, shift, n, ctx, this](CommPkg&, Sh3Task&) mutable {
+            auto fu1 = comm.mPrev.asyncRecvDeviceBorrow(n * sizeof(i64), &sc->s1, big ? ctx->comm() : nullptr).share();
+            self.then([fu0, fu1, sc, &C, shift, n, ctx, big, this](CommPkg&, Sh3Task&) mutable {
                 fu0.get(); fu1.get();
+                if (big) ctx->joinComm();
                 // C[mPartyIdx] += (s0 + s1 + v) >> shift   (:712-718)
                 gpu::check(aby3cu_trunc_finish(ctx->h(), (const i64*)sc->s0.ptr, (const i64*)sc->s1.ptr,
                                                (const i64*)sc->v->ptr(), C.mShares[mPartyIdx].devMut(), n, shift));

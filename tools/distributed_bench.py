@@ -14,8 +14,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from aby3_b200 import harness  # noqa: E402
 
 
-def run(devices, transport, n=4096, steps=10, shift=16):
+def run(devices, transport, n=4096, steps=10, shift=16, blocks=None):
     s = harness.Session(devices=devices, transport=transport)
+    if blocks is not None:
+        s.set_open_blocks(blocks)
     rng = np.random.default_rng(0)
     a = (rng.uniform(-4, 4, (n, n)) * (1 << shift)).astype(np.int64)
     b = (rng.uniform(-4, 4, (n, n)) * (1 << shift)).astype(np.int64)
@@ -34,14 +36,15 @@ def run(devices, transport, n=4096, steps=10, shift=16):
     c = s.reveal(C, 0)
     err = int(np.max(np.abs(c[:8] - ((a[:8] @ b) >> shift))))
     s.close()
-    return {"devices": list(devices), "transport": transport, "ms_per_step": dt * 1e3, "ring_mac_per_s": n ** 3 / dt,
+    return {"devices": list(devices), "transport": transport, "open_blocks": blocks, "ms_per_step": dt * 1e3, "ring_mac_per_s": n ** 3 / dt,
             "bytes_between_parties_per_step": sent, "reshare_GBps": sent / dt / 1e9, "max_abs_err_ulp": err}
 
 
 def main():
     out = [run((0, 0, 0), "local")]
-    out.append(run((0, 1, 2), "local"))
-    out.append(run((0, 1, 2), "nccl"))
+    for blocks in (1, 2, 4, 8):
+        out.append(run((0, 1, 2), "local", blocks=blocks))
+        out.append(run((0, 1, 2), "nccl", blocks=blocks))
     for o in out:
         print(json.dumps(o), flush=True)
 
