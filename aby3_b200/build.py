@@ -43,7 +43,9 @@ def build_cuda(force=False):
     so = os.path.join(PKG, "libaby3cu.so")
     srcs = _sources(os.path.join(PKG, "csrc"), (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "aby3cu.h")]
     if force or _newer(so, srcs):
-        _run([NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+        # ABY3CU_NVCC_DEFS="-DABY3CU_GEMM_STAGES=4 ..." : experiment switches of the kernels
+        extra = os.environ.get("ABY3CU_NVCC_DEFS", "").split()
+        _run([NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", *extra,
               "-o", so, os.path.join(PKG, "csrc", "aby3cu_all.cu")])
     return so
 

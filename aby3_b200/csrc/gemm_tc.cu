@@ -38,7 +38,10 @@ namespace tc {
 constexpr int TM = 128;            // tile rows  (= MMA M, TMEM lanes)
 constexpr int TN = 64;             // tile cols  (per limb accumulator)
 constexpr int TK = 32;             // k per stage (= MMA K for 8-bit operands)
-constexpr int STAGES = 3;
+#ifndef ABY3CU_GEMM_STAGES
+#define ABY3CU_GEMM_STAGES 3
+#endif
+constexpr int STAGES = ABY3CU_GEMM_STAGES;
 constexpr u32 A_CHUNK = 8 * TM * TK;      // 32768 B
 constexpr u32 B_CHUNK = 8 * TN * TK;      // 16384 B
 constexpr u32 STAGE_BYTES = A_CHUNK + B_CHUNK;
@@ -395,6 +398,13 @@ constexpr u32 kProgressSlots = 1024;
 
 static int ensure_ws(aby3cu_ctx* ctx, size_t bytes) {
     if (ctx->gemm_ws.bytes >= bytes) return 0;
+    {   // growing means a host synchronisation and a driver allocation: not inside a stream capture
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(ctx->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+            set_error("gemm_cross(tcgen05): the limb workspace would have to grow during a stream capture; run the shape once before capturing");
+            return 2;
+        }
+    }
     if (ctx->gemm_ws.ptr) {
         ABY3CU_CHECK(cudaStreamSynchronize(ctx->stream));
         ABY3CU_CHECK(cudaFree(ctx->gemm_ws.ptr));
@@ -409,10 +419,19 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
                   u64 M, u64 K, u64 N, i64* C, int accumulate) {
     using namespace tc;
     ABY3CU_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm_cross(tcgen05): C must be 16-byte aligned");
-    ABY3CU_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    if (prefer_max_smem(k_gemm_tc)) return 1;
-    // the limb pre-pass of ANOTHER party is meant to run beside a GEMM CTA: same carve-out, or the SM has to drain first
-    if (prefer_max_smem(k_pack_a) || prefer_max_smem(k_pack_b)) return 1;
+    // function attributes are per device: set once per device, not on every call
+    static std::mutex attr_mtx;
+    static bool attr_done[64] = {};
+    {
+        std::lock_guard<std::mutex> g(attr_mtx);
+        if (ctx->device < 0 || ctx->device >= 64 || !attr_done[ctx->device]) {
+            ABY3CU_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            if (prefer_max_smem(k_gemm_tc)) return 1;
+            // the limb pre-pass of ANOTHER party is meant to run beside a GEMM CTA: same carve-out, or the SM has to drain first
+            if (prefer_max_smem(k_pack_a) || prefer_max_smem(k_pack_b)) return 1;
+            if (ctx->device >= 0 && ctx->device < 64) attr_done[ctx->device] = true;
+        }
+    }
     const u64 ntiles = (N + TN - 1) / TN;
     // bound the limb-plane workspace: B panel for one K chunk + A panel for one row block
     // (ABY3CU_WS_LIMIT_MB shrinks it so that tests can exercise the row-block loop)

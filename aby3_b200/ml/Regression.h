@@ -42,6 +42,7 @@ void SGD_Linear(RegressionParam& params, Engine& engine, sf64Matrix<D>& X, sf64M
                 const std::vector<u64>& batchIndices) {
     if (X.rows() != Y.rows() || Y.cols() != 1) throw std::runtime_error(LOCATION);
     if (batchIndices.size() != params.mIterations * params.mBatchSize) throw std::runtime_error(LOCATION);
+    for (u64 i : batchIndices) if (i >= (u64)X.rows()) throw std::runtime_error("SGD: batch index out of range " LOCATION);
     gpu::Context* ctx = gpu::current();
     gpu::Buffer dIdx(ctx, std::max<size_t>(batchIndices.size() * 8, 16));
     gpu::check(aby3cu_h2d(ctx->h(), dIdx.ptr(), batchIndices.data(), batchIndices.size() * 8));
@@ -88,6 +89,7 @@ void SGD_Logistic(RegressionParam& params, Engine& engine, sf64Matrix<D>& X, sf6
                   const std::vector<u64>& batchIndices) {
     if (X.rows() != Y.rows() || Y.cols() != 1) throw std::runtime_error(LOCATION);
     if (batchIndices.size() != params.mIterations * params.mBatchSize) throw std::runtime_error(LOCATION);
+    for (u64 i : batchIndices) if (i >= (u64)X.rows()) throw std::runtime_error("SGD: batch index out of range " LOCATION);
     gpu::Context* ctx = gpu::current();
     gpu::Buffer dIdx(ctx, std::max<size_t>(batchIndices.size() * 8, 16));
     gpu::check(aby3cu_h2d(ctx->h(), dIdx.ptr(), batchIndices.data(), batchIndices.size() * 8));

@@ -35,6 +35,7 @@ public:
         const u64 F = P[0].X->cols(), rows = P[0].X->rows();
         if (!iters) return 0;
         if (batchIndices.size() != iters * B) throw std::runtime_error(LOCATION);
+        for (u64 i : batchIndices) if (i >= rows) throw std::runtime_error("ColocatedSgdLinear: batch index out of range " LOCATION);
         for (auto& p : P) {
             if (p.ctx->device() != P[0].ctx->device()) throw std::runtime_error("ColocatedSgdLinear: the parties must share one GPU " LOCATION);
             if (p.X->rows() != rows || p.X->cols() != F || p.Y->rows() != rows || p.Y->cols() != 1 || p.w->rows() != F || p.w->cols() != 1)

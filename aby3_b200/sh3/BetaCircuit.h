@@ -104,6 +104,16 @@ public:
     // (construction order): a nonlinear gate may read same-level linear outputs but nothing reads a
     // nonlinear output before the next level, so the nonlinear gates of a level are independent.
     void levelByAndDepth() {
+        // the level sort below may move a gate past another one: only sound when every wire is written once
+        {
+            std::vector<u8> written(mWireCount, 0);
+            for (auto& in : mInputs) for (auto w : in.mWires) written[w] = 1;
+            for (auto& G : mGates) {
+                if (written[G.mOutput]) throw std::runtime_error("BetaCircuit::levelByAndDepth: wire " + std::to_string(G.mOutput) +
+                                                                 " is written more than once; level the circuit by hand (loadFlat) " LOCATION);
+                written[G.mOutput] = 1;
+            }
+        }
         std::vector<u32> ready(mWireCount, 0);     // first level at which the wire's value is usable
         std::vector<u32> lvl(mGates.size());
         u32 maxLevel = 0;

@@ -69,10 +69,22 @@ void Sh3BinaryEvaluator::setCir(oc::BetaCircuit* cir, u64 width, block prevSeed,
         mLevelGateOff.push_back(mLevelGateOff.back() + cir->mLevelCounts[l]);
         mLevelAndOff.push_back(mLevelAndOff.back() + cir->mLevelAndCounts[l]);
     }
+    // The gate x column parallel AND layer assumes that no gate of a level overwrites a wire another gate of the level
+    // reads or writes (every wire written once).  Circuits that reuse wires (hand-made gate lists; validateMemory already
+    // reckons with them) take the sequential in-order kernel for the affected levels.
+    std::vector<u32> writes(cir->mWireCount, 0);
+    for (auto& G : cir->mGates) ++writes[G.mOutput];
+    for (auto& in : cir->mInputs) for (auto w : in.mWires) ++writes[w];
     mLevelLinear.clear();
     for (u64 l = 0; l < cir->mLevelCounts.size(); ++l) {
         u64 g = mLevelGateOff[l];
         const u64 end = mLevelGateOff[l + 1];
+        bool reused = false;
+        for (u64 k = g; k < end; ++k) {
+            const auto& G = cir->mGates[k];
+            reused |= writes[G.mOutput] > 1 || writes[G.mInput[0]] > 1 || writes[G.mInput[1]] > 1;
+        }
+        if (reused) { mLevelLinear.push_back(-1); continue; }
         while (g < end && oc::isLinear(cir->mGates[g].mType)) ++g;
         const u64 nLinear = g - mLevelGateOff[l];
         while (g < end && !oc::isLinear(cir->mGates[g].mType)) ++g;
