@@ -391,7 +391,7 @@ def test_reference_aby3_ml_linear_on_cpu(capfd):
     ref_lib.sgd_linear (the same engine + Regression.h on caller-supplied data) returns replicated w shares."""
     r.main_linear("-N", 600, "-D", 48, "-B", 16, "-I", 40, "-testN", 50)
     out = capfd.readouterr().out
-    assert "iters/s" in out and "N: 600 D:48 B:16 IT:40" in out
+    assert "iters/s" in out and "IT:40 =>" in out        # (party threads interleave their prints)
     rng = np.random.default_rng(1)
     x = rng.normal(1, 1, (300, 40))
     y = x[:, :3] @ np.array([2.0, -1.0, 0.5])
