@@ -302,16 +302,18 @@ __global__ void __launch_bounds__(256) k_bin_level(const uint4* __restrict__ gat
 // AND-depth level, whose linear producers have already run): gate x column parallel, gate g uses
 // the zero-share block range of nonlinear gate and0 + g.  Fills the machine even when the number
 // of instances is small compared with the number of gates.
-__global__ void __launch_bounds__(256) k_bin_and_layer(const uint4* __restrict__ gates, u32 n_gates, u64* mem0, const u64* mem1, u64 rw,
-                                                       const __grid_constant__ AesKey kp, const __grid_constant__ AesKey kn, u64 and0) {
-    aes_table_init();
+template <bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 512 : 256, 1) k_bin_and_layer(const uint4* __restrict__ gates, u32 n_gates, u64* mem0, const u64* mem1, u64 rw,
+                                                                       const __grid_constant__ AesKey kp, const __grid_constant__ AesKey kn, u64 and0) {
+    aes_tables_init<WIDE>();
     __syncthreads();
     const u32 Tl = (threadIdx.x & 31) * 4;
     const u64 chunks = rw / 2;
     for (u32 g = blockIdx.y; g < n_gates; g += gridDim.y) {
         const uint4 G = gates[g];
         const u32 type = G.w;
-        for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (u64)gridDim.x * blockDim.x) {
+        AesStream<WIDE> sp, sn;
+        aes_for_each<WIDE>(chunks, [&](size_t c) {
             const W2 a0 = ldw(mem0, G.x, rw, c), a1 = ldw(mem1, G.x, rw, c);
             const W2 b0 = ldw(mem0, G.y, rw, c), b1 = ldw(mem1, G.y, rw, c);
             W2 x0 = a0, x1 = a1, y0 = b0, y1 = b1;
@@ -323,12 +325,12 @@ __global__ void __launch_bounds__(256) k_bin_and_layer(const uint4* __restrict__
             if (type == 14) { o0.a ^= a0.a ^ b0.a; o0.b ^= a0.b ^ b0.b; }
             u32 p[4], q[4];
             const u64 ctr = (and0 + g) * chunks + c;
-            aes_encrypt_ctr(Tl, kp, ctr, p);
-            aes_encrypt_ctr(Tl, kn, ctr, q);
+            sp.block(Tl, kp, ctr, p);
+            sn.block(Tl, kn, ctr, q);
             o0.a ^= (((u64)(p[1] ^ q[1])) << 32) | (u64)(p[0] ^ q[0]);
             o0.b ^= (((u64)(p[3] ^ q[3])) << 32) | (u64)(p[2] ^ q[2]);
             stw(mem0, G.z, rw, c, o0);
-        }
+        });
     }
 }
 
@@ -358,47 +360,57 @@ __device__ __forceinline__ u32 warp_transpose32(u32 x, u32 lane) {
     return x;
 }
 
-__global__ void __launch_bounds__(256) k_bitwise_rowmajor(const u64* __restrict__ a0, const u64* __restrict__ a1,
+template <bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 512 : 256, 1) k_bitwise_rowmajor(const u64* __restrict__ a0, const u64* __restrict__ a1,
                                                           const u64* __restrict__ b0, const u64* __restrict__ b1,
                                                           u64* __restrict__ out0, u64* __restrict__ out_copy, u64 n, u32 bits, u64 chunks,
                                                           const __grid_constant__ AesKey kp, const __grid_constant__ AesKey kn,
                                                           u64 and0, u32 type) {
-    aes_table_init();
+    aes_tables_init<WIDE>();
     __syncthreads();
     const u32 lane = threadIdx.x & 31, Tl = lane * 4;
     const u64 tiles = (n + 127) / 128;
     const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
     const u64 keep = bits >= 64 ? ~0ull : ((1ull << bits) - 1);
-    for (u64 t = (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5); t < tiles; t += warps) {
-        u32 zl[4] = {0, 0, 0, 0}, zh[4] = {0, 0, 0, 0};
-        if (lane < bits) {
-            u32 p[4], q[4];
-            const u64 ctr = (and0 + lane) * chunks + t;
-            aes_encrypt_ctr(Tl, kp, ctr, p);
-            aes_encrypt_ctr(Tl, kn, ctr, q);
+    // a warp takes runs of kRun CONSECUTIVE tiles: lane l's counters (and0 + l) * chunks + t are then consecutive too,
+    // which is what the wide AES form folds its first two rounds over
+    constexpr u64 kRun = WIDE ? 32 : 1;
+    AesStream<WIDE> lp, ln, hp, hn;
+    for (u64 run = (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5); run * kRun < tiles; run += warps) {
+#pragma unroll 1
+        for (u64 tt = 0; tt < kRun; ++tt) {
+            const u64 t = run * kRun + tt;
+            if (t >= tiles) break;
+            u32 zl[4] = {0, 0, 0, 0}, zh[4] = {0, 0, 0, 0};
+            if (lane < bits) {
+                u32 p[4], q[4];
+                const u64 ctr = (and0 + lane) * chunks + t;
+                lp.block(Tl, kp, ctr, p);
+                ln.block(Tl, kn, ctr, q);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) zl[i] = p[i] ^ q[i];
-        }
-        if (lane + 32 < bits) {
-            u32 p[4], q[4];
-            const u64 ctr = (and0 + lane + 32) * chunks + t;
-            aes_encrypt_ctr(Tl, kp, ctr, p);
-            aes_encrypt_ctr(Tl, kn, ctr, q);
+                for (int i = 0; i < 4; ++i) zl[i] = p[i] ^ q[i];
+            }
+            if (lane + 32 < bits) {
+                u32 p[4], q[4];
+                const u64 ctr = (and0 + lane + 32) * chunks + t;
+                hp.block(Tl, kp, ctr, p);
+                hn.block(Tl, kn, ctr, q);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) zh[i] = p[i] ^ q[i];
-        }
+                for (int i = 0; i < 4; ++i) zh[i] = p[i] ^ q[i];
+            }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const u32 lo = warp_transpose32(zl[q], lane);
-            const u32 hi = bits > 32 ? warp_transpose32(zh[q], lane) : 0u;
-            const u64 j = t * 128 + 32 * q + lane;
-            if (j < n) {
-                const u64 x0 = a0[j], x1 = a1[j], y0 = b0[j], y1 = b1[j];
-                u64 o = (x0 & y0) ^ (x0 & y1) ^ (x1 & y0);
-                if (type == 14) o ^= x0 ^ y0;                                   // Or (:912-981)
-                o = (o ^ (((u64)hi << 32) | lo)) & keep;
-                out0[j] = o;
-                if (out_copy) out_copy[j] = o;
+            for (int q = 0; q < 4; ++q) {
+                const u32 lo = warp_transpose32(zl[q], lane);
+                const u32 hi = bits > 32 ? warp_transpose32(zh[q], lane) : 0u;
+                const u64 j = t * 128 + 32 * q + lane;
+                if (j < n) {
+                    const u64 x0 = a0[j], x1 = a1[j], y0 = b0[j], y1 = b1[j];
+                    u64 o = (x0 & y0) ^ (x0 & y1) ^ (x1 & y0);
+                    if (type == 14) o ^= x0 ^ y0;                                   // Or (:912-981)
+                    o = (o ^ (((u64)hi << 32) | lo)) & keep;
+                    out0[j] = o;
+                    if (out_copy) out_copy[j] = o;
+                }
             }
         }
     }
@@ -535,14 +547,27 @@ int aby3cu_bin_and_layer(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void*
     if (!n_gates || !row_bytes) return 0;
     DeviceGuard g(ctx->device);
     AesKey kp, kn; host_expand_key(key_prev, &kp); host_expand_key(key_next, &kn);
-    ABY3CU_CHECK(cudaFuncSetAttribute(k_bin_and_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
-    if (prefer_max_smem(k_bin_and_layer)) return 1;
     const u64 chunks = row_bytes / 16;
+    static const bool wide_on = [] { const char* e = getenv("ABY3CU_AES_WIDE"); return !(e && e[0] == '0'); }();
+    if (wide_on && !ctx->corun && chunks * n_gates >= (1u << 16) && chunks >= 2048) {
+        ABY3CU_CHECK(cudaFuncSetAttribute(k_bin_and_layer<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesWideTableBytes));
+        if (prefer_max_smem(k_bin_and_layer<true>)) return 1;
+        // one 512-thread CTA per SM; a CTA column covers runs of 256 chunks per warp
+        u64 gx = (chunks + 4095) / 4096;
+        if (gx > (u64)ctx->sm_count) gx = ctx->sm_count;
+        u64 gy = ((u64)ctx->sm_count + gx - 1) / gx;
+        if (gy > n_gates) gy = n_gates;
+        k_bin_and_layer<true><<<dim3((unsigned)gx, (unsigned)gy), 512, kAesWideTableBytes, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0,
+                                                                                                          (const u64*)d_mem1, row_bytes / 8, kp, kn, and_index0);
+        return post_launch(ctx, "k_bin_and_layer");
+    }
+    ABY3CU_CHECK(cudaFuncSetAttribute(k_bin_and_layer<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
+    if (prefer_max_smem(k_bin_and_layer<false>)) return 1;
     const u64 gx = (chunks + 255) / 256 < 32 ? (chunks + 255) / 256 : 32;
     u64 gy = ((u64)ctx->sm_count * 3 + gx - 1) / gx;
     if (gy > n_gates) gy = n_gates;
-    k_bin_and_layer<<<dim3((unsigned)gx, (unsigned)gy), 256, kAesTableBytes, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0,
-                                                                                            (const u64*)d_mem1, row_bytes / 8, kp, kn, and_index0);
+    k_bin_and_layer<false><<<dim3((unsigned)gx, (unsigned)gy), 256, kAesTableBytes, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0,
+                                                                                                   (const u64*)d_mem1, row_bytes / 8, kp, kn, and_index0);
     return post_launch(ctx, "k_bin_and_layer");
 }
 
@@ -556,12 +581,23 @@ int aby3cu_bin_bitwise_rowmajor(aby3cu_ctx* ctx, uint32_t gate_type, const int64
     if (!n) return 0;
     DeviceGuard g(ctx->device);
     AesKey kp, kn; host_expand_key(key_prev, &kp); host_expand_key(key_next, &kn);
-    ABY3CU_CHECK(cudaFuncSetAttribute(k_bitwise_rowmajor, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
-    if (prefer_max_smem(k_bitwise_rowmajor)) return 1;
     const u64 tiles = (n + 127) / 128;
+    static const bool wide_on = [] { const char* e = getenv("ABY3CU_AES_WIDE"); return !(e && e[0] == '0'); }();
+    // (measured: with four keystreams per lane and the transposes the wide form is no faster here -- 0.30 vs 0.28 ms at
+    // 2^23 instances -- so it stays behind an opt-in switch)
+    static const bool wide_bitwise = [] { const char* e = getenv("ABY3CU_AES_WIDE_BITWISE"); return e && e[0] == '1'; }();
+    if (wide_on && wide_bitwise && !ctx->corun && tiles >= 4096) {
+        ABY3CU_CHECK(cudaFuncSetAttribute(k_bitwise_rowmajor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesWideTableBytes));
+        if (prefer_max_smem(k_bitwise_rowmajor<true>)) return 1;
+        k_bitwise_rowmajor<true><<<ctx->sm_count, 512, kAesWideTableBytes, ctx->stream>>>((const u64*)d_a0, (const u64*)d_a1, (const u64*)d_b0, (const u64*)d_b1,
+                                                                                         (u64*)d_out0, (u64*)d_out_copy, n, bits, row_bytes / 16, kp, kn, and_index0, gate_type);
+        return post_launch(ctx, "k_bitwise_rowmajor");
+    }
+    ABY3CU_CHECK(cudaFuncSetAttribute(k_bitwise_rowmajor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
+    if (prefer_max_smem(k_bitwise_rowmajor<false>)) return 1;
     const unsigned grid = ew_grid(ctx, tiles * 32, 256, 3);
-    k_bitwise_rowmajor<<<grid, 256, kAesTableBytes, ctx->stream>>>((const u64*)d_a0, (const u64*)d_a1, (const u64*)d_b0, (const u64*)d_b1,
-                                                                   (u64*)d_out0, (u64*)d_out_copy, n, bits, row_bytes / 16, kp, kn, and_index0, gate_type);
+    k_bitwise_rowmajor<false><<<grid, 256, kAesTableBytes, ctx->stream>>>((const u64*)d_a0, (const u64*)d_a1, (const u64*)d_b0, (const u64*)d_b1,
+                                                                          (u64*)d_out0, (u64*)d_out_copy, n, bits, row_bytes / 16, kp, kn, and_index0, gate_type);
     return post_launch(ctx, "k_bitwise_rowmajor");
 }
 

@@ -12,6 +12,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kCtasPerSm = 3;     // 3 x 64 KiB AES tables fit in 227 KiB of shared memory
+constexpr int kWideThreads = 512; // the wide AES form: one CTA per SM (128 KiB of tables)
+constexpr size_t kWideMinPairs = size_t(1) << 16;   // below this the 128 KiB table fill is not amortised
 
 __device__ __forceinline__ u64 sar(u64 x, unsigned s) { return (u64)((i64)x >> s); }
 
@@ -41,42 +43,43 @@ __host__ __device__ inline bool al16(const void* p) { return (reinterpret_cast<u
 // ---------------------------------------------------------------------------------
 // keystream fill: out[i] = KS[e0 + i]
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_fill(const __grid_constant__ AesKey key, u64 e0, i64* __restrict__ out, size_t n, int vec) {
-    aes_table_init();
+template <bool WIDE>
+__global__ void __launch_bounds__(WIDE ? kWideThreads : kThreads, 1) k_fill(const __grid_constant__ AesKey key, u64 e0, i64* __restrict__ out, size_t n, int vec) {
+    aes_tables_init<WIDE>();
     __syncthreads();
     const u32 Tl = (threadIdx.x & 31) * 4;
-    const size_t pairs = (n + 1) / 2;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += (size_t)gridDim.x * blockDim.x) {
+    AesStream<WIDE> ks;
+    aes_for_each<WIDE>((n + 1) / 2, [&](size_t p) {
         U64x2 v;
-        aes_stream_pair(Tl, key, e0 + 2 * p, v.a, v.b);
+        ks.pair(Tl, key, e0 + 2 * p, v.a, v.b);
         const size_t i = 2 * p;
         st2(out, i, n, vec && i + 1 < n, v);
-    }
+    });
 }
 
 // ---------------------------------------------------------------------------------
 // zero share: out[i] = addend[i] (+|^) (KSp[e0+i] (-|^) KSn[e0+i])
 // ---------------------------------------------------------------------------------
-template <bool BINARY>
-__global__ void __launch_bounds__(kThreads) k_zero_share(const __grid_constant__ AesKey kp, const __grid_constant__ AesKey kn, u64 e0,
+template <bool BINARY, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? kWideThreads : kThreads, 1) k_zero_share(const __grid_constant__ AesKey kp, const __grid_constant__ AesKey kn, u64 e0,
                                                          const i64* __restrict__ addend, i64* __restrict__ out, size_t n, int vec) {
-    aes_table_init();
+    aes_tables_init<WIDE>();
     __syncthreads();
     const u32 Tl = (threadIdx.x & 31) * 4;
-    const size_t pairs = (n + 1) / 2;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += (size_t)gridDim.x * blockDim.x) {
+    AesStream<WIDE> sp, sn;
+    aes_for_each<WIDE>((n + 1) / 2, [&](size_t p) {
         const size_t i = 2 * p;
         const bool v2 = vec && i + 1 < n;
         U64x2 a = {0, 0};
         if (addend) a = ld2(addend, i, n, v2);
         u64 p0, p1, q0, q1;
-        aes_stream_pair(Tl, kp, e0 + i, p0, p1);
-        aes_stream_pair(Tl, kn, e0 + i, q0, q1);
+        sp.pair(Tl, kp, e0 + i, p0, p1);
+        sn.pair(Tl, kn, e0 + i, q0, q1);
         U64x2 r;
         if (BINARY) { r.a = a.a ^ p0 ^ q0; r.b = a.b ^ p1 ^ q1; }
         else        { r.a = a.a + (p0 - q0); r.b = a.b + (p1 - q1); }
         st2(out, i, n, v2, r);
-    }
+    });
 }
 
 // ---------------------------------------------------------------------------------
@@ -84,15 +87,15 @@ __global__ void __launch_bounds__(kThreads) k_zero_share(const __grid_constant__
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ u64 cross(u64 a0, u64 a1, u64 b0, u64 b1) { return a0 * (b0 + b1) + a1 * b0; }
 
-template <bool MASK>
-__global__ void __launch_bounds__(kThreads) k_mul_hadamard(const i64* __restrict__ A0, const i64* __restrict__ A1,
+template <bool MASK, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? kWideThreads : kThreads, 1) k_mul_hadamard(const i64* __restrict__ A0, const i64* __restrict__ A1,
                                                            const i64* __restrict__ B0, const i64* __restrict__ B1,
                                                            const __grid_constant__ AesKey kp, const __grid_constant__ AesKey kn,
                                                            u64 e0, i64* __restrict__ C0, size_t n, int vec) {
-    if (MASK) { aes_table_init(); __syncthreads(); }
+    if (MASK) { aes_tables_init<WIDE>(); __syncthreads(); }
     const u32 Tl = (threadIdx.x & 31) * 4;
-    const size_t pairs = (n + 1) / 2;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += (size_t)gridDim.x * blockDim.x) {
+    AesStream<WIDE> sp, sn;
+    aes_for_each<WIDE>((n + 1) / 2, [&](size_t p) {
         const size_t i = 2 * p;
         const bool v2 = vec && i + 1 < n;
         U64x2 a0 = ld2(A0, i, n, v2), a1 = ld2(A1, i, n, v2), b0 = ld2(B0, i, n, v2), b1 = ld2(B1, i, n, v2);
@@ -101,13 +104,13 @@ __global__ void __launch_bounds__(kThreads) k_mul_hadamard(const i64* __restrict
         r.b = cross(a0.b, a1.b, b0.b, b1.b);
         if (MASK) {
             u64 p0, p1, q0, q1;
-            aes_stream_pair(Tl, kp, e0 + i, p0, p1);
-            aes_stream_pair(Tl, kn, e0 + i, q0, q1);
+            sp.pair(Tl, kp, e0 + i, p0, p1);
+            sn.pair(Tl, kn, e0 + i, q0, q1);
             r.a += p0 - q0;
             r.b += p1 - q1;
         }
         st2(C0, i, n, v2, r);
-    }
+    });
 }
 
 // ---------------------------------------------------------------------------------
@@ -116,26 +119,26 @@ __global__ void __launch_bounds__(kThreads) k_mul_hadamard(const i64* __restrict
 //   CROSS: V = cross - r
 //   else : R = r (if R), NEGR = -r (if NEGR)
 // ---------------------------------------------------------------------------------
-template <bool CROSS, bool RAND>
-__global__ void __launch_bounds__(kThreads) k_trunc(const i64* __restrict__ A0, const i64* __restrict__ A1,
+template <bool CROSS, bool RAND, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? kWideThreads : kThreads, 1) k_trunc(const i64* __restrict__ A0, const i64* __restrict__ A1,
                                                     const i64* __restrict__ B0, const i64* __restrict__ B1,
                                                     const __grid_constant__ AesKey knext, u64 en,
                                                     const __grid_constant__ AesKey kprev, u64 ep, unsigned d2,
                                                     i64* __restrict__ V, i64* __restrict__ R, i64* __restrict__ NEGR,
                                                     i64* __restrict__ RT0, i64* __restrict__ RT1, size_t n, int vec,
                                                     const u64* __restrict__ iter, u64 iter_stride) {
-    if (RAND) { aes_table_init(); __syncthreads(); }
+    if (RAND) { aes_tables_init<WIDE>(); __syncthreads(); }
     // replayed as a CUDA-graph node: the stream offsets advance with a device-resident iteration counter
     if (iter) { const u64 it = *iter; en += it * iter_stride; ep += it * iter_stride; }
     const u32 Tl = (threadIdx.x & 31) * 4;
-    const size_t pairs = (n + 1) / 2;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += (size_t)gridDim.x * blockDim.x) {
+    AesStream<WIDE> sn, sp;
+    aes_for_each<WIDE>((n + 1) / 2, [&](size_t p) {
         const size_t i = 2 * p;
         const bool v2 = vec && i + 1 < n;
         u64 t00 = 0, t01 = 0, t10 = 0, t11 = 0;
         if (RAND) {
-            aes_stream_pair(Tl, knext, en + i, t00, t01);
-            aes_stream_pair(Tl, kprev, ep + i, t10, t11);
+            sn.pair(Tl, knext, en + i, t00, t01);
+            sp.pair(Tl, kprev, ep + i, t10, t11);
         }
         const u64 r0 = sar(t00, 2), r1 = sar(t01, 2);
         U64x2 rt0 = {sar(t00, d2), sar(t01, d2)};
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(kThreads) k_trunc(const i64* __restrict__ A0, 
             if (R) { U64x2 v = {r0, r1}; st2(R, i, n, v2, v); }
             if (NEGR) { U64x2 v = {0 - r0, 0 - r1}; st2(NEGR, i, n, v2, v); }
         }
-    }
+    });
 }
 
 // C += (s0+s1+s2) >> shift
@@ -349,10 +352,16 @@ int upload_aes_constants() {
 }
 
 template <class K>
-static int enable_big_smem(K kernel) {
-    ABY3CU_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
+static int enable_big_smem(K kernel, int bytes = kAesTableBytes) {
+    ABY3CU_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     if (prefer_max_smem(kernel)) return 1;
     return 0;
+}
+// The wide AES form (four tables + CTR folding, aes.cuh) for big launches: whole blocks per pair (even first element), not
+// a context whose kernels are shaped to run under a GEMM (64 KiB is what fits next to it).  ABY3CU_AES_WIDE=0 turns it off.
+static bool use_wide_aes(const aby3cu_ctx* ctx, size_t pairs, u64 e0, u64 e1 = 0) {
+    static const bool on = [] { const char* e = getenv("ABY3CU_AES_WIDE"); return !(e && e[0] == '0'); }();
+    return on && !ctx->corun && pairs >= kWideMinPairs && ((e0 | e1) & 1) == 0;
 }
 
 }  // namespace aby3cu
@@ -370,9 +379,14 @@ int aby3cu_aes_ctr_fill(aby3cu_ctx* ctx, const u8 key[16], u64 byte_off, void* d
     DeviceGuard g(ctx->device);
     AesKey k; host_expand_key(key, &k);
     const size_t n = nbytes / 8;
-    if (enable_big_smem(k_fill)) return 1;
+    if (use_wide_aes(ctx, (n + 1) / 2, byte_off / 8)) {
+        if (enable_big_smem(k_fill<true>, kAesWideTableBytes)) return 1;
+        k_fill<true><<<ctx->sm_count, kWideThreads, kAesWideTableBytes, ctx->stream>>>(k, byte_off / 8, (i64*)d_out, n, al16(d_out));
+        return post_launch(ctx, "k_fill");
+    }
+    if (enable_big_smem(k_fill<false>)) return 1;
     const unsigned grid = ew_grid(ctx, (n + 1) / 2, kThreads, kCtasPerSm);
-    k_fill<<<grid, kThreads, kAesTableBytes, ctx->stream>>>(k, byte_off / 8, (i64*)d_out, n, al16(d_out));
+    k_fill<false><<<grid, kThreads, kAesTableBytes, ctx->stream>>>(k, byte_off / 8, (i64*)d_out, n, al16(d_out));
     return post_launch(ctx, "k_fill");
 }
 
@@ -384,12 +398,22 @@ int aby3cu_zero_share(aby3cu_ctx* ctx, const u8 key_prev[16], const u8 key_next[
     AesKey kp, kn; host_expand_key(key_prev, &kp); host_expand_key(key_next, &kn);
     const int vec = al16(d_out) && (!d_addend || al16(d_addend));
     const unsigned grid = ew_grid(ctx, (n + 1) / 2, kThreads, kCtasPerSm);
+    if (use_wide_aes(ctx, (n + 1) / 2, elem0)) {
+        if (binary) {
+            if (enable_big_smem(k_zero_share<true, true>, kAesWideTableBytes)) return 1;
+            k_zero_share<true, true><<<ctx->sm_count, kWideThreads, kAesWideTableBytes, ctx->stream>>>(kp, kn, elem0, d_addend, d_out, n, vec);
+        } else {
+            if (enable_big_smem(k_zero_share<false, true>, kAesWideTableBytes)) return 1;
+            k_zero_share<false, true><<<ctx->sm_count, kWideThreads, kAesWideTableBytes, ctx->stream>>>(kp, kn, elem0, d_addend, d_out, n, vec);
+        }
+        return post_launch(ctx, "k_zero_share");
+    }
     if (binary) {
-        if (enable_big_smem(k_zero_share<true>)) return 1;
-        k_zero_share<true><<<grid, kThreads, kAesTableBytes, ctx->stream>>>(kp, kn, elem0, d_addend, d_out, n, vec);
+        if (enable_big_smem(k_zero_share<true, false>)) return 1;
+        k_zero_share<true, false><<<grid, kThreads, kAesTableBytes, ctx->stream>>>(kp, kn, elem0, d_addend, d_out, n, vec);
     } else {
-        if (enable_big_smem(k_zero_share<false>)) return 1;
-        k_zero_share<false><<<grid, kThreads, kAesTableBytes, ctx->stream>>>(kp, kn, elem0, d_addend, d_out, n, vec);
+        if (enable_big_smem(k_zero_share<false, false>)) return 1;
+        k_zero_share<false, false><<<grid, kThreads, kAesTableBytes, ctx->stream>>>(kp, kn, elem0, d_addend, d_out, n, vec);
     }
     return post_launch(ctx, "k_zero_share");
 }
@@ -403,12 +427,17 @@ int aby3cu_mul_hadamard(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64
     const int vec = al16(A0) && al16(A1) && al16(B0) && al16(B1) && al16(C0);
     if (key_prev) {
         AesKey kp, kn; host_expand_key(key_prev, &kp); host_expand_key(key_next, &kn);
-        if (enable_big_smem(k_mul_hadamard<true>)) return 1;
-        const unsigned grid = ew_grid(ctx, (n + 1) / 2, kThreads, kCtasPerSm);
-        k_mul_hadamard<true><<<grid, kThreads, kAesTableBytes, ctx->stream>>>(A0, A1, B0, B1, kp, kn, elem0, C0, n, vec);
+        if (use_wide_aes(ctx, (n + 1) / 2, elem0)) {
+            if (enable_big_smem(k_mul_hadamard<true, true>, kAesWideTableBytes)) return 1;
+            k_mul_hadamard<true, true><<<ctx->sm_count, kWideThreads, kAesWideTableBytes, ctx->stream>>>(A0, A1, B0, B1, kp, kn, elem0, C0, n, vec);
+        } else {
+            if (enable_big_smem(k_mul_hadamard<true, false>)) return 1;
+            const unsigned grid = ew_grid(ctx, (n + 1) / 2, kThreads, kCtasPerSm);
+            k_mul_hadamard<true, false><<<grid, kThreads, kAesTableBytes, ctx->stream>>>(A0, A1, B0, B1, kp, kn, elem0, C0, n, vec);
+        }
     } else {
         const unsigned grid = ew_grid(ctx, (n + 1) / 2, kThreads, 8);
-        k_mul_hadamard<false><<<grid, kThreads, 0, ctx->stream>>>(A0, A1, B0, B1, kZeroKey, kZeroKey, 0, C0, n, vec);
+        k_mul_hadamard<false, false><<<grid, kThreads, 0, ctx->stream>>>(A0, A1, B0, B1, kZeroKey, kZeroKey, 0, C0, n, vec);
     }
     return post_launch(ctx, "k_mul_hadamard");
 }
@@ -431,15 +460,22 @@ static int launch_trunc(aby3cu_ctx* ctx, bool crossterm, const i64* A0, const i6
     // A context marked "corun" issues work that should run UNDER another party's tcgen05 GEMM (148 CTAs x 6 warps x 224
     // registers: two of the four register files of an SM are left with 2048 free registers, one 64-register warp).  A
     // 256-thread CTA needs two warps per register file and is never admitted next to the GEMM; a 128-thread CTA is.
-    const unsigned threads = (rnd && ctx->corun) ? 128 : kThreads;
-    const unsigned grid = ew_grid(ctx, (n + 1) / 2, threads, rnd ? kCtasPerSm : 8);
-    const size_t smem = rnd ? kAesTableBytes : 0;
+    const bool wide = rnd && !iter && use_wide_aes(ctx, (n + 1) / 2, en, ep);
+    const unsigned threads = wide ? kWideThreads : (rnd && ctx->corun) ? 128 : kThreads;
+    const unsigned grid = wide ? (unsigned)ctx->sm_count : ew_grid(ctx, (n + 1) / 2, threads, rnd ? kCtasPerSm : 8);
+    const size_t smem = wide ? kAesWideTableBytes : rnd ? kAesTableBytes : 0;
     trace_mark(ctx, "(k_trunc ready)");
 #define ABY3CU_LAUNCH_TRUNC(C, Rn)                                                                              \
     do {                                                                                                        \
-        if (Rn && enable_big_smem(k_trunc<C, Rn>)) return 1;                                                    \
-        k_trunc<C, Rn><<<grid, threads, smem, ctx->stream>>>(A0, A1, B0, B1, kn, en, kp, ep, d2, V, R, NEGR,    \
-                                                              RT0, RT1, n, vec, iter, iter_stride);             \
+        if (wide) {                                                                                             \
+            if (enable_big_smem(k_trunc<C, Rn, Rn>, kAesWideTableBytes)) return 1;                              \
+            k_trunc<C, Rn, Rn><<<grid, threads, smem, ctx->stream>>>(A0, A1, B0, B1, kn, en, kp, ep, d2, V, R, NEGR, \
+                                                                     RT0, RT1, n, vec, iter, iter_stride);      \
+        } else {                                                                                                \
+            if (Rn && enable_big_smem(k_trunc<C, Rn, false>)) return 1;                                         \
+            k_trunc<C, Rn, false><<<grid, threads, smem, ctx->stream>>>(A0, A1, B0, B1, kn, en, kp, ep, d2, V, R, NEGR, \
+                                                                        RT0, RT1, n, vec, iter, iter_stride);   \
+        }                                                                                                       \
     } while (0)
     if (crossterm) { if (rnd) ABY3CU_LAUNCH_TRUNC(true, true); else ABY3CU_LAUNCH_TRUNC(true, false); }
     else           { if (rnd) ABY3CU_LAUNCH_TRUNC(false, true); else ABY3CU_LAUNCH_TRUNC(false, false); }

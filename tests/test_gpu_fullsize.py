@@ -153,6 +153,27 @@ def test_binary_and_layer_2_pow_22_instances():
         s.close()
 
 
+@pytest.mark.parametrize("name", ["lt", "add_msb"])
+def test_binary_engine_share_level_at_the_wide_aes_size(name):
+    """A comparison circuit over 300 000 instances: wire rows of 37 KiB, so the AND layers take the wide AES form
+    (four tables, CTR folding over runs of 256 consecutive row chunks).  Every party's output shares against the oracle."""
+    width = 300000
+    s, r = harness.Session(), o.Session()
+    try:
+        x, y = rnd(31, (width, 1)), rnd(32, (width, 1))
+        cir = harness.library_circuit(name, 64)
+        X, Y = s.share_bin(0, x, 64), s.share_bin(2, y, 64)
+        Xo, Yo = r.share_bin(0, x), r.share_bin(2, y)
+        out = s.bin_eval(cir, [X, Y])[0]
+        outo, _ = o.bin_eval(r, cir, width, [Xo, Yo])
+        assert np.array_equal(s.get_shares(out, binary=True) & 1, outo[0] & 1)
+        for p in range(3):
+            assert list(s.cursors(p)) == list(r.cursors(p))
+    finally:
+        s.close()
+        r.close()
+
+
 def test_empty_inputs_are_no_ops(ctx):
     z = abi.C.c_void_p(None)
     before = ctx.launches

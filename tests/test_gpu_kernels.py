@@ -415,7 +415,9 @@ def test_bitwise_rowmajor_equals_the_sliced_definition(ctx, gate):
     from the oracle.  Ragged instance counts, every bit width class, a non-zero first gate index."""
     rng = np.random.default_rng(gate)
     kp, kn = bytes(range(16)), bytes(range(100, 116))
-    for n, bits, and0 in ((1, 64, 0), (127, 64, 0), (128, 1, 3), (129, 13, 0), (3000, 32, 1), (2049, 33, 0), (70000, 64, 5), (4096, 63, 0)):
+    # (the last two cases are big enough for the wide AES form: four tables + CTR folding over runs of consecutive tiles)
+    for n, bits, and0 in ((1, 64, 0), (127, 64, 0), (128, 1, 3), (129, 13, 0), (3000, 32, 1), (2049, 33, 0), (70000, 64, 5), (4096, 63, 0),
+                          (600011, 64, 2), (524288, 40, 0)):
         rb = int(lib.aby3cu_bin_row_bytes(n))
         a0, a1, b0, b1 = (rng.integers(-2**63, 2**63, n, dtype=np.int64) for _ in range(4))
         d = [ctx.upload(x) for x in (a0, a1, b0, b1)]
