@@ -282,6 +282,32 @@ public:
             for (u64 j = 0; j < w; ++j) B[i * w + j] = A[(r + i) * mCols + c + j];
         return b;
     }
+    // a block of a non-const matrix is a writable view (`res.block(...) = data;`, aby3-Basic/Basic.cpp:48) that also
+    // converts to a matrix (`i64Matrix part = m.block(...);`, :17)
+    struct BlockRef {
+        eMatrix& m; u64 r, c, h, w;
+        BlockRef& operator=(const eMatrix& src) {
+            if (src.rows() != h || src.cols() != w) throw std::runtime_error("eMatrix: block assignment shape mismatch " LOCATION);
+            const T* S = src.hostData();
+            T* D = m.data();
+            for (u64 i = 0; i < h; ++i)
+                for (u64 j = 0; j < w; ++j) D[(r + i) * m.mCols + c + j] = S[i * w + j];
+            return *this;
+        }
+        BlockRef& operator=(const BlockRef& o) { return *this = eMatrix(o); }
+        operator eMatrix() const { return static_cast<const eMatrix&>(m).block(r, c, h, w); }
+        u64 rows() const { return h; }
+        u64 cols() const { return w; }
+        T& operator()(u64 i, u64 j) { return m(r + i, c + j); }
+        BlockRef& setConstant(T v) {
+            T* D = m.data();
+            for (u64 i = 0; i < h; ++i)
+                for (u64 j = 0; j < w; ++j) D[(r + i) * m.mCols + c + j] = v;
+            return *this;
+        }
+        BlockRef& setZero() { return setConstant(T{}); }
+    };
+    BlockRef block(u64 r, u64 c, u64 h, u64 w) { return BlockRef{*this, r, c, h, w}; }
 
 private:
     void ensureDevBuffer() {

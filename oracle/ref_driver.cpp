@@ -27,6 +27,9 @@
 #include <aby3-Basic/BuildingBlocks.h>
 #include <aby3-Basic/Sort.h>
 #include <cryptoTools/Common/CLP.h>
+#include <aby3_tests/Test.h>
+#include <fstream>
+#include <map>
 
 #include <atomic>
 #include <chrono>
@@ -597,3 +600,52 @@ double ref_time_logistic(ref_session* s, uint64_t rows, uint64_t F, uint64_t D, 
 }
 
 }  // extern "C"
+
+// ---- the fork's own role tests (aby3_tests/Test.cpp, BoolTest.cpp, SortTest.cpp; frontend/main.cpp:16-54 dispatches them
+// ---- by flag, Eval/dis_exec.sh starts one process per role).  Here: the named test, compiled unmodified, on three
+// ---- threads of this process with "-role i"; its check_result() lines are counted from DEBUG_FILE.
+namespace {
+typedef int (*RoleTest)(oc::CLP&);
+RoleTest find_role_test(const std::string& n) {
+    static const std::map<std::string, RoleTest> t = {
+        {"arith_basic_test", arith_basic_test}, {"bool_basic_test", bool_basic_test}, {"bool_basic_test2", bool_basic_test2},
+        {"bool_aggregation_test", bool_aggregation_test}, {"get_first_zero_test", get_first_zero_test},
+        {"share_conversion_test", share_conversion_test}, {"initialization_test", initialization_test},
+        {"bc_sort_test", bc_sort_test}, {"bc_sort_corner_test", bc_sort_corner_test}, {"bc_sort_multiple_times", bc_sort_multiple_times},
+        {"quick_sort_test", quick_sort_test}, {"quick_sort_with_duplicate_elements_test", quick_sort_with_duplicate_elements_test},
+        {"odd_even_merge_test", odd_even_merge_test}, {"shuffle_test", shuffle_test}, {"correlation_test", correlation_test}};
+    auto it = t.find(n);
+    return it == t.end() ? nullptr : it->second;
+}
+}  // namespace
+
+extern "C" int ref_role_test(const char* name, int* n_success, int* n_error) {
+    RoleTest fn = find_role_test(name);
+    if (!fn) { g_err = std::string("unknown role test ") + name; return 1; }
+    { std::ofstream trunc(DEBUG_FILE, std::ios_base::trunc); }
+    std::string errs[3];
+    std::thread th[3];
+    for (int i = 0; i < 3; ++i)
+        th[i] = std::thread([&, i] {
+            try {
+                const std::string role = std::to_string(i);
+                const char* argv[] = {"frontend", "-role", role.c_str()};
+                oc::CLP cmd;
+                cmd.parse(3, argv);
+                fn(cmd);
+                
+            } catch (const std::exception& e) { errs[i] = e.what(); } catch (...) { errs[i] = "unknown exception"; }
+        });
+    for (auto& t : th) t.join();
+    for (int i = 0; i < 3; ++i)
+        if (!errs[i].empty()) { g_err = "party " + std::to_string(i) + ": " + errs[i]; return 1; }
+    int ok = 0, bad = 0;
+    std::ifstream in(DEBUG_FILE);
+    for (std::string line; std::getline(in, line);) {
+        if (line.find("SUCCESS") != std::string::npos) ++ok;
+        if (line.find("ERROR") != std::string::npos) ++bad;
+    }
+    if (n_success) *n_success = ok;
+    if (n_error) *n_error = bad;
+    return 0;
+}

@@ -12,7 +12,16 @@ PATH = os.path.join(ROOT, "compat", "_build", "libcompat_apps.so")
 REFERENCE = os.environ.get("ABY3_REFERENCE", "/root/reference")
 APP_SOURCES = ["aby3-ML/aby3ML.cpp", "aby3-ML/LinearModelGen.cpp", "aby3-ML/main-linear.cpp", "aby3-ML/Regression.h", "aby3-ML/aby3ML.h",
                "aby3-Basic/BoolBasic.cpp", "aby3-Basic/ArithBasic.cpp", "aby3-Basic/BuildingBlocks.cpp", "aby3-Basic/Sort.cpp",
-               "aby3-Basic/Basic.cpp", "aby3-Basic/debug.cpp", "aby3-Basic/Basics.h", "aby3-Basic/BuildingBlocks.h"]
+               "aby3-Basic/Basic.cpp", "aby3-Basic/debug.cpp", "aby3-Basic/Shuffle.cpp", "aby3-Basic/Basics.h",
+               "aby3-Basic/BuildingBlocks.h", "aby3_tests/Test.cpp", "aby3_tests/BoolTest.cpp", "aby3_tests/SortTest.cpp",
+               "aby3_tests/Test.h"]
+
+# the fork's own role tests (aby3_tests/Test.h; frontend/main.cpp:16-54 dispatches them by flag) -> check_result() lines each
+# one writes per party 0 run, as counted from the reference's own CPU build (tests/test_ref_parity.py pins these)
+ROLE_TESTS = {"arith_basic_test": 7, "bool_basic_test": 17, "bool_basic_test2": 6, "bool_aggregation_test": 2,
+              "get_first_zero_test": 2, "share_conversion_test": 2, "initialization_test": 6, "bc_sort_test": 1,
+              "bc_sort_corner_test": 1, "bc_sort_multiple_times": 1, "quick_sort_test": 1, "odd_even_merge_test": 6,
+              "shuffle_test": 3, "correlation_test": 6}
 
 _p, _u64, _int = C.c_void_p, C.c_uint64, C.c_int
 
@@ -62,6 +71,7 @@ def lib():
         l.cmp_main_linear.argtypes = [_int, _p]
         l.cmp_sgd_linear.restype = C.c_double
         l.cmp_sgd_linear.argtypes = [_p, _p, _u64, _u64, _u64, _u64, C.c_double, _p]
+        l.cmp_role_test.argtypes = [C.c_char_p, _p, _p]
         _lib = l
     return _lib
 
@@ -166,3 +176,11 @@ def main_linear(*args):
     argv = [b"main-linear"] + [str(a).encode() for a in args]
     arr = (C.c_char_p * len(argv))(*argv)
     _chk(lib().cmp_main_linear(len(argv), arr))
+
+
+def role_test(name):
+    """One of the fork's own role tests (aby3_tests/Test.cpp, BoolTest.cpp, SortTest.cpp), compiled unmodified, on three
+    threads with "-role i" -> (number of check_result SUCCESS lines, number of ERROR lines)"""
+    ok, bad = C.c_int(0), C.c_int(0)
+    _chk(lib().cmp_role_test(name.encode(), C.byref(ok), C.byref(bad)))
+    return ok.value, bad.value

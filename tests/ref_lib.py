@@ -67,6 +67,7 @@ def lib():
         l.ref_basic_cipher_gt.argtypes = [_p, _p, _p, _u64, _p, _p]
         l.ref_basic_max_min_split.argtypes = [_p, _p, _p, _u64, _p, _p, _p]
         l.ref_basic_odd_even_merge.argtypes = [_p, _p, _u64, _p, _u64, _p, _p]
+        l.ref_role_test.argtypes = [C.c_char_p, _p, _p]
         _lib = l
     return _lib
 
@@ -319,3 +320,11 @@ def conv_packed_roundtrip(planes, bits):
     out = np.zeros_like(planes)
     _chk(lib().ref_conv_packed_roundtrip(ptr(planes), rows, bits, ptr(packed), simd, ptr(out)))
     return packed, out
+
+
+def role_test(name):
+    """One of the fork's own role tests (aby3_tests/Test.cpp, BoolTest.cpp, SortTest.cpp), compiled unmodified, on three
+    threads with "-role i" -> (number of check_result SUCCESS lines, number of ERROR lines)"""
+    ok, bad = C.c_int(0), C.c_int(0)
+    _chk(lib().ref_role_test(name.encode(), C.byref(ok), C.byref(bad)))
+    return ok.value, bad.value

@@ -25,7 +25,7 @@ def test_reference_applications_compile_unmodified_against_the_facade():
     # the objects come from the reference's own files: every compile line names a path under the reference root, and
     # nothing under compat/ or aby3_b200/ carries a copy of those sources
     mk = open(os.path.join(ROOT, "compat", "Makefile")).read()
-    assert "vpath %.cpp $(REF)/aby3-ML $(REF)/aby3-Basic" in mk
+    assert "vpath %.cpp $(REF)/aby3-ML $(REF)/aby3-Basic $(REF)/aby3_tests" in mk
     for f in c.APP_SOURCES:
         assert os.path.exists(os.path.join(c.REFERENCE, f)), f
         assert not os.path.exists(os.path.join(ROOT, "compat", os.path.basename(f)))
@@ -34,7 +34,8 @@ def test_reference_applications_compile_unmodified_against_the_facade():
     assert "undefined symbol" not in r.stdout, r.stdout[-2000:]
     nm = subprocess.run(["nm", "-D", "--defined-only", c.PATH], stdout=subprocess.PIPE, text=True).stdout
     for sym in ("cmp_sgd_linear", "cmp_main_linear", "cmp_basic_bool", "cmp_basic_odd_even_merge",
-                "_Z18linear_main_3pc_shRN2oc3CLPE", "_Z14bool_cipher_lt"):
+                "_Z18linear_main_3pc_shRN2oc3CLPE", "_Z14bool_cipher_lt", "cmp_role_test",
+                "_Z16arith_basic_testRN2oc3CLPE", "_Z19odd_even_merge_testRN2oc3CLPE"):
         assert sym in nm, sym
     assert out is not None
 
@@ -165,3 +166,14 @@ def test_reference_aby3_basic_on_the_facade_matches_plaintext_and_the_cpu_refere
         s.close()
         if rs is not None:
             rs.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(c.ROLE_TESTS))
+def test_reference_role_tests_pass_on_the_facade(name):
+    """The fork's own test programs (aby3_tests/Test.cpp, BoolTest.cpp, SortTest.cpp -- what `frontend -Arith`, `-Bool`,
+    `-Sort` ... run, frontend/main.cpp:16-54), compiled unmodified against the facade, three party threads with `-role i`:
+    every check_result() (aby3-Basic/debug.h) reports SUCCESS, and as many of them as on the reference's CPU build."""
+    ok, bad = c.role_test(name)
+    assert bad == 0, (name, ok, bad)
+    assert ok == c.ROLE_TESTS[name], (name, ok)

@@ -399,3 +399,13 @@ def test_reference_aby3_ml_linear_on_cpu(capfd):
     assert t > 0
     for p in range(3):
         assert np.array_equal(w[(p + 1) % 3, 1], w[p, 0])
+
+
+def test_reference_role_tests_on_cpu():
+    """aby3_tests/Test.cpp, BoolTest.cpp, SortTest.cpp compiled unmodified into oracle/_ref: the number of check_result()
+    SUCCESS lines each writes is what tests/test_compat.py expects of the same programs on the GPU facade."""
+    import compat_lib
+    for name, n in compat_lib.ROLE_TESTS.items():
+        if name == "quick_sort_test":
+            continue                                   # 2.6 s of CPU; its count is pinned by the GPU-side test
+        assert r.role_test(name) == (n, 0), name
