@@ -309,28 +309,49 @@ __global__ void __launch_bounds__(WIDE ? 512 : 256, 1) k_bin_and_layer(const uin
     __syncthreads();
     const u32 Tl = (threadIdx.x & 31) * 4;
     const u64 chunks = rw / 2;
-    for (u32 g = blockIdx.y; g < n_gates; g += gridDim.y) {
-        const uint4 G = gates[g];
+    auto gate_chunk = [&](const uint4 G, u32 g, size_t c, AesStream<WIDE>& sp, AesStream<WIDE>& sn) {
         const u32 type = G.w;
+        const W2 a0 = ldw(mem0, G.x, rw, c), a1 = ldw(mem1, G.x, rw, c);
+        const W2 b0 = ldw(mem0, G.y, rw, c), b1 = ldw(mem1, G.y, rw, c);
+        W2 x0 = a0, x1 = a1, y0 = b0, y1 = b1;
+        if (type == 1) { x0 = {~a0.a, ~a0.b}; x1 = {~a1.a, ~a1.b}; y0 = {~b0.a, ~b0.b}; y1 = {~b1.a, ~b1.b}; }
+        else if (type == 4) { x0 = {~a0.a, ~a0.b}; x1 = {~a1.a, ~a1.b}; }
+        W2 o0;
+        o0.a = (x0.a & y0.a) ^ (x0.a & y1.a) ^ (x1.a & y0.a);
+        o0.b = (x0.b & y0.b) ^ (x0.b & y1.b) ^ (x1.b & y0.b);
+        if (type == 14) { o0.a ^= a0.a ^ b0.a; o0.b ^= a0.b ^ b0.b; }
+        u32 p[4], q[4];
+        const u64 ctr = (and0 + g) * chunks + c;
+        sp.block(Tl, kp, ctr, p);
+        sn.block(Tl, kn, ctr, q);
+        o0.a ^= (((u64)(p[1] ^ q[1])) << 32) | (u64)(p[0] ^ q[0]);
+        o0.b ^= (((u64)(p[3] ^ q[3])) << 32) | (u64)(p[2] ^ q[2]);
+        stw(mem0, G.z, rw, c, o0);
+    };
+    if (WIDE) {
+        // ONE wave of one CTA per SM over the flat list of (gate, run of 256 chunks): a 2-D grid of gx x ceil(SMs / gx) CTAs
+        // is a few CTAs more than there are SMs, and with one 128 KiB CTA per SM those few ran as a second wave (the
+        // 26-gate levels of the comparison circuit took 0.122 ms instead of 0.06)
+        const u64 rpg = (chunks + 255) / 256, total = rpg * n_gates;
+        const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
+        const u32 lane = threadIdx.x & 31;
         AesStream<WIDE> sp, sn;
-        aes_for_each<WIDE>(chunks, [&](size_t c) {
-            const W2 a0 = ldw(mem0, G.x, rw, c), a1 = ldw(mem1, G.x, rw, c);
-            const W2 b0 = ldw(mem0, G.y, rw, c), b1 = ldw(mem1, G.y, rw, c);
-            W2 x0 = a0, x1 = a1, y0 = b0, y1 = b1;
-            if (type == 1) { x0 = {~a0.a, ~a0.b}; x1 = {~a1.a, ~a1.b}; y0 = {~b0.a, ~b0.b}; y1 = {~b1.a, ~b1.b}; }
-            else if (type == 4) { x0 = {~a0.a, ~a0.b}; x1 = {~a1.a, ~a1.b}; }
-            W2 o0;
-            o0.a = (x0.a & y0.a) ^ (x0.a & y1.a) ^ (x1.a & y0.a);
-            o0.b = (x0.b & y0.b) ^ (x0.b & y1.b) ^ (x1.b & y0.b);
-            if (type == 14) { o0.a ^= a0.a ^ b0.a; o0.b ^= a0.b ^ b0.b; }
-            u32 p[4], q[4];
-            const u64 ctr = (and0 + g) * chunks + c;
-            sp.block(Tl, kp, ctr, p);
-            sn.block(Tl, kn, ctr, q);
-            o0.a ^= (((u64)(p[1] ^ q[1])) << 32) | (u64)(p[0] ^ q[0]);
-            o0.b ^= (((u64)(p[3] ^ q[3])) << 32) | (u64)(p[2] ^ q[2]);
-            stw(mem0, G.z, rw, c, o0);
-        });
+        for (u64 r = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < total; r += warps) {
+            const u32 g = (u32)(r / rpg);
+            const u64 run = r - (u64)g * rpg;
+            const uint4 G = gates[g];
+#pragma unroll 1
+            for (int t = 0; t < 8; ++t) {
+                const u64 c = run * 256 + t * 32 + lane;
+                if (c < chunks) gate_chunk(G, g, c, sp, sn);
+            }
+        }
+    } else {
+        for (u32 g = blockIdx.y; g < n_gates; g += gridDim.y) {
+            const uint4 G = gates[g];
+            AesStream<WIDE> sp, sn;
+            aes_for_each<WIDE>(chunks, [&](size_t c) { gate_chunk(G, g, c, sp, sn); });
+        }
     }
 }
 
@@ -552,12 +573,10 @@ int aby3cu_bin_and_layer(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void*
     if (wide_on && !ctx->corun && chunks * n_gates >= (1u << 16) && chunks >= 2048) {
         ABY3CU_CHECK(cudaFuncSetAttribute(k_bin_and_layer<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesWideTableBytes));
         if (prefer_max_smem(k_bin_and_layer<true>)) return 1;
-        // one 512-thread CTA per SM; a CTA column covers runs of 256 chunks per warp
-        u64 gx = (chunks + 4095) / 4096;
+        // one 512-thread CTA per SM, one wave: the warps walk the flat list of (gate, run of 256 chunks)
+        u64 gx = (((chunks + 255) / 256) * n_gates + 15) / 16;
         if (gx > (u64)ctx->sm_count) gx = ctx->sm_count;
-        u64 gy = ((u64)ctx->sm_count + gx - 1) / gx;
-        if (gy > n_gates) gy = n_gates;
-        k_bin_and_layer<true><<<dim3((unsigned)gx, (unsigned)gy), 512, kAesWideTableBytes, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0,
+        k_bin_and_layer<true><<<(unsigned)gx, 512, kAesWideTableBytes, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0,
                                                                                                           (const u64*)d_mem1, row_bytes / 8, kp, kn, and_index0);
         return post_launch(ctx, "k_bin_and_layer");
     }

@@ -83,6 +83,21 @@ __device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// the same copy with an L2 eviction-priority hint (createpolicy) for the line it leaves behind in L2
+__device__ __forceinline__ void bulk_g2s_hint(u32 dst, const void* src, u32 bytes, u32 bar, u64 policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(u32 bar) {
@@ -200,6 +215,7 @@ struct Params {
     u64 N;
     u32 mtiles, ntiles, kblocks;
     int accumulate;
+    int l2hint;         // 0 none; 1: A panels evict_last, B panels evict_first; 2: A panels evict_last only (ABY3CU_GEMM_L2HINT)
     u32* progress;      // may be NULL: progress[g] += 1 per epilogue warp per finished tile of raster group g
 };
 
@@ -244,6 +260,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         // ================================ TMA producer ================================
         if (lane == 0) {
             u32 stage = 0, phase = 0;
+            // A raster group's 8 A panels (64 MiB at K = 4096) are re-read by every tile column of the group and fit L2; the
+            // B panels stream through once per group: tell L2 which of the two to keep
+            const u64 pol_a = l2_policy_evict_last(), pol_b = l2_policy_evict_first();
             for (u32 t = blockIdx.x; t < ntiles_total; t += gridDim.x) {
                 u32 mt, nt;
                 tile_coords(t, mt, nt);
@@ -253,8 +272,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), STAGE_BYTES);
                     const u32 dst = sbase + stage * STAGE_BYTES;
-                    bulk_g2s(dst, a + (u64)kb * A_CHUNK, A_CHUNK, full_bar(stage));
-                    bulk_g2s(dst + A_CHUNK, b + (u64)kb * B_CHUNK, B_CHUNK, full_bar(stage));
+                    if (p.l2hint) bulk_g2s_hint(dst, a + (u64)kb * A_CHUNK, A_CHUNK, full_bar(stage), pol_a);
+                    else bulk_g2s(dst, a + (u64)kb * A_CHUNK, A_CHUNK, full_bar(stage));
+                    if (p.l2hint == 1) bulk_g2s_hint(dst + A_CHUNK, b + (u64)kb * B_CHUNK, B_CHUNK, full_bar(stage), pol_b);
+                    else bulk_g2s(dst + A_CHUNK, b + (u64)kb * B_CHUNK, B_CHUNK, full_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -503,6 +524,8 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
             p.pa = pa; p.pb = pb; p.C = (u64*)C; p.row0 = r0; p.rows_end = r0 + rows; p.N = N;
             p.mtiles = (u32)mtiles; p.ntiles = (u32)ntiles; p.kblocks = (u32)kblocks; p.accumulate = acc_this;
             p.progress = progress ? ctx->progress : nullptr;
+            static const int l2hint = [] { const char* e = getenv("ABY3CU_GEMM_L2HINT"); return e ? atoi(e) : 0; }();
+            p.l2hint = l2hint;
             const u64 tiles = mtiles * ntiles;
             const unsigned grid = (unsigned)(tiles < (u64)ctx->sm_count ? tiles : (u64)ctx->sm_count);
             if (ctx->c_ready) { ABY3CU_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->c_ready, 0)); ctx->c_ready = nullptr; }   // after the limb pre-pass
