@@ -7,6 +7,7 @@
 // are device kernels, so a compare-exchange stage never touches host memory.
 #pragma once
 #include <cmath>
+#include <cstdlib>
 
 #include "../sh3/Sh3BinaryEvaluator.h"
 #include "../sh3/Sh3Encryptor.h"
@@ -22,6 +23,7 @@ inline void runCircuit(oc::BetaCircuit* cir, const sbMatrix& in0, const sbMatrix
                        Sh3Evaluator& eval, Sh3Runtime& runtime) {
     Sh3BinaryEvaluator binEng;
     const u64 n = in0.rows();
+    binEng.sharePlanes(runtime.mComm);   // in0 / in1 are sharings the protocols produced: plane 1 is the neighbour's plane 0
     binEng.setCir(cir, n, eval.mShareGen);
     binEng.setInputRef(0, in0);          // in0 / in1 outlive the .get() below
     binEng.setInputRef(1, in1);
@@ -74,6 +76,27 @@ inline void bool_cipher_max_min_split(int pIdx, sbMatrix& A, sbMatrix& B, sbMatr
     const u64 n = A.rows();
     sbMatrix comp;
     bool_cipher_lt(pIdx, A, B, comp, enc, eval, rt);
+    static const bool fused = [] { const char* e = std::getenv("ABY3_FUSED_MAXMIN"); return !(e && e[0] == '0'); }();
+    if (fused && n && A.i64Cols() == 1 && B.i64Cols() == 1 && B.rows() == n && pIdx >= 0 && pIdx <= 2) {
+        // Both bitwiseAnd runs, the NOT between them and the xors as one pass per party (aby3cu_bin_maxmin_rowmajor):
+        // the two engine runs would draw their zero-share keys in this order (Sh3BinaryEvaluator.h:98-101), and since xor is
+        // linear the second plane of min / max is the previous party's first plane -- one reshare instead of two.
+        // Same share words as the path below (ABY3_FUSED_MAXMIN=0).
+        const block p1 = eval.mShareGen.mPrevCommon.get<block>(), n1 = eval.mShareGen.mNextCommon.get<block>();
+        const block p2 = eval.mShareGen.mPrevCommon.get<block>(), n2 = eval.mShareGen.mNextCommon.get<block>();
+        res_max.resize(n, BITSIZE);
+        res_min.resize(n, BITSIZE);
+        gpu::check(aby3cu_bin_maxmin_rowmajor(ctx->h(), comp.mShares[0].dev(), comp.mShares[1].dev(), A.mShares[0].dev(), A.mShares[1].dev(),
+                                              B.mShares[0].dev(), B.mShares[1].dev(), res_min.mShares[0].devOut(), res_max.mShares[0].devOut(), n,
+                                              aby3cu_bin_row_bytes(2 * n), p1.data(), n1.data(), p2.data(), n2.data(), (u32)pIdx));
+        rt.mComm.mNext.asyncSendDevice(res_min.mShares[0].dev(), n * 8);
+        rt.mComm.mNext.asyncSendDevice(res_max.mShares[0].dev(), n * 8);
+        auto f0 = rt.mComm.mPrev.asyncRecvDevice(res_min.mShares[1].devOut(), n * 8);
+        auto f1 = rt.mComm.mPrev.asyncRecvDevice(res_max.mShares[1].devOut(), n * 8);
+        f0.get();
+        f1.get();
+        return;
+    }
     sbMatrix extComp(2 * n, BITSIZE), extAB(2 * n, BITSIZE), tmp1, tmp2;
     for (int s = 0; s < 2; ++s) {
         i64* m = extComp.mShares[s].devOut();

@@ -252,7 +252,9 @@ struct alignas(16) W2 { u64 a, b; };
 __device__ __forceinline__ W2 ldw(const u64* mem, u64 row, u64 rw, u64 c) { return *reinterpret_cast<const W2*>(mem + row * rw + 2 * c); }
 __device__ __forceinline__ void stw(u64* mem, u64 row, u64 rw, u64 c, W2 v) { *reinterpret_cast<W2*>(mem + row * rw + 2 * c) = v; }
 
-template <bool AES>
+// ONE: plane 0 only, linear gates only -- the second plane of a wire is the previous party's first plane (replicated sharing),
+// so co-located parties read it there instead of recomputing it (Sh3BinaryEvaluator "shared planes")
+template <bool AES, bool ONE = false>
 __global__ void __launch_bounds__(256) k_bin_level(const uint4* __restrict__ gates, u32 n_gates, u64* mem0, u64* mem1, u64 rw,
                                                    const __grid_constant__ AesKey kp, const __grid_constant__ AesKey kn, u64 and0) {
     if (AES) { aes_table_init(); __syncthreads(); }
@@ -263,6 +265,17 @@ __global__ void __launch_bounds__(256) k_bin_level(const uint4* __restrict__ gat
         for (u32 g = 0; g < n_gates; ++g) {
             const uint4 G = gates[g];
             const u32 type = G.w;
+            if (ONE) {
+                const W2 a = ldw(mem0, G.x, rw, c);
+                W2 o = a;
+                if (type != 10) {
+                    const W2 b = ldw(mem0, G.y, rw, c);
+                    o = {a.a ^ b.a, a.b ^ b.b};
+                    if (type == 9) o = {~o.a, ~o.b};
+                }
+                stw(mem0, G.z, rw, c, o);
+                continue;
+            }
             const W2 a0 = ldw(mem0, G.x, rw, c), a1 = ldw(mem1, G.x, rw, c);
             W2 b0 = {0, 0}, b1 = {0, 0};
             if (type != 10) { b0 = ldw(mem0, G.y, rw, c); b1 = ldw(mem1, G.y, rw, c); }
@@ -309,10 +322,16 @@ __global__ void __launch_bounds__(WIDE ? 512 : 256, 1) k_bin_and_layer(const uin
     __syncthreads();
     const u32 Tl = (threadIdx.x & 31) * 4;
     const u64 chunks = rw / 2;
-    auto gate_chunk = [&](const uint4 G, u32 g, size_t c, AesStream<WIDE>& sp, AesStream<WIDE>& sn) {
+    struct Ops { W2 a0, a1, b0, b1; };
+    auto load_ops = [&](const uint4 G, size_t c) {
+        Ops o;
+        o.a0 = ldw(mem0, G.x, rw, c); o.a1 = ldw(mem1, G.x, rw, c);
+        o.b0 = ldw(mem0, G.y, rw, c); o.b1 = ldw(mem1, G.y, rw, c);
+        return o;
+    };
+    auto gate_ops = [&](const uint4 G, u32 g, size_t c, const Ops& in, AesStream<WIDE>& sp, AesStream<WIDE>& sn) {
         const u32 type = G.w;
-        const W2 a0 = ldw(mem0, G.x, rw, c), a1 = ldw(mem1, G.x, rw, c);
-        const W2 b0 = ldw(mem0, G.y, rw, c), b1 = ldw(mem1, G.y, rw, c);
+        const W2 a0 = in.a0, a1 = in.a1, b0 = in.b0, b1 = in.b1;
         W2 x0 = a0, x1 = a1, y0 = b0, y1 = b1;
         if (type == 1) { x0 = {~a0.a, ~a0.b}; x1 = {~a1.a, ~a1.b}; y0 = {~b0.a, ~b0.b}; y1 = {~b1.a, ~b1.b}; }
         else if (type == 4) { x0 = {~a0.a, ~a0.b}; x1 = {~a1.a, ~a1.b}; }
@@ -328,6 +347,7 @@ __global__ void __launch_bounds__(WIDE ? 512 : 256, 1) k_bin_and_layer(const uin
         o0.b ^= (((u64)(p[3] ^ q[3])) << 32) | (u64)(p[2] ^ q[2]);
         stw(mem0, G.z, rw, c, o0);
     };
+    auto gate_chunk = [&](const uint4 G, u32 g, size_t c, AesStream<WIDE>& sp, AesStream<WIDE>& sn) { gate_ops(G, g, c, load_ops(G, c), sp, sn); };
     if (WIDE) {
         // ONE wave of one CTA per SM over the flat list of (gate, run of 256 chunks): a 2-D grid of gx x ceil(SMs / gx) CTAs
         // is a few CTAs more than there are SMs, and with one 128 KiB CTA per SM those few ran as a second wave (the
@@ -340,10 +360,18 @@ __global__ void __launch_bounds__(WIDE ? 512 : 256, 1) k_bin_and_layer(const uin
             const u32 g = (u32)(r / rpg);
             const u64 run = r - (u64)g * rpg;
             const uint4 G = gates[g];
+            // the operands of step t + 1 are in flight while step t draws its two keystream blocks (4 warps per scheduler
+            // do not hide a DRAM round trip by themselves: long-scoreboard was the top stall)
+            const u64 cbase = run * 256 + lane;
+            Ops cur = {};
+            if (cbase < chunks) cur = load_ops(G, cbase);
 #pragma unroll 1
             for (int t = 0; t < 8; ++t) {
-                const u64 c = run * 256 + t * 32 + lane;
-                if (c < chunks) gate_chunk(G, g, c, sp, sn);
+                const u64 c = cbase + t * 32;
+                Ops nxt = {};
+                if (t + 1 < 8 && c + 32 < chunks) nxt = load_ops(G, c + 32);
+                if (c < chunks) gate_ops(G, g, c, cur, sp, sn);
+                cur = nxt;
             }
         }
     } else {
@@ -402,6 +430,15 @@ __global__ void __launch_bounds__(WIDE ? 512 : 256, 1) k_bitwise_rowmajor(const 
         for (u64 tt = 0; tt < kRun; ++tt) {
             const u64 t = run * kRun + tt;
             if (t >= tiles) break;
+            // the four instances' operand words first: their DRAM latency hides under ~2000 keystream instructions (they
+            // used to be loaded after the transposes and waited for -- long-scoreboard was the top stall, issue 54 % active)
+            u64 x0[4], x1[4], y0[4], y1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const u64 j = t * 128 + 32 * q + lane;
+                if (j < n) { x0[q] = __ldcs(a0 + j); x1[q] = __ldcs(a1 + j); y0[q] = __ldcs(b0 + j); y1[q] = __ldcs(b1 + j); }
+                else { x0[q] = x1[q] = y0[q] = y1[q] = 0; }
+            }
             u32 zl[4] = {0, 0, 0, 0}, zh[4] = {0, 0, 0, 0};
             if (lane < bits) {
                 u32 p[4], q[4];
@@ -425,13 +462,84 @@ __global__ void __launch_bounds__(WIDE ? 512 : 256, 1) k_bitwise_rowmajor(const 
                 const u32 hi = bits > 32 ? warp_transpose32(zh[q], lane) : 0u;
                 const u64 j = t * 128 + 32 * q + lane;
                 if (j < n) {
-                    const u64 x0 = a0[j], x1 = a1[j], y0 = b0[j], y1 = b1[j];
-                    u64 o = (x0 & y0) ^ (x0 & y1) ^ (x1 & y0);
-                    if (type == 14) o ^= x0 ^ y0;                                   // Or (:912-981)
+                    u64 o = (x0[q] & y0[q]) ^ (x0[q] & y1[q]) ^ (x1[q] & y0[q]);
+                    if (type == 14) o ^= x0[q] ^ y0[q];                             // Or (:912-981)
                     o = (o ^ (((u64)hi << 32) | lo)) & keep;
                     out0[j] = o;
                     if (out_copy) out_copy[j] = o;
                 }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// aby3-Basic's compare-exchange selection (BoolBasic.cpp:275-312) after its comparison: with m = the comparison bit
+// widened to a 0 / -1 mask (share by share), the reference evaluates int_int_bitwiseAnd(64) TWICE over the stacked
+// 2n-row operands  [m; m] & [A; B]  and  NOT[m; m] & [A; B]  (two engine runs with their own zero-share keys, a
+// reshare each) and xors halves of the two results:  min = t1[0:n] ^ t2[n:2n],  max = t1[n:2n] ^ t2[0:n].
+// Here both evaluations and the xors are ONE pass over the row-major words per party: lane l draws the keystream blocks
+// of gates l and l + 32 of BOTH evaluations for tile t of the 2n-wide instance range (8 AES blocks), the 32 x 32
+// transposes turn them into the z words of instances 128 t + 32 q + l, and the instance's two products go to the min /
+// max word of element (j mod n) by xor-reduction (element i receives one contribution from instance i and one from
+// instance n + i, which live in different tiles when n is not a multiple of 128).  min0 / max0 must be zero on entry.
+// Plane 0 of the results only; plane 1 is the previous party's plane 0 (xor is linear), i.e. ONE reshare instead of two.
+// Same share words as the two bitwise_rowmajor runs + share_op xors.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) k_maxmin_rowmajor(const u64* __restrict__ c0, const u64* __restrict__ c1,
+                                                            const u64* __restrict__ A0, const u64* __restrict__ A1,
+                                                            const u64* __restrict__ B0, const u64* __restrict__ B1,
+                                                            u64* min0, u64* max0, u64 n, u64 chunks,
+                                                            const __grid_constant__ AesKey kp1, const __grid_constant__ AesKey kn1,
+                                                            const __grid_constant__ AesKey kp2, const __grid_constant__ AesKey kn2,
+                                                            u32 not_plane) {
+    aes_table_init();
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31, Tl = lane * 4;
+    const u64 n2 = 2 * n, tiles = (n2 + 127) / 128;
+    const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 t = (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5); t < tiles; t += warps) {
+        u64 m0[4], m1[4], y0[4], y1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u64 j = t * 128 + 32 * q + lane;
+            if (j < n2) {
+                const bool first = j < n;
+                const u64 i = first ? j : j - n;
+                m0[q] = 0 - __ldg(c0 + i); m1[q] = 0 - __ldg(c1 + i);          // a share of the bit is 0 or 1: its mask share 0 or -1 (:279-284)
+                y0[q] = __ldcs((first ? A0 : B0) + i); y1[q] = __ldcs((first ? A1 : B1) + i);
+            } else { m0[q] = m1[q] = y0[q] = y1[q] = 0; }
+        }
+        u32 z1l[4], z1h[4], z2l[4], z2h[4];
+        {
+            u32 p[4], q[4];
+            const u64 cl = (u64)lane * chunks + t, ch = (u64)(lane + 32) * chunks + t;
+            aes_encrypt_ctr(Tl, kp1, cl, p); aes_encrypt_ctr(Tl, kn1, cl, q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) z1l[i] = p[i] ^ q[i];
+            aes_encrypt_ctr(Tl, kp1, ch, p); aes_encrypt_ctr(Tl, kn1, ch, q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) z1h[i] = p[i] ^ q[i];
+            aes_encrypt_ctr(Tl, kp2, cl, p); aes_encrypt_ctr(Tl, kn2, cl, q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) z2l[i] = p[i] ^ q[i];
+            aes_encrypt_ctr(Tl, kp2, ch, p); aes_encrypt_ctr(Tl, kn2, ch, q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) z2h[i] = p[i] ^ q[i];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u64 z1 = ((u64)warp_transpose32(z1h[q], lane) << 32) | warp_transpose32(z1l[q], lane);
+            const u64 z2 = ((u64)warp_transpose32(z2h[q], lane) << 32) | warp_transpose32(z2l[q], lane);
+            const u64 j = t * 128 + 32 * q + lane;
+            if (j < n2) {
+                const u64 nx0 = not_plane == 1 ? ~m0[q] : m0[q], nx1 = not_plane == 2 ? ~m1[q] : m1[q];   // the complemented share x_1 (:315-343)
+                const u64 t1 = (m0[q] & y0[q]) ^ (m0[q] & y1[q]) ^ (m1[q] & y0[q]) ^ z1;
+                const u64 t2 = (nx0 & y0[q]) ^ (nx0 & y1[q]) ^ (nx1 & y0[q]) ^ z2;
+                const bool first = j < n;
+                const u64 i = first ? j : j - n;
+                atomicXor(reinterpret_cast<unsigned long long*>(min0 + i), (unsigned long long)(first ? t1 : t2));
+                atomicXor(reinterpret_cast<unsigned long long*>(max0 + i), (unsigned long long)(first ? t2 : t1));
             }
         }
     }
@@ -541,7 +649,7 @@ int aby3cu_bit_transpose_gather(aby3cu_ctx* ctx, const void* d_in, const u32* d_
 
 int aby3cu_bin_level(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void* d_mem0, void* d_mem1, u64 row_bytes,
                      const u8 key_prev[16], const u8 key_next[16], u64 and_index0) {
-    ABY3CU_REQUIRE(ctx && ((d_gates && d_mem0 && d_mem1) || !n_gates), "bin_level: null argument");
+    ABY3CU_REQUIRE(ctx && ((d_gates && d_mem0 && (d_mem1 || !key_prev)) || !n_gates), "bin_level: null argument");
     ABY3CU_REQUIRE(row_bytes % 16 == 0, "bin_level: row_bytes must be a multiple of 16");
     ABY3CU_REQUIRE((key_prev == nullptr) == (key_next == nullptr), "bin_level: give both keys or neither");
     if (!n_gates || !row_bytes) return 0;
@@ -556,7 +664,8 @@ int aby3cu_bin_level(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void* d_m
     } else {
         static const AesKey zero = {};
         const unsigned grid = ew_grid(ctx, chunks, 256, 8);
-        k_bin_level<false><<<grid, 256, 0, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0, (u64*)d_mem1, rw, zero, zero, and_index0);
+        if (!d_mem1) k_bin_level<false, true><<<grid, 256, 0, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0, nullptr, rw, zero, zero, and_index0);
+        else k_bin_level<false><<<grid, 256, 0, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0, (u64*)d_mem1, rw, zero, zero, and_index0);
     }
     return post_launch(ctx, "k_bin_level");
 }
@@ -614,10 +723,33 @@ int aby3cu_bin_bitwise_rowmajor(aby3cu_ctx* ctx, uint32_t gate_type, const int64
     }
     ABY3CU_CHECK(cudaFuncSetAttribute(k_bitwise_rowmajor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
     if (prefer_max_smem(k_bitwise_rowmajor<false>)) return 1;
-    const unsigned grid = ew_grid(ctx, tiles * 32, 256, 3);
+    // 128 registers x 256 threads: two CTAs per SM are resident; a grid of three per SM ran as 1.5 waves (ncu), the second one half empty
+    const unsigned grid = ew_grid(ctx, tiles * 32, 256, 2);
     k_bitwise_rowmajor<false><<<grid, 256, kAesTableBytes, ctx->stream>>>((const u64*)d_a0, (const u64*)d_a1, (const u64*)d_b0, (const u64*)d_b1,
                                                                           (u64*)d_out0, (u64*)d_out_copy, n, bits, row_bytes / 16, kp, kn, and_index0, gate_type);
     return post_launch(ctx, "k_bitwise_rowmajor");
+}
+
+int aby3cu_bin_maxmin_rowmajor(aby3cu_ctx* ctx, const int64_t* d_c0, const int64_t* d_c1, const int64_t* d_a0, const int64_t* d_a1,
+                               const int64_t* d_b0, const int64_t* d_b1, int64_t* d_min0, int64_t* d_max0, uint64_t n, uint64_t row_bytes,
+                               const u8 key_prev1[16], const u8 key_next1[16], const u8 key_prev2[16], const u8 key_next2[16], uint32_t not_plane) {
+    ABY3CU_REQUIRE(ctx && key_prev1 && key_next1 && key_prev2 && key_next2 && ((d_c0 && d_c1 && d_a0 && d_a1 && d_b0 && d_b1 && d_min0 && d_max0) || !n),
+                   "bin_maxmin_rowmajor: null argument");
+    ABY3CU_REQUIRE(not_plane <= 2, "bin_maxmin_rowmajor: not_plane is 0 (none), 1 (plane 0) or 2 (plane 1)");
+    ABY3CU_REQUIRE(row_bytes % 16 == 0 && row_bytes * 8 >= 2 * n, "bin_maxmin_rowmajor: row_bytes must be the wire-row size of a circuit over 2 n instances");
+    if (!n) return 0;
+    DeviceGuard g(ctx->device);
+    AesKey kp1, kn1, kp2, kn2;
+    host_expand_key(key_prev1, &kp1); host_expand_key(key_next1, &kn1); host_expand_key(key_prev2, &kp2); host_expand_key(key_next2, &kn2);
+    ABY3CU_CHECK(cudaMemsetAsync(d_min0, 0, n * 8, ctx->stream));
+    ABY3CU_CHECK(cudaMemsetAsync(d_max0, 0, n * 8, ctx->stream));
+    ABY3CU_CHECK(cudaFuncSetAttribute(k_maxmin_rowmajor, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
+    if (prefer_max_smem(k_maxmin_rowmajor)) return 1;
+    const u64 tiles = (2 * n + 127) / 128;
+    const unsigned grid = ew_grid(ctx, tiles * 32, 256, 2);
+    k_maxmin_rowmajor<<<grid, 256, kAesTableBytes, ctx->stream>>>((const u64*)d_c0, (const u64*)d_c1, (const u64*)d_a0, (const u64*)d_a1, (const u64*)d_b0,
+                                                                  (const u64*)d_b1, (u64*)d_min0, (u64*)d_max0, n, row_bytes / 16, kp1, kn1, kp2, kn2, not_plane);
+    return post_launch(ctx, "k_maxmin_rowmajor");
 }
 
 // The shadow evaluator of the reference's BINARY_ENGINE_DEBUG build (Sh3BinaryEvaluator.cpp:1469-1601), on the device:

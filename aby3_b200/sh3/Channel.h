@@ -155,6 +155,8 @@ struct Transport {
     virtual std::function<void()> postRecvDeviceOn(aby3::gpu::Context* on, void* d, size_t n) = 0;
     virtual void flushOn(aby3::gpu::Context*) {}
     virtual void flush() {}
+    // both ends are device contexts on the SAME GPU (known when the pair is made, so both ends always agree)
+    virtual bool colocated() const { return false; }
     virtual aby3::gpu::Context* context() const = 0;
     // late binding of the endpoint's device context (a Session hands out channels before it knows which party
     // thread -- and so which device -- will hold each end)
@@ -233,6 +235,7 @@ struct LocalTransport : Transport {
     // Parties whose contexts share ONE stream are ordered by enqueue order alone: the receiver's host thread
     // only learns of a message after the sender has enqueued its producer, so no event is needed.
     bool sameStream() const { return peerStream && peerStream == ctx->stream(); }
+    bool colocated() const override { return ctx && peerStream != nullptr; }
     void markReady(Message& m) {
         if (sameStream()) return;
         m.ready = ctx->recordEvent();
@@ -439,6 +442,8 @@ public:
     }
 
     bool isConnected() const { return (bool)mT; }
+    // the party at the other end runs on the same GPU: device pointers of one are valid for the other
+    bool colocated() const { return mT && mT->colocated(); }
     void waitForConnection() {}
     void close() {}
     void cancel() {}

@@ -23,8 +23,38 @@ bool Sh3BinaryEvaluator::fastEligible(const oc::BetaCircuit& cir, u32& type, u32
     return true;
 }
 
+void Sh3BinaryEvaluator::sharePlanes(CommPkg& comm) {
+    static const bool on = [] { const char* e = std::getenv("ABY3_BIN_SHARED_PLANES"); return !(e && e[0] == '0'); }();
+    mShareWanted = on && comm.mPrev.colocated() && comm.mNext.colocated();
+}
+
+void Sh3BinaryEvaluator::releaseBorrows() {
+    // (every kernel of ours that reads the neighbour's plane has been enqueued: the reader events are recorded now)
+    for (auto& b : mBorrows) b.release(mCtx);
+    mBorrows.clear();
+    mPrevMem = nullptr;
+}
+
+// One message per AND level instead of the level's rows: the next party reads plane 0 in place once everything we have
+// enqueued so far (the level's linear gates and all earlier levels) has run; `logicalBytes` = what the copying path moves.
+void Sh3BinaryEvaluator::exchangeReady(CommPkg& comm, u64 logicalBytes) {
+    comm.mNext.asyncSendDeviceShared(mMem0Shared, logicalBytes);
+    oc::Borrowed b;
+    comm.mPrev.asyncRecvDeviceBorrow(logicalBytes, &b).get();
+    if (!b.shared) throw std::runtime_error("binary engine (shared planes): the previous party did not share its wire memory " LOCATION);
+    mPrevMem = (const u8*)b.ptr;
+    mBorrows.push_back(std::move(b));
+}
+
 void Sh3BinaryEvaluator::allocWireMemory() {
     const u64 planeBytes = std::max<u64>((u64)mCir->mWireCount * mRowBytes, 16);
+    if (mShare) {
+        mMem[0].free(); mMem[1].free();
+        mMem0Shared = std::make_shared<gpu::SharedBuffer>(mCtx, planeBytes);
+        gpu::check(aby3cu_memset(mCtx->h(), mMem0Shared->ptr(), 0, planeBytes));
+        return;
+    }
+    mMem0Shared.reset();
     for (int s = 0; s < 2; ++s) {
         mMem[s].reset(mCtx, planeBytes);
         gpu::check(aby3cu_memset(mCtx->h(), mMem[s].ptr(), 0, planeBytes));
@@ -42,13 +72,13 @@ void Sh3BinaryEvaluator::setCir(oc::BetaCircuit* cir, u64 width, block prevSeed,
     mShareAES[0].setKey(prevSeed);                                     // :87-88
     mShareAES[1].setKey(nextSeed);
 
+    releaseBorrows();
     mFast = !mDebug && width && fastEligible(*cir, mFastType, mFastBits);
     mFastTaken = false;
     mFastPtr = {};
     for (auto& in : mFastIn) for (auto& b : in) b.free();
     for (auto& b : mFastOut) b.free();
-    if (mFast) { mMem[0].free(); mMem[1].free(); }
-    else allocWireMemory();
+    mShare = false;
     // gate list and the per-level AND output wires, uploaded once
     std::vector<u32> flat(4 * cir->mGates.size()), locs;
     for (u64 g = 0; g < cir->mGates.size(); ++g) {
@@ -90,6 +120,12 @@ void Sh3BinaryEvaluator::setCir(oc::BetaCircuit* cir, u64 width, block prevSeed,
         while (g < end && !oc::isLinear(cir->mGates[g].mType)) ++g;
         mLevelLinear.push_back(g == end ? (i64)nLinear : -1);
     }
+    // shared planes need every level in the split form (linear gates, then independent nonlinear ones): a level evaluated
+    // by the in-order kernel would need the neighbour's SAME kernel to have finished -- around the ring, a deadlock
+    mShare = mShareWanted && !mDebug && !mFast && width != 0;
+    for (i64 nl : mLevelLinear) mShare = mShare && nl >= 0;
+    if (mFast) { mMem[0].free(); mMem[1].free(); mMem0Shared.reset(); }
+    else allocWireMemory();
     mGatesDev.reset(mCtx, std::max<size_t>(flat.size() * 4, 16));
     mAndLocsDev.reset(mCtx, std::max<size_t>(locs.size() * 4, 16));
     if (!flat.empty()) gpu::check(aby3cu_h2d(mCtx->h(), mGatesDev.ptr(), flat.data(), flat.size() * 4));
@@ -174,8 +210,8 @@ void Sh3BinaryEvaluator::setInput(const oc::BetaBundle& inWires, const sbMatrix&
     if (in.rows() != mWidth) throw std::invalid_argument("incorrect number of rows");
     for (u64 k = 0; k + 1 < inWires.size(); ++k)
         if (inWires[k] + 1 != inWires[k + 1]) throw std::runtime_error("expecting contiguous input wires. " LOCATION);
-    for (int s = 0; s < 2; ++s) {
-        u8* dst = (u8*)mMem[s].ptr() + (u64)inWires.front() * mRowBytes;
+    for (int s = 0; s < (mShare ? 1 : 2); ++s) {          // shared planes: plane 1 is the previous party's plane 0
+        u8* dst = (s == 0 ? mem0() : (u8*)mMem[1].ptr()) + (u64)inWires.front() * mRowBytes;
         gpu::check(aby3cu_bit_transpose(mCtx->h(), in.mShares[s].dev(), mWidth, in.bitCount(), in.i64Cols() * 8,
                                         dst, mRowBytes, nullptr));
     }
@@ -193,8 +229,8 @@ void Sh3BinaryEvaluator::setInput(u64 idx, const sPackedBin& in) {
     std::vector<u32> idxs(wires.begin(), wires.end());
     gpu::Buffer dIdx(mCtx, std::max<size_t>(idxs.size() * 4, 16));
     gpu::check(aby3cu_h2d(mCtx->h(), dIdx.ptr(), idxs.data(), idxs.size() * 4));
-    for (int s = 0; s < 2; ++s)
-        gpu::check(aby3cu_bin_scatter_rows(mCtx->h(), mMem[s].ptr(), mRowBytes, (const u32*)dIdx.ptr(), (u32)idxs.size(),
+    for (int s = 0; s < (mShare ? 1 : 2); ++s)
+        gpu::check(aby3cu_bin_scatter_rows(mCtx->h(), s == 0 ? (void*)mem0() : mMem[1].ptr(), mRowBytes, (const u32*)dIdx.ptr(), (u32)idxs.size(),
                                            in.simdWidth() * 8, in.mShares[s].dev()));
 }
 
@@ -239,6 +275,30 @@ void Sh3BinaryEvaluator::roundCallback(CommPkg& comm, Sh3Task task) {
     // each AND output row travels as ceil(width/8) bytes (.cpp:795-796), padded to 16 so that the
     // pack / scatter kernels move whole 128-bit words (the pad carries bits beyond `width` only)
     const u64 sendBytes = (((mWidth + 7) / 8) + 15) & ~15ull;
+
+    if (mShare) {
+        if (mLevel < levels) {
+            const u64 g0 = mLevelGateOff[mLevel];
+            const u64 a0 = mLevelAndOff[mLevel], nAnd = mLevelAndOff[mLevel + 1] - a0;
+            if (a0 != mShareIdx) throw RTE_LOC;
+            const u64 nLin = (u64)mLevelLinear[mLevel];
+            if (nLin) gpu::check(aby3cu_bin_level(mCtx->h(), (const u32*)mGatesDev.ptr() + 4 * g0, (u32)nLin, mem0(), nullptr, mRowBytes, nullptr, nullptr, mShareIdx));
+            if (nAnd) {
+                exchangeReady(comm, nAnd * sendBytes);
+                gpu::check(aby3cu_bin_and_layer(mCtx->h(), (const u32*)mGatesDev.ptr() + 4 * (g0 + nLin), (u32)nAnd, mem0(), mem1(), mRowBytes,
+                                                mShareAES[0].key().data(), mShareAES[1].key().data(), mShareIdx));
+                mShareIdx += nAnd;
+            }
+        } else {
+            exchangeReady(comm, 0);        // the neighbour's last level (and its trailing linear gates) precede getOutput
+        }
+        mLevel++;
+        if (hasMoreRounds()) {
+            auto t = task.then([this](CommPkg& comm, Sh3Task& task) { roundCallback(comm, task); });
+            t.name() = "callback";
+        }
+        return;
+    }
 
     if (mLevel) {                                                     // :555-573
         const u64 prev = mLevel - 1;
@@ -368,7 +428,7 @@ void Sh3BinaryEvaluator::getOutput(const std::vector<oc::BetaWire>& outWires, sb
     for (int s = 0; s < 2; ++s) {
         i64* dst = out.mShares[s].devOut();
         gpu::check(aby3cu_memset(mCtx->h(), dst, 0, out.i64Size() * 8));
-        gpu::check(aby3cu_bit_transpose_gather(mCtx->h(), mMem[s].ptr(), (const u32*)dIdx.ptr(), bits, mWidth, mRowBytes,
+        gpu::check(aby3cu_bit_transpose_gather(mCtx->h(), s == 0 ? (const void*)mem0() : (const void*)mem1(), (const u32*)dIdx.ptr(), bits, mWidth, mRowBytes,
                                                dst, out.i64Cols() * 8, anyInv ? (const u8*)dInv.ptr() : nullptr));
     }
 }
@@ -396,7 +456,7 @@ void Sh3BinaryEvaluator::getOutput(const std::vector<oc::BetaWire>& outWires, sP
     gpu::check(aby3cu_h2d(mCtx->h(), dIdx.ptr(), idx.data(), n * 4));
     if (anyInv) gpu::check(aby3cu_h2d(mCtx->h(), dInv.ptr(), inv.data(), n));
     for (int s = 0; s < 2; ++s)
-        gpu::check(aby3cu_bin_pack_rows(mCtx->h(), mMem[s].ptr(), mRowBytes, (const u32*)dIdx.ptr(), (u32)n, out.simdWidth() * 8,
+        gpu::check(aby3cu_bin_pack_rows(mCtx->h(), s == 0 ? (const void*)mem0() : (const void*)mem1(), mRowBytes, (const u32*)dIdx.ptr(), (u32)n, out.simdWidth() * 8,
                                         out.mShares[s].devOut(), anyInv ? (const u8*)dInv.ptr() : nullptr));
 }
 

@@ -8,6 +8,8 @@
 // outputs to the next party.  The BINARY_ENGINE_DEBUG shadow evaluator of the
 // reference is a run-time switch here (enableDebug): a device-side gate checker.
 #pragma once
+#include <memory>
+
 #include "BetaCircuit.h"
 #include "Sh3Runtime.h"
 #include "Sh3ShareGen.h"
@@ -69,7 +71,7 @@ public:
     u64 shareCount() const { return mWidth; }
     u64 rowBytes() const { return mRowBytes; }
     // raw wire memory of one share plane (tests): wires x rowBytes
-    const void* planeDevice(int s) const { return mMem[s].ptr(); }
+    const void* planeDevice(int s) const { return s == 0 ? (const void*)mem0() : (const void*)mem1(); }
 
     std::array<oc::AES, 2> mShareAES;   // [0] prev key, [1] next key
     u64 mShareIdx = 0;                  // nonlinear gates evaluated so far (z counter = mShareIdx * rowBytes/16)
@@ -77,6 +79,22 @@ public:
     // One-level bitwise circuits (int_int_bitwiseAnd / bitwiseOr) are evaluated on the row-major share words
     // (aby3cu_bin_bitwise_rowmajor): no wire memory, no transposes; identical shares.  ABY3_BIN_ROWMAJOR=0 turns it off.
     bool rowMajorPath() const { return mFast; }
+
+    // "Shared planes" (round 2): in a replicated sharing the second plane of every wire IS the previous party's first plane
+    // (linear gates keep that invariant, and an AND output's second plane is by definition the neighbour's first,
+    // Sh3BinaryEvaluator.cpp:1161-1171).  When both neighbours sit on the same GPU the party therefore keeps plane 0 only:
+    // linear gates are evaluated on one plane, an AND level reads its second-plane operands in the previous party's wire
+    // memory (ordered by one event per level, which is all the reshare message carries then), setInput transposes one plane,
+    // getOutput reads the second plane of the output wires next door.  No pack / copy / scatter of the AND rows, half the
+    // linear work, half the wire memory.  Identical share words.  Opt-in per evaluation (call before setCir): the INPUT
+    // sharings must be consistent (mShares[1] == previous party's mShares[0]) -- true for every sharing the protocols
+    // produce; a caller that feeds unrelated planes (a kernel test) must not ask for it.  ABY3_BIN_SHARED_PLANES=0 turns it off.
+    void sharePlanes(CommPkg& comm);
+    bool sharedPlanes() const { return mShare; }
+    ~Sh3BinaryEvaluator() { releaseBorrows(); }
+    Sh3BinaryEvaluator() = default;
+    Sh3BinaryEvaluator(const Sh3BinaryEvaluator&) = delete;
+    Sh3BinaryEvaluator& operator=(const Sh3BinaryEvaluator&) = delete;
 
 private:
     // ---- the row-major path ------------------------------------------------------------------------------------
@@ -91,6 +109,20 @@ private:
     void fastRound(CommPkg& comm);
     void materialize();                                          // leave the row-major path: build the wire memory
     void allocWireMemory();
+
+    // ---- shared planes -----------------------------------------------------------------------------------------
+    bool mShareWanted = false, mShare = false;
+    std::shared_ptr<gpu::SharedBuffer> mMem0Shared;             // plane 0 of the wire memory, read in place by the next party
+    std::vector<oc::Borrowed> mBorrows;                          // the previous party's plane 0 (one handle per level message)
+    const u8* mPrevMem = nullptr;
+    void exchangeReady(CommPkg& comm, u64 logicalBytes);
+    void releaseBorrows();
+    u8* mem0() const { return (u8*)(mShare ? mMem0Shared->ptr() : mMem[0].ptr()); }
+    const u8* mem1() const {
+        if (!mShare) return (const u8*)mMem[1].ptr();
+        if (!mPrevMem) throw std::runtime_error("binary engine (shared planes): the second plane is read before the first exchange " LOCATION);
+        return mPrevMem;
+    }
 
     gpu::Context* mCtx = nullptr;
     u64 mWidth = 0, mRowBytes = 0;

@@ -694,6 +694,7 @@ int sh3h_bin_eval(sh3h* h, const uint32_t* gates, uint32_t gate_count, uint32_t 
                      output_off, output_bits, output_wires, output_invert, num_outputs);
         Sh3BinaryEvaluator ev;
         const u64 width = P.bins.at(input_ids[0])->rows();
+        ev.sharePlanes(P.rt.mComm);              // the inputs are sharings made by the encryptor
         ev.setCir(&cir, width, P.eval.mShareGen);
         for (uint32_t k = 0; k < num_inputs; ++k) ev.setInput(k, *P.bins.at(input_ids[k]));
         ev.asyncEvaluate(P.rt).get();
@@ -776,6 +777,7 @@ int sh3h_bin_eval_packed(sh3h* h, const uint32_t* gates, uint32_t gate_count, ui
             }
         }
         Sh3BinaryEvaluator ev;
+        ev.sharePlanes(P.rt.mComm);
         ev.setCir(&cir, width, P.eval.mShareGen);
         for (uint32_t k = 0; k < num_inputs; ++k) ev.setInput(k, packed[k]);
         ev.asyncEvaluate(P.rt).get();

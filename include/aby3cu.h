@@ -300,7 +300,9 @@ int aby3cu_bit_transpose_gather(aby3cu_ctx* ctx, const void* d_in, const uint32_
  * Nor=1, na_And=4, Xor=6, And=8, Nxor=9, a(copy)=10, Or=14), executed in order.
  * mem0/mem1: the two share planes, wires x row_bytes.  Nonlinear gates use
  * z = KS_prev ^ KS_next starting at AES block  and_index0*(row_bytes/16)
- * (getShares, :1406-1442), and_index0 = number of nonlinear gates before this level. */
+ * (getShares, :1406-1442), and_index0 = number of nonlinear gates before this level.
+ * d_mem1 == NULL (no keys, LINEAR gates only): plane 0 alone is evaluated -- the second plane of every wire is the previous
+ * party's first plane, and a party that can read it there (same GPU) need not recompute it. */
 int aby3cu_bin_level(aby3cu_ctx* ctx, const uint32_t* d_gates, uint32_t n_gates,
                      void* d_mem0, void* d_mem1, uint64_t row_bytes,
                      const uint8_t key_prev[16], const uint8_t key_next[16], uint64_t and_index0);
@@ -318,6 +320,17 @@ int aby3cu_bin_and_layer(aby3cu_ctx* ctx, const uint32_t* d_gates, uint32_t n_ga
 int aby3cu_bin_bitwise_rowmajor(aby3cu_ctx* ctx, uint32_t gate_type /* 8 = And, 14 = Or */, const int64_t* d_a0, const int64_t* d_a1,
                                 const int64_t* d_b0, const int64_t* d_b1, int64_t* d_out0, int64_t* d_out_copy, uint64_t n, uint32_t bits,
                                 uint64_t row_bytes, const uint8_t key_prev[16], const uint8_t key_next[16], uint64_t and_index0);
+/* aby3-Basic/BoolBasic.cpp:275-312 (bool_cipher_max_min_split) after its comparison, one pass per party on row-major words:
+ * with m = -c (the comparison bit's shares widened to 0 / -1 masks, :279-284) the reference runs int_int_bitwiseAnd(64) twice
+ * over the stacked 2n-row operands, t1 = [m; m] & [A; B] under keys (key_prev1, key_next1) and t2 = NOT[m; m] & [A; B] under
+ * (key_prev2, key_next2) -- NOT complements share x_1 only (:315-343): not_plane = 1 at party 1 (its plane 0), 2 at party 2
+ * (its plane 1), 0 at party 0 -- and xors  min = t1[0:n] ^ t2[n:2n],  max = t1[n:2n] ^ t2[0:n].  This entry writes plane 0 of
+ * min and max (the same words as two aby3cu_bin_bitwise_rowmajor runs with and_index0 = 0 + aby3cu_share_op xors); plane 1 of
+ * either is the previous party's plane 0.  row_bytes = aby3cu_bin_row_bytes(2 n). */
+int aby3cu_bin_maxmin_rowmajor(aby3cu_ctx* ctx, const int64_t* d_c0, const int64_t* d_c1, const int64_t* d_a0, const int64_t* d_a1,
+                               const int64_t* d_b0, const int64_t* d_b1, int64_t* d_min0, int64_t* d_max0, uint64_t n, uint64_t row_bytes,
+                               const uint8_t key_prev1[16], const uint8_t key_next1[16], const uint8_t key_prev2[16],
+                               const uint8_t key_next2[16], uint32_t not_plane);
 /* sendBuff packing (:795-796) and getOutput(sPackedBin) (:1213-1283):
  * out[j*nbytes .. ) = first nbytes of row locs[j] of mem, complemented where d_invert[j] != 0
  * (d_invert may be NULL). */

@@ -435,3 +435,37 @@ def test_bitwise_rowmajor_equals_the_sliced_definition(ctx, gate):
             f ^= a0 ^ b0
         keep = np.int64(-1) if bits == 64 else np.int64((1 << bits) - 1)
         assert np.array_equal(got, (f ^ zt) & keep), (n, bits, and0)
+
+
+@pytest.mark.parametrize("not_plane", [0, 1, 2])
+def test_maxmin_rowmajor_equals_two_bitwise_and_runs(ctx, not_plane):
+    """aby3cu_bin_maxmin_rowmajor (aby3-Basic/BoolBasic.cpp:275-312 after the comparison: two int_int_bitwiseAnd(64) runs over
+    the stacked 2n-row operands, the NOT between them, the xors of their halves) against the definition, keystreams from the
+    oracle: t = f([m; m], [A; B]) ^ z with z bit g of instance j = bit j of key stream block range g of the run's keys;
+    min = t1[0:n] ^ t2[n:2n], max = t1[n:2n] ^ t2[0:n].  Ragged n (the two halves of an element sit in different tiles)."""
+    rng = np.random.default_rng(40 + not_plane)
+    keys = [bytes(range(k, k + 16)) for k in (0, 100, 30, 200)]
+    for n in (1, 63, 64, 100, 1000, 4099, 70001):
+        rb = int(lib.aby3cu_bin_row_bytes(2 * n))
+        c0, c1 = (rng.integers(0, 2, n, dtype=np.int64) for _ in range(2))
+        a0, a1, b0, b1 = (rng.integers(-2**63, 2**63, n, dtype=np.int64) for _ in range(4))
+        d = [ctx.upload(x) for x in (c0, c1, a0, a1, b0, b1)]
+        mn, mx = ctx.alloc(8 * n), ctx.alloc(8 * n)
+        abi.check(lib.aby3cu_aes_ctr_fill(ctx.h, keys[0], 0, mn.p, 8 * n))          # the entry clears its outputs itself
+        abi.check(lib.aby3cu_bin_maxmin_rowmajor(ctx.h, *[x.p for x in d], mn.p, mx.p, n, rb, keys[0], keys[1], keys[2], keys[3], not_plane))
+        m0, m1 = -c0, -c1
+        y0, y1 = np.concatenate([a0, b0]), np.concatenate([a1, b1])
+
+        def run(x0, x1, kp, kn):
+            z = np.zeros((64, rb), dtype=np.uint8)
+            for g in range(64):
+                z[g] = o.keystream(kp, g * rb, rb) ^ o.keystream(kn, g * rb, rb)
+            zt = o.bit_transpose(z.reshape(-1), 64, 2 * n, rb, 8).view(np.int64)[:2 * n]
+            x0, x1 = np.concatenate([x0, x0]), np.concatenate([x1, x1])
+            return (x0 & y0) ^ (x0 & y1) ^ (x1 & y0) ^ zt
+
+        t1 = run(m0, m1, keys[0], keys[1])
+        t2 = run(~m0 if not_plane == 1 else m0, ~m1 if not_plane == 2 else m1, keys[2], keys[3])
+        assert np.array_equal(ctx.download(mn, n), t1[:n] ^ t2[n:]), n
+        assert np.array_equal(ctx.download(mx, n), t1[n:] ^ t2[:n]), n
+
