@@ -192,7 +192,16 @@ inline int odd_even_merge(sbMatrix& data1, sbMatrix& data2, sbMatrix& res, int p
     while (d > 0) {
         // compare positions i and i + d for i = r0, r0 + 2, ... < 2*length - d   (:366-371)
         const u64 m = (length * 2 > r0 + d) ? (length * 2 - d - r0 + 1) / 2 : 0;
-        if (m) {
+        if (m && (d & 1)) {
+            // d is q - 1 or 1, i.e. odd: X and Y are the two parities of ONE contiguous range of `result`, read and
+            // written once for both planes (aby3cu_cmpx_gather / _scatter) instead of eight indexed passes
+            sbMatrix X(m, BITSIZE), Y(m, BITSIZE), mx, mn;
+            gpu::check(aby3cu_cmpx_gather(ctx->h(), result.mShares[0].dev(), result.mShares[1].dev(), r0, d, m, X.mShares[0].devOut(),
+                                          X.mShares[1].devOut(), Y.mShares[0].devOut(), Y.mShares[1].devOut()));
+            bool_cipher_max_min_split(pIdx, X, Y, mx, mn, enc, eval, rt);
+            gpu::check(aby3cu_cmpx_scatter(ctx->h(), mn.mShares[0].dev(), mn.mShares[1].dev(), mx.mShares[0].dev(), mx.mShares[1].dev(), r0, d, m,
+                                           result.mShares[0].devMut(), result.mShares[1].devMut()));
+        } else if (m) {
             gpu::Buffer dX = iota(r0, 2, m), dY = iota(r0 + d, 2, m);
             sbMatrix X(m, BITSIZE), Y(m, BITSIZE), mx, mn;
             for (int s = 0; s < 2; ++s) {

@@ -225,6 +225,39 @@ __device__ __forceinline__ void aes_wide_encrypt_ctr(u32 lane4, const AesKey& ke
 #undef ABY3CU_LASTW
 }
 
+// the same function through the four wide tables WITHOUT the run constants: for kernels that keep several keystreams per lane
+// and have no registers left for their AesRun states (240 alu operations, 160 lookups per block)
+__device__ __forceinline__ void aes_wide_encrypt_plain(u32 lane4, const AesKey& key, u64 ctr, u32 out[4]) {
+    u32 s0 = (u32)ctr ^ key.rk[0];
+    u32 s1 = (u32)(ctr >> 32) ^ key.rk[1];
+    u32 s2 = key.rk[2];
+    u32 s3 = key.rk[3];
+#pragma unroll
+    for (int r = 1; r < 10; ++r) {
+        const u32 a0 = tw<0, 0>(s0, lane4), b0 = tw<1, 1>(s1, lane4), c0 = tw<2, 2>(s2, lane4), d0 = tw<3, 3>(s3, lane4);
+        const u32 a1 = tw<0, 0>(s1, lane4), b1 = tw<1, 1>(s2, lane4), c1 = tw<2, 2>(s3, lane4), d1 = tw<3, 3>(s0, lane4);
+        const u32 a2 = tw<0, 0>(s2, lane4), b2 = tw<1, 1>(s3, lane4), c2 = tw<2, 2>(s0, lane4), d2 = tw<3, 3>(s1, lane4);
+        const u32 a3 = tw<0, 0>(s3, lane4), b3 = tw<1, 1>(s0, lane4), c3 = tw<2, 2>(s1, lane4), d3 = tw<3, 3>(s2, lane4);
+        s0 = xor3(xor3(a0, b0, c0), d0, key.rk[4 * r + 0]);
+        s1 = xor3(xor3(a1, b1, c1), d1, key.rk[4 * r + 1]);
+        s2 = xor3(xor3(a2, b2, c2), d2, key.rk[4 * r + 2]);
+        s3 = xor3(xor3(a3, b3, c3), d3, key.rk[4 * r + 3]);
+    }
+#define ABY3CU_LASTW(o, x0, x1, x2, x3, kk)                                             \
+    {                                                                                   \
+        u32 u = tw<0, 0>(x0, lane4), v = tw<0, 1>(x1, lane4);                           \
+        u32 w = tw<1, 2>(x2, lane4), y = tw<1, 3>(x3, lane4);                           \
+        u32 lo = __byte_perm(u, v, 0x0051);                                             \
+        u32 hi = __byte_perm(w, y, 0x7200);                                             \
+        o = __byte_perm(lo, hi, 0x7610) ^ key.rk[kk];                                   \
+    }
+    ABY3CU_LASTW(out[0], s0, s1, s2, s3, 40)
+    ABY3CU_LASTW(out[1], s1, s2, s3, s0, 41)
+    ABY3CU_LASTW(out[2], s2, s3, s0, s1, 42)
+    ABY3CU_LASTW(out[3], s3, s0, s1, s2, 43)
+#undef ABY3CU_LASTW
+}
+
 // One interface for both forms.  WIDE needs an even first element (a whole block per pair).
 template <bool WIDE>
 struct AesStream {

@@ -486,16 +486,22 @@ __global__ void __launch_bounds__(WIDE ? 512 : 256, 1) k_bitwise_rowmajor(const 
 // Plane 0 of the results only; plane 1 is the previous party's plane 0 (xor is linear), i.e. ONE reshare instead of two.
 // Same share words as the two bitwise_rowmajor runs + share_op xors.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) k_maxmin_rowmajor(const u64* __restrict__ c0, const u64* __restrict__ c1,
+template <bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 512 : 256, WIDE ? 1 : 2) k_maxmin_rowmajor(const u64* __restrict__ c0, const u64* __restrict__ c1,
                                                             const u64* __restrict__ A0, const u64* __restrict__ A1,
                                                             const u64* __restrict__ B0, const u64* __restrict__ B1,
                                                             u64* min0, u64* max0, u64 n, u64 chunks,
                                                             const __grid_constant__ AesKey kp1, const __grid_constant__ AesKey kn1,
                                                             const __grid_constant__ AesKey kp2, const __grid_constant__ AesKey kn2,
                                                             u32 not_plane) {
-    aes_table_init();
+    // WIDE: the four-table AES (no rotates: 240 instead of 312 alu operations per block; the kernel is alu-bound, ncu: alu
+    // 79 %, lsu 70 %) without the run constants -- eight keystreams per lane leave no registers for eight AesRun states
+    aes_tables_init<WIDE>();
     __syncthreads();
     const u32 lane = threadIdx.x & 31, Tl = lane * 4;
+    auto enc = [&](const AesKey& k, u64 ctr, u32* o) {
+        if (WIDE) aes_wide_encrypt_plain(Tl, k, ctr, o); else aes_encrypt_ctr(Tl, k, ctr, o);
+    };
     const u64 n2 = 2 * n, tiles = (n2 + 127) / 128;
     const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
     for (u64 t = (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5); t < tiles; t += warps) {
@@ -514,16 +520,16 @@ __global__ void __launch_bounds__(256, 2) k_maxmin_rowmajor(const u64* __restric
         {
             u32 p[4], q[4];
             const u64 cl = (u64)lane * chunks + t, ch = (u64)(lane + 32) * chunks + t;
-            aes_encrypt_ctr(Tl, kp1, cl, p); aes_encrypt_ctr(Tl, kn1, cl, q);
+            enc(kp1, cl, p); enc(kn1, cl, q);
 #pragma unroll
             for (int i = 0; i < 4; ++i) z1l[i] = p[i] ^ q[i];
-            aes_encrypt_ctr(Tl, kp1, ch, p); aes_encrypt_ctr(Tl, kn1, ch, q);
+            enc(kp1, ch, p); enc(kn1, ch, q);
 #pragma unroll
             for (int i = 0; i < 4; ++i) z1h[i] = p[i] ^ q[i];
-            aes_encrypt_ctr(Tl, kp2, cl, p); aes_encrypt_ctr(Tl, kn2, cl, q);
+            enc(kp2, cl, p); enc(kn2, cl, q);
 #pragma unroll
             for (int i = 0; i < 4; ++i) z2l[i] = p[i] ^ q[i];
-            aes_encrypt_ctr(Tl, kp2, ch, p); aes_encrypt_ctr(Tl, kn2, ch, q);
+            enc(kp2, ch, p); enc(kn2, ch, q);
 #pragma unroll
             for (int i = 0; i < 4; ++i) z2h[i] = p[i] ^ q[i];
         }
@@ -743,11 +749,20 @@ int aby3cu_bin_maxmin_rowmajor(aby3cu_ctx* ctx, const int64_t* d_c0, const int64
     host_expand_key(key_prev1, &kp1); host_expand_key(key_next1, &kn1); host_expand_key(key_prev2, &kp2); host_expand_key(key_next2, &kn2);
     ABY3CU_CHECK(cudaMemsetAsync(d_min0, 0, n * 8, ctx->stream));
     ABY3CU_CHECK(cudaMemsetAsync(d_max0, 0, n * 8, ctx->stream));
-    ABY3CU_CHECK(cudaFuncSetAttribute(k_maxmin_rowmajor, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
-    if (prefer_max_smem(k_maxmin_rowmajor)) return 1;
     const u64 tiles = (2 * n + 127) / 128;
+    static const bool wide_on = [] { const char* e = getenv("ABY3CU_AES_WIDE"); return !(e && e[0] == '0'); }();
+    if (wide_on && !ctx->corun && tiles >= 4096) {
+        ABY3CU_CHECK(cudaFuncSetAttribute(k_maxmin_rowmajor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesWideTableBytes));
+        if (prefer_max_smem(k_maxmin_rowmajor<true>)) return 1;
+        k_maxmin_rowmajor<true><<<ew_grid(ctx, tiles * 32, 512, 1), 512, kAesWideTableBytes, ctx->stream>>>(
+            (const u64*)d_c0, (const u64*)d_c1, (const u64*)d_a0, (const u64*)d_a1, (const u64*)d_b0, (const u64*)d_b1, (u64*)d_min0, (u64*)d_max0, n,
+            row_bytes / 16, kp1, kn1, kp2, kn2, not_plane);
+        return post_launch(ctx, "k_maxmin_rowmajor");
+    }
+    ABY3CU_CHECK(cudaFuncSetAttribute(k_maxmin_rowmajor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesTableBytes));
+    if (prefer_max_smem(k_maxmin_rowmajor<false>)) return 1;
     const unsigned grid = ew_grid(ctx, tiles * 32, 256, 2);
-    k_maxmin_rowmajor<<<grid, 256, kAesTableBytes, ctx->stream>>>((const u64*)d_c0, (const u64*)d_c1, (const u64*)d_a0, (const u64*)d_a1, (const u64*)d_b0,
+    k_maxmin_rowmajor<false><<<grid, 256, kAesTableBytes, ctx->stream>>>((const u64*)d_c0, (const u64*)d_c1, (const u64*)d_a0, (const u64*)d_a1, (const u64*)d_b0,
                                                                   (const u64*)d_b1, (u64*)d_min0, (u64*)d_max0, n, row_bytes / 16, kp1, kn1, kp2, kn2, not_plane);
     return post_launch(ctx, "k_maxmin_rowmajor");
 }

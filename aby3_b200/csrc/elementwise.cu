@@ -316,6 +316,31 @@ __global__ void __launch_bounds__(256) k_gather_rows(const i64* __restrict__ in,
     }
 }
 
+// One compare-exchange stage of the merge network (aby3-Basic/Sort.cpp:366-393) pairs positions r0 + 2i and r0 + d + 2i
+// with d ODD: the two operand vectors are the two parities of ONE contiguous range.  Pair p = (src[r0 + 2p], src[r0 + 2p + 1])
+// holds X[p] and Y[p - (d - 1) / 2], so the range is read (or written) exactly once, contiguously, instead of four strided
+// passes through index vectors.  PLANES share planes per launch (blockIdx.y).
+struct CmpxPlanes { const i64* src[2]; i64* x[2]; i64* y[2]; };
+__global__ void __launch_bounds__(256) k_cmpx_gather(CmpxPlanes P, u64 r0, u64 h /* (d - 1) / 2 */, u64 m) {
+    const i64* __restrict__ src = P.src[blockIdx.y] + r0;
+    i64* __restrict__ X = P.x[blockIdx.y];
+    i64* __restrict__ Y = P.y[blockIdx.y];
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < m + h; p += (u64)gridDim.x * blockDim.x) {
+        if (p < m) X[p] = __ldcs(src + 2 * p);
+        if (p >= h) Y[p - h] = __ldcs(src + 2 * p + 1);
+    }
+}
+struct CmpxScatter { i64* dst[2]; const i64* x[2]; const i64* y[2]; };
+__global__ void __launch_bounds__(256) k_cmpx_scatter(CmpxScatter P, u64 r0, u64 h, u64 m) {
+    i64* __restrict__ dst = P.dst[blockIdx.y] + r0;
+    const i64* __restrict__ X = P.x[blockIdx.y];
+    const i64* __restrict__ Y = P.y[blockIdx.y];
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < m + h; p += (u64)gridDim.x * blockDim.x) {
+        if (p < m) dst[2 * p] = __ldcs(X + p);
+        if (p >= h) dst[2 * p + 1] = __ldcs(Y + p - h);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_iota(u64 start, u64 step, u64* __restrict__ out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = start + step * i;
 }
@@ -640,6 +665,26 @@ int aby3cu_iota_u64(aby3cu_ctx* ctx, u64 start, u64 step, u64* out, size_t n) {
     DeviceGuard g(ctx->device);
     k_iota<<<ew_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(start, step, out, n);
     return post_launch(ctx, "k_iota");
+}
+
+int aby3cu_cmpx_gather(aby3cu_ctx* ctx, const i64* src0, const i64* src1, u64 r0, u64 d, u64 m, i64* x0, i64* x1, i64* y0, i64* y1) {
+    ABY3CU_REQUIRE(ctx && ((src0 && src1 && x0 && x1 && y0 && y1) || !m), "cmpx_gather: null argument");
+    ABY3CU_REQUIRE(d & 1, "cmpx_gather: the distance must be odd (the two operands are the two parities of one range)");
+    if (!m) return 0;
+    DeviceGuard g(ctx->device);
+    CmpxPlanes P = {{src0, src1}, {x0, x1}, {y0, y1}};
+    k_cmpx_gather<<<dim3(ew_grid(ctx, m + d / 2, 256, 8), 2), 256, 0, ctx->stream>>>(P, r0, d / 2, m);
+    return post_launch(ctx, "k_cmpx_gather");
+}
+
+int aby3cu_cmpx_scatter(aby3cu_ctx* ctx, const i64* x0, const i64* x1, const i64* y0, const i64* y1, u64 r0, u64 d, u64 m, i64* dst0, i64* dst1) {
+    ABY3CU_REQUIRE(ctx && ((dst0 && dst1 && x0 && x1 && y0 && y1) || !m), "cmpx_scatter: null argument");
+    ABY3CU_REQUIRE(d & 1, "cmpx_scatter: the distance must be odd");
+    if (!m) return 0;
+    DeviceGuard g(ctx->device);
+    CmpxScatter P = {{dst0, dst1}, {x0, x1}, {y0, y1}};
+    k_cmpx_scatter<<<dim3(ew_grid(ctx, m + d / 2, 256, 8), 2), 256, 0, ctx->stream>>>(P, r0, d / 2, m);
+    return post_launch(ctx, "k_cmpx_scatter");
 }
 
 int aby3cu_scatter_rows(aby3cu_ctx* ctx, const i64* in, u64 cols, const u64* idx, u64 nrows, i64* out) {

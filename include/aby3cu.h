@@ -278,6 +278,15 @@ int aby3cu_iota_u64(aby3cu_ctx* ctx, uint64_t start, uint64_t step, uint64_t* d_
 int aby3cu_scatter_rows(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t cols, const uint64_t* d_idx,
                         uint64_t nrows, int64_t* d_out);
 
+/* One compare-exchange stage of odd_even_merge (aby3-Basic/Sort.cpp:366-393) on both share planes in one pass:
+ * gather  x[i] = src[r0 + 2 i],  y[i] = src[r0 + d + 2 i]   (i < m; the index vectors of :366-371 are these progressions),
+ * scatter dst[r0 + 2 i] = x[i],  dst[r0 + d + 2 i] = y[i]    (:388-393).  d must be odd (it is q - 1 or 1 in the network): the
+ * operands are then the two parities of one contiguous range, which is read / written once. */
+int aby3cu_cmpx_gather(aby3cu_ctx* ctx, const int64_t* d_src0, const int64_t* d_src1, uint64_t r0, uint64_t d, uint64_t m,
+                       int64_t* d_x0, int64_t* d_x1, int64_t* d_y0, int64_t* d_y1);
+int aby3cu_cmpx_scatter(aby3cu_ctx* ctx, const int64_t* d_x0, const int64_t* d_x1, const int64_t* d_y0, const int64_t* d_y1,
+                        uint64_t r0, uint64_t d, uint64_t m, int64_t* d_dst0, int64_t* d_dst1);
+
 /* ---- binary engine: Sh3BinaryEvaluator ----------------------------------------- */
 /* row stride (bytes) of the bit-sliced wire memory for `width` instances
  * (mMem.reset(width, wires, 8) with 256-bit blocks, Sh3BinaryEvaluator.cpp:84). */

@@ -445,7 +445,8 @@ def test_maxmin_rowmajor_equals_two_bitwise_and_runs(ctx, not_plane):
     min = t1[0:n] ^ t2[n:2n], max = t1[n:2n] ^ t2[0:n].  Ragged n (the two halves of an element sit in different tiles)."""
     rng = np.random.default_rng(40 + not_plane)
     keys = [bytes(range(k, k + 16)) for k in (0, 100, 30, 200)]
-    for n in (1, 63, 64, 100, 1000, 4099, 70001):
+    # (the last case is big enough for the four-table AES form of the kernel)
+    for n in (1, 63, 64, 100, 1000, 4099, 70001) + ((300007,) if not_plane == 1 else ()):
         rb = int(lib.aby3cu_bin_row_bytes(2 * n))
         c0, c1 = (rng.integers(0, 2, n, dtype=np.int64) for _ in range(2))
         a0, a1, b0, b1 = (rng.integers(-2**63, 2**63, n, dtype=np.int64) for _ in range(4))
@@ -468,4 +469,29 @@ def test_maxmin_rowmajor_equals_two_bitwise_and_runs(ctx, not_plane):
         t2 = run(~m0 if not_plane == 1 else m0, ~m1 if not_plane == 2 else m1, keys[2], keys[3])
         assert np.array_equal(ctx.download(mn, n), t1[:n] ^ t2[n:]), n
         assert np.array_equal(ctx.download(mx, n), t1[n:] ^ t2[:n]), n
+
+
+def test_cmpx_gather_scatter_equal_the_indexed_passes(ctx):
+    """aby3cu_cmpx_gather / _scatter (one compare-exchange stage of aby3-Basic/Sort.cpp:366-393 on both planes, the range read /
+    written once) against the index-vector definition x[i] = src[r0 + 2i], y[i] = src[r0 + d + 2i]."""
+    rng = np.random.default_rng(77)
+    for L, r0, d in ((2, 0, 1), (148, 0, 1), (148, 1, 127), (148, 1, 1), (5000, 1, 4095), (5000, 1, 3), (70001, 0, 1), (70001, 1, 65535)):
+        total = 2 * L
+        m = (total - d - r0 + 1) // 2 if total > r0 + d else 0
+        src = [rng.integers(-2**63, 2**63, total, dtype=np.int64) for _ in range(2)]
+        dsrc = [ctx.upload(a) for a in src]
+        outs = [ctx.alloc(8 * max(m, 2)) for _ in range(4)]
+        abi.check(lib.aby3cu_cmpx_gather(ctx.h, dsrc[0].p, dsrc[1].p, r0, d, m, outs[0].p, outs[1].p, outs[2].p, outs[3].p))
+        ix, iy = r0 + 2 * np.arange(m), r0 + d + 2 * np.arange(m)
+        for s in range(2):
+            assert np.array_equal(ctx.download(outs[s], m), src[s][ix]), (L, r0, d)
+            assert np.array_equal(ctx.download(outs[2 + s], m), src[s][iy]), (L, r0, d)
+        nx = [rng.integers(-2**63, 2**63, m, dtype=np.int64) for _ in range(4)]
+        dn = [ctx.upload(a) if m else ctx.alloc(16) for a in nx]
+        abi.check(lib.aby3cu_cmpx_scatter(ctx.h, dn[0].p, dn[1].p, dn[2].p, dn[3].p, r0, d, m, dsrc[0].p, dsrc[1].p))
+        for s in range(2):
+            want = src[s].copy()
+            want[ix] = nx[s]
+            want[iy] = nx[2 + s]
+            assert np.array_equal(ctx.download(dsrc[s], total), want), (L, r0, d)
 
