@@ -48,17 +48,33 @@ void Sh3BinaryEvaluator::exchangeReady(CommPkg& comm, u64 logicalBytes) {
 
 void Sh3BinaryEvaluator::allocWireMemory() {
     const u64 planeBytes = std::max<u64>((u64)mCir->mWireCount * mRowBytes, 16);
+    // Rows a gate writes are overwritten in full (every 16-byte chunk of the row) before anything reads them; only the other
+    // wires -- the input bundles, until setInput fills them, and wires no gate drives -- start as zero like the reference's
+    // freshly reset wire memory (Sh3BinaryEvaluator.cpp:84).  For the 64-bit comparison that is 128 of 505 rows.
+    std::vector<u8> written(mCir->mWireCount, 0);
+    for (auto& G : mCir->mGates) written[G.mOutput] = 1;
+    auto clear = [&](void* base) {
+        if (!mCir->mWireCount) { gpu::check(aby3cu_memset(mCtx->h(), base, 0, planeBytes)); return; }
+        for (u64 w = 0; w < mCir->mWireCount;) {
+            if (written[w]) { ++w; continue; }
+            u64 e = w;
+            while (e < mCir->mWireCount && !written[e]) ++e;
+            gpu::check(aby3cu_memset(mCtx->h(), (u8*)base + w * mRowBytes, 0, (e - w) * mRowBytes));
+            w = e;
+        }
+    };
     if (mShare) {
         mMem[0].free(); mMem[1].free();
         mMem0Shared = std::make_shared<gpu::SharedBuffer>(mCtx, planeBytes);
-        gpu::check(aby3cu_memset(mCtx->h(), mMem0Shared->ptr(), 0, planeBytes));
+        clear(mMem0Shared->ptr());
         return;
     }
     mMem0Shared.reset();
-    for (int s = 0; s < 2; ++s) {
-        mMem[s].reset(mCtx, planeBytes);
-        gpu::check(aby3cu_memset(mCtx->h(), mMem[s].ptr(), 0, planeBytes));
-    }
+    for (int s = 0; s < 2; ++s) mMem[s].reset(mCtx, planeBytes);
+    clear(mMem[0].ptr());
+    // plane 1 of an AND output arrives as ceil(width / 8) bytes (rounded to 16): the rest of its 256-byte-aligned row is
+    // never written, so this plane is cleared as a whole (pad bits only, but they stay deterministic)
+    gpu::check(aby3cu_memset(mCtx->h(), mMem[1].ptr(), 0, planeBytes));
 }
 
 void Sh3BinaryEvaluator::setCir(oc::BetaCircuit* cir, u64 width, block prevSeed, block nextSeed) {

@@ -86,6 +86,7 @@ Sh3Task Sh3Piecewise::getInputRegions(const si64Matrix& inputs, u64 decimal, Com
         }
 
     auto cir = lib.int_Sh3Piecewise_helper(64, T);
+    binEng.sharePlanes(comm);            // both circuit inputs are consistent sharings (plane 1 == the previous party's plane 0)
     binEng.setCir(cir, n, gen);
     binEng.setInput(T, circuitInput1);
     for (u64 t = 0; t < T; ++t) binEng.setInput(t, circuitInput0[t]);

@@ -592,22 +592,30 @@ def basic_bench(sess, n):
     d1 = np.sort(a[:half, 0]).reshape(-1, 1)
     d2 = np.sort(b[:half, 0]).reshape(-1, 1)
     D1, D2 = sess.share_bin(0, d1, 64), sess.share_bin(0, d2, 64)
-    sess.free(sess.odd_even_merge(D1, D2))          # warm-up: the stages' buffer sizes enter the pool
+    for _ in range(2):                                # warm-up: the stages' buffer sizes enter the pool (the second pass still allocates a few)
+        sess.free(sess.odd_even_merge(D1, D2))
     sess.sync()
-    l0 = sess.launches
-    sess.timer_begin()
-    t0 = time.perf_counter()
-    m = sess.odd_even_merge(D1, D2)
-    ms_merge = sess.timer_end()
-    wall = time.perf_counter() - t0
-    l_merge = sess.launches - l0
+    # three timed merges: the median is reported, the spread says whether the buffer pool has settled
+    runs = []
+    for rep in range(3):
+        l0 = sess.launches
+        sess.timer_begin()
+        t0 = time.perf_counter()
+        m = sess.odd_even_merge(D1, D2)
+        ms_rep = sess.timer_end()
+        runs.append((ms_rep, (time.perf_counter() - t0) * 1e3, sess.launches - l0))
+        if rep < 2:
+            sess.free(m)
+    ms_all = sorted(r[0] for r in runs)
+    ms_merge, wall, l_merge = ms_all[1], sorted(r[1] for r in runs)[1] / 1e3, runs[-1][2]
     merged = sess.reveal(m, 0, binary=True).reshape(-1)
     ok_merge = bool(np.all(np.diff(merged) >= 0)) and merged.size == 2 * half
     for h in (m, D1, D2):
         sess.free(h)
     return {"elements": n, "gt_elements_per_s": n / (ms_gt * 1e-3), "gt_ms": ms_gt, "gt_kernel_launches": l_gt, "gt_correct": ok_gt,
             "merge_elements_per_s": 2 * half / (ms_merge * 1e-3), "merge_ms": ms_merge, "merge_wall_ms": wall * 1e3,
-            "merge_kernel_launches": l_merge, "merge_sorted": ok_merge,
+            "merge_kernel_launches": l_merge, "merge_sorted": ok_merge, "merge_ms_runs": [round(x, 3) for x in ms_all],
+            "merge_spread": (ms_all[-1] - ms_all[0]) / ms_all[1],
             "timing": "CUDA events across the three party streams"}
 
 

@@ -737,3 +737,20 @@ def test_block_wise_open_of_the_truncating_product_matches_oracle(pair, blocks, 
         assert np.array_equal(s.get_shares(C), r.mul_trunc(Ao, Bo, 16))
         s.free(C)
     assert_cursors(s, r)
+
+
+def test_copying_reshare_and_two_run_selection_still_match():
+    """The round-2 shortcuts for co-located parties -- shared planes in the binary engine (ABY3_BIN_SHARED_PLANES) and the
+    one-pass compare-exchange selection (ABY3_FUSED_MAXMIN) -- are switches read once per process: with both OFF (the paths
+    parties on different GPUs take: AND rows packed / sent / scattered, two bitwiseAnd runs) the same tests give the same
+    share planes against the oracle."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ABY3_BIN_SHARED_PLANES="0", ABY3_FUSED_MAXMIN="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "basic_blocks or binary_engine or piecewise_logistic or random_circuits"],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert " passed" in r.stdout
+
