@@ -61,3 +61,36 @@ def test_three_gpu_binary_engine_nccl():
     finally:
         s.close()
         r.close()
+
+
+@pytest.mark.skipif(abi.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("devices,transport", [((0, 1, 2), "local"), ((0, 1, 2), "nccl"), ((0, 0, 1), "local"), ((1, 0, 0), "local")])
+def test_compare_exchange_blocks_across_gpus(devices, transport):
+    """aby3-Basic's selection and merge with the parties on different GPUs (and on a MIXED placement, where only one of a
+    party's neighbours shares its GPU): the binary engine must take the copying reshare there (no shared planes), the one-pass
+    selection sends its result plane over the channel -- same share planes as the oracle."""
+    import basic_ref as br
+    if max(devices) >= abi.device_count():
+        pytest.skip("needs %d GPUs" % (max(devices) + 1))
+    s, r = harness.Session(devices=devices, transport=transport), o.Session()
+    try:
+        rng = np.random.default_rng(11)
+        n = 3001
+        a, b = rng.integers(-2**62, 2**62, (n, 1), dtype=np.int64), rng.integers(-2**62, 2**62, (n, 1), dtype=np.int64)
+        X, Y = s.share_bin(0, a, 64), s.share_bin(2, b, 64)
+        Xo, Yo = r.share_bin(0, a), r.share_bin(2, b)
+        mx, mn = s.max_min_split(X, Y)
+        mxo, mno = br.max_min_split(r, Xo, Yo)
+        assert np.array_equal(s.get_shares(mx, binary=True), mxo)
+        assert np.array_equal(s.get_shares(mn, binary=True), mno)
+        d1 = np.sort(rng.integers(-2**40, 2**40, 50)).reshape(-1, 1).astype(np.int64)
+        d2 = np.sort(rng.integers(-2**40, 2**40, 98)).reshape(-1, 1).astype(np.int64)
+        m = s.odd_even_merge(s.share_bin(0, d1, 64), s.share_bin(0, d2, 64))
+        mo = br.odd_even_merge(r, r.share_bin(0, d1), r.share_bin(0, d2))
+        assert np.array_equal(s.get_shares(m, binary=True), mo)
+        for p in range(3):
+            assert list(s.cursors(p)) == list(r.cursors(p))
+    finally:
+        s.close()
+        r.close()
+
