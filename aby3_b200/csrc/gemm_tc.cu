@@ -527,7 +527,11 @@ int gemm_cross_tc(aby3cu_ctx* ctx, const i64* A0, const i64* A1, const i64* B0, 
             static const int l2hint = [] { const char* e = getenv("ABY3CU_GEMM_L2HINT"); return e ? atoi(e) : 0; }();
             p.l2hint = l2hint;
             const u64 tiles = mtiles * ntiles;
-            const unsigned grid = (unsigned)(tiles < (u64)ctx->sm_count ? tiles : (u64)ctx->sm_count);
+            // ABY3CU_GEMM_SMS=n: the persistent grid leaves SMs free for the other parties' keystream / pre-pass kernels (the GEMM
+            // is bound by the board's power limit, not by its SM count: DESIGN 3.1)
+            static const u64 gemm_sms = [] { const char* e = getenv("ABY3CU_GEMM_SMS"); const long v = e ? atol(e) : 0; return (u64)(v > 0 ? v : 0); }();
+            const u64 sms = (gemm_sms && gemm_sms < (u64)ctx->sm_count) ? gemm_sms : (u64)ctx->sm_count;
+            const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
             if (ctx->c_ready) { ABY3CU_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->c_ready, 0)); ctx->c_ready = nullptr; }   // after the limb pre-pass
             if (k0 == 0 && r0 == 0) ABY3CU_CHECK(cudaEventRecord(ctx->ev_gemm0, ctx->stream));
             trace_mark(ctx, "(k_gemm_tc ready)");
