@@ -109,7 +109,7 @@ public:
         mDevReady = copy->recordEvent();
         mDevReadyDevice = copy->device();
         mDevValid = true;
-        mUploadInFlight = true;
+        noteUpload(copy);
     }
     // Download the device copy on a copy stream once the calling party's stream has produced it; waitHost() (or any
     // host access) completes it.  The host vector keeps its address when the shape is unchanged.
@@ -335,7 +335,7 @@ private:
             gpu::check(aby3cu_h2d(mDev.ctx()->h(), mDev.ptr(), mHost.data(), size() * sizeof(T)));
             // large host copies are page-locked (gpu::HostAllocator): the upload is truly
             // asynchronous and the host copy must not be written before it has run
-            self->mUploadInFlight = size() * sizeof(T) >= gpu::HostAllocator<T>::kPinThreshold;
+            if (size() * sizeof(T) >= gpu::HostAllocator<T>::kPinThreshold) noteUpload(mDev.ctx());
         } else if (size()) {
             // never written on either side: the host path reads such a matrix as zeros (touchHost zero-fills), so the
             // device path must too -- a recycled pool block holds someone else's old data
@@ -357,8 +357,7 @@ private:
         }
         if (willWrite) {
             dropEvent(self->mDevReady, mDevReadyDevice);          // a prefetch still reads the host copy
-            if (mUploadInFlight && mDev.ctx()) mDev.ctx()->sync();
-            self->mUploadInFlight = false;
+            waitUpload();
             self->mDevValid = false;
         }
     }
@@ -367,8 +366,26 @@ private:
     void settleUpload() {
         dropEvent(mDevReady, mDevReadyDevice);
         dropEvent(mHostReady, mHostReadyDevice);
-        if (mUploadInFlight && mDev.ctx()) {
-            try { mDev.ctx()->sync(); } catch (...) {}
+        try { waitUpload(); } catch (...) {}
+        mUploadInFlight = false;
+    }
+    // An asynchronous upload reads the page-locked host copy: remember an event right behind it, so that a later host WRITE
+    // (or the release of the host block) waits for that copy alone.  (It used to synchronise the party's whole stream: in a
+    // pipelined caller "touch the next step's input buffer" then meant "wait for the step that is running", and the next
+    // step's uploads never overlapped anything -- tools/e2e_trace.py.)
+    void noteUpload(gpu::Context* c) const {
+        if (mUploadDone) { gpu::EventPool::put(mUploadDoneDevice, mUploadDone); mUploadDone = nullptr; }
+        mUploadDone = c->recordEvent();
+        mUploadDoneDevice = c->device();
+        mUploadInFlight = true;
+    }
+    void waitUpload() const {
+        if (mUploadDone) {
+            gpu::check(aby3cu_event_sync(mUploadDone));
+            gpu::EventPool::put(mUploadDoneDevice, mUploadDone);
+            mUploadDone = nullptr;
+        } else if (mUploadInFlight && mDev.ctx()) {
+            mDev.ctx()->sync();
         }
         mUploadInFlight = false;
     }
@@ -394,6 +411,7 @@ private:
         mHost = std::move(o.mHost); mHostValid = o.mHostValid;
         mDev = std::move(o.mDev); mDevValid = o.mDevValid;
         mUploadInFlight = o.mUploadInFlight; o.mUploadInFlight = false;
+        mUploadDone = o.mUploadDone; mUploadDoneDevice = o.mUploadDoneDevice; o.mUploadDone = nullptr;
         mDevReady = o.mDevReady; mDevReadyDevice = o.mDevReadyDevice; o.mDevReady = nullptr;
         mHostReady = o.mHostReady; mHostReadyDevice = o.mHostReadyDevice; o.mHostReady = nullptr;
         o.mRows = o.mCols = 0; o.mHostValid = false; o.mDevValid = false; o.mHost.clear();
@@ -443,7 +461,8 @@ private:
     mutable bool mUploadInFlight = false;
     mutable void* mDevReady = nullptr;      // prefetch in flight on a copy stream
     mutable void* mHostReady = nullptr;     // download in flight on a copy stream
-    mutable int mDevReadyDevice = 0, mHostReadyDevice = 0;
+    mutable void* mUploadDone = nullptr;    // right behind the last asynchronous upload of the host copy (any stream)
+    mutable int mDevReadyDevice = 0, mHostReadyDevice = 0, mUploadDoneDevice = 0;
 };
 
 template <typename T>

@@ -832,6 +832,71 @@ def distributed_leg(steps, warmup, n=SIZE):
             "timing": "host wall clock over the steps with the three devices drained on both sides (the parties' streams live on three devices)"}
 
 
+class E2EPipe:
+    """The end-to-end step through the public calls (localIntMatrix / asyncMul(..., shift) / revealAll) of ONE Session with HOST
+    buffers: two sets of page-locked input / output buffers, uploads prefetched on the owner's copy stream, downloads on a
+    second copy stream, consecutive steps pipelined two deep."""
+
+    def __init__(self, sess, a, b, nb):
+        self.sess, self.nb = sess, nb
+        self.M, self.K = a.shape
+        self.N = b.shape[1]
+        self.rb = self.M // nb
+        self.sets = [self._make_set(a, b), self._make_set(a, b)]
+
+    def _make_set(self, a, b):
+        sess = self.sess
+        st = {"pb": sess.plain(0, self.K, self.N), "pa": [], "pc": []}
+        st["pb"][1][...] = b
+        for i in range(self.nb):
+            pid, view = sess.plain(0, self.rb, self.K)
+            view[...] = a[i * self.rb:(i + 1) * self.rb]
+            st["pa"].append(pid)
+            st["pc"].append(sess.plain(0, self.rb, self.N))
+        return st
+
+    def upload(self, st):
+        sess = self.sess
+        sess.plain_touch(0, st["pb"][0])          # the host buffers count as freshly written: device copies are stale
+        for pid in st["pa"]:
+            sess.plain_touch(0, pid)
+        sess.plain_prefetch(0, st["pb"][0])
+        for pid in st["pa"]:
+            sess.plain_prefetch(0, pid)
+
+    def compute(self, st):
+        sess = self.sess
+        hb = sess.share_plain(0, st["pb"][0], self.K, self.N)
+        live = [hb]
+        for i in range(self.nb):
+            ha = sess.share_plain(0, st["pa"][i], self.rb, self.K)
+            hc = sess.mul(ha, hb, shift=SHIFT)
+            sess.reveal_plain_async(hc, 0, st["pc"][i][0])
+            live += [ha, hc]
+        return live
+
+    def finish(self, st, live):
+        for i in range(self.nb):
+            self.sess.plain_wait(0, st["pc"][i][0])
+        for h in live:
+            self.sess.free(h)
+
+    def run(self, nsteps):
+        self.upload(self.sets[0])
+        prev = None
+        for k in range(nsteps):
+            live = self.compute(self.sets[k % 2])
+            if prev is not None:
+                self.finish(*prev)
+            prev = (self.sets[k % 2], live)
+            if k + 1 < nsteps:
+                self.upload(self.sets[(k + 1) % 2])
+        self.finish(*prev)
+
+    def close(self):
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -961,69 +1026,22 @@ def main():
     # issued (into the other set of page-locked buffers) while step k computes, and step k's download is only awaited
     # after step k+1's kernels have been queued.  Same public calls (localIntMatrix / asyncMul / revealAll), the same
     # bytes over PCIe in EVERY step, all of it inside the timed region.
-    NB = int(os.environ.get("ABY3_BENCH_ROW_BLOCKS", "2"))      # 2048-row blocks: 1024 tiles = 6.9 waves of 148 (4 blocks: 3.5 waves, 86% full)
+    NB = int(os.environ.get("ABY3_BENCH_ROW_BLOCKS", "1"))      # row blocks per step (1: one product; 2: 1024 tiles = 6.9 waves of 148 each)
     if NB < 1 or M % NB:
         NB = 1
-    rb = M // NB
-
-    def make_set():
-        st = {"pb": sess.plain(0, K, N), "pa": [], "pc": []}
-        st["pb"][1][...] = b
-        for i in range(NB):
-            pid, view = sess.plain(0, rb, K)
-            view[...] = a[i * rb:(i + 1) * rb]
-            st["pa"].append(pid)
-            st["pc"].append(sess.plain(0, rb, N))
-        return st
-
-    sets = [make_set(), make_set()]
-
-    def upload(st):
-        sess.plain_touch(0, st["pb"][0])          # the host buffers count as freshly written: device copies are stale
-        for pid in st["pa"]:
-            sess.plain_touch(0, pid)
-        sess.plain_prefetch(0, st["pb"][0])
-        for pid in st["pa"]:
-            sess.plain_prefetch(0, pid)
-
-    def compute(st):
-        hb = sess.share_plain(0, st["pb"][0], K, N)
-        live = [hb]
-        for i in range(NB):
-            ha = sess.share_plain(0, st["pa"][i], rb, K)
-            hc = sess.mul(ha, hb, shift=SHIFT)
-            sess.reveal_plain_async(hc, 0, st["pc"][i][0])
-            live += [ha, hc]
-        return live
-
-    def finish(st, live):
-        for i in range(NB):
-            sess.plain_wait(0, st["pc"][i][0])
-        for h in live:
-            sess.free(h)
-
-    def e2e_pipelined(nsteps):
-        upload(sets[0])
-        prev = None
-        for k in range(nsteps):
-            live = compute(sets[k % 2])
-            if prev is not None:
-                finish(*prev)
-            prev = (sets[k % 2], live)
-            if k + 1 < nsteps:
-                upload(sets[(k + 1) % 2])
-        finish(*prev)
+    pipe = E2EPipe(sess, a, b, NB)
+    sets = pipe.sets
 
     pipe_steps = max(4, min(args.steps, 10))
-    e2e_pipelined(3)
-    e2e_pipelined(3)
+    pipe.run(3)
+    pipe.run(3)
     barrier()
     best = None
     for _ in range(2):
         sess.sync()
         barrier()
         t0 = time.perf_counter()
-        e2e_pipelined(pipe_steps)
+        pipe.run(pipe_steps)
         sess.sync()
         dt = (time.perf_counter() - t0) / pipe_steps
         best = dt if best is None else min(best, dt)
@@ -1034,7 +1052,7 @@ def main():
     if e2e_single < e2e_t:          # report the better public-API path
         e2e_t, e2e_path, e2e_steps_used = e2e_single, "single call", e2e_steps
     else:
-        e2e_path, e2e_steps_used = "row-block streamed, steps pipelined two deep", pipe_steps
+        e2e_path, e2e_steps_used = "transfers on copy streams, steps pipelined two deep (%d row block(s) per step)" % NB, pipe_steps
     barrier()
     pcie = None
     try:
@@ -1131,6 +1149,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": world * step_macs / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * (M * K + K * N), "d2h_bytes_per_step": 8 * M * N,
                     "ms_per_step": e2e_t * 1e3, "steps": e2e_steps_used, "repetitions": "better of 2 x %d steps" % e2e_steps_used, "single_call_ms_per_step": e2e_single * 1e3, "variant": e2e_path,
+                    "tried": "two protocol instances in flight (a second Session taking every other step from a second host thread): 13.98 vs 13.66 ms/step -- the GPU is bound by the sum of the kernels' work, one instance's sharing phase under the other's GEMMs buys nothing (profiles/r2_e2e_notes.md)",
                     "pcie_GBps_per_step_effective": {"h2d": 8 * (M * K + K * N) / e2e_t / 1e9, "d2h": 8 * M * N / e2e_t / 1e9},
                     "pcie_probe_rank0": pcie,
                     "driver_allocations_during_single_call_steps": int(pool1[0] - pool0[0]),
