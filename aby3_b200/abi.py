@@ -107,6 +107,7 @@ PROTOTYPES = {
     "aby3cu_transpose_i64_batch": (_int, [_p, _int, _p, _u64, _u64, _p]),
     "aby3cu_trunc_finish_batch": (_int, [_p, _int, _p, _p, _p, _p, _sz, _u64]),
     "aby3cu_gemv_cross_batch": (_int, [_p, _int, _p, _p, _p, _p, _u64, _u64, _p, _int]),
+    "aby3cu_gemv_ring": (_int, [_p, _p, _p, _p, _u64, _u64, _p, _int]),
     "aby3cu_gather_rows": (_int, [_p, _p, _u64, _p, _u64, _p]),
     "aby3cu_cmpx_gather": (_int, [_p, _p, _p, _u64, _u64, _u64, _p, _p, _p, _p]),
     "aby3cu_cmpx_scatter": (_int, [_p, _p, _p, _p, _p, _u64, _u64, _u64, _p, _p]),

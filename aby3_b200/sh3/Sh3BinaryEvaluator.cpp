@@ -373,7 +373,7 @@ void Sh3BinaryEvaluator::validateMemory() {
     if (!mDebugPrev.isConnected() || !mDebugNext.isConnected()) throw std::runtime_error("enableDebug needs both debug channels " LOCATION);
     const u64 planeBytes = (u64)mCir->mWireCount * mRowBytes;
     gpu::Buffer third(mCtx, std::max<u64>(planeBytes, 16)), res(mCtx, 16);
-    mDebugPrev.asyncSendDevice(mMem[0].ptr(), planeBytes);              // our x_i is the previous party's x_{(i-1)+1}
+    mDebugPrev.asyncSendDevice(mem0(), planeBytes);                     // our x_i is the previous party's x_{(i-1)+1}
     mDebugNext.recvDevice(third.ptr(), planeBytes);
     // a wire written by more than one gate holds only its last value: gates touching such wires are exempt
     std::vector<u32> writes(mCir->mWireCount, 0);
@@ -396,7 +396,7 @@ void Sh3BinaryEvaluator::validateMemory() {
     gpu::Buffer dSkip(mCtx, std::max<size_t>(skip.size(), 16));
     if (anySkip) gpu::check(aby3cu_h2d(mCtx->h(), dSkip.ptr(), skip.data(), skip.size()));
     gpu::check(aby3cu_bin_check_gates(mCtx->h(), (const u32*)mGatesDev.ptr(), anySkip ? (const u8*)dSkip.ptr() : nullptr,
-                                      (u32)mCir->mGates.size(), mMem[0].ptr(), mMem[1].ptr(), third.ptr(), mRowBytes, mWidth,
+                                      (u32)mCir->mGates.size(), mem0(), mem1(), third.ptr(), mRowBytes, mWidth,
                                       (u64*)res.ptr(), (u32*)((u8*)res.ptr() + 8)));
     u64 host[2] = {0, 0};
     gpu::check(aby3cu_d2h(mCtx->h(), host, res.ptr(), 16));

@@ -91,7 +91,10 @@ public:
     // produce; a caller that feeds unrelated planes (a kernel test) must not ask for it.  ABY3_BIN_SHARED_PLANES=0 turns it off.
     void sharePlanes(CommPkg& comm);
     bool sharedPlanes() const { return mShare; }
-    ~Sh3BinaryEvaluator() { releaseBorrows(); }
+    // hand the neighbour's wire memory back (reader events recorded at this point of the party's stream): evaluators that
+    // outlive an evaluation (Sh3Piecewise::binEng) call it after their last getOutput
+    void releaseSharedPlanes() { releaseBorrows(); }
+    ~Sh3BinaryEvaluator() { try { releaseBorrows(); } catch (...) {} }
     Sh3BinaryEvaluator() = default;
     Sh3BinaryEvaluator(const Sh3BinaryEvaluator&) = delete;
     Sh3BinaryEvaluator& operator=(const Sh3BinaryEvaluator&) = delete;

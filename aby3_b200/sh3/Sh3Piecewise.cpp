@@ -95,6 +95,7 @@ Sh3Task Sh3Piecewise::getInputRegions(const si64Matrix& inputs, u64 decimal, Com
             mInputRegions[t].resize(n, 1);
             binEng.getOutput(t, mInputRegions[t]);
         }
+        binEng.releaseSharedPlanes();
     }, "binEval-continuation").get();
     return self.getRuntime();
 }

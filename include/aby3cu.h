@@ -267,6 +267,13 @@ int aby3cu_gemv_cross_batch(aby3cu_ctx* ctx, int njobs, const int64_t* const* d_
                             const int64_t* const* d_B0, const int64_t* const* d_B1, uint64_t M, uint64_t K,
                             int64_t* const* d_C, int accumulate);
 
+/* The same cross terms (Sh3Evaluator.cpp:662-665, N = 1) for the THREE parties of one product when they share a GPU, every
+ * share plane of A read once: party p's second plane of A is the previous party's first plane (replicated sharing), so only the
+ * three first planes are passed.  C_p (+)= A0_p (B0_p + B1_p) + A0_{p-1} B0_p.  Same words as three aby3cu_gemm_cross calls
+ * on consistent sharings (logistic inference, aby3-ML/aby3ML.h:102-139: X is 2^22 x 512). */
+int aby3cu_gemv_ring(aby3cu_ctx* ctx, const int64_t* const* d_A0, const int64_t* const* d_B0, const int64_t* const* d_B1,
+                     uint64_t M, uint64_t K, int64_t* const* d_C, int accumulate);
+
 /* gather rows: out[r,:] = in[idx[r],:]  (extractBatch, aby3-ML/Regression.h:43-58) */
 int aby3cu_gather_rows(aby3cu_ctx* ctx, const int64_t* d_in, uint64_t cols, const uint64_t* d_idx,
                        uint64_t nrows, int64_t* d_out);
