@@ -171,7 +171,19 @@ Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64Matrix& A, const si
             const i64 *a0 = A.mShares[0].dev(), *a1 = A.mShares[1].dev(), *b0 = B.mShares[0].dev(), *b1 = B.mShares[1].dev();
             void* pairDone = early ? ctx->aux()->recordEvent() : nullptr;
             int rc;
-            if (nBlocks > 1) {
+            static const bool ringOn = [] { const char* e = std::getenv("ABY3_RING_GEMV"); return e && e[0] == '1'; }();     // (opt-in until verified on hardware)
+            if (ringOn && mColocated && N == 1 && nBlocks == 1 && M * A.cols() >= kRingMin) {
+                // co-located parties: one launch for the three cross terms, every plane of A read once (a1 is the previous
+                // party's a0 and is read there)
+                gpu::ColocatedGroup::GemvJob job;
+                job.ctx = ctx; job.a0 = a0; job.b0 = b0; job.b1 = b1; job.c = V; job.M = M; job.K = A.cols();
+                job.ready = ctx->recordEvent();
+                job.ready2 = pairDone;
+                rc = 0;
+                try { mColocated->ringGemv((int)self.getRuntime().mPartyIdx, job); }
+                catch (...) { ctx->recycleEvent(job.ready); if (pairDone) ctx->aux()->recycleEvent(pairDone); throw; }
+                ctx->recycleEvent(job.ready);
+            } else if (nBlocks > 1) {
                 for (u64 b = 0; b < nBlocks; ++b) blockDone.push_back(ctx->newEvent());
                 rc = aby3cu_gemm_cross_blocks(ctx->h(), mGemmAlgo, a0, a1, b0, b1, M, A.cols(), N, V, 1, pairDone, blockRows,
                                               blockDone.data(), (u32)nBlocks);

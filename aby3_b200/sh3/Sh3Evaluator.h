@@ -11,6 +11,9 @@
 // n x 1 vectors expect); anything else throws.
 #pragma once
 #include <cstdlib>
+#include <memory>
+
+#include "Colocated.h"
 #include "Sh3FixedPoint.h"
 #include "Sh3Runtime.h"
 #include "Sh3ShareGen.h"
@@ -146,6 +149,12 @@ public:
     // mOpenBlocks row blocks, each on the party's communication stream as soon as its rows are final, while the later
     // blocks still multiply.  A protocol parameter: every party must use the same value (1 = one message, the default).
     u64 mOpenBlocks = 1;
+
+    // The three parties of this evaluator's protocol instance run on ONE GPU (set by whoever placed them, e.g. the harness
+    // Session): GEMV-shaped truncating products (N = 1, at least kRingMin elements of A) meet in the group and run as one
+    // launch that reads every share plane of A once (sh3/Colocated.h).  ABY3_RING_GEMV=0 turns it off.
+    std::shared_ptr<gpu::ColocatedGroup> mColocated;
+    static constexpr u64 kRingMin = u64(1) << 22;
 
     Sh3Task asyncMul(Sh3Task dependency, const si64& A, const si64& B, si64& C);
     Sh3Task asyncMul(Sh3Task dependency, const si64Matrix& A, const si64Matrix& B, si64Matrix& C);

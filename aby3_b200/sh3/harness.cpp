@@ -162,6 +162,11 @@ static sh3h* create_impl(int dev0, int dev1, int dev2, const uint8_t* enc_seeds,
         h->p[2].comm = CommPkg{c12.second, c02.second};
         }
         for (int i = 0; i < 3; ++i) h->w[i].th = std::thread([hp = h.get(), i] { hp->w[i].loop(); });
+        // three parties on one GPU: GEMV-shaped products meet in one launch (sh3/Colocated.h)
+        if (use_nccl != 1 && dev0 == dev1 && dev1 == dev2) {
+            auto group = std::make_shared<gpu::ColocatedGroup>();
+            for (int i = 0; i < 3; ++i) h->p[i].eval.mColocated = group;
+        }
         auto blk = [](const uint8_t* p) { block b; memcpy(b.data(), p, 16); return b; };
         int rc = h->run([&](int i) {
             Party& P = h->p[i];

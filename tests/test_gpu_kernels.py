@@ -495,3 +495,24 @@ def test_cmpx_gather_scatter_equal_the_indexed_passes(ctx):
             want[iy] = nx[2 + s]
             assert np.array_equal(ctx.download(dsrc[s], total), want), (L, r0, d)
 
+
+def test_gemv_ring_equals_three_cross_terms(ctx):
+    """aby3cu_gemv_ring (the three co-located parties' GEMV cross terms in one launch, every plane of A read once) against the
+    oracle's cross term per party on a CONSISTENT sharing (party p's second plane = party p-1's first plane)."""
+    ptr3 = lambda bufs: (C.c_void_p * 3)(*[b.p for b in bufs])
+    for (M, K) in ((1, 1), (5, 3), (130, 64), (1000, 511), (257, 1024), (300, 2050)):
+        A0 = [rnd(500 + p, M * K).reshape(M, K) for p in range(3)]
+        B0 = [rnd(510 + p, K).reshape(K, 1) for p in range(3)]
+        C0 = [rnd(520 + p, M).reshape(M, 1) for p in range(3)]
+        dA, dB0, dC = [ctx.upload(a) for a in A0], [ctx.upload(b) for b in B0], [ctx.upload(c) for c in C0]
+        dB1 = [dB0[(p + 2) % 3] for p in range(3)]                 # plane 1 = the previous party's plane 0
+        abi.check(lib.aby3cu_gemv_ring(ctx.h, ptr3(dA), ptr3(dB0), ptr3(dB1), M, K, ptr3(dC), 1))
+        for p in range(3):
+            q = (p + 2) % 3
+            want = o.cross_term(A0[p], A0[q], B0[p], B0[q]).view(U64) + C0[p].view(U64)
+            assert np.array_equal(ctx.download(dC[p], (M, 1), U64), want), (M, K, p)
+        abi.check(lib.aby3cu_gemv_ring(ctx.h, ptr3(dA), ptr3(dB0), ptr3(dB1), M, K, ptr3(dC), 0))
+        for p in range(3):
+            q = (p + 2) % 3
+            assert np.array_equal(ctx.download(dC[p], (M, 1), U64), o.cross_term(A0[p], A0[q], B0[p], B0[q]).view(U64)), (M, K, p)
+

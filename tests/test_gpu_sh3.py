@@ -741,16 +741,34 @@ def test_block_wise_open_of_the_truncating_product_matches_oracle(pair, blocks, 
 
 def test_copying_reshare_and_two_run_selection_still_match():
     """The round-2 shortcuts for co-located parties -- shared planes in the binary engine (ABY3_BIN_SHARED_PLANES) and the
-    one-pass compare-exchange selection (ABY3_FUSED_MAXMIN) -- are switches read once per process: with both OFF (the paths
-    parties on different GPUs take: AND rows packed / sent / scattered, two bitwiseAnd runs) the same tests give the same
-    share planes against the oracle."""
+    one-pass compare-exchange selection (ABY3_FUSED_MAXMIN), the common GEMV launch (ABY3_RING_GEMV) -- are switches read once
+    per process: with all of them OFF (the paths parties on different GPUs take: AND rows packed / sent / scattered, two
+    bitwiseAnd runs, one cross-term launch per party) the same tests give the same share planes against the oracle."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, ABY3_BIN_SHARED_PLANES="0", ABY3_FUSED_MAXMIN="0")
+    env = dict(os.environ, ABY3_BIN_SHARED_PLANES="0", ABY3_FUSED_MAXMIN="0", ABY3_RING_GEMV="0")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
-                        "-k", "basic_blocks or binary_engine or piecewise_logistic or random_circuits"],
+                        "-k", "basic_blocks or binary_engine or piecewise_logistic or random_circuits or colocated_ring"],
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:]
     assert " passed" in r.stdout
+
+
+def test_colocated_ring_gemv_shares_bit_exact(pair):
+    """A GEMV-shaped truncating product big enough for the co-located parties' common launch (sh3/Colocated.h: 2^22 elements of
+    A, every share plane read once): all six share planes and the PRNG cursors against the oracle, twice (recycled buffers)."""
+    s, r = pair
+    M, K, d = 8192, 512, 16
+    a = (np.random.default_rng(71).normal(0, 3, (M, K)) * (1 << d)).astype(np.int64)
+    w = (np.random.default_rng(72).normal(0, 0.5, (K, 1)) * (1 << d)).astype(np.int64)
+    A, W = s.share_int(0, a), s.share_int(1, w)
+    Ao, Wo = r.share_int(0, a), r.share_int(1, w)
+    for _ in range(2):
+        C = s.mul(A, W, shift=d)
+        Co = r.mul_trunc(Ao, Wo, d)
+        assert np.array_equal(s.get_shares(C), Co)
+        assert np.all(np.abs(s.reveal(C, 2) - (o.plain_mul(a, w) >> d)) <= 4)
+        s.free(C)
+    assert_cursors(s, r)
 
