@@ -171,7 +171,7 @@ Sh3Task Sh3Evaluator::asyncMul(Sh3Task dependency, const si64Matrix& A, const si
             const i64 *a0 = A.mShares[0].dev(), *a1 = A.mShares[1].dev(), *b0 = B.mShares[0].dev(), *b1 = B.mShares[1].dev();
             void* pairDone = early ? ctx->aux()->recordEvent() : nullptr;
             int rc;
-            static const bool ringOn = [] { const char* e = std::getenv("ABY3_RING_GEMV"); return e && e[0] == '1'; }();     // (opt-in until verified on hardware)
+            static const bool ringOn = [] { const char* e = std::getenv("ABY3_RING_GEMV"); return !(e && e[0] == '0'); }();
             if (ringOn && mColocated && N == 1 && nBlocks == 1 && M * A.cols() >= kRingMin) {
                 // co-located parties: one launch for the three cross terms, every plane of A read once (a1 is the previous
                 // party's a0 and is read there)
