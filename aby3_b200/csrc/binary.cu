@@ -581,6 +581,17 @@ __global__ void __launch_bounds__(256) k_bin_rows(u8* mem, u64 row_bytes, const 
     }
 }
 
+// One wire row -> one 64-bit word per instance holding that bit (the output of a comparison circuit: getOutput of a 1-bit
+// bundle, Sh3BinaryEvaluator.cpp:1285-1404).  A thread per instance, 8-byte coalesced stores; the general 8 x 8 staged kernel
+// ran this shape at 0.24 of the HBM write rate.
+__global__ void __launch_bounds__(256) k_row_to_bit_words(const u8* __restrict__ mem, const u32* __restrict__ row_index, u64 row_bytes, u64 width,
+                                                          u64* __restrict__ out, const u8* __restrict__ invert) {
+    const u64* row = reinterpret_cast<const u64*>(mem + (u64)(row_index ? row_index[0] : 0u) * row_bytes);
+    const u64 flip = (invert && invert[0]) ? 1 : 0;
+    for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < width; c += (u64)gridDim.x * blockDim.x)
+        __stcs(out + c, ((row[c >> 6] >> (c & 63)) & 1) ^ flip);
+}
+
 int launch_transpose(aby3cu_ctx* ctx, const void* in, const u32* row_index, u64 rows, u64 cols, u64 in_stride,
                      void* out, u64 out_stride, const u8* invert) {
     ABY3CU_REQUIRE(ctx && ((in && out) || !(rows * cols)), "bit_transpose: null argument");
@@ -607,6 +618,12 @@ int launch_transpose(aby3cu_ctx* ctx, const void* in, const u32* row_index, u64 
         const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
         k_bits_to_sliced<<<grid, 256, 0, ctx->stream>>>((const u64*)in, rows, cols, W, (u8*)out, out_stride);
         return post_launch(ctx, "k_bits_to_sliced");
+    }
+    // fast path 3: ONE bit-sliced row -> one word per instance
+    if (rows == 1 && out_stride == 8 && cols > 64 && in_stride % 8 == 0 && al(in, 8) && al(out, 8)) {
+        const u64 blocks = (cols + 255) / 256, capb = (u64)ctx->sm_count * 8;
+        k_row_to_bit_words<<<(unsigned)(blocks < capb ? blocks : capb), 256, 0, ctx->stream>>>((const u8*)in, row_index, in_stride, cols, (u64*)out, invert);
+        return post_launch(ctx, "k_row_to_bit_words");
     }
     // fast path 2: bit-sliced rows -> instances x 64-bit words (getOutput)
     if (out_stride % 8 == 0 && out_stride <= 128 && cols > rows && rows <= out_stride * 8 && in_stride % 16 == 0 &&

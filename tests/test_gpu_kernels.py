@@ -516,3 +516,19 @@ def test_gemv_ring_equals_three_cross_terms(ctx):
             q = (p + 2) % 3
             assert np.array_equal(ctx.download(dC[p], (M, 1), U64), o.cross_term(A0[p], A0[q], B0[p], B0[q]).view(U64)), (M, K, p)
 
+
+def test_one_row_to_bit_words(ctx):
+    """getOutput of a one-bit bundle (a comparison's result): one wire row, gathered through a row index and optionally
+    complemented, becomes one 64-bit word per instance (fast path of aby3cu_bit_transpose_gather) -- against the oracle transpose."""
+    rng = np.random.default_rng(9)
+    for width in (65, 128, 1000, 70001):
+        rb = int(lib.aby3cu_bin_row_bytes(width))
+        mem = rng.integers(0, 256, 5 * rb, dtype=np.uint8)
+        d_mem = ctx.upload(mem)
+        for row, inv in ((0, 0), (3, 0), (4, 1)):
+            d_idx, d_inv = ctx.upload(np.array([row], dtype=np.uint32)), ctx.upload(np.array([inv] + [0] * 15, dtype=np.uint8))
+            out = ctx.alloc(8 * width)
+            abi.check(lib.aby3cu_bit_transpose_gather(ctx.h, d_mem.p, d_idx.p, 1, width, rb, out.p, 8, d_inv.p if inv else None))
+            bits = np.unpackbits(mem[row * rb:(row + 1) * rb], bitorder="little")[:width].astype(np.int64)
+            assert np.array_equal(ctx.download(out, width), bits ^ inv), (width, row, inv)
+
