@@ -20,7 +20,7 @@ APP_SOURCES = ["aby3-ML/aby3ML.cpp", "aby3-ML/LinearModelGen.cpp", "aby3-ML/main
 # one writes per party 0 run, as counted from the reference's own CPU build (tests/test_ref_parity.py pins these)
 ROLE_TESTS = {"arith_basic_test": 7, "bool_basic_test": 17, "bool_basic_test2": 6, "bool_aggregation_test": 2,
               "get_first_zero_test": 2, "share_conversion_test": 2, "initialization_test": 6, "bc_sort_test": 1,
-              "bc_sort_corner_test": 1, "bc_sort_multiple_times": 1, "quick_sort_test": 1, "odd_even_merge_test": 6,
+              "bc_sort_corner_test": 1, "bc_sort_multiple_times": 1, "quick_sort_test": 1, "quick_sort_with_duplicate_elements_test": 1, "odd_even_merge_test": 6,
               "shuffle_test": 3, "correlation_test": 6}
 
 _p, _u64, _int = C.c_void_p, C.c_uint64, C.c_int

@@ -406,6 +406,6 @@ def test_reference_role_tests_on_cpu():
     SUCCESS lines each writes is what tests/test_compat.py expects of the same programs on the GPU facade."""
     import compat_lib
     for name, n in compat_lib.ROLE_TESTS.items():
-        if name == "quick_sort_test":
-            continue                                   # 2.6 s of CPU; its count is pinned by the GPU-side test
+        if name.startswith("quick_sort"):
+            continue                                   # 2.6 s / 66 s of CPU: their counts (1, 0) were taken from a run of oracle/_ref and are pinned by the GPU-side test
         assert r.role_test(name) == (n, 0), name
