@@ -592,7 +592,7 @@ def basic_bench(sess, n):
     d1 = np.sort(a[:half, 0]).reshape(-1, 1)
     d2 = np.sort(b[:half, 0]).reshape(-1, 1)
     D1, D2 = sess.share_bin(0, d1, 64), sess.share_bin(0, d2, 64)
-    for _ in range(2):                                # warm-up: the stages' buffer sizes enter the pool (the second pass still allocates a few)
+    for _ in range(3):                                # warm-up: the stages' buffer sizes enter the pool (the second and third pass still allocate a few)
         sess.free(sess.odd_even_merge(D1, D2))
     sess.sync()
     # three timed merges: the median is reported, the spread says whether the buffer pool has settled
