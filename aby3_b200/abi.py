@@ -118,6 +118,7 @@ PROTOTYPES = {
     "aby3cu_bit_transpose_gather": (_int, [_p, _p, _p, _u64, _u64, _u64, _p, _u64, _p]),
     "aby3cu_bin_level": (_int, [_p, _p, C.c_uint32, _p, _p, _u64, _key, _key, _u64]),
     "aby3cu_bin_and_layer": (_int, [_p, _p, C.c_uint32, _p, _p, _u64, _key, _key, _u64]),
+    "aby3cu_bin_linear_plane0": (_int, [_p, _p, C.c_uint32, _p, _p, _u64]),
     "aby3cu_bin_maxmin_rowmajor": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _u64, _u64, _key, _key, _key, _key, C.c_uint32]),
     "aby3cu_bin_bitwise_rowmajor": (_int, [_p, C.c_uint32, _p, _p, _p, _p, _p, _p, _u64, C.c_uint32, _u64, _key, _key, _u64]),
     "aby3cu_bin_pack_rows": (_int, [_p, _p, _u64, _p, C.c_uint32, _u64, _p, _p]),

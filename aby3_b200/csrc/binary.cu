@@ -311,6 +311,45 @@ __global__ void __launch_bounds__(256) k_bin_level(const uint4* __restrict__ gat
     }
 }
 
+// The linear gates of one level on plane 0 only (shared planes), with memory-level parallelism: the in-order interpreter above
+// is one dependent chain of "load descriptor -> load operands -> store" per gate (15-27 us for the ~20 gates of a level, whatever
+// the row size).  The host cuts the list into batches of up to 8 mutually independent gates (no gate of a batch reads or writes a
+// wire another gate of the batch writes; `first[g]` != 0 starts a batch): all operand rows of a batch are loaded before any of its
+// outputs is stored, so up to 16 row loads per thread are in flight.  Same values as the in-order walk.
+constexpr int kLinBatch = 8;
+__global__ void __launch_bounds__(256) k_bin_linear_plane0(const uint4* __restrict__ gates, const u8* __restrict__ first, u32 n_gates,
+                                                           u64* mem0, u64 rw) {
+    const u64 chunks = rw / 2;
+    for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (u64)gridDim.x * blockDim.x) {
+        u32 g = 0;
+        while (g < n_gates) {
+            u32 e = g + 1;
+            while (e < n_gates && e - g < kLinBatch && !first[e]) ++e;
+            const u32 cnt = e - g;
+            uint4 G[kLinBatch];
+            W2 a[kLinBatch], b[kLinBatch];
+#pragma unroll
+            for (int k = 0; k < kLinBatch; ++k)
+                if ((u32)k < cnt) {
+                    G[k] = __ldg(gates + g + k);
+                    a[k] = ldw(mem0, G[k].x, rw, c);
+                    b[k] = (G[k].w != 10) ? ldw(mem0, G[k].y, rw, c) : W2{0, 0};
+                }
+#pragma unroll
+            for (int k = 0; k < kLinBatch; ++k)
+                if ((u32)k < cnt) {
+                    W2 o = a[k];
+                    if (G[k].w != 10) {
+                        o = {a[k].a ^ b[k].a, a[k].b ^ b[k].b};
+                        if (G[k].w == 9) o = {~o.a, ~o.b};
+                    }
+                    stw(mem0, G[k].z, rw, c, o);
+                }
+            g = e;
+        }
+    }
+}
+
 // All gates of the list are NONLINEAR and mutually independent (the nonlinear gates of one
 // AND-depth level, whose linear producers have already run): gate x column parallel, gate g uses
 // the zero-share block range of nonlinear gate and0 + g.  Fills the machine even when the number
@@ -691,6 +730,16 @@ int aby3cu_bin_level(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void* d_m
         else k_bin_level<false><<<grid, 256, 0, ctx->stream>>>((const uint4*)d_gates, n_gates, (u64*)d_mem0, (u64*)d_mem1, rw, zero, zero, and_index0);
     }
     return post_launch(ctx, "k_bin_level");
+}
+
+int aby3cu_bin_linear_plane0(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, const u8* d_batch_first, void* d_mem0, u64 row_bytes) {
+    ABY3CU_REQUIRE(ctx && ((d_gates && d_batch_first && d_mem0) || !n_gates), "bin_linear_plane0: null argument");
+    ABY3CU_REQUIRE(row_bytes % 16 == 0, "bin_linear_plane0: row_bytes must be a multiple of 16");
+    if (!n_gates || !row_bytes) return 0;
+    DeviceGuard g(ctx->device);
+    const u64 rw = row_bytes / 8, chunks = rw / 2;
+    k_bin_linear_plane0<<<ew_grid(ctx, chunks, 256, 8), 256, 0, ctx->stream>>>((const uint4*)d_gates, d_batch_first, n_gates, (u64*)d_mem0, rw);
+    return post_launch(ctx, "k_bin_linear_plane0");
 }
 
 int aby3cu_bin_and_layer(aby3cu_ctx* ctx, const u32* d_gates, u32 n_gates, void* d_mem0, const void* d_mem1, u64 row_bytes,

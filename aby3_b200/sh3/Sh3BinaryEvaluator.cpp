@@ -142,6 +142,29 @@ void Sh3BinaryEvaluator::setCir(oc::BetaCircuit* cir, u64 width, block prevSeed,
     for (i64 nl : mLevelLinear) mShare = mShare && nl >= 0;
     if (mFast) { mMem[0].free(); mMem[1].free(); mMem0Shared.reset(); }
     else allocWireMemory();
+    if (mShare) {
+        // batches of mutually independent linear gates for aby3cu_bin_linear_plane0: a gate that reads or writes a wire an
+        // earlier gate of the running batch writes starts a new batch (so does the ninth gate and every level)
+        std::vector<u8> first(cir->mGates.size(), 1);
+        static const bool batched = [] { const char* e = std::getenv("ABY3_BIN_LINEAR_BATCH"); return !(e && e[0] == '0'); }();
+        if (batched)
+            for (u64 l = 0; l < cir->mLevelCounts.size(); ++l) {
+                const u64 g0 = mLevelGateOff[l], nLin = (u64)mLevelLinear[l];
+                std::vector<u32> written;
+                u64 inBatch = 0;
+                for (u64 g = g0; g < g0 + nLin; ++g) {
+                    const auto& G = cir->mGates[g];
+                    bool dep = inBatch == 0 || inBatch == 8;
+                    for (u32 w : written) dep = dep || w == G.mInput[0] || w == G.mInput[1] || w == G.mOutput;
+                    if (dep) { written.clear(); inBatch = 0; }
+                    first[g] = dep ? 1 : 0;
+                    written.push_back(G.mOutput);
+                    ++inBatch;
+                }
+            }
+        mLinBatchDev.reset(mCtx, std::max<size_t>(first.size(), 16));
+        if (!first.empty()) gpu::check(aby3cu_h2d(mCtx->h(), mLinBatchDev.ptr(), first.data(), first.size()));
+    }
     mGatesDev.reset(mCtx, std::max<size_t>(flat.size() * 4, 16));
     mAndLocsDev.reset(mCtx, std::max<size_t>(locs.size() * 4, 16));
     if (!flat.empty()) gpu::check(aby3cu_h2d(mCtx->h(), mGatesDev.ptr(), flat.data(), flat.size() * 4));
@@ -298,7 +321,8 @@ void Sh3BinaryEvaluator::roundCallback(CommPkg& comm, Sh3Task task) {
             const u64 a0 = mLevelAndOff[mLevel], nAnd = mLevelAndOff[mLevel + 1] - a0;
             if (a0 != mShareIdx) throw RTE_LOC;
             const u64 nLin = (u64)mLevelLinear[mLevel];
-            if (nLin) gpu::check(aby3cu_bin_level(mCtx->h(), (const u32*)mGatesDev.ptr() + 4 * g0, (u32)nLin, mem0(), nullptr, mRowBytes, nullptr, nullptr, mShareIdx));
+            if (nLin) gpu::check(aby3cu_bin_linear_plane0(mCtx->h(), (const u32*)mGatesDev.ptr() + 4 * g0, (u32)nLin, (const u8*)mLinBatchDev.ptr() + g0,
+                                                          mem0(), mRowBytes));
             if (nAnd) {
                 exchangeReady(comm, nAnd * sendBytes);
                 gpu::check(aby3cu_bin_and_layer(mCtx->h(), (const u32*)mGatesDev.ptr() + 4 * (g0 + nLin), (u32)nAnd, mem0(), mem1(), mRowBytes,

@@ -132,6 +132,7 @@ private:
     std::array<gpu::Buffer, 2> mMem;
     gpu::Buffer mGatesDev;              // [gates][4] u32
     gpu::Buffer mAndLocsDev;            // output wires of the nonlinear gates, in gate order
+    gpu::Buffer mLinBatchDev;           // per gate: 1 = first gate of a batch of mutually independent linear gates (shared planes)
     std::vector<u64> mLevelGateOff, mLevelAndOff;
     std::vector<i64> mLevelLinear;      // leading linear gates of the level when the rest is all nonlinear, else -1
     gpu::Buffer mRecvBuf;

@@ -322,6 +322,13 @@ int aby3cu_bit_transpose_gather(aby3cu_ctx* ctx, const void* d_in, const uint32_
 int aby3cu_bin_level(aby3cu_ctx* ctx, const uint32_t* d_gates, uint32_t n_gates,
                      void* d_mem0, void* d_mem1, uint64_t row_bytes,
                      const uint8_t key_prev[16], const uint8_t key_next[16], uint64_t and_index0);
+/* The LINEAR gates (Xor = 6, Nxor = 9, copy = 10) of one level on plane 0 only, in batches of mutually independent gates:
+ * d_batch_first[g] != 0 marks the first gate of a batch (at most 8 gates are taken together); no gate of a batch may read or
+ * write a wire that another gate of the same batch writes.  All operand rows of a batch are loaded before its outputs are
+ * stored -- the same values as aby3cu_bin_level(..., d_mem1 = NULL) walking the list in order (roundCallback's gate loop,
+ * Sh3BinaryEvaluator.cpp:671-1080, restricted to the linear types). */
+int aby3cu_bin_linear_plane0(aby3cu_ctx* ctx, const uint32_t* d_gates, uint32_t n_gates, const uint8_t* d_batch_first,
+                             void* d_mem0, uint64_t row_bytes);
 /* The nonlinear gates of one level when they are listed AFTER the level's linear gates (they are
  * then mutually independent): gate x instance parallel.  Gate g of the list uses the zero-share
  * block range of nonlinear gate and_index0 + g, exactly as aby3cu_bin_level would. */

@@ -532,3 +532,42 @@ def test_one_row_to_bit_words(ctx):
             bits = np.unpackbits(mem[row * rb:(row + 1) * rb], bitorder="little")[:width].astype(np.int64)
             assert np.array_equal(ctx.download(out, width), bits ^ inv), (width, row, inv)
 
+
+def test_batched_linear_level_equals_the_in_order_walk(ctx):
+    """aby3cu_bin_linear_plane0 (linear gates of a level in batches of independent gates, operands of a batch loaded before its
+    outputs are stored) against aby3cu_bin_level(..., mem1 = NULL) walking the same list in order: random Xor / Nxor / copy
+    gates with chains (a gate reading an earlier gate's output), write-after-read pairs, and the greedy batching of
+    Sh3BinaryEvaluator::setCir."""
+    rng = np.random.default_rng(123)
+    for width, wires, n_gates in ((100, 12, 9), (5000, 40, 37), (70001, 64, 120)):
+        rb = int(lib.aby3cu_bin_row_bytes(width))
+        gates = np.zeros((n_gates, 4), dtype=np.uint32)
+        outs_free = list(range(wires // 2, wires))
+        rng.shuffle(outs_free)
+        for g in range(n_gates):
+            t = int(rng.choice([6, 9, 10, 6]))
+            o = outs_free[g % len(outs_free)] if g < len(outs_free) else int(rng.integers(wires // 2, wires))
+            a, b = int(rng.integers(0, wires)), int(rng.integers(0, wires))
+            while a == o:
+                a = int(rng.integers(0, wires))
+            while b == o or b == a:
+                b = int(rng.integers(0, wires))
+            gates[g] = (a, b, o, t)
+        first = np.ones(n_gates, dtype=np.uint8)
+        written, in_batch = [], 0
+        for g in range(n_gates):
+            a, b, o, _ = gates[g]
+            dep = in_batch == 0 or in_batch == 8 or any(w in (a, b, o) for w in written)
+            if dep:
+                written, in_batch = [], 0
+            first[g] = 1 if dep else 0
+            written.append(o)
+            in_batch += 1
+        assert first.sum() < n_gates or n_gates < 3          # (some gates do share a batch)
+        mem = rng.integers(0, 256, wires * rb, dtype=np.uint8)
+        d_ref, d_new = ctx.upload(mem), ctx.upload(mem)
+        dg, df = ctx.upload(gates), ctx.upload(np.concatenate([first, np.zeros(16, dtype=np.uint8)]))
+        abi.check(lib.aby3cu_bin_level(ctx.h, dg.p, n_gates, d_ref.p, None, rb, None, None, 0))
+        abi.check(lib.aby3cu_bin_linear_plane0(ctx.h, dg.p, n_gates, df.p, d_new.p, rb))
+        assert np.array_equal(ctx.download(d_new, wires * rb, np.uint8), ctx.download(d_ref, wires * rb, np.uint8)), (width, n_gates)
+
