@@ -493,13 +493,18 @@ def linreg_bench(sess, samples, features=1024, batch=128, iters=300, lr=2.0 ** -
     fsampler = ClockSampler(0)
     fsampler.start()
     fsampler.mark()
-    t0 = time.perf_counter()
-    sess.linreg_fused(X, Y, W, fidx, fiters, batch, lr)
-    sess.sync()
-    dtf = time.perf_counter() - t0
+    # three training runs of fiters iterations each (the weights keep training), the median is reported: one run is 80 ms of a
+    # latency-bound kernel and moves by +-5 % with the box
+    runs = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        sess.linreg_fused(X, Y, W, fidx, fiters, batch, lr)
+        sess.sync()
+        runs.append(time.perf_counter() - t0)
+    dtf = sorted(runs)[1]
     fclocks = fsampler.stop()
     out = {"iters_per_s": fiters / dtf, "iters": fiters, "batch": batch, "features": features, "samples": samples,
-           "decimal": "D16", "lr": lr, "kernel_launches": sess.launches - l0, "ms_total": dtf * 1e3, "clocks": fclocks,
+           "decimal": "D16", "lr": lr, "kernel_launches": (sess.launches - l0) // 3, "ms_total": dtf * 1e3, "ms_runs": [round(r * 1e3, 3) for r in runs], "clocks": fclocks,
            "path": "SGD_Linear, three co-located parties, the whole run as one persistent cooperative kernel "
                    "(upload of the batch indices and the final sync included in the time)",
            "graph_replay_iters_per_s": giters / dt, "graph_replay_kernels_per_iter": graph_kernels,
